@@ -1,0 +1,202 @@
+"""Oracle (TEST INFRASTRUCTURE): generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden            # rewrites tests/golden/
+
+Every fixture holds the backbone state dict (reference parameter names), the
+inputs (condition, optional src_spec, every random draw the reference made, in
+draw order) and the reference's output, plus a JSON ``meta`` blob describing the
+hparams / constructor arguments.  Sizes are kept tiny so the fixtures stay a few
+hundred KB in total.  The reference publishes no golden vectors of its own
+(SURVEY.md section 4); these are outputs of the reference code itself.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader  # noqa: E402
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+WN_SMALL = dict(num_layers=3, num_channels=32, dilation_cycle_length=2)
+WN_CYC = dict(num_layers=5, num_channels=32, dilation_cycle_length=5)        # dilations 1..16
+LX_SMALL = dict(num_layers=2, num_channels=32, expansion_factor=2, kernel_size=31, strong_cond=True)
+LX_WEAK = dict(num_layers=2, num_channels=32, expansion_factor=2, kernel_size=7, strong_cond=False, activation='SiLU')
+HIDDEN = 24
+SIGMA_W = 0.05
+WEIGHT_SEED = 100
+
+
+def _reinit(backbone, seed):
+    g = torch.Generator().manual_seed(seed)
+    w = backbone.output_projection.weight
+    with torch.no_grad():
+        w.copy_(torch.randn(w.shape, generator=g) * SIGMA_W)
+        # exercise affine / PReLU parameters that default to constants
+        for name, p in backbone.named_parameters():
+            if name.endswith('net.0.weight') or name == 'norm.weight':
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            elif name.endswith('net.0.bias') or name == 'norm.bias':
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            elif name.endswith('net.5.weight'):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+
+
+def _save(name, meta, arrays, sd):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    # state dicts are shared between cases built from the same weight seed: store each once
+    sd_np = {k: v.detach().numpy() for k, v in sd.items()}
+    h = hashlib.sha1()
+    for k in sorted(sd_np):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd_np[k]).tobytes())
+    sd_name = f'weights_{h.hexdigest()[:12]}'
+    sd_path = os.path.join(OUT_DIR, sd_name + '.npz')
+    if not os.path.exists(sd_path):
+        np.savez_compressed(sd_path, **sd_np)
+    meta = dict(meta, weights=sd_name)
+    payload = {f'in.{k}': (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrays.items()}
+    payload['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    path = os.path.join(OUT_DIR, name + '.npz')
+    np.savez_compressed(path, **payload)
+    print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
+
+
+def backbone_case(name, btype, bargs, in_dims, n_feats, B, T, t, seed):
+    ref = ref_loader.load()
+    ref.hparams.update(hidden_size=HIDDEN)
+    torch.manual_seed(seed)
+    net = ref.backbones.build_backbone(in_dims, n_feats, btype, bargs).eval()
+    _reinit(net, seed + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    spec = torch.randn((B, n_feats, in_dims, T), generator=g)
+    cond = torch.randn((B, HIDDEN, T), generator=g)
+    with torch.no_grad():
+        out = net(spec, t, cond)
+    meta = dict(kind='backbone', backbone_type=btype, backbone_args=bargs, in_dims=in_dims, n_feats=n_feats,
+                hidden_size=HIDDEN)
+    _save(name, meta, dict(spec=spec, t=t, cond=cond, out=out), net.state_dict())
+
+
+def diffusion_case(name, cls_name, ctor, hp, B, T, seed, src=None, n_draws=1, variance_inputs=None):
+    """Runs ``model(condition, src_spec=src, infer=True)`` of a ddpm.py / reflow.py class."""
+    ref = ref_loader.load()
+    ref.hparams.clear()
+    ref.hparams.update(hidden_size=HIDDEN, schedule_type='linear', infer=False)
+    ref.hparams.update(hp)
+    mod = ref.ddpm if hasattr(ref.ddpm, cls_name) else ref.reflow
+    torch.manual_seed(WEIGHT_SEED)
+    model = getattr(mod, cls_name)(**ctor).eval()
+    bb = model.denoise_fn if hasattr(model, 'denoise_fn') else model.velocity_fn
+    _reinit(bb, WEIGHT_SEED + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    condition = torch.randn((B, T, HIDDEN), generator=g)
+    arrays = dict(condition=condition)
+    if src == 'mel':
+        smin, smax = ctor['spec_min'][0], ctor['spec_max'][0]
+        src_spec = torch.rand((B, T, ctor['out_dims']), generator=g) * (smax - smin) + smin
+        arrays['src_spec'] = src_spec
+    elif src == 'curve':
+        src_spec = torch.randn((B, T), generator=g) * 3
+        arrays['src_spec'] = src_spec
+    elif src == 'curves':
+        src_spec = [torch.randn((B, T), generator=g) * 20 - 50 for _ in ctor['ranges']]
+        for i, s in enumerate(src_spec):
+            arrays[f'src_spec{i}'] = s
+    else:
+        src_spec = None
+    F_, M_ = model.num_feats, model.out_dims
+    torch.manual_seed(seed + 3)
+    with torch.no_grad():
+        out = model(condition, src_spec=src_spec, infer=True)
+    torch.manual_seed(seed + 3)
+    draws = torch.stack([torch.randn(B, F_, M_, T) for _ in range(n_draws)])
+    arrays['draws'] = draws
+    if isinstance(out, (list, tuple)):
+        for i, o in enumerate(out):
+            arrays[f'out{i}'] = o
+    else:
+        arrays['out'] = out
+    meta = dict(kind='diffusion', cls=cls_name, ctor=ctor, hparams=hp, hidden_size=HIDDEN, n_draws=n_draws)
+    _save(name, meta, arrays, bb.state_dict())
+
+
+def main():
+    # ---- backbone forward ------------------------------------------------------------------
+    backbone_case('bb_wavenet_int_t', 'wavenet', WN_SMALL, 16, 1, 2, 37, torch.tensor([950, 3]), 10)
+    backbone_case('bb_wavenet_float_t1', 'wavenet', WN_CYC, 16, 1, 3, 41, torch.tensor([437.25]), 11)
+    backbone_case('bb_wavenet_feats2', 'wavenet', WN_SMALL, 8, 2, 2, 19, torch.tensor([12.5, 700.0]), 12)
+    backbone_case('bb_lynxnet_strong', 'lynxnet', LX_SMALL, 16, 1, 2, 37, torch.tensor([950, 3]), 13)
+    backbone_case('bb_lynxnet_weak_silu', 'lynxnet', LX_WEAK, 8, 2, 2, 23, torch.tensor([333.5]), 14)
+
+    mel = dict(out_dims=16, num_feats=1, spec_min=[-12.], spec_max=[0.])
+    wn = dict(backbone_type='wavenet', backbone_args=WN_SMALL)
+    lx = dict(backbone_type='lynxnet', backbone_args=LX_SMALL)
+    base = dict(use_shallow_diffusion=False, diff_speedup=1, diff_accelerator='ddim')
+
+    # ---- GaussianDiffusion, every sampler ---------------------------------------------------
+    # full-depth DDPM on a short schedule (timesteps=30): 30 ancestral steps, 31 draws
+    diffusion_case('gd_ddpm_full_T30', 'GaussianDiffusion', dict(mel, timesteps=30, k_step=30, **wn),
+                   dict(base), 2, 21, 20, n_draws=31)
+    # shallow DDPM: K_step=12 of 1000, q_sample start from src_spec
+    diffusion_case('gd_ddpm_shallow_K12', 'GaussianDiffusion', dict(mel, timesteps=1000, k_step=12, **wn),
+                   dict(base, use_shallow_diffusion=True, K_step_infer=12), 2, 21, 21, src='mel', n_draws=13)
+    for acc, b in (('ddim', 2), ('pndm', 1), ('dpm-solver', 2), ('unipc', 2)):
+        tag = acc.replace('-', '')
+        diffusion_case(f'gd_{tag}_10', 'GaussianDiffusion', dict(mel, timesteps=1000, k_step=1000, **wn),
+                       dict(base, diff_speedup=100, diff_accelerator=acc), b, 21, 22)
+        diffusion_case(f'gd_{tag}_5', 'GaussianDiffusion', dict(mel, timesteps=1000, k_step=1000, **wn),
+                       dict(base, diff_speedup=200, diff_accelerator=acc), b, 17, 23)
+    # shallow + accelerated (schedule is betas[:t_max], N = 400)
+    for acc in ('ddim', 'dpm-solver', 'unipc'):
+        tag = acc.replace('-', '')
+        diffusion_case(f'gd_{tag}_shallow400_8', 'GaussianDiffusion', dict(mel, timesteps=1000, k_step=400, **wn),
+                       dict(base, use_shallow_diffusion=True, K_step_infer=400, diff_speedup=50,
+                            diff_accelerator=acc), 2, 19, 24, src='mel')
+    # cosine schedule: DPM-Solver clips lambda (total_N 996), UniPC does not
+    for acc in ('dpm-solver', 'unipc'):
+        tag = acc.replace('-', '')
+        diffusion_case(f'gd_{tag}_cosine_10', 'GaussianDiffusion', dict(mel, timesteps=1000, k_step=1000, **wn),
+                       dict(base, schedule_type='cosine', diff_speedup=100, diff_accelerator=acc), 2, 19, 25)
+    # LYNXNet under DDIM
+    diffusion_case('gd_ddim_lynx_10', 'GaussianDiffusion', dict(mel, timesteps=1000, k_step=1000, **lx),
+                   dict(base, diff_speedup=100, diff_accelerator='ddim'), 2, 33, 26)
+
+    # ---- RectifiedFlow ---------------------------------------------------------------------
+    rf = dict(mel, time_scale_factor=1000)
+    for alg in ('euler', 'rk2', 'rk4', 'rk5'):
+        diffusion_case(f'rf_{alg}_4_lynx', 'RectifiedFlow', dict(rf, t_start=0., **lx),
+                       dict(use_shallow_diffusion=False, sampling_algorithm=alg, sampling_steps=4), 2, 33, 30)
+    diffusion_case('rf_euler_shallow_6_lynx', 'RectifiedFlow', dict(rf, t_start=0.4, **lx),
+                   dict(use_shallow_diffusion=True, T_start_infer=0.4, sampling_algorithm='euler', sampling_steps=6),
+                   2, 33, 31, src='mel')
+    diffusion_case('rf_euler_5_wavenet', 'RectifiedFlow', dict(rf, t_start=0., **wn),
+                   dict(use_shallow_diffusion=False, sampling_algorithm='euler', sampling_steps=5), 2, 21, 32)
+
+    # ---- variance models (repeat bins, clamps, mean over bins) ------------------------------
+    diffusion_case('var_pitch_ddim_10', 'PitchDiffusion',
+                   dict(vmin=-8., vmax=8., cmin=-12., cmax=12., repeat_bins=8, timesteps=1000, k_step=1000, **wn),
+                   dict(base, diff_speedup=100, diff_accelerator='ddim'), 2, 21, 40)
+    diffusion_case('var_multi_unipc_10', 'MultiVarianceDiffusion',
+                   dict(ranges=[(-96., -12.), (-96., -20.)], clamps=[(-96., -12.), (-96., -20.)], repeat_bins=6,
+                        timesteps=1000, k_step=1000, **wn),
+                   dict(base, diff_speedup=100, diff_accelerator='unipc'), 2, 21, 41)
+    diffusion_case('var_pitch_reflow_euler_4', 'PitchRectifiedFlow',
+                   dict(vmin=-8., vmax=8., cmin=-12., cmax=12., repeat_bins=8, time_scale_factor=1000, **wn),
+                   dict(use_shallow_diffusion=False, sampling_algorithm='euler', sampling_steps=4), 2, 21, 42)
+    diffusion_case('var_multi_reflow_rk4_3', 'MultiVarianceRectifiedFlow',
+                   dict(ranges=[(-96., -12.), (-96., -20.)], clamps=[(-96., -12.), None], repeat_bins=6,
+                        time_scale_factor=1000, **wn),
+                   dict(use_shallow_diffusion=False, sampling_algorithm='rk4', sampling_steps=3), 2, 21, 43)
+
+
+if __name__ == '__main__':
+    main()
