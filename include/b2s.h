@@ -1,0 +1,121 @@
+/*
+ * b2s.h - C ABI of libb2s: B200-native (sm_100a) kernels for the DiffSinger acoustic / variance
+ *         sampling hot path (reference: vsingerxiaoice-rwkv/xiaoicesing-io, an OpenVPI DiffSinger fork).
+ *
+ * The reference has NO native code and NO FFI for this path: its boundary is
+ * Python (backbone registry modules/backbones/__init__.py:6-18, GaussianDiffusion / RectifiedFlow in
+ * modules/core/ddpm.py:55-383 and reflow.py:13-144).  This header is therefore the NEW seam that sits
+ * directly under that Python surface; every entry point names the reference code it replaces.
+ * The Python binding a maintainer adds is a ctypes stub (xiaoicesing_io_b200/_cabi.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host;
+ *   - the caller owns every buffer; no entry point allocates, synchronises or keeps state, so all of them
+ *     are CUDA-graph capturable on the stream passed as the last argument (a cudaStream_t as void*);
+ *   - activations are TIME-MAJOR: a "frame matrix" is [rows = B*T, channels] row-major, row r = b*T + t.
+ *     (The reference keeps [B, channels, T]; its final op is a transpose to [B, T, M], ddpm.py:350.)
+ *   - return value 0 = success, negative = error (b2s_last_error() gives the text, thread-local).
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_ABI_VERSION 1
+
+#define B2S_OK 0
+#define B2S_ERR_INVALID_ARGUMENT (-1)
+#define B2S_ERR_CUDA (-2)
+#define B2S_ERR_UNSUPPORTED (-3)
+
+/* activation codes for b2s_linear_f32 */
+#define B2S_ACT_NONE 0
+#define B2S_ACT_RELU 1 /* wavenet.py:88,98 */
+#define B2S_ACT_MISH 2 /* wavenet.py:60 */
+#define B2S_ACT_GELU 3 /* exact erf GELU, lynxnet.py:107,143 */
+#define B2S_ACT_SILU 4
+
+int b2s_abi_version(void);
+const char* b2s_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout helpers
+ * ---------------------------------------------------------------------------------------------- */
+
+/* in [batch, rows, cols] -> out [batch, cols, rows] (fp32).  Replaces the .transpose() calls at
+ * ddpm.py:350,357,370 / reflow.py:44,58,137 when crossing between the reference layout [B, M, T]
+ * and the time-major internal layout. */
+int b2s_transpose_f32(const float* in, float* out, int batch, int rows, int cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampler update: dst = sum_i coef[i] * src[i]   (one vectorised elementwise kernel)
+ *
+ * Covers p_sample (ddpm.py:149-156), p_sample_ddim (:158-167), p_sample_plms (:169-204), q_sample
+ * (:206-210), the DPM-Solver++ 2M updates (dpm_solver_pytorch.py:547-580, 796-831) incl. the
+ * eps -> x0 conversion (:434-442), the UniPC-bh2 predictor / corrector (uni_pc.py:548-567) and the
+ * Euler / RK stages (reflow.py:66-102).  coef is a DEVICE array so a captured graph can be replayed.
+ * n_src <= 8.  dst may alias any src.
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host, const float* coef, int n_src,
+                            int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step embedding:  SinusoidalPosEmb (common_layers.py:266-278)
+ * t [n] fp32 (the model time: int step index, (t-1/N)*N, or 1000*t) -> out [n, dim]
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_sinusoid_f32(const float* t, float* out, int n, int dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 reference-precision path (CUDA cores): out[M,N] = act(alpha * A[M,K] . W[N,K]^T + bias[N])
+ * Replaces nn.Linear / Conv1d(k=1): wavenet.py:34,35,58-62,86,97,99; lynxnet.py:71,72,104-109,154.
+ * If y is non-null also writes y = out + dvec[b * d_stride + n]  (b = row / T), the next layer's
+ * pre-added step embedding (wavenet.py:36).  K % 4 == 0, lda/ldw/ldo % 4 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* out, int ldo,
+                   int M, int N, int K, float alpha, int act, float* y, const float* dvec, int d_stride, int T,
+                   void* stream);
+
+/* WaveNet residual block, first half (wavenet.py:36-42): z = sigmoid(g) * tanh(f),
+ * [g|f] = dilated_conv_k3(y) + cond, y = x + step embedding (zero outside [0,T) per utterance, H1).
+ *   y      [B*T, C]        pre-added activations
+ *   Wd     [2C, 3C]        packed: row 2j = gate j, 2j+1 = filter j; column = tap*C + c
+ *   cond   [B*T, ld_cond]  hoisted conditioner projection of THIS layer (+ both biases), same interleave
+ *   z      [B*T, C]
+ * C % 16 == 0. */
+int b2s_wavenet_gate_f32(const float* y, const float* Wd, const float* cond, int ld_cond, float* z, int B, int T,
+                         int C, int dilation, void* stream);
+
+/* WaveNet residual block, second half (wavenet.py:44-48): [r|s] = Wo z + bo;
+ * x <- (x + r)/sqrt(2);  y_next <- x + dvec_next (if y_next != NULL);  skip <- s (first) or skip + s.
+ *   Wo [2C, C] rows 0..C-1 residual, C..2C-1 skip (reference order). */
+int b2s_wavenet_out_f32(const float* z, const float* Wo, const float* bo, float* x, float* y_next, float* skip,
+                        const float* dvec_next, int d_stride, int first_layer, int B, int T, int C, void* stream);
+
+/* LYNXNet (lynxnet.py:76-87, 52-62) fp32 building blocks ------------------------------------------ */
+
+/* u = x + cond + d;  res = strong_cond ? x + cond : x (written back to x);  h = LayerNorm_C(u)*gamma+beta */
+int b2s_lynx_prenorm_f32(float* x, const float* cond, int ld_cond, const float* dvec, int d_stride,
+                         const float* gamma, const float* beta, float* h, int B, int T, int C, int strong_cond,
+                         void* stream);
+/* plain LayerNorm over channels (final norm, lynxnet.py:151) */
+int b2s_layernorm_f32(const float* x, const float* gamma, const float* beta, float* h, int rows, int C,
+                      void* stream);
+/* g = out * silu(gate), [out|gate] = W h + b; W packed [2*inner, C] interleaved (row 2j = out j, 2j+1 = gate j) */
+int b2s_lynx_glu_f32(const float* h, const float* W, const float* bias, float* g, int rows, int C, int inner,
+                     void* stream);
+/* depthwise conv along time (k taps, zero pad k/2 per utterance) + bias + activation
+ * act: 0 = PReLU(slope[inner]), B2S_ACT_SILU, B2S_ACT_RELU.  Wdw [inner, k]. */
+int b2s_lynx_dwconv_f32(const float* g, const float* Wdw, const float* bias, const float* slope, float* p, int B,
+                        int T, int inner, int ksize, int act, void* stream);
+/* x <- W p + b + x   (W [C, inner]) */
+int b2s_linear_residual_f32(const float* p, const float* W, const float* bias, float* x, int rows, int C,
+                            int inner, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */

@@ -1,0 +1,187 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything here goes through the C ABI of
+libb2s.so via the product's public API and is compared with (a) the committed fixtures produced by
+the unmodified reference and (b) the CPU oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): max-abs de-normalised mel error <= 1e-3 for the fp32 path."""
+import math
+
+import pytest
+import torch
+
+import golden_util as GU
+import product_util as PU
+from oracle import denoisers as OD
+from oracle import samplers as OS
+from oracle import weights as OW
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3
+BB = GU.fixture_names('bb_')
+DF = [n for n in GU.fixture_names() if not n.startswith('bb_')]
+
+
+def _maxabs(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max())
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device'
+    import xiaoicesing_io_b200 as P
+    P.hparams.pop('b2s_precision', None)
+    return torch.device('cuda:0')
+
+
+def _inject(model, draws, dev):
+    it = iter(draws)
+    model._noise_source = lambda shape: next(it).to(dev)
+
+
+@pytest.mark.parametrize('name', BB)
+def test_backbone_forward_vs_reference_fixture(name, dev):
+    fx = GU.Fixture(name)
+    net = PU.build_backbone(fx, dev)
+    out = net(fx['spec'].to(dev), fx['t'].to(dev), fx['cond'].to(dev))
+    ref = fx['out']
+    assert out.shape == ref.shape
+    assert _maxabs(out, ref) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('name', DF)
+def test_sampling_vs_reference_fixture(name, dev):
+    fx = GU.Fixture(name)
+    model = PU.build_model(fx, dev)
+    _inject(model, fx['draws'], dev)
+    kw = {}
+    if 'src_spec' in fx:
+        kw['src_spec'] = fx['src_spec'].to(dev)
+    out = model(fx['condition'].to(dev), infer=True, **kw)
+    ref = GU.expected_outputs(fx)
+    outs = out if isinstance(out, (list, tuple)) else [out]
+    refs = ref if isinstance(ref, list) else [ref]
+    assert len(outs) == len(refs)
+    for o, r in zip(outs, refs):
+        assert tuple(o.shape) == tuple(r.shape)
+        assert _maxabs(o, r) <= FP32_TOL, (name, _maxabs(o, r), float(r.abs().max()))
+
+
+def _oracle_and_product(cfg, hp, sampler_kw, B, T, dev, seed=1234, sigma_w=0.01, n_draws=1, src=False):
+    import xiaoicesing_io_b200 as P
+    P.hparams.clear()
+    P.hparams.update(hidden_size=cfg.hidden_size, schedule_type='linear', infer=False, **hp)
+    bargs = dict(num_layers=cfg.num_layers, num_channels=cfg.num_channels,
+                 dilation_cycle_length=cfg.dilation_cycle_length)
+    model = P.GaussianDiffusion(cfg.in_dims, backbone_type='wavenet', backbone_args=bargs,
+                                spec_min=[-12.], spec_max=[0.], **sampler_kw)
+    sd = OW.make_state_dict(cfg, seed=0, sigma_w=sigma_w)
+    model.denoise_fn.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(seed)
+    condition = torch.randn((B, T, cfg.hidden_size), generator=g)
+    draws = [torch.randn((B, 1, cfg.in_dims, T), generator=g) for _ in range(n_draws)]
+    src_spec = (torch.rand((B, T, cfg.in_dims), generator=g) * 12 - 12) if src else None
+    _inject(model, draws, dev)
+    out = model(condition.to(dev), src_spec=None if src_spec is None else src_spec.to(dev), infer=True).cpu()
+    sch = OS.DiffusionSchedule(sampler_kw.get('timesteps', 1000), 'linear')
+    x_start = None
+    if src:
+        x_start = OS.norm_spec(src_spec, torch.tensor(-12.), torch.tensor(0.)).transpose(-2, -1)[:, None]
+    use_shallow = hp.get('use_shallow_diffusion', False)
+    k_step = sampler_kw.get('k_step', 1000) if use_shallow else sampler_kw.get('timesteps', 1000)
+    x = OS.gaussian_diffusion_inference(
+        OD.make_denoiser(sd, cfg), sch, condition.transpose(1, 2), k_step=k_step,
+        timesteps=sampler_kw.get('timesteps', 1000), use_shallow=use_shallow,
+        K_step_infer=hp.get('K_step_infer', k_step), speedup=hp['diff_speedup'],
+        accelerator=hp.get('diff_accelerator', 'ddim'), noise0=draws[0], x_start=x_start, step_noise=draws[1:])
+    ref = OS.denorm_spec(x, torch.tensor(-12.), torch.tensor(0.))
+    return out, ref
+
+
+@pytest.mark.parametrize('acc', ['ddim', 'dpm-solver', 'unipc'])
+def test_config1_full_size_wavenet_20x256(acc, dev):
+    """BASELINE config 1: WaveNet 20x256, 128 mel, one 8-s utterance (690 frames), 20 steps."""
+    cfg = OD.WaveNetCfg()
+    out, ref = _oracle_and_product(cfg, dict(use_shallow_diffusion=False, diff_speedup=50, diff_accelerator=acc),
+                                   {}, 1, 690, dev)
+    err = _maxabs(out, ref)
+    print(f'config1 {acc}: max-abs {err:.3e}, |mel|max {float(ref.abs().max()):.1f}')
+    assert err <= FP32_TOL
+
+
+def test_config2_shape_shallow_ddpm_ragged_T(dev):
+    """BASELINE config 2 at a size the oracle finishes in seconds: shallow DDPM full-step (K=40 of 1000),
+    WaveNet 20x256, B=3, T=173 (not a tile multiple), per-step ancestral noise."""
+    cfg = OD.WaveNetCfg()
+    out, ref = _oracle_and_product(
+        cfg, dict(use_shallow_diffusion=True, K_step_infer=40, diff_speedup=1), dict(k_step=40),
+        3, 173, dev, n_draws=41, src=True)
+    err = _maxabs(out, ref)
+    print(f'config2-shape ddpm K=40: max-abs {err:.3e}, |mel|max {float(ref.abs().max()):.1f}')
+    assert err <= FP32_TOL
+
+
+def test_config5_shape_wavenet_20x512_unipc(dev):
+    cfg = OD.WaveNetCfg(num_channels=512)
+    out, ref = _oracle_and_product(cfg, dict(use_shallow_diffusion=False, diff_speedup=100, diff_accelerator='unipc'),
+                                   {}, 2, 131, dev)
+    err = _maxabs(out, ref)
+    print(f'config5-shape unipc-10 C=512: max-abs {err:.3e}, |mel|max {float(ref.abs().max()):.1f}')
+    assert err <= FP32_TOL
+
+
+def test_config3_shape_lynxnet_reflow(dev):
+    """BASELINE config 3 shape: rectified-flow Euler 20 with LYNXNet (C=1024 shrunk to 256 for the oracle)."""
+    import xiaoicesing_io_b200 as P
+    cfg = OD.LYNXNetCfg(num_channels=256, num_layers=6, kernel_size=31, strong_cond=True, hidden_size=256)
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, use_shallow_diffusion=False, sampling_algorithm='euler', sampling_steps=20,
+                     infer=False)
+    bargs = dict(num_layers=6, num_channels=256, kernel_size=31, strong_cond=True)
+    model = P.RectifiedFlow(128, backbone_type='lynxnet', backbone_args=bargs, spec_min=[-12.], spec_max=[0.])
+    sd = OW.make_state_dict(cfg, seed=0, sigma_w=0.01)
+    model.velocity_fn.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(7)
+    B, T = 2, 211
+    condition = torch.randn((B, T, 256), generator=g)
+    noise0 = torch.randn((B, 1, 128, T), generator=g)
+    _inject(model, [noise0], dev)
+    out = model(condition.to(dev), infer=True).cpu()
+    x = OS.rectified_flow_inference(OD.make_denoiser(sd, cfg), condition.transpose(1, 2), t_start=0.,
+                                    use_shallow=False, algorithm='euler', steps=20, noise0=noise0)
+    ref = OS.denorm_spec(x, torch.tensor(-12.), torch.tensor(0.))
+    err = _maxabs(out, ref)
+    print(f'config3-shape lynx euler-20: max-abs {err:.3e}, |mel|max {float(ref.abs().max()):.1f}')
+    assert err <= FP32_TOL
+
+
+def test_seeded_rng_order_matches_torch(dev):
+    """Without injection the product draws with torch.randn in the reference's order: initial noise
+    first, then one draw per ancestral step -> a seeded run is reproducible and equals the injected run."""
+    fx = GU.Fixture('gd_ddpm_shallow_K12')
+    model = PU.build_model(fx, dev)
+    src = fx['src_spec'].to(dev)
+    cond = fx['condition'].to(dev)
+    torch.manual_seed(99)
+    a = model(cond, src_spec=src, infer=True)
+    torch.manual_seed(99)
+    shape = tuple(fx['draws'][0].shape)
+    draws = [torch.randn(shape, device=dev) for _ in range(13)]
+    _inject(model, draws, dev)
+    b = model(cond, src_spec=src, infer=True)
+    assert torch.equal(a, b)
+
+
+def test_batch_rows_are_independent(dev):
+    """No op on the path mixes utterances: sampling a batch equals sampling each
+    utterance alone, bit for bit - the property the multi-GPU partition relies on."""
+    fx = GU.Fixture('gd_unipc_10')
+    model = PU.build_model(fx, dev)
+    draws = fx['draws']
+    _inject(model, draws, dev)
+    full = model(fx['condition'].to(dev), infer=True)
+    for i in range(fx['condition'].shape[0]):
+        _inject(model, [d[i:i + 1] for d in draws], dev)
+        one = model(fx['condition'][i:i + 1].to(dev), infer=True)
+        assert torch.equal(one[0], full[i])

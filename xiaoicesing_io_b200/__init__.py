@@ -1,0 +1,22 @@
+"""xiaoicesing_io_b200 - B200-native (sm_100a) implementation of ONE hot path of the DiffSinger fork
+``vsingerxiaoice-rwkv/xiaoicesing-io``: the repeated denoiser forward inside the diffusion /
+rectified-flow sampling loop over mel tensors [B, 128 bins, T frames].
+
+Public surface (same names and contracts as the reference's ``modules.backbones`` / ``modules.core``):
+
+    BACKBONES, build_backbone, WaveNet, LYNXNet
+    GaussianDiffusion, RepetitiveDiffusion, PitchDiffusion, MultiVarianceDiffusion
+    RectifiedFlow, RepetitiveRectifiedFlow, PitchRectifiedFlow, MultiVarianceRectifiedFlow
+    hparams  (the global config dict, utils/hparams.py:13)
+
+Importing the package loads ``libb2s.so`` (hand-written CUDA kernels behind the C ABI of
+``include/b2s.h``); it raises ImportError if the library has not been built.  There is no CPU or
+PyTorch fallback anywhere in this package.
+"""
+from . import _cabi  # noqa: F401  (fails loudly when libb2s.so is missing)
+from .backbones import BACKBONES, LYNXNet, WaveNet, build_backbone, filter_kwargs
+from .core import (GaussianDiffusion, MultiVarianceDiffusion, MultiVarianceRectifiedFlow, PitchDiffusion,
+                   PitchRectifiedFlow, RectifiedFlow, RepetitiveDiffusion, RepetitiveRectifiedFlow)
+from .hparams import hparams, set_hparams
+
+__version__ = '0.1.0'

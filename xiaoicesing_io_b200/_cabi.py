@@ -1,0 +1,142 @@
+"""ctypes binding of libb2s.so (the C ABI declared in include/b2s.h).
+
+This is the ONLY way the Python host code reaches the GPU kernels; there is no CPU or PyTorch fallback.
+If the shared library is missing the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch
+
+from . import _build
+
+_vp, _i, _f, _i64 = c_void_p, c_int, c_float, c_int64
+
+# name -> argtypes (all return int except where noted); mirrors include/b2s.h line by line
+_SIGNATURES = {
+    'b2s_transpose_f32': [_vp, _vp, _i, _i, _i, _vp],
+    'b2s_sampler_lincomb_f32': [_vp, ctypes.POINTER(_vp), _vp, _i, _i64, _vp],
+    'b2s_sinusoid_f32': [_vp, _vp, _i, _i, _vp],
+    'b2s_linear_f32': [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _i, _i, _vp],
+    'b2s_wavenet_gate_f32': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    'b2s_wavenet_out_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    'b2s_lynx_prenorm_f32': [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    'b2s_layernorm_f32': [_vp, _vp, _vp, _vp, _i, _i, _vp],
+    'b2s_lynx_glu_f32': [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    'b2s_lynx_dwconv_f32': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    'b2s_linear_residual_f32': [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+}
+
+EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', *_SIGNATURES]
+
+ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU, ACT_SILU = 0, 1, 2, 3, 4
+
+
+class B2SError(RuntimeError):
+    pass
+
+
+def _load():
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(
+            f'{path} is missing: the CUDA extension has not been built.  Run '
+            f'`python -c "import __graft_entry__ as g; g.build()"` (needs nvcc).  '
+            f'There is no CPU fallback for this path.')
+    lib = ctypes.CDLL(path)
+    lib.b2s_abi_version.restype = c_int
+    lib.b2s_abi_version.argtypes = []
+    lib.b2s_last_error.restype = c_char_p
+    lib.b2s_last_error.argtypes = []
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+LIB_PATH = _build.LIB_PATH
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        raise B2SError(f'{what} failed (code {rc}): {lib.b2s_last_error().decode()}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise B2SError(f'{name} must be a CUDA tensor: this path has no CPU fallback (got {t.device})')
+    if t.dtype != dtype:
+        raise B2SError(f'{name} must be {dtype} (got {t.dtype})')
+    if not t.is_contiguous():
+        raise B2SError(f'{name} must be contiguous')
+    return t
+
+
+# ---- thin typed wrappers (argument order = include/b2s.h) ------------------------------------------
+def transpose(inp, out, batch, rows, cols):
+    check(lib.b2s_transpose_f32(ptr(inp), ptr(out), batch, rows, cols, stream_ptr()), 'b2s_transpose_f32')
+
+
+def lincomb(dst, srcs, coef_dev):
+    """dst = sum_i coef_dev[i] * srcs[i]; coef_dev is a device fp32 tensor (view) of len(srcs) entries."""
+    arr = (_vp * len(srcs))(*[s.data_ptr() for s in srcs])
+    check(lib.b2s_sampler_lincomb_f32(ptr(dst), arr, ptr(coef_dev), len(srcs), dst.numel(), stream_ptr()),
+          'b2s_sampler_lincomb_f32')
+
+
+def sinusoid(t, out, n, dim):
+    check(lib.b2s_sinusoid_f32(ptr(t), ptr(out), n, dim, stream_ptr()), 'b2s_sinusoid_f32')
+
+
+def linear(A, lda, W, ldw, bias, out, ldo, M, N, K, alpha=1.0, act=ACT_NONE, y=None, dvec=None, d_stride=0, T=0):
+    check(lib.b2s_linear_f32(ptr(A), lda, ptr(W), ldw, ptr(bias), ptr(out), ldo, M, N, K, alpha, act,
+                             ptr(y), ptr(dvec), d_stride, T, stream_ptr()), 'b2s_linear_f32')
+
+
+def wavenet_gate(y, Wd, cond, ld_cond, z, B, T, C, dilation):
+    check(lib.b2s_wavenet_gate_f32(ptr(y), ptr(Wd), ptr(cond), ld_cond, ptr(z), B, T, C, dilation, stream_ptr()),
+          'b2s_wavenet_gate_f32')
+
+
+def wavenet_out(z, Wo, bo, x, y_next, skip, dvec_next, d_stride, first, B, T, C):
+    check(lib.b2s_wavenet_out_f32(ptr(z), ptr(Wo), ptr(bo), ptr(x), ptr(y_next), ptr(skip), ptr(dvec_next),
+                                  d_stride, int(first), B, T, C, stream_ptr()), 'b2s_wavenet_out_f32')
+
+
+def lynx_prenorm(x, cond, ld_cond, dvec, d_stride, gamma, beta, h, B, T, C, strong):
+    check(lib.b2s_lynx_prenorm_f32(ptr(x), ptr(cond), ld_cond, ptr(dvec), d_stride, ptr(gamma), ptr(beta), ptr(h),
+                                   B, T, C, int(strong), stream_ptr()), 'b2s_lynx_prenorm_f32')
+
+
+def layernorm(x, gamma, beta, h, rows, C):
+    check(lib.b2s_layernorm_f32(ptr(x), ptr(gamma), ptr(beta), ptr(h), rows, C, stream_ptr()), 'b2s_layernorm_f32')
+
+
+def lynx_glu(h, W, bias, g, rows, C, inner):
+    check(lib.b2s_lynx_glu_f32(ptr(h), ptr(W), ptr(bias), ptr(g), rows, C, inner, stream_ptr()), 'b2s_lynx_glu_f32')
+
+
+def lynx_dwconv(g, Wdw, bias, slope, p, B, T, inner, ksize, act):
+    check(lib.b2s_lynx_dwconv_f32(ptr(g), ptr(Wdw), ptr(bias), ptr(slope), ptr(p), B, T, inner, ksize, act,
+                                  stream_ptr()), 'b2s_lynx_dwconv_f32')
+
+
+def linear_residual(p, W, bias, x, rows, C, inner):
+    check(lib.b2s_linear_residual_f32(ptr(p), ptr(W), ptr(bias), ptr(x), rows, C, inner, stream_ptr()),
+          'b2s_linear_residual_f32')

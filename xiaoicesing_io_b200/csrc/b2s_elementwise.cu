@@ -1,0 +1,282 @@
+// HBM-bound helper kernels of the sampling path: layout transposes, the sampler update
+// (linear combination), the sinusoidal step embedding, LayerNorm(+cond/step add) and the LYNXNet
+// depthwise convolution.  All fp32, vectorised, grid sized from the problem (grid-stride where useful).
+#include "b2s_common.cuh"
+
+#include <string.h>
+
+namespace b2s {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// [batch, rows, cols] -> [batch, cols, rows]; 32x32 tile through shared memory, both sides coalesced
+// ------------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const long long boff = (long long)blockIdx.z * rows * cols;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = in[boff + (long long)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[boff + (long long)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dst = sum_i coef[i] * src[i]
+// ------------------------------------------------------------------------------------------------
+struct LinCombArgs {
+    const float* src[8];
+    float* dst;
+    const float* coef;
+    int n_src;
+    long long n4;     // number of float4 groups
+    long long n;      // total elements
+};
+
+template <int NS>
+__global__ void __launch_bounds__(256) lincomb_kernel(const LinCombArgs a) {
+    float c[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) c[i] = __ldg(a.coef + i);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n4; idx += stride) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(a.src[i] + idx * 4);
+            acc.x = fmaf(c[i], v.x, acc.x);
+            acc.y = fmaf(c[i], v.y, acc.y);
+            acc.z = fmaf(c[i], v.z, acc.z);
+            acc.w = fmaf(c[i], v.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(a.dst + idx * 4) = acc;
+    }
+    // scalar tail (n % 4)
+    if (blockIdx.x == 0 && threadIdx.x < (a.n - a.n4 * 4)) {
+        long long idx = a.n4 * 4 + threadIdx.x;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) acc = fmaf(c[i], a.src[i][idx], acc);
+        a.dst[idx] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SinusoidalPosEmb (common_layers.py:266-278): freq_j = exp(-j * ln(1e4)/(half-1)) in fp32,
+// out = [sin(t*freq), cos(t*freq)]
+// ------------------------------------------------------------------------------------------------
+__global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int n, int dim) {
+    const int half = dim / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * half) return;
+    const int k = idx / half, j = idx - k * half;
+    const float step = (float)(9.210340371976184 / (double)(half - 1));   // ln(10000)/(half-1), rounded as fp32 like torch
+    const float freq = expf((float)j * -step);
+    const float arg = t[k] * freq;
+    out[(long long)k * dim + j] = sinf(arg);
+    out[(long long)k * dim + half + j] = cosf(arg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over channels, one warp per frame row; optional fused (x + cond + d) prologue with the
+// residual write-back of LYNXNetResidualLayer (lynxnet.py:76-84).  eps = 1e-5 (nn.LayerNorm default).
+// ------------------------------------------------------------------------------------------------
+template <bool PRE>
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const float* __restrict__ cond, int ld_cond,
+                                                        const float* __restrict__ dvec, int d_stride,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float* __restrict__ h, int rows, int T, int C, int strong) {
+    extern __shared__ float srow[];                 // [warps][C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= rows) return;
+    float* u = srow + (long long)warp * C;
+    const int b = PRE ? r / T : 0;
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float v = x[(long long)r * C + c];
+        if (PRE) {
+            const float cc = cond[(long long)r * ld_cond + c];
+            const float xc = v + cc;
+            if (strong) { x[(long long)r * C + c] = xc; }       // res = x + cond  (front_cond_inject)
+            v = xc + dvec[(long long)b * d_stride + c];
+        }
+        u[c] = v;
+        sum += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float d = u[c] - mean;
+        var += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / (float)C + 1e-5f);
+    for (int c = lane; c < C; c += 32) h[(long long)r * C + c] = (u[c] - mean) * rstd * gamma[c] + beta[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise conv along time + bias + activation (lynxnet.py:57-58).  Time-major: thread = channel
+// (coalesced across channels), loops over a strip of frames keeping nothing but the weights in
+// registers; zero padding at utterance edges.
+// ------------------------------------------------------------------------------------------------
+constexpr int DW_TSTRIP = 16;
+constexpr int DW_MAXK = 31;
+
+__global__ void __launch_bounds__(128) dwconv_kernel(const float* __restrict__ g, const float* __restrict__ Wdw,
+                                                     const float* __restrict__ bias, const float* __restrict__ slope,
+                                                     float* __restrict__ p, int T, int inner, int ksize, int act) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= inner) return;
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.y * DW_TSTRIP;
+    const int pad = ksize / 2;
+    float w[DW_MAXK];
+#pragma unroll
+    for (int k = 0; k < DW_MAXK; ++k) w[k] = k < ksize ? __ldg(Wdw + (long long)ch * ksize + k) : 0.f;
+    const float bb = __ldg(bias + ch);
+    const float sl = slope ? __ldg(slope + ch) : 0.f;
+    const float* gb = g + (long long)b * T * inner + ch;
+    float* pb = p + (long long)b * T * inner + ch;
+    // sliding window over DW_TSTRIP + ksize - 1 input frames
+    float win[DW_MAXK];
+#pragma unroll
+    for (int k = 0; k < DW_MAXK; ++k) {
+        const int ts = t0 - pad + k;
+        win[k] = (k < ksize && ts >= 0 && ts < T) ? gb[(long long)ts * inner] : 0.f;
+    }
+    for (int i = 0; i < DW_TSTRIP; ++i) {
+        const int t = t0 + i;
+        if (t >= T) break;
+        float acc = bb;
+#pragma unroll
+        for (int k = 0; k < DW_MAXK; ++k) acc = fmaf(w[k], win[k], acc);
+        float o;
+        if (act == 0) o = acc >= 0.f ? acc : sl * acc;        // PReLU
+        else o = apply_act(acc, act);
+        pb[(long long)t * inner] = o;
+        // slide
+#pragma unroll
+        for (int k = 0; k < DW_MAXK - 1; ++k) win[k] = win[k + 1];
+        const int tn = t + 1 - pad + (ksize - 1);
+        const float nv = (tn >= 0 && tn < T) ? gb[(long long)tn * inner] : 0.f;
+        // place the incoming frame at index ksize-1 (the window is left-aligned)
+#pragma unroll
+        for (int k = 0; k < DW_MAXK; ++k)
+            if (k == ksize - 1) win[k] = nv;
+    }
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b2s_abi_version(void) { return B2S_ABI_VERSION; }
+extern "C" const char* b2s_last_error(void) { return g_err; }
+
+extern "C" int b2s_transpose_f32(const float* in, float* out, int batch, int rows, int cols, void* stream) {
+    B2S_CHECK_ARG(in && out, "b2s_transpose_f32: null pointer");
+    B2S_CHECK_ARG(batch >= 0 && rows >= 0 && cols >= 0 && batch < 65536, "b2s_transpose_f32: bad dims");
+    if (batch == 0 || rows == 0 || cols == 0) return B2S_OK;
+    dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch), block(32, 8);
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, rows, cols);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host, const float* coef, int n_src,
+                                       int64_t n, void* stream) {
+    B2S_CHECK_ARG(dst && srcs_host && coef, "b2s_sampler_lincomb_f32: null pointer");
+    B2S_CHECK_ARG(n_src >= 1 && n_src <= 8, "b2s_sampler_lincomb_f32: n_src must be in [1, 8] (got %d)", n_src);
+    if (n <= 0) return B2S_OK;
+    LinCombArgs a{};
+    for (int i = 0; i < n_src; ++i) {
+        B2S_CHECK_ARG(srcs_host[i] && (reinterpret_cast<uintptr_t>(srcs_host[i]) & 15) == 0,
+                      "b2s_sampler_lincomb_f32: src %d null or not 16B aligned", i);
+        a.src[i] = srcs_host[i];
+    }
+    B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "b2s_sampler_lincomb_f32: dst not 16B aligned");
+    a.dst = dst; a.coef = coef; a.n_src = n_src; a.n = n; a.n4 = n / 4;
+    long long want = (a.n4 + 255) / 256;
+    int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (n_src) {
+        case 1: lincomb_kernel<1><<<blocks, 256, 0, st>>>(a); break;
+        case 2: lincomb_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+        case 3: lincomb_kernel<3><<<blocks, 256, 0, st>>>(a); break;
+        case 4: lincomb_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+        case 5: lincomb_kernel<5><<<blocks, 256, 0, st>>>(a); break;
+        case 6: lincomb_kernel<6><<<blocks, 256, 0, st>>>(a); break;
+        case 7: lincomb_kernel<7><<<blocks, 256, 0, st>>>(a); break;
+        default: lincomb_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    }
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_sinusoid_f32(const float* t, float* out, int n, int dim, void* stream) {
+    B2S_CHECK_ARG(t && out, "b2s_sinusoid_f32: null pointer");
+    B2S_CHECK_ARG(dim >= 4 && dim % 2 == 0, "b2s_sinusoid_f32: dim must be even and >= 4");
+    if (n <= 0) return B2S_OK;
+    int total = n * (dim / 2);
+    sinusoid_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(t, out, n, dim);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_lynx_prenorm_f32(float* x, const float* cond, int ld_cond, const float* dvec, int d_stride,
+                                    const float* gamma, const float* beta, float* h, int B, int T, int C,
+                                    int strong_cond, void* stream) {
+    B2S_CHECK_ARG(x && cond && dvec && gamma && beta && h, "b2s_lynx_prenorm_f32: null pointer");
+    B2S_CHECK_ARG(C > 0 && C <= 8192, "b2s_lynx_prenorm_f32: C out of range");
+    const int rows = B * T;
+    if (rows <= 0) return B2S_OK;
+    const int warps = C <= 1024 ? 8 : (C <= 2048 ? 4 : 1);
+    size_t smem = (size_t)warps * C * sizeof(float);
+    layernorm_kernel<true><<<ceil_div(rows, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        x, cond, ld_cond, dvec, d_stride, gamma, beta, h, rows, T, C, strong_cond);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_layernorm_f32(const float* x, const float* gamma, const float* beta, float* h, int rows, int C,
+                                 void* stream) {
+    B2S_CHECK_ARG(x && gamma && beta && h, "b2s_layernorm_f32: null pointer");
+    B2S_CHECK_ARG(C > 0 && C <= 8192, "b2s_layernorm_f32: C out of range");
+    if (rows <= 0) return B2S_OK;
+    const int warps = C <= 1024 ? 8 : (C <= 2048 ? 4 : 1);
+    size_t smem = (size_t)warps * C * sizeof(float);
+    layernorm_kernel<false><<<ceil_div(rows, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        const_cast<float*>(x), nullptr, 0, nullptr, 0, gamma, beta, h, rows, 1, C, 0);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_lynx_dwconv_f32(const float* g, const float* Wdw, const float* bias, const float* slope, float* p,
+                                   int B, int T, int inner, int ksize, int act, void* stream) {
+    B2S_CHECK_ARG(g && Wdw && bias && p, "b2s_lynx_dwconv_f32: null pointer");
+    B2S_CHECK_ARG(ksize >= 1 && ksize <= DW_MAXK && (ksize & 1), "b2s_lynx_dwconv_f32: kernel size must be odd and <= %d", DW_MAXK);
+    B2S_CHECK_ARG(act != 0 || slope, "b2s_lynx_dwconv_f32: PReLU needs slope");
+    B2S_CHECK_ARG(B < 65536, "b2s_lynx_dwconv_f32: B too large");
+    if (B <= 0 || T <= 0) return B2S_OK;
+    dim3 grid(ceil_div(inner, 128), ceil_div(T, DW_TSTRIP), B);
+    dwconv_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g, Wdw, bias, slope, p, T, inner, ksize, act);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}

@@ -1,0 +1,351 @@
+"""Device-side orchestration of the hot path: weight packing, the per-utterance hoisted tables, one
+denoiser evaluation as a sequence of libb2s launches, and the sampler-program executor.
+
+Data layout in HBM (all time-major, row r = b*T + t):
+    state / eps / history buffers   [B*T, M*F]   fp32
+    x (residual stream), y = x + step embedding, z (gated), skip accumulator   [B*T, C]
+    cond table   [B*T, L*2C] (WaveNet, gate/filter interleaved, both conv biases folded in)
+                 [B*T, L*C]  (LYNXNet)                      - computed ONCE per utterance batch
+    step table   [K, L*C]    one row per denoiser evaluation of the whole sampling loop
+                             - computed ONCE per sampling call (all K model times are known up front)
+
+The reference recomputes the conditioner projection (wavenet.py:35, lynxnet.py:77-82) and the step
+embedding MLP (wavenet.py:89-90, :34) inside every denoiser call; its own ONNX exporter hoists the
+former (utils/onnx_helper.py:231-314), which is the precedent for doing it here.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import _cabi as C
+from .schedules import NOISE0, XSTART, Program, Z
+
+PRECISIONS = ('fp32',)
+
+
+def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+# =====================================================================================================
+# WaveNet
+# =====================================================================================================
+class WaveNetEngine:
+    """Packed weights + launch sequence for ``WaveNet.forward`` (reference wavenet.py:75-107)."""
+
+    def __init__(self, net, precision: str = 'fp32'):
+        if precision not in PRECISIONS:
+            raise ValueError(f'unknown precision {precision!r}; available: {PRECISIONS}')
+        self.net = net
+        self.precision = precision
+        self.C = net.num_channels
+        self.L = net.num_layers
+        self.MF = net.in_dims * net.n_feats
+        self.H = net.hidden_size
+        self.dilations = [layer.dilation for layer in net.residual_layers]
+        self._packed_version = None
+        self.device = None
+
+    # -- weights ------------------------------------------------------------------------------------
+    def _version(self):
+        return tuple(p._version for p in self.net.parameters()) + (str(next(self.net.parameters()).device),)
+
+    def pack(self, force=False):
+        v = self._version()
+        if not force and v == self._packed_version:
+            return
+        net = self.net
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise C.B2SError('the denoiser lives on the CPU; this path has no CPU fallback - move the module to a CUDA device')
+        Cc, L = self.C, self.L
+        f = lambda t: _dev_f32(t, dev)
+        self.device = dev
+        self.w_in = f(net.input_projection.weight[:, :, 0])                  # [C, MF]
+        self.b_in = f(net.input_projection.bias)
+        self.w_mlp0, self.b_mlp0 = f(net.mlp[0].weight), f(net.mlp[0].bias)  # [4C, C]
+        self.w_mlp2, self.b_mlp2 = f(net.mlp[2].weight), f(net.mlp[2].bias)  # [C, 4C]
+        layers = net.residual_layers
+        # all L diffusion projections as one [L*C, C] matrix -> one GEMM for the whole step table
+        self.w_dp = f(torch.cat([l.diffusion_projection.weight for l in layers], 0))
+        self.b_dp = f(torch.cat([l.diffusion_projection.bias for l in layers], 0))
+        # gate/filter interleave: packed row 2j = gate j (reference row j), 2j+1 = filter j (row C+j)
+        perm = torch.stack([torch.arange(Cc), torch.arange(Cc) + Cc], 1).reshape(-1).to(dev)
+        wc, bc, wd = [], [], []
+        for l in layers:
+            wc.append(l.conditioner_projection.weight[:, :, 0][perm])         # [2C, H]
+            bc.append((l.conditioner_projection.bias + l.dilated_conv.bias)[perm])   # both biases folded
+            w = l.dilated_conv.weight[perm]                                   # [2C, C, 3]
+            wd.append(w.permute(0, 2, 1).reshape(2 * Cc, 3 * Cc))             # column = tap*C + c
+        self.w_cond = f(torch.cat(wc, 0))                                     # [L*2C, H]
+        self.b_cond = f(torch.cat(bc, 0))
+        self.w_dil = f(torch.stack(wd, 0))                                    # [L, 2C, 3C]
+        self.w_out = f(torch.stack([l.output_projection.weight[:, :, 0] for l in layers], 0))   # [L, 2C, C]
+        self.b_out = f(torch.stack([l.output_projection.bias for l in layers], 0))             # [L, 2C]
+        self.w_sp, self.b_sp = f(net.skip_projection.weight[:, :, 0]), f(net.skip_projection.bias)
+        self.w_fin, self.b_fin = f(net.output_projection.weight[:, :, 0]), f(net.output_projection.bias)
+        self._packed_version = v
+
+    # -- per-call tables ---------------------------------------------------------------------------
+    def step_table(self, t_values: torch.Tensor) -> torch.Tensor:
+        """t_values [K] fp32 (device) -> [K, L*C]: diffusion_projection_l(mlp(sinusoid(t))) for all l."""
+        K = t_values.numel()
+        Cc = self.C
+        dev = self.device
+        sin = torch.empty((K, Cc), device=dev)
+        C.sinusoid(t_values, sin, K, Cc)
+        h = torch.empty((K, 4 * Cc), device=dev)
+        C.linear(sin, Cc, self.w_mlp0, Cc, self.b_mlp0, h, 4 * Cc, K, 4 * Cc, Cc, act=C.ACT_MISH)
+        e = torch.empty((K, Cc), device=dev)
+        C.linear(h, 4 * Cc, self.w_mlp2, 4 * Cc, self.b_mlp2, e, Cc, K, Cc, 4 * Cc)
+        tab = torch.empty((K, self.L * Cc), device=dev)
+        C.linear(e, Cc, self.w_dp, Cc, self.b_dp, tab, self.L * Cc, K, self.L * Cc, Cc)
+        return tab
+
+    def cond_table(self, cond_bth: torch.Tensor) -> torch.Tensor:
+        """cond [B, T, H] (time-major, contiguous) -> [B*T, L*2C], ONE batched GEMM for all layers."""
+        B, T, H = cond_bth.shape
+        N = self.L * 2 * self.C
+        tab = torch.empty((B * T, N), device=self.device)
+        C.linear(cond_bth, H, self.w_cond, H, self.b_cond, tab, N, B * T, N, H)
+        return tab
+
+    def begin(self, cond_bth: torch.Tensor, t_values: torch.Tensor, per_row_t: bool = False) -> 'WaveNetSession':
+        self.pack()
+        C.require_cuda(cond_bth, 'cond')
+        C.require_cuda(t_values, 't_values')
+        return WaveNetSession(self, cond_bth, t_values, per_row_t)
+
+
+class WaveNetSession:
+    """Everything that is constant across the K denoiser evaluations of one sampling call."""
+
+    def __init__(self, eng: WaveNetEngine, cond_bth, t_values, per_row_t):
+        self.eng = eng
+        B, T, H = cond_bth.shape
+        if H != eng.H:
+            raise C.B2SError(f'condition has {H} channels, backbone expects hidden_size={eng.H}')
+        if per_row_t and t_values.numel() != B:
+            raise C.B2SError('per-row step embedding needs one time value per utterance')
+        self.B, self.T = B, T
+        self.rows = B * T
+        self.per_row_t = per_row_t
+        self.cond = eng.cond_table(cond_bth)
+        self.dtab = eng.step_table(t_values)                 # [K, L*C]
+        dev = eng.device
+        rows, Cc = self.rows, eng.C
+        self.x = torch.empty((rows, Cc), device=dev)
+        self.y = torch.empty((rows, Cc), device=dev)
+        self.z = torch.empty((rows, Cc), device=dev)
+        self.skip = torch.empty((rows, Cc), device=dev)
+        self.h = torch.empty((rows, Cc), device=dev)
+
+    def _dvec(self, k, l):
+        LC = self.eng.L * self.eng.C
+        if self.per_row_t:
+            return self.dtab[0, l * self.eng.C:], LC
+        return self.dtab[k, l * self.eng.C:], 0
+
+    def eval(self, x_in: torch.Tensor, k: int, out: torch.Tensor):
+        """One denoiser call: x_in [B*T, MF] -> out [B*T, MF] using step-table row k."""
+        e = self.eng
+        B, T, rows, Cc, L, MF = self.B, self.T, self.rows, e.C, e.L, e.MF
+        d0, ds = self._dvec(k, 0)
+        # input_projection + ReLU (wavenet.py:86-88); y = x + d_0 (wavenet.py:36)
+        C.linear(x_in, MF, e.w_in, MF, e.b_in, self.x, Cc, rows, Cc, MF, act=C.ACT_RELU,
+                 y=self.y, dvec=d0, d_stride=ds, T=T)
+        ldc = L * 2 * Cc
+        for l in range(L):
+            C.wavenet_gate(self.y, e.w_dil[l], self.cond[:, l * 2 * Cc:], ldc, self.z, B, T, Cc, e.dilations[l])
+            if l + 1 < L:
+                dn, ds = self._dvec(k, l + 1)
+                C.wavenet_out(self.z, e.w_out[l], e.b_out[l], self.x, self.y, self.skip, dn, ds, l == 0, B, T, Cc)
+            else:
+                C.wavenet_out(self.z, e.w_out[l], e.b_out[l], self.x, None, self.skip, None, 0, l == 0, B, T, Cc)
+        # sum(skip)/sqrt(L) -> skip_projection -> ReLU -> output_projection (wavenet.py:96-99)
+        C.linear(self.skip, Cc, e.w_sp, Cc, e.b_sp, self.h, Cc, rows, Cc, Cc, alpha=1.0 / math.sqrt(L), act=C.ACT_RELU)
+        C.linear(self.h, Cc, e.w_fin, Cc, e.b_fin, out, MF, rows, MF, Cc)
+
+    @property
+    def launches_per_eval(self) -> int:
+        return 1 + 2 * self.eng.L + 2
+
+
+# =====================================================================================================
+# LYNXNet
+# =====================================================================================================
+class LYNXNetEngine:
+    """Packed weights + launch sequence for ``LYNXNet.forward`` (reference lynxnet.py:128-163)."""
+
+    ACT_CODES = {'PReLU': 0, 'SiLU': C.ACT_SILU, 'ReLU': C.ACT_RELU}
+
+    def __init__(self, net, precision: str = 'fp32'):
+        if precision not in PRECISIONS:
+            raise ValueError(f'unknown precision {precision!r}; available: {PRECISIONS}')
+        self.net = net
+        self.precision = precision
+        self.C = net.num_channels
+        self.L = net.num_layers
+        self.MF = net.in_dims * net.n_feats
+        self.H = net.hidden_size
+        self.inner = net.num_channels * net.expansion_factor
+        self.ksize = net.kernel_size
+        self.strong = bool(net.strong_cond)
+        self.act = self.ACT_CODES[net.activation]
+        self._packed_version = None
+        self.device = None
+
+    def _version(self):
+        return tuple(p._version for p in self.net.parameters()) + (str(next(self.net.parameters()).device),)
+
+    def pack(self, force=False):
+        v = self._version()
+        if not force and v == self._packed_version:
+            return
+        net = self.net
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise C.B2SError('the denoiser lives on the CPU; this path has no CPU fallback - move the module to a CUDA device')
+        f = lambda t: _dev_f32(t, dev)
+        self.device = dev
+        inner = self.inner
+        self.w_in, self.b_in = f(net.input_projection.weight[:, :, 0]), f(net.input_projection.bias)
+        de = net.diffusion_embedding
+        self.w_e1, self.b_e1 = f(de[1].weight), f(de[1].bias)
+        self.w_e3, self.b_e3 = f(de[3].weight), f(de[3].bias)
+        layers = net.residual_layers
+        self.w_dp = f(torch.cat([l.diffusion_projection.weight[:, :, 0] for l in layers], 0))   # [L*C, C]
+        self.b_dp = f(torch.cat([l.diffusion_projection.bias for l in layers], 0))
+        self.w_cond = f(torch.cat([l.conditioner_projection.weight[:, :, 0] for l in layers], 0))   # [L*C, H]
+        self.b_cond = f(torch.cat([l.conditioner_projection.bias for l in layers], 0))
+        perm = torch.stack([torch.arange(inner), torch.arange(inner) + inner], 1).reshape(-1).to(dev)
+        self.ln_g = f(torch.stack([l.convmodule.net[0].weight for l in layers], 0))
+        self.ln_b = f(torch.stack([l.convmodule.net[0].bias for l in layers], 0))
+        self.w_up = f(torch.stack([l.convmodule.net[2].weight[:, :, 0][perm] for l in layers], 0))   # [L, 2*inner, C]
+        self.b_up = f(torch.stack([l.convmodule.net[2].bias[perm] for l in layers], 0))
+        self.w_dw = f(torch.stack([l.convmodule.net[4].weight[:, 0, :] for l in layers], 0))         # [L, inner, k]
+        self.b_dw = f(torch.stack([l.convmodule.net[4].bias for l in layers], 0))
+        if self.act == 0:
+            self.slope = f(torch.stack([l.convmodule.net[5].weight for l in layers], 0))            # [L, inner]
+        else:
+            self.slope = None
+        self.w_down = f(torch.stack([l.convmodule.net[6].weight[:, :, 0] for l in layers], 0))      # [L, C, inner]
+        self.b_down = f(torch.stack([l.convmodule.net[6].bias for l in layers], 0))
+        self.norm_g, self.norm_b = f(net.norm.weight), f(net.norm.bias)
+        self.w_fin, self.b_fin = f(net.output_projection.weight[:, :, 0]), f(net.output_projection.bias)
+        self._packed_version = v
+
+    def step_table(self, t_values):
+        K = t_values.numel()
+        Cc, dev = self.C, self.device
+        sin = torch.empty((K, Cc), device=dev)
+        C.sinusoid(t_values, sin, K, Cc)
+        h = torch.empty((K, 4 * Cc), device=dev)
+        C.linear(sin, Cc, self.w_e1, Cc, self.b_e1, h, 4 * Cc, K, 4 * Cc, Cc, act=C.ACT_GELU)
+        e = torch.empty((K, Cc), device=dev)
+        C.linear(h, 4 * Cc, self.w_e3, 4 * Cc, self.b_e3, e, Cc, K, Cc, 4 * Cc)
+        tab = torch.empty((K, self.L * Cc), device=dev)
+        C.linear(e, Cc, self.w_dp, Cc, self.b_dp, tab, self.L * Cc, K, self.L * Cc, Cc)
+        return tab
+
+    def cond_table(self, cond_bth):
+        B, T, H = cond_bth.shape
+        N = self.L * self.C
+        tab = torch.empty((B * T, N), device=self.device)
+        C.linear(cond_bth, H, self.w_cond, H, self.b_cond, tab, N, B * T, N, H)
+        return tab
+
+    def begin(self, cond_bth, t_values, per_row_t=False):
+        self.pack()
+        C.require_cuda(cond_bth, 'cond')
+        C.require_cuda(t_values, 't_values')
+        return LYNXNetSession(self, cond_bth, t_values, per_row_t)
+
+
+class LYNXNetSession:
+    def __init__(self, eng: LYNXNetEngine, cond_bth, t_values, per_row_t):
+        self.eng = eng
+        B, T, H = cond_bth.shape
+        if H != eng.H:
+            raise C.B2SError(f'condition has {H} channels, backbone expects hidden_size={eng.H}')
+        if per_row_t and t_values.numel() != B:
+            raise C.B2SError('per-row step embedding needs one time value per utterance')
+        self.B, self.T, self.rows = B, T, B * T
+        self.per_row_t = per_row_t
+        self.cond = eng.cond_table(cond_bth)
+        self.dtab = eng.step_table(t_values)
+        dev = eng.device
+        self.x = torch.empty((self.rows, eng.C), device=dev)
+        self.h = torch.empty((self.rows, eng.C), device=dev)
+        self.g = torch.empty((self.rows, eng.inner), device=dev)
+        self.p = torch.empty((self.rows, eng.inner), device=dev)
+
+    def _dvec(self, k, l):
+        LC = self.eng.L * self.eng.C
+        if self.per_row_t:
+            return self.dtab[0, l * self.eng.C:], LC
+        return self.dtab[k, l * self.eng.C:], 0
+
+    def eval(self, x_in, k, out):
+        e = self.eng
+        B, T, rows, Cc, L, MF, inner = self.B, self.T, self.rows, e.C, e.L, e.MF, e.inner
+        # input projection (+ exact GELU unless strong_cond, lynxnet.py:141-143)
+        C.linear(x_in, MF, e.w_in, MF, e.b_in, self.x, Cc, rows, Cc, MF, act=C.ACT_NONE if e.strong else C.ACT_GELU)
+        ldc = L * Cc
+        for l in range(L):
+            dv, ds = self._dvec(k, l)
+            C.lynx_prenorm(self.x, self.cond[:, l * Cc:], ldc, dv, ds, e.ln_g[l], e.ln_b[l], self.h, B, T, Cc, e.strong)
+            C.lynx_glu(self.h, e.w_up[l], e.b_up[l], self.g, rows, Cc, inner)
+            C.lynx_dwconv(self.g, e.w_dw[l], e.b_dw[l], None if e.slope is None else e.slope[l], self.p, B, T, inner,
+                          e.ksize, e.act)
+            C.linear_residual(self.p, e.w_down[l], e.b_down[l], self.x, rows, Cc, inner)
+        C.layernorm(self.x, e.norm_g, e.norm_b, self.h, rows, Cc)
+        C.linear(self.h, Cc, e.w_fin, Cc, e.b_fin, out, MF, rows, MF, Cc)
+
+    @property
+    def launches_per_eval(self) -> int:
+        return 1 + 4 * self.eng.L + 2
+
+
+# =====================================================================================================
+# sampler-program executor
+# =====================================================================================================
+class CompiledProgram:
+    """A Program bound to a device: flat coefficient table in HBM, per-op offsets."""
+
+    def __init__(self, prog: Program, device):
+        self.prog = prog
+        flat: List[float] = []
+        self.offsets: List[int] = []
+        for op in prog.ops:
+            self.offsets.append(len(flat))
+            if op.kind == 'lin':
+                flat.extend(c for _, c in op.terms)
+                while len(flat) % 4:                       # keep rows 16B aligned
+                    flat.append(0.0)
+        self.coef = torch.tensor(flat if flat else [0.0], dtype=torch.float64).to(torch.float32).to(device)
+        self.t_values = torch.tensor(prog.t_values, dtype=torch.float32, device=device)
+        self.n_lin = sum(1 for op in prog.ops if op.kind == 'lin')
+
+
+def run_program(cp: CompiledProgram, session, bufs: Dict[str, torch.Tensor],
+                draw_noise: Optional[Callable[[int, torch.Tensor], None]] = None) -> torch.Tensor:
+    """Executes the program.  ``bufs`` maps buffer names to [B*T, MF] fp32 device tensors (NOISE0 /
+    XSTART pre-filled by the caller); ``draw_noise(j, dst)`` fills ``dst`` with the j-th per-step draw."""
+    prog = cp.prog
+    for op, off in zip(prog.ops, cp.offsets):
+        if op.kind == 'nfe':
+            session.eval(bufs[op.src], op.t_index, bufs[op.dst])
+        elif op.kind == 'lin':
+            n = len(op.terms)
+            C.lincomb(bufs[op.dst], [bufs[b] for b, _ in op.terms], cp.coef[off:off + n])
+        else:
+            draw_noise(op.draw, bufs[op.dst])
+    return bufs[prog.result]
+
+
+def allocate_buffers(prog: Program, rows: int, mf: int, device) -> Dict[str, torch.Tensor]:
+    return {name: torch.empty((rows, mf), device=device) for name in prog.buffers()}

@@ -1,0 +1,18 @@
+"""The process-global config dict the hot path reads (reference: utils/hparams.py:13).
+
+Inside the reference tree the reference's own dict object is re-used, so ``set_hparams()`` there
+configures this package too - that *is* the drop-in contract.  Stand-alone, a
+local dict with the same role is used.  Keys read on the path: hidden_size, schedule_type,
+use_shallow_diffusion, K_step_infer, diff_speedup, diff_accelerator, T_start_infer,
+sampling_algorithm, sampling_steps, infer; plus this package's own ``b2s_precision``
+('fp32' | 'bf16' | 'fp16', default from $B2S_PRECISION or 'fp32') and ``b2s_cuda_graph`` (bool).
+"""
+try:                                    # pragma: no cover - only inside the reference tree
+    from utils.hparams import hparams   # type: ignore
+except Exception:                       # noqa: BLE001
+    hparams = {}
+
+
+def set_hparams(**kw):
+    hparams.update(kw)
+    return hparams
