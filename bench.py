@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 sampling hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp32|bf16|fp16]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+    shallow-diffusion DDPM, K_step = 400 full-step ancestral sampling (400 denoiser evaluations),
+    WaveNet 20 layers x 256 channels, 128 mel bins, hidden 256, batch 16 utterances x 690 frames (8 s)
+    PER GPU (weak scaling: utterances are independent units, no collective inside the loop; the only
+    exchange is the final mel gather), synthetic condition / shallow source, random-init weights.
+
+One "step" = one full sampling call over the batch.  Metric: denoised mel-frames x NFE per second.
+    value : inputs resident in HBM, `model(condition_dev, src_spec=src_dev, infer=True)`
+    e2e   : the same public call from PINNED HOST buffers, H2D + D2H inside the timed region
+Also reported: roofline of the dominant kernel (CUDA events, isolated launches at the bench shapes),
+the CPU baseline (oracle port on the host cores, bounded sample), SM clocks during the timed region.
+
+`--impl reference` times the reference's algorithm on the host CPU (the oracle port; the reference is
+pure Python/PyTorch and is not present on the GPU box) on the same metric, one bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, T, K_step, sampler)
+    'config2': dict(B=16, T=690, k_step=400, layers=20, channels=256, mel=128, hidden=256, cycle=4,
+                    desc='shallow DDPM K_step=400 full-step, WaveNet 20x256, 128 mel, B=16 x T=690 per GPU'),
+}
+SIGMA_W = 0.01
+
+
+def flops_per_frame_nfe(L, C, MF):
+    """F_step(WaveNet) = 2*[L*8C^2 + MF*C + C^2 + C*MF]."""
+    return 2 * (L * 8 * C * C + MF * C + C * C + C * MF)
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16_burst=p['bf16_tflops'], bf16_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    hbm=p['hbm_gbs'], source='measured (MEASURED_PEAKS.json)')
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.idx}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:                                   # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:                                   # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def make_model(w, precision, device):
+    import xiaoicesing_io_b200 as P
+    P.hparams.clear()
+    P.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=True,
+                     K_step_infer=w['k_step'], diff_speedup=1, diff_accelerator='ddim', infer=False,
+                     b2s_precision=precision)
+    torch.manual_seed(0)
+    model = P.GaussianDiffusion(
+        w['mel'], timesteps=1000, k_step=w['k_step'], backbone_type='wavenet',
+        backbone_args=dict(num_layers=w['layers'], num_channels=w['channels'], dilation_cycle_length=w['cycle']),
+        spec_min=[-12.], spec_max=[0.])
+    # the reference zero-initialises this weight (wavenet.py:73); re-draw it or the output is constant
+    torch.nn.init.normal_(model.denoise_fn.output_projection.weight, std=SIGMA_W)
+    return model.to(device).eval()
+
+
+def synth_inputs(w, seed):
+    g = torch.Generator().manual_seed(seed)
+    condition = torch.randn((w['B'], w['T'], w['hidden']), generator=g)
+    src_spec = torch.rand((w['B'], w['T'], w['mel']), generator=g) * 12 - 12
+    return condition, src_spec
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample_throughput(w, sd, n_utt, n_nfe, repeats, warmup):
+    """frame*NFE/s of the reference algorithm (oracle port, fp32, all host threads) on a bounded sample:
+    ``n_utt`` utterances x T frames, the first ``n_nfe`` ancestral steps of the K_step=400 chain."""
+    from oracle import denoisers as OD
+    from oracle import samplers as OS
+    cfg = OD.WaveNetCfg(in_dims=w['mel'], n_feats=1, num_layers=w['layers'], num_channels=w['channels'],
+                        dilation_cycle_length=w['cycle'], hidden_size=w['hidden'])
+    sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+    denoise = OD.make_denoiser(sd, cfg)
+    sch = OS.DiffusionSchedule(1000, 'linear')
+    g = torch.Generator().manual_seed(5)
+    T = w['T']
+    cond = torch.randn((n_utt, w['hidden'], T), generator=g)
+    x0 = torch.randn((n_utt, 1, w['mel'], T), generator=g)
+    noises = [torch.randn((n_utt, 1, w['mel'], T), generator=g) for _ in range(n_nfe)]
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + repeats):
+            t0 = time.perf_counter()
+            x = x0
+            for j in range(n_nfe):
+                i = w['k_step'] - 1 - j
+                eps = denoise(x, torch.full((n_utt,), i, dtype=torch.long), cond)
+                xr = sch.sqrt_recip_alphas_cumprod[i] * x - sch.sqrt_recipm1_alphas_cumprod[i] * eps
+                mean = sch.posterior_mean_coef1[i] * xr + sch.posterior_mean_coef2[i] * x
+                x = mean + (0.5 * sch.posterior_log_variance_clipped[i]).exp() * noises[j]
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    per = n_utt * T * n_nfe
+    return per / statistics.median(times), times
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    import xiaoicesing_io_b200 as P   # module construction only (CPU parameters); no kernels are launched
+    model = make_model(w, 'fp32', 'cpu')
+    n_utt, n_nfe = 4, 4
+    t0 = time.perf_counter()
+    thr, times = cpu_sample_throughput(w, model.denoise_fn.state_dict(), n_utt, n_nfe, args.steps, args.warmup)
+    sample = f'{n_utt} utterances x {w["T"]} frames x first {n_nfe} of {w["k_step"]} ancestral steps per step'
+    line = {
+        'impl': 'reference', 'metric': 'denoised mel-frames x NFE per second', 'value': thr, 'unit': 'frame*NFE/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * statistics.median(times), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': w['desc'], 'sample': sample},
+        'cpu_baseline': {'value': thr, 'unit': 'frame*NFE/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': thr, 'unit': 'frame*NFE/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+        'wall_s': time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def dominant_kernel_roofline(model, w, precision, reps=3):
+    """Times the dominant kernel of one denoiser evaluation in isolation, at the bench shapes, with CUDA
+    events on the launching stream: all L per-layer launches back to back, ``reps`` times."""
+    from xiaoicesing_io_b200 import _cabi as C
+    eng = model.denoise_fn._engine()
+    eng.pack()
+    dev = eng.device
+    B, T, Cc, L = w['B'], w['T'], w['channels'], w['layers']
+    cond = torch.randn((B, T, w['hidden']), device=dev)
+    tvals = torch.tensor([float(w['k_step'] - 1)], device=dev)
+    sess = eng.begin(cond, tvals)
+    x_in = torch.randn((B * T, w['mel']), device=dev)
+    out = torch.empty_like(x_in)
+    sess.eval(x_in, 0, out)                       # fills y / z with realistic values
+    rows = B * T
+    p = peaks()
+    if precision == 'fp32':
+        name = 'sgemm_fused_kernel<EPI_GATE,CONV> (b2s_wavenet_gate_f32)'
+        flops = 2.0 * rows * (3 * Cc) * (2 * Cc)
+
+        def launch_all():
+            for l in range(L):
+                C.wavenet_gate(sess.y, eng.w_dil[l], sess.cond[:, l * 2 * Cc:], L * 2 * Cc, sess.z, B, T, Cc,
+                               eng.dilations[l])
+    else:
+        name, flops, launch_all = sess.dominant_kernel(w)
+    for _ in range(2):
+        launch_all()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch_all()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * L)
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': p['bf16_burst'], 'unit': 'TFLOP/s',
+            'frac': achieved / p['bf16_burst'], 'traffic': None, 'avg_launch_ms': ms,
+            'flops_per_launch': flops, 'peak_source': p['source'],
+            'note': 'algorithmic FLOPs of the launch / avg CUDA-event duration of isolated back-to-back launches'}
+
+
+def run_b200_arm(args, w):
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device - the B200 arm has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import xiaoicesing_io_b200 as P
+    from xiaoicesing_io_b200.partition import gather_mels
+
+    model = make_model(w, args.precision, dev)
+    cond_h, src_h = synth_inputs(w, seed=1000 + rank)          # every rank owns its utterances (weak scaling)
+    cond_h, src_h = cond_h.pin_memory(), src_h.pin_memory()
+    cond_d, src_d = cond_h.to(dev), src_h.to(dev)
+    B, T = w['B'], w['T']
+    prog = model.build_program()
+    nfe = prog.n_nfe
+    index = list(range(rank * B, (rank + 1) * B))
+
+    def step_resident():
+        mel = model(cond_d, src_spec=src_d, infer=True)
+        if world > 1:
+            gather_mels(mel.contiguous(), index, world * B, dst=0)     # the ONLY exchange: final mel gather
+        return mel
+
+    def step_e2e():
+        c = cond_h.to(dev, non_blocking=True)
+        s = src_h.to(dev, non_blocking=True)
+        mel = model(c, src_spec=s, infer=True)
+        if world > 1:
+            full = gather_mels(mel.contiguous(), index, world * B, dst=0)
+            return full.cpu() if full is not None else None
+        return mel.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        ms = max(e0.elapsed_time(e1), 0.0)
+        ms = max(ms, 0.0)
+        t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), clocks
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, wall_ms, clocks = timed(step_resident, args.steps, args.warmup, sampler)
+    e2e_ms, e2e_wall_ms, _ = timed(step_e2e, args.steps, max(1, args.warmup // 3))
+    units = world * B * T * nfe * args.steps
+    value = units / (ms_total * 1e-3)
+    e2e_value = units / (max(e2e_ms, e2e_wall_ms) * 1e-3)      # host copies: wall clock bounds it from above
+
+    roof = cpu = None
+    if rank == 0:
+        roof = dominant_kernel_roofline(model, w, args.precision)
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            n_utt, n_nfe = 4, 4
+            thr, _ = cpu_sample_throughput(w, model.denoise_fn.state_dict(), n_utt, n_nfe, repeats=3, warmup=1)
+            cpu = {'value': thr, 'unit': 'frame*NFE/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                   'sample': f'{n_utt} utterances x {T} frames x first {n_nfe} of {w["k_step"]} ancestral steps, median of 3'}
+    if rank == 0:
+        sess_launches = 1 + 2 * w['layers'] + 2 if args.precision == 'fp32' else model.denoise_fn._engine().launches_per_eval
+        n_lin = sum(1 for op in prog.ops if op.kind == 'lin')
+        n_noise = prog.n_draws
+        launches_per_step = nfe * sess_launches + n_lin + n_noise + 2 + 4   # + start transposes + tables
+        F = flops_per_frame_nfe(w['layers'], w['channels'], w['mel'])
+        p = peaks()
+        line = {
+            'metric': 'denoised mel-frames x NFE per second', 'value': value, 'unit': 'frame*NFE/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'fp16': 'f16'}[args.precision], 'data': 'synthetic',
+            'config': {'workload': w['desc'], 'nfe_per_step': nfe, 'global_batch': world * B, 'frames': T,
+                       'parallelism': f'utterance-partition x{world}', 'precision': args.precision,
+                       'l2': 'working set (hoisted cond table %.0f MB) exceeds the 126 MB L2; no explicit flush'
+                             % (B * T * w['layers'] * 2 * w['channels'] * 4 / 1e6),
+                       'sigma_w': SIGMA_W},
+            'e2e': {'value': e2e_value, 'unit': 'frame*NFE/s', 'ms_per_step': max(e2e_ms, e2e_wall_ms) / args.steps,
+                    'h2d_bytes_per_step': int(cond_h.numel() * 4 + src_h.numel() * 4) * world,
+                    'd2h_bytes_per_step': int(world * B * T * w['mel'] * 4)},
+            'gpu_launches': int(launches_per_step * args.steps),
+            'rtf': (ms_total / args.steps * 1e-3) / (world * B * T * 512 / 44100.0),
+            'tflops_algorithmic': value * F / 1e12,
+            'frac_of_bf16_peak': value * F / 1e12 / (world * p['bf16_sustained']),
+            'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks,
+            'wall_ms_per_step': wall_ms / args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('B2S_PRECISION', 'fp32'), choices=['fp32', 'bf16', 'fp16'])
+    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
+    ap.add_argument('--k-step', type=int, default=None, help='override K_step (debug only; invalidates the metric)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.k_step:
+        w['k_step'] = args.k_step
+        w['desc'] += f' [DEBUG K_step={args.k_step}]'
+    if args.impl == 'reference':
+        run_reference_arm(args, w)
+    else:
+        run_b200_arm(args, w)
+
+
+if __name__ == '__main__':
+    main()

@@ -59,7 +59,8 @@ def test_sinusoid_matches_reference_formula(C):
         freq = torch.exp(torch.arange(half) * -emb)
         arg = t.cpu()[:, None] * freq[None, :]
         want = torch.cat((arg.sin(), arg.cos()), -1)
-        assert float((out.cpu() - want).abs().max()) < 5e-6
+        # freq = exp(.) differs by 1 fp32 ulp between libm implementations; times t ~ 1e3 that is ~6e-5 in phase
+        assert float((out.cpu() - want).abs().max()) < 1e-4
 
 
 @pytest.mark.parametrize('M,N,K', [(1, 4, 4), (130, 36, 24), (257, 512, 256), (20, 1024, 256), (1000, 48, 192)])

@@ -63,7 +63,10 @@ def test_sampling_vs_reference_fixture(name, dev):
     assert len(outs) == len(refs)
     for o, r in zip(outs, refs):
         assert tuple(o.shape) == tuple(r.shape)
-        assert _maxabs(o, r) <= FP32_TOL, (name, _maxabs(o, r), float(r.abs().max()))
+        # 1e-3 absolute; the cosine-schedule fixtures blow up to |mel| ~ 4e5 under random init, where one
+        # fp32 ulp is already 0.03 - there the bound is 16 ulps of the largest magnitude.
+        tol = max(FP32_TOL, 16 * 1.1920929e-07 * float(r.abs().max()))
+        assert _maxabs(o, r) <= tol, (name, _maxabs(o, r), float(r.abs().max()))
 
 
 def _oracle_and_product(cfg, hp, sampler_kw, B, T, dev, seed=1234, sigma_w=0.01, n_draws=1, src=False):

@@ -191,9 +191,9 @@ extern "C" int b2s_abi_version(void) { return B2S_ABI_VERSION; }
 extern "C" const char* b2s_last_error(void) { return g_err; }
 
 extern "C" int b2s_transpose_f32(const float* in, float* out, int batch, int rows, int cols, void* stream) {
-    B2S_CHECK_ARG(in && out, "b2s_transpose_f32: null pointer");
     B2S_CHECK_ARG(batch >= 0 && rows >= 0 && cols >= 0 && batch < 65536, "b2s_transpose_f32: bad dims");
-    if (batch == 0 || rows == 0 || cols == 0) return B2S_OK;
+    if (batch == 0 || rows == 0 || cols == 0) return B2S_OK;       // empty input: nothing to do, pointers may be null
+    B2S_CHECK_ARG(in && out, "b2s_transpose_f32: null pointer");
     dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch), block(32, 8);
     transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, rows, cols);
     B2S_CHECK_LAUNCH();
@@ -202,9 +202,9 @@ extern "C" int b2s_transpose_f32(const float* in, float* out, int batch, int row
 
 extern "C" int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host, const float* coef, int n_src,
                                        int64_t n, void* stream) {
-    B2S_CHECK_ARG(dst && srcs_host && coef, "b2s_sampler_lincomb_f32: null pointer");
     B2S_CHECK_ARG(n_src >= 1 && n_src <= 8, "b2s_sampler_lincomb_f32: n_src must be in [1, 8] (got %d)", n_src);
     if (n <= 0) return B2S_OK;
+    B2S_CHECK_ARG(dst && srcs_host && coef, "b2s_sampler_lincomb_f32: null pointer");
     LinCombArgs a{};
     for (int i = 0; i < n_src; ++i) {
         B2S_CHECK_ARG(srcs_host[i] && (reinterpret_cast<uintptr_t>(srcs_host[i]) & 15) == 0,

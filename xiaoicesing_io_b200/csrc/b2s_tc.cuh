@@ -1,0 +1,194 @@
+// Blackwell (sm_100a) primitives used by the tensor-core kernels: mbarrier, TMA (cp.async.bulk.tensor),
+// tcgen05 (alloc / mma / commit / ld / fences), UMMA shared-memory + instruction descriptors.
+// Hand-written inline PTX; bit layouts follow the PTX ISA "tcgen05" chapter (matrix descriptor,
+// instruction descriptor for .kind::f16) - see DESIGN.md for the field tables.
+#pragma once
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include "b2s_common.cuh"
+
+namespace b2s {
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------------
+// shared-memory addressing
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a lost arrival traps (launch error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    printf("b2s: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, addr,
+           parity);
+    __trap();
+}
+
+// generic-proxy writes (st.shared) -> visible to the async proxy (TMA store / UMMA operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// TMA
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {     // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {       // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// tcgen05: descriptors
+// ---------------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 bytes (64 x 16-bit) with
+// the 128-byte swizzle (what TMA SWIZZLE_128B writes):
+//   [ 0,14) start address >> 4      [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups     [46,48) version = 1 (Blackwell)
+//   [49,52) base offset = 0 (tiles are 1024 B aligned)                [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor for .kind::f16, fp32 accumulate, both operands K-major:
+//   [4,6) D format = 1 (F32)   [7,10) A format   [10,13) B format  (0 = F16, 1 = BF16)
+//   [15] A major = 0 (K)  [16] B major = 0 (K)   [17,23) N >> 3    [24,29) M >> 4
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int is_bf16) {
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= (uint32_t)(is_bf16 ? 1 : 0) << 7;
+    d |= (uint32_t)(is_bf16 ? 1 : 0) << 10;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T ; issued by ONE thread
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tcgen05: TMEM -> registers.  32 lanes x 32 consecutive fp32 columns; thread i of the warp gets lane
+// (warp_quarter * 32 + i); the warp may only touch the lane quarter (warp_id % 4).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// 16-bit operand types (bf16 or fp16: same tensor-core rate; fp16 has 3 more mantissa bits)
+// ---------------------------------------------------------------------------------------------------
+template <int BF16>
+struct Half16;
+template <>
+struct Half16<1> {
+    __device__ __forceinline__ static uint32_t pack2(float a, float b) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __device__ __forceinline__ static float2 unpack2(uint32_t u) {
+        __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+        return __bfloat1622float2(h);
+    }
+};
+template <>
+struct Half16<0> {
+    __device__ __forceinline__ static uint32_t pack2(float a, float b) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __device__ __forceinline__ static float2 unpack2(uint32_t u) {
+        __half2 h = *reinterpret_cast<__half2*>(&u);
+        return __half22float2(h);
+    }
+};
+
+}  // namespace tc
+}  // namespace b2s
