@@ -320,7 +320,7 @@ def run_b200_arm(args, w):
             cpu = {'value': thr, 'unit': 'frame*NFE/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                    'sample': f'{n_utt} utterances x {T} frames x first {n_nfe} of {w["k_step"]} ancestral steps, median of 3'}
     if rank == 0:
-        sess_launches = 1 + 2 * w['layers'] + 2 if args.precision == 'fp32' else model.denoise_fn._engine().launches_per_eval
+        sess_launches = (1 if args.precision == 'fp32' else 2) + 2 * w['layers'] + 2   # (cast +) stem + 2/layer + 2 head
         n_lin = sum(1 for op in prog.ops if op.kind == 'lin')
         n_noise = prog.n_draws
         launches_per_step = nfe * sess_launches + n_lin + n_noise + 2 + 4   # + start transposes + tables

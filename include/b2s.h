@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2S_ABI_VERSION 1
+#define B2S_ABI_VERSION 2
 
 #define B2S_OK 0
 #define B2S_ERR_INVALID_ARGUMENT (-1)
@@ -114,6 +114,43 @@ int b2s_lynx_dwconv_f32(const float* g, const float* Wdw, const float* bias, con
 /* x <- W p + b + x   (W [C, inner]) */
 int b2s_linear_residual_f32(const float* p, const float* W, const float* bias, float* x, int rows, int C,
                             int inner, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 16-bit tensor-core path (tcgen05.mma with TMEM accumulators, TMA-staged operands; b2s_tc_gemm.cu).
+ * "_h" pointers are 16-bit arrays: bf16 when the trailing `bf16` flag is 1, IEEE fp16 when 0.
+ * Accumulation, the residual stream x, the skip sum and every bias / step-embedding row stay fp32.
+ * Operand requirements: 16B-aligned bases, leading dimensions that are multiples of 8 elements.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out = fp32 -> 16-bit cast (feeds the TMA-staged A operands; n elements) */
+int b2s_cast_f32_h(const float* in, void* out_h, int64_t n, int bf16, void* stream);
+
+/* Same contract as b2s_linear_f32 with 16-bit A [rows, K] / W [N, K]:
+ *   v = act(alpha * A.W^T + bias);  out_f32 (nullable) <- v;  out_h (nullable) <- v;
+ *   y_h (nullable) <- v + dvec[(row / T) * d_stride + n]   (wavenet.py:36, next layer's pre-added embedding)
+ * Replaces wavenet.py:35,86-88,97-99 / lynxnet.py:72,141-143,154 on the tensor cores. */
+int b2s_tc_linear(const void* A_h, int lda, int rows, int T, const void* W_h, int ldw, const float* bias, int N, int K,
+                  float alpha, int act, float* out_f32, int ldo, void* out_h, int ldoh, void* y_h, int ldy,
+                  const float* dvec, int d_stride, int bf16, void* stream);
+
+/* b2s_wavenet_gate_f32 on the tensor cores: implicit-GEMM dilated conv (3 TMA tiles per K slab at time
+ * offsets -d, 0, +d; out-of-bounds zero fill = the per-utterance zero padding), epilogue adds the hoisted
+ * 16-bit conditioner projection and applies sigmoid*tanh (wavenet.py:38-42).  C % 64 == 0. */
+int b2s_tc_wavenet_gate(const void* y_h, const void* Wd_h, const void* cond_h, int ld_cond, void* z_h, int B, int T,
+                        int C, int dilation, int bf16, void* stream);
+
+/* b2s_wavenet_out_f32 on the tensor cores (wavenet.py:44-48).  x / skip fp32 in place; y_next_h 16-bit;
+ * skip_h (nullable): 16-bit copy of the running skip sum (the head GEMM's A operand after the last layer). */
+int b2s_tc_wavenet_out(const void* z_h, const void* Wo_h, const float* bo, float* x, void* y_next_h, float* skip,
+                       void* skip_h, const float* dvec_next, int d_stride, int first_layer, int B, int T, int C,
+                       int bf16, void* stream);
+
+/* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
+ * down-projection with the residual add into the fp32 stream. */
+int b2s_tc_lynx_glu(const void* h_h, const void* W_h, const float* bias, void* g_h, int rows, int C, int inner, int bf16,
+                    void* stream);
+int b2s_tc_linear_residual(const void* p_h, const void* W_h, const float* bias, float* x, int rows, int C, int inner,
+                           int bf16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,3 +94,85 @@ def test_gate_edges_and_dilations(C):
         f = conv[:, Cc:].transpose(1, 2) + c[..., 1]
         want = torch.sigmoid(g) * torch.tanh(f)
         assert float((z.reshape(B, T, Cc).double() - want).abs().max()) < 1e-5, d
+
+
+# ------------------------------------------------------------------------------------------------------
+# 16-bit tensor-core path (tcgen05 / TMEM / TMA).  Reference = the same op in fp64 on the SAME 16-bit-rounded
+# operands, so the only differences are fp32 accumulation order and the 16-bit rounding of the outputs.
+# ------------------------------------------------------------------------------------------------------
+HALF = [('bf16', torch.bfloat16, 2 ** -8), ('fp16', torch.float16, 2 ** -11)]
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+@pytest.mark.parametrize('M,N,K', [(1, 32, 64), (130, 48, 48), (257, 512, 256), (1000, 128, 192), (690 * 3, 10240, 256)])
+def test_tc_linear(C, kind, hd, eps, M, N, K):
+    bf = kind == 'bf16'
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device='cuda').to(hd)
+    W = (torch.randn(N, K, device='cuda') / K ** 0.5).to(hd)
+    b = torch.randn(N, device='cuda')
+    dvec = torch.randn(N, device='cuda')
+    want = 0.5 * (A.double() @ W.double().t()) + b.double()
+    out = torch.full((M, N), float('nan'), device='cuda')
+    out_h = torch.zeros((M, N), device='cuda', dtype=hd) if N % 8 == 0 else None
+    y_h = torch.zeros((M, N), device='cuda', dtype=hd) if N % 8 == 0 else None
+    C.tc_linear(A, K, M, M, W, K, b, N, K, bf, alpha=0.5, out_f32=out, ldo=N, out_h=out_h, ldoh=N, y_h=y_h, ldy=N,
+                dvec=dvec, d_stride=0)
+    scale = float(want.abs().max())
+    assert float((out.double() - want).abs().max()) < 2e-5 * max(1.0, scale)
+    if out_h is not None:
+        assert float((out_h.double() - want).abs().max()) < eps * scale
+        assert float((y_h.double() - (want + dvec.double())).abs().max()) < eps * (scale + 4)
+    # activation variant
+    C.tc_linear(A, K, M, M, W, K, b, N, K, bf, alpha=0.5, act=C.ACT_RELU, out_f32=out, ldo=N)
+    assert float((out.double() - torch.relu(want)).abs().max()) < 2e-5 * max(1.0, scale)
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+def test_tc_gate_edges_and_dilations(C, kind, hd, eps):
+    import torch.nn.functional as F
+    bf = kind == 'bf16'
+    for (B, T, Cc) in [(3, 45, 64), (2, 300, 256)]:
+        for d in (1, 2, 4, 8, 16):
+            torch.manual_seed(d)
+            y = torch.randn(B, T, Cc, device='cuda').to(hd)
+            Wref = (torch.randn(2 * Cc, Cc, 3, device='cuda') / (3 * Cc) ** 0.5).to(hd)
+            cond = torch.randn(B * T, 2 * Cc + 8, device='cuda').to(hd)      # ld_cond > 2C on purpose
+            perm = torch.stack([torch.arange(Cc), torch.arange(Cc) + Cc], 1).reshape(-1).cuda()
+            Wd = Wref[perm].permute(0, 2, 1).reshape(2 * Cc, 3 * Cc).contiguous()
+            z = torch.zeros(B * T, Cc, device='cuda', dtype=hd)
+            C.tc_wavenet_gate(y, Wd, cond, 2 * Cc + 8, z, B, T, Cc, d, bf)
+            conv = F.conv1d(y.transpose(1, 2).double(), Wref.double(), padding=d, dilation=d)
+            c = cond[:, :2 * Cc].reshape(B, T, Cc, 2).double()
+            g = conv[:, :Cc].transpose(1, 2) + c[..., 0]
+            f = conv[:, Cc:].transpose(1, 2) + c[..., 1]
+            want = torch.sigmoid(g) * torch.tanh(f)
+            # tanh.approx (2^-11 relative) + 16-bit rounding of z
+            assert float((z.reshape(B, T, Cc).double() - want).abs().max()) < 2e-3 + eps, (B, T, Cc, d)
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+def test_tc_out_resskip(C, kind, hd, eps):
+    bf = kind == 'bf16'
+    B, T, Cc = 2, 333, 128
+    rows = B * T
+    torch.manual_seed(3)
+    z = torch.randn(rows, Cc, device='cuda').to(hd)
+    Wo = (torch.randn(2 * Cc, Cc, device='cuda') / Cc ** 0.5).to(hd)
+    bo = torch.randn(2 * Cc, device='cuda')
+    x0 = torch.randn(rows, Cc, device='cuda')
+    skip0 = torch.randn(rows, Cc, device='cuda')
+    dvec = torch.randn(B, Cc, device='cuda')
+    o = z.double() @ Wo.double().t() + bo.double()
+    x_want = (x0.double() + o[:, :Cc]) / 2 ** 0.5
+    y_want = x_want + dvec.double().repeat_interleave(T, 0)
+    for first in (True, False):
+        x, skip = x0.clone(), skip0.clone()
+        y = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+        sh = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+        C.tc_wavenet_out(z, Wo, bo, x, y, skip, sh, dvec, Cc, first, B, T, Cc, bf)
+        s_want = o[:, Cc:] + (0 if first else skip0.double())
+        assert float((x.double() - x_want).abs().max()) < 2e-5
+        assert float((skip.double() - s_want).abs().max()) < 2e-5
+        assert float((y.double() - y_want).abs().max()) < eps * float(y_want.abs().max())
+        assert float((sh.double() - s_want).abs().max()) < eps * float(s_want.abs().max())

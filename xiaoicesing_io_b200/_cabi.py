@@ -28,6 +28,13 @@ _SIGNATURES = {
     'b2s_lynx_glu_f32': [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     'b2s_lynx_dwconv_f32': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_linear_residual_f32': [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    # 16-bit tensor-core path
+    'b2s_cast_f32_h': [_vp, _vp, _i64, _i, _vp],
+    'b2s_tc_linear': [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp],
+    'b2s_tc_wavenet_gate': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    'b2s_tc_wavenet_out': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
 }
 
 EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', *_SIGNATURES]
@@ -140,3 +147,39 @@ def lynx_dwconv(g, Wdw, bias, slope, p, B, T, inner, ksize, act):
 def linear_residual(p, W, bias, x, rows, C, inner):
     check(lib.b2s_linear_residual_f32(ptr(p), ptr(W), ptr(bias), ptr(x), rows, C, inner, stream_ptr()),
           'b2s_linear_residual_f32')
+
+
+# ---- 16-bit tensor-core path ------------------------------------------------------------------------
+HALF_DTYPES = {'bf16': torch.bfloat16, 'fp16': torch.float16}
+
+
+def cast_h(inp, out, bf16):
+    check(lib.b2s_cast_f32_h(ptr(inp), ptr(out), inp.numel(), int(bf16), stream_ptr()), 'b2s_cast_f32_h')
+
+
+def tc_linear(A, lda, rows, T, W, ldw, bias, N, K, bf16, alpha=1.0, act=ACT_NONE, out_f32=None, ldo=0, out_h=None,
+              ldoh=0, y_h=None, ldy=0, dvec=None, d_stride=0):
+    check(lib.b2s_tc_linear(ptr(A), lda, rows, T, ptr(W), ldw, ptr(bias), N, K, alpha, act, ptr(out_f32), ldo,
+                            ptr(out_h), ldoh, ptr(y_h), ldy, ptr(dvec), d_stride, int(bf16), stream_ptr()),
+          'b2s_tc_linear')
+
+
+def tc_wavenet_gate(y_h, Wd_h, cond_h, ld_cond, z_h, B, T, C, dilation, bf16):
+    check(lib.b2s_tc_wavenet_gate(ptr(y_h), ptr(Wd_h), ptr(cond_h), ld_cond, ptr(z_h), B, T, C, dilation, int(bf16),
+                                  stream_ptr()), 'b2s_tc_wavenet_gate')
+
+
+def tc_wavenet_out(z_h, Wo_h, bo, x, y_next_h, skip, skip_h, dvec_next, d_stride, first, B, T, C, bf16):
+    check(lib.b2s_tc_wavenet_out(ptr(z_h), ptr(Wo_h), ptr(bo), ptr(x), ptr(y_next_h), ptr(skip), ptr(skip_h),
+                                 ptr(dvec_next), d_stride, int(first), B, T, C, int(bf16), stream_ptr()),
+          'b2s_tc_wavenet_out')
+
+
+def tc_lynx_glu(h_h, W_h, bias, g_h, rows, C, inner, bf16):
+    check(lib.b2s_tc_lynx_glu(ptr(h_h), ptr(W_h), ptr(bias), ptr(g_h), rows, C, inner, int(bf16), stream_ptr()),
+          'b2s_tc_lynx_glu')
+
+
+def tc_linear_residual(p_h, W_h, bias, x, rows, C, inner, bf16):
+    check(lib.b2s_tc_linear_residual(ptr(p_h), ptr(W_h), ptr(bias), ptr(x), rows, C, inner, int(bf16), stream_ptr()),
+          'b2s_tc_linear_residual')

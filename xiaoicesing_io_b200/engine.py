@@ -23,7 +23,7 @@ import torch
 from . import _cabi as C
 from .schedules import NOISE0, XSTART, Program, Z
 
-PRECISIONS = ('fp32',)
+PRECISIONS = ('fp32', 'bf16', 'fp16')
 
 
 def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
@@ -87,6 +87,16 @@ class WaveNetEngine:
         self.b_out = f(torch.stack([l.output_projection.bias for l in layers], 0))             # [L, 2C]
         self.w_sp, self.b_sp = f(net.skip_projection.weight[:, :, 0]), f(net.skip_projection.bias)
         self.w_fin, self.b_fin = f(net.output_projection.weight[:, :, 0]), f(net.output_projection.bias)
+        if self.precision != 'fp32':
+            if Cc % 64:
+                raise C.B2SError(f'the {self.precision} tensor-core path needs num_channels % 64 == 0 (got {Cc}); '
+                                 f"use b2s_precision='fp32'")
+            hd = C.HALF_DTYPES[self.precision]
+            self.bf16 = self.precision == 'bf16'
+            h = lambda t: t.to(hd).contiguous()
+            self.w_in_h = h(_pad_cols(self.w_in, 8))
+            self.w_cond_h, self.w_dil_h, self.w_out_h = h(self.w_cond), h(self.w_dil), h(self.w_out)
+            self.w_sp_h, self.w_fin_h = h(self.w_sp), h(self.w_fin)
         self._packed_version = v
 
     # -- per-call tables ---------------------------------------------------------------------------
@@ -117,7 +127,17 @@ class WaveNetEngine:
         self.pack()
         C.require_cuda(cond_bth, 'cond')
         C.require_cuda(t_values, 't_values')
+        if self.precision != 'fp32':
+            return WaveNetSessionTC(self, cond_bth, t_values, per_row_t)
         return WaveNetSession(self, cond_bth, t_values, per_row_t)
+
+
+def _pad_cols(w: torch.Tensor, mult: int) -> torch.Tensor:
+    """Zero-pads the K (last) dimension to a multiple of ``mult`` (16B-aligned rows for TMA)."""
+    k = w.shape[-1]
+    if k % mult == 0:
+        return w
+    return torch.nn.functional.pad(w, (0, mult - k % mult))
 
 
 class WaveNetSession:
@@ -174,6 +194,82 @@ class WaveNetSession:
         return 1 + 2 * self.eng.L + 2
 
 
+class WaveNetSessionTC:
+    """16-bit tensor-core session (tcgen05 kernels): same launch structure as ``WaveNetSession`` with
+    bf16 / fp16 MMA operands (y, z, hoisted cond table, weights) and fp32 residual stream, skip sum,
+    biases, step embeddings and sampler state."""
+
+    def __init__(self, eng: WaveNetEngine, cond_bth, t_values, per_row_t):
+        self.eng = eng
+        B, T, H = cond_bth.shape
+        if H != eng.H:
+            raise C.B2SError(f'condition has {H} channels, backbone expects hidden_size={eng.H}')
+        if per_row_t and t_values.numel() != B:
+            raise C.B2SError('per-row step embedding needs one time value per utterance')
+        if H % 8 or eng.MF % 8:
+            raise C.B2SError(f'the tensor-core path needs hidden_size and in_dims*n_feats to be multiples of 8 '
+                             f'(got {H}, {eng.MF})')
+        self.B, self.T, self.rows = B, T, B * T
+        self.per_row_t = per_row_t
+        dev, hd, bf = eng.device, C.HALF_DTYPES[eng.precision], eng.bf16
+        rows, Cc, L = self.rows, eng.C, eng.L
+        self.dtab = eng.step_table(t_values)                 # [K, L*C] fp32 (tiny; CUDA-core GEMMs)
+        # hoisted conditioner projection of ALL layers: one tensor-core GEMM, 16-bit table [rows, L*2C]
+        cond_h = torch.empty((rows, H), device=dev, dtype=hd)
+        C.cast_h(cond_bth, cond_h, bf)
+        N = L * 2 * Cc
+        self.cond = torch.empty((rows, N), device=dev, dtype=hd)
+        C.tc_linear(cond_h, H, rows, T, eng.w_cond_h, H, eng.b_cond, N, H, bf, out_h=self.cond, ldoh=N)
+        self.xin_h = torch.empty((rows, eng.MF), device=dev, dtype=hd)
+        self.x = torch.empty((rows, Cc), device=dev)
+        self.skip = torch.empty((rows, Cc), device=dev)
+        self.y_h = torch.empty((rows, Cc), device=dev, dtype=hd)
+        self.z_h = torch.empty((rows, Cc), device=dev, dtype=hd)
+        self.skip_h = torch.empty((rows, Cc), device=dev, dtype=hd)
+        self.h_h = torch.empty((rows, Cc), device=dev, dtype=hd)
+
+    def _dvec(self, k, l):
+        LC = self.eng.L * self.eng.C
+        if self.per_row_t:
+            return self.dtab[0, l * self.eng.C:], LC
+        return self.dtab[k, l * self.eng.C:], 0
+
+    def eval(self, x_in: torch.Tensor, k: int, out: torch.Tensor):
+        e = self.eng
+        B, T, rows, Cc, L, MF, bf = self.B, self.T, self.rows, e.C, e.L, e.MF, e.bf16
+        C.cast_h(x_in, self.xin_h, bf)
+        d0, ds = self._dvec(k, 0)
+        C.tc_linear(self.xin_h, MF, rows, T, e.w_in_h, e.w_in_h.shape[1], e.b_in, Cc, MF, bf, act=C.ACT_RELU,
+                    out_f32=self.x, ldo=Cc, y_h=self.y_h, ldy=Cc, dvec=d0, d_stride=ds)
+        ldc = L * 2 * Cc
+        for l in range(L):
+            C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[:, l * 2 * Cc:], ldc, self.z_h, B, T, Cc,
+                              e.dilations[l], bf)
+            last = l + 1 == L
+            dn, ds = (None, 0) if last else self._dvec(k, l + 1)
+            C.tc_wavenet_out(self.z_h, e.w_out_h[l], e.b_out[l], self.x, None if last else self.y_h, self.skip,
+                             self.skip_h if last else None, dn, ds, l == 0, B, T, Cc, bf)
+        C.tc_linear(self.skip_h, Cc, rows, T, e.w_sp_h, Cc, e.b_sp, Cc, Cc, bf, alpha=1.0 / math.sqrt(L),
+                    act=C.ACT_RELU, out_h=self.h_h, ldoh=Cc)
+        C.tc_linear(self.h_h, Cc, rows, T, e.w_fin_h, Cc, e.b_fin, MF, Cc, bf, out_f32=out, ldo=MF)
+
+    @property
+    def launches_per_eval(self) -> int:
+        return 2 + 2 * self.eng.L + 2
+
+    def dominant_kernel(self, w=None):
+        """(name, algorithmic FLOPs per launch, callable launching it once per layer) for bench.py's roofline."""
+        e = self.eng
+        B, T, Cc, L = self.B, self.T, e.C, e.L
+        flops = 2.0 * self.rows * (3 * Cc) * (2 * Cc)
+
+        def launch_all():
+            for l in range(L):
+                C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[:, l * 2 * Cc:], L * 2 * Cc, self.z_h, B, T, Cc,
+                                  e.dilations[l], e.bf16)
+        return f'tc_gemm_kernel<EPI_GATE,{e.precision}> (b2s_tc_wavenet_gate)', flops, launch_all
+
+
 # =====================================================================================================
 # LYNXNet
 # =====================================================================================================
@@ -185,6 +281,8 @@ class LYNXNetEngine:
     def __init__(self, net, precision: str = 'fp32'):
         if precision not in PRECISIONS:
             raise ValueError(f'unknown precision {precision!r}; available: {PRECISIONS}')
+        if precision != 'fp32':
+            raise C.B2SError("LYNXNet runs on the fp32 path only in this build; set b2s_precision='fp32'")
         self.net = net
         self.precision = precision
         self.C = net.num_channels
