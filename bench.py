@@ -107,12 +107,12 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
-def make_model(w, precision, device):
+def make_model(w, precision, device, cuda_graph=True):
     import xiaoicesing_io_b200 as P
     P.hparams.clear()
     P.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=True,
                      K_step_infer=w['k_step'], diff_speedup=1, diff_accelerator='ddim', infer=False,
-                     b2s_precision=precision)
+                     b2s_precision=precision, b2s_cuda_graph=cuda_graph)
     torch.manual_seed(0)
     model = P.GaussianDiffusion(
         w['mel'], timesteps=1000, k_step=w['k_step'], backbone_type='wavenet',
@@ -252,7 +252,7 @@ def run_b200_arm(args, w):
     import xiaoicesing_io_b200 as P
     from xiaoicesing_io_b200.partition import gather_mels
 
-    model = make_model(w, args.precision, dev)
+    model = make_model(w, args.precision, dev, cuda_graph=not args.no_graph)
     cond_h, src_h = synth_inputs(w, seed=1000 + rank)          # every rank owns its utterances (weak scaling)
     cond_h, src_h = cond_h.pin_memory(), src_h.pin_memory()
     cond_d, src_d = cond_h.to(dev), src_h.to(dev)
@@ -332,7 +332,7 @@ def run_b200_arm(args, w):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'fp16': 'f16'}[args.precision], 'data': 'synthetic',
             'config': {'workload': w['desc'], 'nfe_per_step': nfe, 'global_batch': world * B, 'frames': T,
-                       'parallelism': f'utterance-partition x{world}', 'precision': args.precision,
+                       'parallelism': f'utterance-partition x{world}', 'precision': args.precision, 'cuda_graph': not args.no_graph,
                        'l2': 'working set (hoisted cond table %.0f MB) exceeds the 126 MB L2; no explicit flush'
                              % (B * T * w['layers'] * 2 * w['channels'] * 4 / 1e6),
                        'sigma_w': SIGMA_W},
@@ -362,6 +362,7 @@ def main():
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
     ap.add_argument('--k-step', type=int, default=None, help='override K_step (debug only; invalidates the metric)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the captured CUDA graph')
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.k_step:

@@ -10,6 +10,7 @@ from torch import nn
 from .. import _cabi as C
 from ..backbones.wavenet import _time_major_cond
 from ..engine import CompiledProgram, allocate_buffers, run_program
+from ..hparams import hparams
 from ..schedules import NOISE0, XSTART, Program
 
 
@@ -65,6 +66,59 @@ class SamplerBase(nn.Module):
         return self._training_forward(self._source_to_state(gt_spec), cond, b, device)
 
 
+class _GraphedLoop:
+    """The WHOLE sampling call - hoisted cond / step tables, initial noise draw, every denoiser evaluation,
+    every sampler update and per-step noise draw - captured once as a CUDA graph over static buffers and
+    replayed with a single launch.  Noise comes from ``torch.randn`` inside the graph (graph-safe Philox:
+    a replay consumes the default generator exactly like the eager loop, so seeded runs stay reproducible)."""
+
+    def __init__(self, eng, cp: CompiledProgram, B, T, H, F_, M, device):
+        prog = cp.prog
+        self.cp = cp                     # the coefficient / model-time tables are read by the captured kernels
+        self.cond = torch.empty((B, T, H), device=device)
+        self.x_start = torch.empty((B, F_ * M, T), device=device) if prog.needs_x_start else None
+        shape = (B, F_ * M, T)
+
+        def body():
+            sess = eng.begin(self.cond, cp.t_values, per_row_t=False)
+            bufs = allocate_buffers(prog, B * T, F_ * M, device)
+
+            def load(src, dst):
+                C.transpose(src, dst, B, F_ * M, T)
+
+            noise0 = torch.randn(shape, device=device)
+            if NOISE0 in bufs:
+                load(noise0, bufs[NOISE0])
+            if prog.needs_x_start:
+                load(self.x_start, bufs[XSTART])
+            self.keep = (sess, bufs)     # every buffer a captured kernel touches stays owned by this object
+            return run_program(cp, sess, bufs, lambda j, dst: load(torch.randn(shape, device=device), dst))
+
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = body()
+
+    def run(self, cond_bth, x_start_bfmt):
+        self.cond.copy_(cond_bth)
+        if self.x_start is not None:
+            self.x_start.copy_(x_start_bfmt.reshape(self.x_start.shape))
+        self.graph.replay()
+        return self.out.clone()
+
+
+_GRAPH_CACHE: 'dict[tuple, object]' = {}
+_GRAPH_CACHE_MAX = 4
+
+
+def _program_key(prog: Program):
+    return hash((tuple((op.kind, op.dst, op.src, op.t_index, tuple(op.terms), op.draw) for op in prog.ops),
+                 tuple(prog.t_values)))
+
+
+def clear_graph_cache():
+    _GRAPH_CACHE.clear()
+
+
 def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: int, out_dims: int,
            x_start: Optional[torch.Tensor], device,
            noise_source: Optional[Callable[[tuple], torch.Tensor]] = None) -> torch.Tensor:
@@ -75,6 +129,10 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
     default is ``torch.randn`` on ``device``, called in the reference's order (initial draw first,
     then one draw per ancestral step), so a seeded run consumes the same Philox stream as the
     reference on the same device.
+
+    With the default noise source and ``hparams['b2s_cuda_graph']`` (default True) the second call
+    with the same (backbone weights, program, B, T) captures the whole loop as a CUDA graph; from
+    then on a sampling call is one graph launch.
     """
     if device is None:
         device = cond_bht.device
@@ -86,12 +144,34 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
         raise C.B2SError(f'batch size mismatch: cond has {B} utterances, b={b}')
     F_, M = num_feats, out_dims
     shape = (B, F_, M, T)
-    if noise_source is None:
-        noise_source = lambda s: torch.randn(s, device=device)
     eng = backbone._engine()
     eng.pack()
+    if prog.needs_x_start:
+        assert x_start is not None, 'Missing shallow diffusion source.'
+    cond_bth = _time_major_cond(cond_bht.float())
+
+    def finish(x):
+        x = x.reshape(B, T, F_, M)
+        if F_ == 1:
+            return x[:, :, 0, :]                            # [B, T, M]
+        return x.permute(0, 2, 1, 3).contiguous()           # [B, F, T, M]
+
+    graph_key = None
+    if noise_source is None and hparams.get('b2s_cuda_graph', True) and B * T > 0:
+        graph_key = (id(backbone), eng._packed_version, eng.precision, _program_key(prog), B, T, F_, M, str(device))
+        entry = _GRAPH_CACHE.get(graph_key)
+        if entry is not None:
+            if entry == 'seen':                             # second call with this key: capture
+                if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+                    _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
+                entry = _GraphedLoop(eng, CompiledProgram(prog, device), B, T, H, F_, M, device)
+                _GRAPH_CACHE[graph_key] = entry
+            xs = None if x_start is None else x_start.to(device=device, dtype=torch.float32)
+            return finish(entry.run(cond_bth, xs))
+    if noise_source is None:
+        noise_source = lambda s: torch.randn(s, device=device)
     cp = CompiledProgram(prog, device)
-    sess = eng.begin(_time_major_cond(cond_bht.float()), cp.t_values, per_row_t=False)
+    sess = eng.begin(cond_bth, cp.t_values, per_row_t=False)
     bufs = allocate_buffers(prog, B * T, F_ * M, device)
 
     def load(src_bfmt, dst):
@@ -102,11 +182,11 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
     if NOISE0 in bufs:
         load(noise0, bufs[NOISE0])
     if prog.needs_x_start:
-        assert x_start is not None, 'Missing shallow diffusion source.'
         load(x_start, bufs[XSTART])
 
     x = run_program(cp, sess, bufs, lambda j, dst: load(noise_source(shape), dst))   # [B*T, F*M]
-    x = x.reshape(B, T, F_, M)
-    if F_ == 1:
-        return x[:, :, 0, :]                            # [B, T, M]
-    return x.permute(0, 2, 1, 3).contiguous()           # [B, F, T, M]
+    if graph_key is not None:
+        if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+            _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
+        _GRAPH_CACHE[graph_key] = 'seen'
+    return finish(x)

@@ -29,7 +29,9 @@ constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;          // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;          // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int STG_LD = 36;                                // floats per staged row: 32 + 4 pad -> conflict-free 128-bit accesses
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;            // one 32x32 fp32 transpose buffer per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
 constexpr int NTHREADS = 256;
 
@@ -57,155 +59,122 @@ __device__ __forceinline__ void store_h1(void* base, long long idx, float v) {
     else reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
 }
 template <int BF16>
-__device__ __forceinline__ void store_h32(void* base, long long idx, const float* v) {   // 32 values, 64 B
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + idx);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint4 o;
-        o.x = Half16<BF16>::pack2(v[8 * i + 0], v[8 * i + 1]);
-        o.y = Half16<BF16>::pack2(v[8 * i + 2], v[8 * i + 3]);
-        o.z = Half16<BF16>::pack2(v[8 * i + 4], v[8 * i + 5]);
-        o.w = Half16<BF16>::pack2(v[8 * i + 6], v[8 * i + 7]);
-        dst[i] = o;
-    }
+__device__ __forceinline__ void store_h4(void* base, long long idx, float4 v) {          // 4 values, 8 B
+    uint2 o;
+    o.x = Half16<BF16>::pack2(v.x, v.y);
+    o.y = Half16<BF16>::pack2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = o;
 }
 template <int BF16>
-__device__ __forceinline__ void store_h16(void* base, long long idx, const float* v) {   // 16 values, 32 B
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + idx);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        uint4 o;
-        o.x = Half16<BF16>::pack2(v[8 * i + 0], v[8 * i + 1]);
-        o.y = Half16<BF16>::pack2(v[8 * i + 2], v[8 * i + 3]);
-        o.z = Half16<BF16>::pack2(v[8 * i + 4], v[8 * i + 5]);
-        o.w = Half16<BF16>::pack2(v[8 * i + 6], v[8 * i + 7]);
-        dst[i] = o;
-    }
+__device__ __forceinline__ void store_h2(void* base, long long idx, float a, float b) {  // 2 values, 4 B
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(base) + idx) = Half16<BF16>::pack2(a, b);
 }
-__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
+__device__ __forceinline__ uint2 ldg_nc_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// ---- epilogues: one thread = one output row, 32 consecutive columns [col0, col0+32) ------------------
+__device__ __noinline__ float4 act4_slow(float4 v, int act) {
+    return make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act), apply_act(v.w, act));
+}
+
+// Per-chunk constants that do not depend on the row (one float4 = the lane's 4 columns).
+struct EpiConst {
+    float4 bias;
+    float4 d;          // step-embedding row when it is shared by every utterance (d_stride == 0)
+};
+
+template <int EPI>
+__device__ __forceinline__ EpiConst epilogue_consts(const TcP& p, int col) {
+    EpiConst c;
+    c.bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    c.d = c.bias;
+    if (EPI == EPI_GATE) return c;
+    if (p.bias) {
+        if (EPI != EPI_LINEAR || col + 4 <= p.N) c.bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        else {
+            float* bb = &c.bias.x;
+            for (int i = 0; i < 4; ++i) bb[i] = col + i < p.N ? __ldg(p.bias + col + i) : 0.f;
+        }
+    }
+    if ((EPI == EPI_LINEAR || EPI == EPI_RESSKIP) && p.y_h && p.d_stride == 0 && col + 4 <= p.N && (EPI != EPI_RESSKIP || col < p.C))
+        c.d = __ldg(reinterpret_cast<const float4*>(p.dvec + col));
+    return c;
+}
+
+// ---- epilogues in the COALESCED layout: a lane owns 4 consecutive columns [col, col+4) of one row; the 8
+// lanes of a quarter-warp cover 128 contiguous bytes of an fp32 row.  Two phases per chunk so that the 8
+// independent row loads of a lane are all in flight before the first dependent store is issued. ------------
 template <int EPI, int BF16>
-__device__ __forceinline__ void epilogue_chunk(const TcP& p, float* acc, long long r, int b, int col0) {
-    if (EPI == EPI_LINEAR) {
-        const int nvalid = min(32, p.N - col0);
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float bias = (p.bias && i < nvalid) ? __ldg(p.bias + col0 + i) : 0.f;
-            v[i] = apply_act(fmaf(p.alpha, acc[i], bias), p.act);
-        }
-        if (nvalid == 32) {
-            if (p.out_f) {
-                float4* dst = reinterpret_cast<float4*>(p.out_f + r * p.ldo + col0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (p.out_h) store_h32<BF16>(p.out_h, r * p.ldoh + col0, v);
-            if (p.y_h) {
-                const float4* d = reinterpret_cast<const float4*>(p.dvec + (long long)b * p.d_stride + col0);
-                float yv[32];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 dd = __ldg(d + i);
-                    yv[4 * i] = v[4 * i] + dd.x; yv[4 * i + 1] = v[4 * i + 1] + dd.y;
-                    yv[4 * i + 2] = v[4 * i + 2] + dd.z; yv[4 * i + 3] = v[4 * i + 3] + dd.w;
-                }
-                store_h32<BF16>(p.y_h, r * p.ldy + col0, yv);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (i < nvalid) {
-                    if (p.out_f) p.out_f[r * p.ldo + col0 + i] = v[i];
-                    if (p.out_h) store_h1<BF16>(p.out_h, r * p.ldoh + col0 + i, v[i]);
-                    if (p.y_h)
-                        store_h1<BF16>(p.y_h, r * p.ldy + col0 + i, v[i] + __ldg(p.dvec + (long long)b * p.d_stride + col0 + i));
-                }
-            }
-        }
-    } else if (EPI == EPI_GATE || EPI == EPI_SWIGLU) {
-        // packed columns: even = gate (GATE) / out (SWIGLU), odd = filter (GATE) / gate (SWIGLU)
-        float z[16];
-        if (EPI == EPI_GATE) {
-            const uint16_t* cp = reinterpret_cast<const uint16_t*>(p.cond) + r * p.ldc + col0;
-            uint4 c[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) c[i] = ldg_nc_u4(cp + 8 * i);
-            const uint32_t* cw = reinterpret_cast<const uint32_t*>(c);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float2 cf = Half16<BF16>::unpack2(cw[i]);
-                z[i] = sigmoid_fast(acc[2 * i] + cf.x) * tanh_fast(acc[2 * i + 1] + cf.y);
-            }
-        } else {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 bb = __ldg(bp + i);
-                const float g0 = acc[4 * i + 1] + bb.y, g1 = acc[4 * i + 3] + bb.w;
-                z[2 * i] = (acc[4 * i] + bb.x) * (g0 * sigmoid_fast(g0));
-                z[2 * i + 1] = (acc[4 * i + 2] + bb.z) * (g1 * sigmoid_fast(g1));
-            }
-        }
-        store_h16<BF16>(p.out_h, r * p.ldoh + (col0 >> 1), z);
+__device__ __forceinline__ float4 epilogue_load(const TcP& p, long long r, int col) {
+    if (EPI == EPI_GATE) {
+        // hoisted conditioner projection, same (gate j, filter j) interleave as the packed weight rows
+        const uint2 c = ldg_nc_u2(reinterpret_cast<const uint16_t*>(p.cond) + r * p.ldc + col);
+        const float2 c0 = Half16<BF16>::unpack2(c.x), c1 = Half16<BF16>::unpack2(c.y);
+        return make_float4(c0.x, c0.y, c1.x, c1.y);
     } else if (EPI == EPI_RESIDUAL) {
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-        float4* xp = reinterpret_cast<float4*>(p.x + r * p.C + col0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(bp + i);
-            float4 xo = xp[i];
-            xo.x += acc[4 * i] + bb.x; xo.y += acc[4 * i + 1] + bb.y;
-            xo.z += acc[4 * i + 2] + bb.z; xo.w += acc[4 * i + 3] + bb.w;
-            xp[i] = xo;
+        return *reinterpret_cast<const float4*>(p.x + r * p.C + col);
+    } else if (EPI == EPI_RESSKIP) {
+        if (col < p.C) return *reinterpret_cast<const float4*>(p.x + r * p.C + col);
+        if (!p.first) return *reinterpret_cast<const float4*>(p.skip + r * p.C + (col - p.C));
+    }
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <int EPI, int BF16>
+__device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 in, const EpiConst& k, long long r, int b,
+                                              int col) {
+    if (EPI == EPI_LINEAR) {
+        // ReLU / identity inline (the hot cases: stem, head, cond table); Mish / GELU / SiLU through ONE
+        // out-of-line call so the unrolled epilogue stays small enough for the instruction cache
+        const float lo = p.act == ACT_RELU ? 0.f : -INFINITY;
+        float4 v = make_float4(fmaxf(fmaf(p.alpha, acc.x, k.bias.x), lo), fmaxf(fmaf(p.alpha, acc.y, k.bias.y), lo),
+                               fmaxf(fmaf(p.alpha, acc.z, k.bias.z), lo), fmaxf(fmaf(p.alpha, acc.w, k.bias.w), lo));
+        if (p.act > ACT_RELU) v = act4_slow(v, p.act);
+        if (col + 4 <= p.N) {
+            if (p.out_f) *reinterpret_cast<float4*>(p.out_f + r * p.ldo + col) = v;
+            if (p.out_h) store_h4<BF16>(p.out_h, r * p.ldoh + col, v);
+            if (p.y_h) {
+                const float4 d = p.d_stride == 0 ? k.d : __ldg(reinterpret_cast<const float4*>(p.dvec + (long long)b * p.d_stride + col));
+                store_h4<BF16>(p.y_h, r * p.ldy + col, add4(v, d));
+            }
+        } else {
+            const float* vv = &v.x;
+            for (int i = 0; i < 4; ++i) {
+                if (col + i < p.N) {
+                    if (p.out_f) p.out_f[r * p.ldo + col + i] = vv[i];
+                    if (p.out_h) store_h1<BF16>(p.out_h, r * p.ldoh + col + i, vv[i]);
+                    if (p.y_h) store_h1<BF16>(p.y_h, r * p.ldy + col + i, vv[i] + __ldg(p.dvec + (long long)b * p.d_stride + col + i));
+                }
+            }
         }
+    } else if (EPI == EPI_GATE) {
+        const float z0 = sigmoid_fast(acc.x + in.x) * tanh_fast(acc.y + in.y);
+        const float z1 = sigmoid_fast(acc.z + in.z) * tanh_fast(acc.w + in.w);
+        store_h2<BF16>(p.out_h, r * p.ldoh + (col >> 1), z0, z1);
+    } else if (EPI == EPI_SWIGLU) {
+        const float g0 = acc.y + k.bias.y, g1 = acc.w + k.bias.w;
+        store_h2<BF16>(p.out_h, r * p.ldoh + (col >> 1), (acc.x + k.bias.x) * (g0 * sigmoid_fast(g0)),
+                       (acc.z + k.bias.z) * (g1 * sigmoid_fast(g1)));
+    } else if (EPI == EPI_RESIDUAL) {
+        *reinterpret_cast<float4*>(p.x + r * p.C + col) = add4(in, add4(acc, k.bias));
     } else {   // EPI_RESSKIP: reference column order, [0, C) residual, [C, 2C) skip
         const float inv_sqrt2 = 0.70710678118654752440f;
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-        if (col0 < p.C) {
-            float4* xp = reinterpret_cast<float4*>(p.x + r * p.C + col0);
-            float xn[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 bb = __ldg(bp + i);
-                const float4 xo = xp[i];
-                xn[4 * i] = (xo.x + acc[4 * i] + bb.x) * inv_sqrt2;
-                xn[4 * i + 1] = (xo.y + acc[4 * i + 1] + bb.y) * inv_sqrt2;
-                xn[4 * i + 2] = (xo.z + acc[4 * i + 2] + bb.z) * inv_sqrt2;
-                xn[4 * i + 3] = (xo.w + acc[4 * i + 3] + bb.w) * inv_sqrt2;
-                xp[i] = make_float4(xn[4 * i], xn[4 * i + 1], xn[4 * i + 2], xn[4 * i + 3]);
-            }
+        const float4 o = add4(acc, k.bias);
+        if (col < p.C) {
+            const float4 xn = make_float4((in.x + o.x) * inv_sqrt2, (in.y + o.y) * inv_sqrt2, (in.z + o.z) * inv_sqrt2,
+                                          (in.w + o.w) * inv_sqrt2);
+            *reinterpret_cast<float4*>(p.x + r * p.C + col) = xn;
             if (p.y_h) {
-                const float4* d = reinterpret_cast<const float4*>(p.dvec + (long long)b * p.d_stride + col0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 dd = __ldg(d + i);
-                    xn[4 * i] += dd.x; xn[4 * i + 1] += dd.y; xn[4 * i + 2] += dd.z; xn[4 * i + 3] += dd.w;
-                }
-                store_h32<BF16>(p.y_h, r * p.ldy + col0, xn);
+                const float4 d = p.d_stride == 0 ? k.d : __ldg(reinterpret_cast<const float4*>(p.dvec + (long long)b * p.d_stride + col));
+                store_h4<BF16>(p.y_h, r * p.ldy + col, add4(xn, d));
             }
         } else {
-            float4* sp = reinterpret_cast<float4*>(p.skip + r * p.C + (col0 - p.C));
-            float s[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 bb = __ldg(bp + i);
-                s[4 * i] = acc[4 * i] + bb.x; s[4 * i + 1] = acc[4 * i + 1] + bb.y;
-                s[4 * i + 2] = acc[4 * i + 2] + bb.z; s[4 * i + 3] = acc[4 * i + 3] + bb.w;
-                if (!p.first) {
-                    const float4 so = sp[i];
-                    s[4 * i] += so.x; s[4 * i + 1] += so.y; s[4 * i + 2] += so.z; s[4 * i + 3] += so.w;
-                }
-                sp[i] = make_float4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
-            }
-            if (p.skip_h) store_h32<BF16>(p.skip_h, r * p.C + (col0 - p.C), s);
+            const float4 s = add4(o, in);                  // in = 0 on the first layer
+            *reinterpret_cast<float4*>(p.skip + r * p.C + (col - p.C)) = s;
+            if (p.skip_h) store_h4<BF16>(p.skip_h, r * p.C + (col - p.C), s);
         }
     }
 }
@@ -215,7 +184,8 @@ template <int EPI, int BF16>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ TcP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    float* stg_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STG_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -304,13 +274,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int bt = m_tile / p.tiles_m_per_b, t0 = (m_tile - bt * p.tiles_m_per_b) * BLOCK_M;
             const int n0 = n_tile * BLOCK_N;
-            const int t = t0 + q * 32 + lane;
-            const bool valid = t < p.T;
-            const long long r = (long long)bt * p.T + t;
-            const int b = p.T_utt > 0 ? (int)(r / p.T_utt) : 0;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+            float* stg = stg_all + q * (32 * STG_LD);
+            const int cl = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll 1
             for (int j = 0; j < BLOCK_N / 32; ++j) {
                 const int col0 = n0 + 32 * j;
@@ -318,7 +286,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                 float acc[32];
                 tmem_ld32(taddr + j * 32, acc);
                 tmem_ld_wait();
-                if (valid) epilogue_chunk<EPI, BF16>(p, acc, r, b, col0);
+                // transpose through the warp's private staging tile: thread = row  ->  lane = 4 columns
+                float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) srow[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                __syncwarp();
+                const int col = col0 + cl;
+                if (col < p.N) {
+                    const EpiConst kc = epilogue_consts<EPI>(p, col);
+                    const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
+                    float4 in[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        in[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tq + 4 * i < p.T) in[i] = epilogue_load<EPI, BF16>(p, (long long)bt * p.T + tq + 4 * i, col);
+                    }
+#pragma unroll(EPI == EPI_LINEAR ? 1 : 8)
+                    for (int i = 0; i < 8; ++i) {
+                        const int t = tq + 4 * i;
+                        if (t < p.T) {
+                            const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * STG_LD + cl);
+                            const int b = (p.d_stride != 0 && p.T_utt > 0) ? (bt * p.T + t) / p.T_utt : 0;
+                            epilogue_quad<EPI, BF16>(p, v, in[i], kc, (long long)bt * p.T + t, b, col);
+                        }
+                    }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
