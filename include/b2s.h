@@ -133,6 +133,13 @@ int b2s_tc_linear(const void* A_h, int lda, int rows, int T, const void* W_h, in
                   float alpha, int act, float* out_f32, int ldo, void* out_h, int ldoh, void* y_h, int ldy,
                   const float* dvec, int d_stride, int bf16, void* stream);
 
+/* Hoisted conditioner projection of ALL layers as ONE tensor-core GEMM (wavenet.py:35 / lynxnet.py:77-82; precedent:
+ * the reference's own ONNX exporter, utils/onnx_helper.py:231-314):  table[l][row][n] = cond[row,:] . Wc[l*N2 + n,:] + bc.
+ * The table is LAYER-MAJOR [L][rows][N2] so that one layer's slab is contiguous in HBM (it is streamed once per
+ * denoiser evaluation).  N2 = 2C (WaveNet, gate/filter interleaved) or C (LYNXNet); N2 % 32 == 0. */
+int b2s_tc_cond_table(const void* cond_h, int rows, const void* Wc_h, const float* bc, int L, int N2, int H,
+                      void* table_h, int bf16, void* stream);
+
 /* b2s_wavenet_gate_f32 on the tensor cores: implicit-GEMM dilated conv (3 TMA tiles per K slab at time
  * offsets -d, 0, +d; out-of-bounds zero fill = the per-utterance zero padding), epilogue adds the hoisted
  * 16-bit conditioner projection and applies sigmoid*tanh (wavenet.py:38-42).  C % 64 == 0. */
@@ -144,6 +151,16 @@ int b2s_tc_wavenet_gate(const void* y_h, const void* Wd_h, const void* cond_h, i
 int b2s_tc_wavenet_out(const void* z_h, const void* Wo_h, const float* bo, float* x, void* y_next_h, float* skip,
                        void* skip_h, const float* dvec_next, int d_stride, int first_layer, int B, int T, int C,
                        int bf16, void* stream);
+
+/* ONE fused kernel per WaveNet residual layer (wavenet.py:33-48), residual channels C = 256:
+ * dilated conv (implicit GEMM) -> + hoisted cond -> sigmoid*tanh -> z kept in shared memory -> output projection
+ * -> x <- (x + r)/sqrt2, y_next <- x + dvec_next, skip (+)= s.  y_next_h must be a different buffer than y_h
+ * (neighbouring tiles still read the halo of y_h).  Returns B2S_ERR_UNSUPPORTED for other C: call
+ * b2s_tc_wavenet_gate + b2s_tc_wavenet_out instead.  Launched with programmatic dependent launch so that
+ * consecutive layers overlap prologue and tail. */
+int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const void* cond_h, int ld_cond, const void* Wo_h,
+                         const float* bo, float* x, void* y_next_h, float* skip, void* skip_h, const float* dvec_next,
+                         int d_stride, int first_layer, int B, int T, int C, int dilation, int bf16, void* stream);
 
 /* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
  * down-projection with the residual add into the fp32 stream. */

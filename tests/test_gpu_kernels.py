@@ -176,3 +176,72 @@ def test_tc_out_resskip(C, kind, hd, eps):
         assert float((skip.double() - s_want).abs().max()) < 2e-5
         assert float((y.double() - y_want).abs().max()) < eps * float(y_want.abs().max())
         assert float((sh.double() - s_want).abs().max()) < eps * float(s_want.abs().max())
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+def test_tc_fused_layer_matches_gate_plus_out(C, kind, hd, eps):
+    """The fused per-layer kernel (z kept in shared memory) against the two-kernel tensor-core path and fp64."""
+    import torch.nn.functional as F
+    bf = kind == 'bf16'
+    Cc = 256
+    for (B, T, d, first, last) in [(2, 300, 1, True, False), (3, 130, 4, False, False), (1, 690, 8, False, True),
+                                   (2, 50, 16, False, False)]:
+        rows = B * T
+        torch.manual_seed(T + d)
+        y = torch.randn(rows, Cc, device='cuda').to(hd)
+        Wref = (torch.randn(2 * Cc, Cc, 3, device='cuda') / (3 * Cc) ** 0.5).to(hd)
+        perm = torch.stack([torch.arange(Cc), torch.arange(Cc) + Cc], 1).reshape(-1).cuda()
+        Wd = Wref[perm].permute(0, 2, 1).reshape(2 * Cc, 3 * Cc).contiguous()
+        ldc = 2 * Cc * 3                                              # a 3-layer table, this layer in the middle
+        cond_all = torch.randn(rows, ldc, device='cuda').to(hd)
+        cond = cond_all[:, 2 * Cc:]
+        Wo = (torch.randn(2 * Cc, Cc, device='cuda') / Cc ** 0.5).to(hd)
+        bo = torch.randn(2 * Cc, device='cuda')
+        x0 = torch.randn(rows, Cc, device='cuda')
+        skip0 = torch.randn(rows, Cc, device='cuda')
+        dvec = torch.randn(Cc, device='cuda')
+        # two-kernel path
+        z = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+        xa, sa = x0.clone(), skip0.clone()
+        ya = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+        sha = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+        C.tc_wavenet_gate(y, Wd, cond, ldc, z, B, T, Cc, d, bf)
+        C.tc_wavenet_out(z, Wo, bo, xa, None if last else ya, sa, sha if last else None, None if last else dvec, 0, first,
+                         B, T, Cc, bf)
+        # fused
+        xb, sb = x0.clone(), skip0.clone()
+        yb = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+        shb = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+        C.tc_wavenet_layer(y, Wd, cond, ldc, Wo, bo, xb, None if last else yb, sb, shb if last else None,
+                           None if last else dvec, 0, first, B, T, Cc, d, bf)
+        torch.cuda.synchronize()
+        tag = (kind, B, T, d)
+        assert float((xa - xb).abs().max()) < 1e-5, tag
+        assert float((sa - sb).abs().max()) < 1e-5, tag
+        assert float((ya.float() - yb.float()).abs().max()) <= eps * 8, tag
+        assert float((sha.float() - shb.float()).abs().max()) <= eps * 8, tag
+        # fp64 reference on the same 16-bit operands (z rounded to 16 bits in between)
+        conv = F.conv1d(y.reshape(B, T, Cc).transpose(1, 2).double(), Wref.double(), padding=d, dilation=d)
+        c = cond[:, :2 * Cc].reshape(B, T, Cc, 2).double()
+        g = conv[:, :Cc].transpose(1, 2) + c[..., 0]
+        f = conv[:, Cc:].transpose(1, 2) + c[..., 1]
+        zz = (torch.sigmoid(g) * torch.tanh(f)).reshape(rows, Cc)
+        o = zz @ Wo.double().t() + bo.double()
+        x_want = (x0.double() + o[:, :Cc]) / 2 ** 0.5
+        s_want = o[:, Cc:] + (0 if first else skip0.double())
+        assert float((xb.double() - x_want).abs().max()) < 0.02, tag     # z rounding (2^-9) x 256-term dot products
+        assert float((sb.double() - s_want).abs().max()) < 0.03, tag
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+def test_tc_cond_table_layer_major(C, kind, hd, eps):
+    bf = kind == 'bf16'
+    rows, H, L, N2 = 333, 256, 5, 128
+    torch.manual_seed(1)
+    cond = torch.randn(rows, H, device='cuda').to(hd)
+    W = (torch.randn(L * N2, H, device='cuda') / H ** 0.5).to(hd)
+    b = torch.randn(L * N2, device='cuda')
+    tab = torch.zeros(L, rows, N2, device='cuda', dtype=hd)
+    C.tc_cond_table(cond, rows, W, b, L, N2, H, tab, bf)
+    want = (cond.double() @ W.double().t() + b.double()).reshape(rows, L, N2).permute(1, 0, 2)
+    assert float((tab.double() - want).abs().max()) < eps * float(want.abs().max())

@@ -17,6 +17,20 @@ from test_gpu_parity import _maxabs, _oracle_and_product
 pytestmark = pytest.mark.gpu
 
 TC_TOL = 2e-2
+# bf16 keeps 8 mantissa bits: with |mel| ~ 300 (random-init from-noise sampling, eps_hat ~ 0) the hidden activations
+# reach ~70 and one bf16 ulp of the conv input alone is 0.5, so the ABSOLUTE 2e-2 bound is only reachable while the
+# mel stays in a realistic range (|mel| <= 64; real log-mels live in [-12, 0]).  Above that the bf16 bound is relative,
+# 2e-4 * |mel|max (measured: 1.1e-4 .. 1.5e-4; torch's own bf16 autocast of the reference is 1.2e-4).
+# fp16 (same tensor-core rate, 11 mantissa bits) meets the absolute 2e-2 everywhere.
+BF16_REL = 2e-4
+
+
+def _tol(precision, scale):
+    if precision == 'bf16' and scale > 64.0:
+        return BF16_REL * scale
+    return TC_TOL
+
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -68,7 +82,7 @@ def test_config1_tensor_core(acc, precision, dev):
         {}, 1, 690, dev)
     err, scale = _maxabs(out, ref), float(ref.abs().max())
     _report(test='config1', sampler=acc, precision=precision, max_abs=err, ref_absmax=scale, sigma_w=0.01)
-    assert err <= TC_TOL, (acc, precision, err, scale)
+    assert err <= _tol(precision, scale), (acc, precision, err, scale)
 
 
 @pytest.mark.parametrize('precision', ['bf16', 'fp16'])
@@ -79,7 +93,7 @@ def test_config2_shape_tensor_core(precision, dev):
         dict(k_step=40), 3, 173, dev, n_draws=41, src=True)
     err, scale = _maxabs(out, ref), float(ref.abs().max())
     _report(test='config2_shape_ddpm40', precision=precision, max_abs=err, ref_absmax=scale, sigma_w=0.01)
-    assert err <= TC_TOL, (precision, err, scale)
+    assert err <= _tol(precision, scale), (precision, err, scale)
 
 
 @pytest.mark.parametrize('precision', ['bf16', 'fp16'])
@@ -90,4 +104,4 @@ def test_config5_shape_tensor_core(precision, dev):
         {}, 2, 131, dev)
     err, scale = _maxabs(out, ref), float(ref.abs().max())
     _report(test='config5_shape_unipc10_C512', precision=precision, max_abs=err, ref_absmax=scale, sigma_w=0.01)
-    assert err <= TC_TOL, (precision, err, scale)
+    assert err <= _tol(precision, scale), (precision, err, scale)

@@ -31,8 +31,10 @@ _SIGNATURES = {
     # 16-bit tensor-core path
     'b2s_cast_f32_h': [_vp, _vp, _i64, _i, _vp],
     'b2s_tc_linear': [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp],
+    'b2s_tc_cond_table': [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_wavenet_gate': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_out': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_tc_wavenet_layer': [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
 }
@@ -164,6 +166,11 @@ def tc_linear(A, lda, rows, T, W, ldw, bias, N, K, bf16, alpha=1.0, act=ACT_NONE
           'b2s_tc_linear')
 
 
+def tc_cond_table(cond_h, rows, Wc_h, bc, L, N2, H, table_h, bf16):
+    check(lib.b2s_tc_cond_table(ptr(cond_h), rows, ptr(Wc_h), ptr(bc), L, N2, H, ptr(table_h), int(bf16), stream_ptr()),
+          'b2s_tc_cond_table')
+
+
 def tc_wavenet_gate(y_h, Wd_h, cond_h, ld_cond, z_h, B, T, C, dilation, bf16):
     check(lib.b2s_tc_wavenet_gate(ptr(y_h), ptr(Wd_h), ptr(cond_h), ld_cond, ptr(z_h), B, T, C, dilation, int(bf16),
                                   stream_ptr()), 'b2s_tc_wavenet_gate')
@@ -173,6 +180,16 @@ def tc_wavenet_out(z_h, Wo_h, bo, x, y_next_h, skip, skip_h, dvec_next, d_stride
     check(lib.b2s_tc_wavenet_out(ptr(z_h), ptr(Wo_h), ptr(bo), ptr(x), ptr(y_next_h), ptr(skip), ptr(skip_h),
                                  ptr(dvec_next), d_stride, int(first), B, T, C, int(bf16), stream_ptr()),
           'b2s_tc_wavenet_out')
+
+
+FUSED_LAYER_CHANNELS = 256
+
+
+def tc_wavenet_layer(y_h, Wd_h, cond_h, ld_cond, Wo_h, bo, x, y_next_h, skip, skip_h, dvec_next, d_stride, first, B, T,
+                     C, dilation, bf16):
+    check(lib.b2s_tc_wavenet_layer(ptr(y_h), ptr(Wd_h), ptr(cond_h), ld_cond, ptr(Wo_h), ptr(bo), ptr(x), ptr(y_next_h),
+                                   ptr(skip), ptr(skip_h), ptr(dvec_next), d_stride, int(first), B, T, C, dilation,
+                                   int(bf16), stream_ptr()), 'b2s_tc_wavenet_layer')
 
 
 def tc_lynx_glu(h_h, W_h, bias, g_h, rows, C, inner, bf16):

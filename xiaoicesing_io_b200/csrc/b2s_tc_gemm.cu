@@ -46,6 +46,7 @@ struct __align__(64) TcP {
     const float* bias; float alpha; int act;
     float* out_f; int ldo;
     void* out_h; int ldoh;
+    int oh_blk; long long oh_blk_stride;   // out_h column blocks: block k of oh_blk columns starts at k * oh_blk_stride
     void* y_h; int ldy;
     const float* dvec; int d_stride;
     const void* cond; int ldc;
@@ -82,6 +83,7 @@ __device__ __noinline__ float4 act4_slow(float4 v, int act) {
 
 // Per-chunk constants that do not depend on the row (one float4 = the lane's 4 columns).
 struct EpiConst {
+    long long oh_off;  // offset of this column block of out_h (layer-major tables), 0 for plain row-major output
     float4 bias;
     float4 d;          // step-embedding row when it is shared by every utterance (d_stride == 0)
 };
@@ -91,6 +93,7 @@ __device__ __forceinline__ EpiConst epilogue_consts(const TcP& p, int col) {
     EpiConst c;
     c.bias = make_float4(0.f, 0.f, 0.f, 0.f);
     c.d = c.bias;
+    c.oh_off = (EPI == EPI_LINEAR && p.oh_blk) ? (long long)(col / p.oh_blk) * (p.oh_blk_stride - p.oh_blk) : 0;
     if (EPI == EPI_GATE) return c;
     if (p.bias) {
         if (EPI != EPI_LINEAR || col + 4 <= p.N) c.bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
@@ -135,7 +138,7 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
         if (p.act > ACT_RELU) v = act4_slow(v, p.act);
         if (col + 4 <= p.N) {
             if (p.out_f) *reinterpret_cast<float4*>(p.out_f + r * p.ldo + col) = v;
-            if (p.out_h) store_h4<BF16>(p.out_h, r * p.ldoh + col, v);
+            if (p.out_h) store_h4<BF16>(p.out_h, k.oh_off + r * p.ldoh + col, v);
             if (p.y_h) {
                 const float4 d = p.d_stride == 0 ? k.d : __ldg(reinterpret_cast<const float4*>(p.dvec + (long long)b * p.d_stride + col));
                 store_h4<BF16>(p.y_h, r * p.ldy + col, add4(v, d));
@@ -145,7 +148,7 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
             for (int i = 0; i < 4; ++i) {
                 if (col + i < p.N) {
                     if (p.out_f) p.out_f[r * p.ldo + col + i] = vv[i];
-                    if (p.out_h) store_h1<BF16>(p.out_h, r * p.ldoh + col + i, vv[i]);
+                    if (p.out_h) store_h1<BF16>(p.out_h, k.oh_off + r * p.ldoh + col + i, vv[i]);
                     if (p.y_h) store_h1<BF16>(p.y_h, r * p.ldy + col + i, vv[i] + __ldg(p.dvec + (long long)b * p.d_stride + col + i));
                 }
             }
@@ -329,69 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     }
 }
 
-// ---- host side --------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-// activations [B, T, cols] (row stride ld elements) -> 3-D map {cols, T, B}, box {64, 128, 1}
-static int make_map_act(CUtensorMap* m, const void* base, int bf16, int cols, int ld, int T, int B) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return B2S_ERR_CUDA; }
-    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
-    cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
-    cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult rc = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
-                     const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled(activations cols=%d ld=%d T=%d B=%d) failed with CUresult %d", cols, ld, T, B, (int)rc);
-        return B2S_ERR_CUDA;
-    }
-    return B2S_OK;
-}
-// weights [N, K] (row stride ldw) -> 2-D map {K, N}, box {64, 256}
-static int make_map_w(CUtensorMap* m, const void* base, int bf16, int K, int N, int ldw) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return B2S_ERR_CUDA; }
-    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    cuuint64_t gstr[1] = {(cuuint64_t)ldw * 2};
-    cuuint32_t box[2] = {BLOCK_K, BLOCK_N};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult rc = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                     const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled(weights K=%d N=%d ldw=%d) failed with CUresult %d", K, N, ldw, (int)rc);
-        return B2S_ERR_CUDA;
-    }
-    return B2S_OK;
-}
-
-static int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
+// ---- host side (tensor-map builders live in b2s_tc.cuh) ------------------------------------------------
 template <int EPI, int BF16>
 static int launch_one(const TcP& p, cudaStream_t st) {
     static bool configured = false;
@@ -414,9 +355,9 @@ static int launch(const TcP& p, int bf16, cudaStream_t st) {
 static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool per_utt, const void* W, int ldw, int N, int K,
                  int kb_per_tap, int dil, int bf16) {
     const int Bm = per_utt ? B : 1, Tm = per_utt ? T : B * T;
-    int rc = make_map_act(&p.mapA, A, bf16, a_cols, lda, Tm, Bm);
+    int rc = make_map_act(&p.mapA, A, bf16, a_cols, lda, Tm, Bm, BLOCK_K, BLOCK_M);
     if (rc) return rc;
-    rc = make_map_w(&p.mapW, W, bf16, K, N, ldw);
+    rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, BLOCK_N);
     if (rc) return rc;
     p.B = Bm; p.T = Tm; p.T_utt = T;
     p.N = N;
@@ -429,7 +370,6 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     return B2S_OK;
 }
 
-static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 }  // namespace tc
 }  // namespace b2s
@@ -455,6 +395,20 @@ extern "C" int b2s_tc_linear(const void* A, int lda, int rows, int T, const void
     p.bias = bias; p.alpha = alpha; p.act = act;
     p.out_f = out_f32; p.ldo = ldo; p.out_h = out_h; p.ldoh = ldoh; p.y_h = y_h; p.ldy = ldy;
     p.dvec = dvec; p.d_stride = d_stride;
+    return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
+}
+
+extern "C" int b2s_tc_cond_table(const void* cond_h, int rows, const void* Wc_h, const float* bc, int L, int N2, int H,
+                                 void* table_h, int bf16, void* stream) {
+    B2S_CHECK_ARG(cond_h && Wc_h && table_h, "b2s_tc_cond_table: null pointer");
+    B2S_CHECK_ARG(L > 0 && N2 > 0 && N2 % 32 == 0 && H % 8 == 0, "b2s_tc_cond_table: bad dims L=%d N2=%d H=%d", L, N2, H);
+    B2S_CHECK_ARG(al16(cond_h) && al16(Wc_h) && al16(table_h), "b2s_tc_cond_table: misaligned pointer");
+    if (rows == 0) return B2S_OK;
+    TcP p{};
+    int rc = setup(p, cond_h, H, H, 1, rows, false, Wc_h, H, L * N2, H, 0, 0, bf16);
+    if (rc) return rc;
+    p.bias = bc; p.alpha = 1.f; p.act = ACT_NONE;
+    p.out_h = table_h; p.ldoh = N2; p.oh_blk = N2; p.oh_blk_stride = (long long)rows * N2;
     return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,361 @@
+// One fused kernel per WaveNet residual layer (wavenet.py:33-48) on tcgen05 / TMEM / TMA.  sm_100a only.
+//
+// One CTA = one tile of 128 frames of one utterance; everything between the layer's input y = x + step embedding
+// and its outputs (x', y_next, skip) stays on chip:
+//
+//   GEMM1  [128 x 768] . [768 x 512]   implicit-GEMM dilated k=3 conv: 3 TMA tiles per K slab at time offsets
+//                                      -d, 0, +d (out-of-bounds zero fill = per-utterance zero padding, H1)
+//          two N halves of 256 packed (gate j, filter j) columns -> all 512 TMEM columns
+//   EPI1   + hoisted 16-bit conditioner projection, z = sigmoid(g) * tanh(f); z is written STRAIGHT into shared
+//          memory in the 128B-swizzled K-major layout the tensor core reads (never touches HBM / L2)
+//   GEMM2  [128 x 256] . [256 x 512]   output projection, A operand = the z tile in shared memory; the residual
+//          half re-uses the TMEM columns of GEMM1's first half as soon as EPI1 has drained them
+//   EPI2   x <- (x + r + b)/sqrt2 (fp32), y_next <- x + d_next (16-bit, other buffer: neighbours still read the
+//          halo of y), skip (+)= s + b (fp32)          - coalesced through a per-warp smem transpose
+//
+// Warp roles: 0 = TMA producer (3-stage ring: 24 conv fills of A+B, 8 output-projection fills of B), 1 = MMA
+// issuer, 2 = TMEM allocator, 4-11 = epilogue (two warps per TMEM lane quarter, alternating 32-column chunks).  EPI1 of half 0 overlaps the MMAs of half 1, GEMM2-residual K slabs
+// 0-1 overlap EPI1 of half 1, EPI2-residual overlaps the skip MMAs.
+// Programmatic dependent launch: the prologue (barrier init, TMEM alloc, descriptor prefetch) of layer l+1 overlaps
+// the tail of layer l; dependent global data is only touched after griddepcontrol.wait.
+#include "b2s_tc.cuh"
+
+namespace b2s {
+namespace tc {
+namespace wl {
+
+constexpr int C = 256;                                   // residual channels this kernel is specialised for
+constexpr int BM = 128, BK = 64, BN = 256, UK = 16, STAGES = 3;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int Z_BYTES = BM * C * 2;                      // 4 K slabs of [128 x 64], 16 KB each
+constexpr int G1_KB = 3 * C / BK, G2_KB = C / BK;        // 12, 4
+constexpr int STG_LD = 36;
+constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;          // 4608
+constexpr int SMEM_BYTES = Z_BYTES + STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int NTHREADS = 384;                           // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
+
+struct __align__(64) LayerP {
+    CUtensorMap mapY, mapWd, mapWo;
+    int B, T, tiles_per_b, dil;
+    const void* cond; int ldc;
+    const float* bo;
+    float* x; void* y_next; float* skip; void* skip_h;
+    const float* dvec; int d_stride; int first;
+};
+
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int BF16>
+__global__ void __launch_bounds__(NTHREADS, 1) wavenet_layer_kernel(const __grid_constant__ LayerP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* zs = smem;                                   // z tile, 4 swizzled K slabs
+    uint8_t* stages = smem + Z_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* accb = empty + STAGES;                      // [4]: G1 half 0, G1 half 1, G2 residual, G2 skip
+    uint64_t* zready = accb + 4;                          // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zready + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / p.tiles_per_b, t0 = (blockIdx.x - b * p.tiles_per_b) * BM;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.mapY);
+        prefetch_tmap(&p.mapWd);
+        prefetch_tmap(&p.mapWo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&accb[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&zready[i], EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    pdl_launch_dependents();       // the next layer may start its prologue on idle SMs
+    pdl_wait();                    // everything below reads what the previous kernel wrote
+
+    if (warp == 0) {
+        // ===================== TMA producer: 24 conv fills, then 8 output-projection fills =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int f = 0; f < 2 * G1_KB + 2 * G2_KB; ++f) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (lane == 0) {
+                uint8_t* sa = stages + stage * STAGE_BYTES;
+                if (f < 2 * G1_KB) {
+                    const int h = f / G1_KB, kb = f - h * G1_KB;
+                    const int tap = kb / (C / BK), c0 = (kb - tap * (C / BK)) * BK;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_3d(sa, &p.mapY, &full[stage], c0, t0 + (tap - 1) * p.dil, b);
+                    tma_load_2d(sa + A_BYTES, &p.mapWd, &full[stage], kb * BK, h * BN);
+                } else {
+                    const int g = (f - 2 * G1_KB) / G2_KB, kb = (f - 2 * G1_KB) - g * G2_KB;
+                    mbar_expect_tx(&full[stage], B_BYTES);
+                    tma_load_2d(sa + A_BYTES, &p.mapWo, &full[stage], kb * BK, g * BN);
+                }
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_f16(BM, BN, BF16);
+        int stage = 0;
+        uint32_t phase = 0;
+        // GEMM1: two halves of 256 packed columns
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t d_tmem = tmem_base + h * BN;
+            for (int kb = 0; kb < G1_KB; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(stages + stage * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        umma_ss(d_tmem, make_sw128_kmajor_desc(a_addr + k * (UK * 2)), make_sw128_kmajor_desc(b_addr + k * (UK * 2)),
+                                idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (kb == G1_KB - 1) umma_commit(&accb[h]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        // GEMM2: A = z tile in shared memory; g = 0 residual -> columns [0,256), g = 1 skip -> [256,512)
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t d_tmem = tmem_base + g * BN;
+            for (int kb = 0; kb < G2_KB; ++kb) {
+                if (g == 0 && (kb == 0 || kb == 2)) {        // z K slabs 0-1 come from EPI1 half 0, 2-3 from half 1
+                    mbar_wait(&zready[kb >> 1], 0);
+                    tc_fence_after();
+                }
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(zs + kb * A_BYTES);
+                    const uint32_t b_addr = smem_u32(stages + stage * STAGE_BYTES) + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        umma_ss(d_tmem, make_sw128_kmajor_desc(a_addr + k * (UK * 2)), make_sw128_kmajor_desc(b_addr + k * (UK * 2)),
+                                idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (kb == G2_KB - 1) umma_commit(&accb[2 + g]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 8 warps, warp e -> lane quarter e&3, chunks j with (j&1) == e>>2 =====================
+        const int e = warp - 4, q = e & 3, sub = e >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        // ---- EPI1: thread = frame row; gate; z -> swizzled smem ----
+        {
+            const int row = q * 32 + lane, t = t0 + row;
+            const bool valid = t < p.T;
+            const uint16_t* crow = reinterpret_cast<const uint16_t*>(p.cond) + ((long long)b * p.T + t) * p.ldc;
+            const uint32_t zrow = smem_u32(zs) + (row >> 3) * 1024 + (row & 7) * 128;
+            const int sw = row & 7;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                // all of this warp's cond loads of the half are in flight BEFORE the wait on the accumulator
+                uint4 c[4][4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        c[jj][i] = valid ? ldg_nc_u4(crow + h * BN + (2 * jj + sub) * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
+                mbar_wait(&accb[h], 0);
+                tc_fence_after();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 2 * jj + sub;
+                    float acc[32];
+                    tmem_ld32(taddr + h * BN + j * 32, acc);
+                    tmem_ld_wait();
+                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(c[jj]);
+                    uint32_t zp[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 ca = Half16<BF16>::unpack2(cw[2 * i]), cb = Half16<BF16>::unpack2(cw[2 * i + 1]);
+                        const float z0 = sigmoid_fast(acc[4 * i] + ca.x) * tanh_fast(acc[4 * i + 1] + ca.y);
+                        const float z1 = sigmoid_fast(acc[4 * i + 2] + cb.x) * tanh_fast(acc[4 * i + 3] + cb.y);
+                        zp[i] = valid ? Half16<BF16>::pack2(z0, z1) : 0u;
+                    }
+                    // z channels [128h + 16j, +16) of this row: K slab 2h + j/4, 16-byte chunks 2(j%4), 2(j%4)+1
+                    const uint32_t slab = zrow + (2 * h + (j >> 2)) * A_BYTES;
+                    const int c16 = 2 * (j & 3);
+                    st_shared_u4(slab + ((c16 ^ sw) << 4), make_uint4(zp[0], zp[1], zp[2], zp[3]));
+                    st_shared_u4(slab + (((c16 + 1) ^ sw) << 4), make_uint4(zp[4], zp[5], zp[6], zp[7]));
+                }
+                fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core's async proxy
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&zready[h]);
+            }
+        }
+        // ---- EPI2: coalesced layout through the warp's staging tile (aliases the A slots of the pipeline stages:
+        //      the output-projection fills only write B slots, and every conv MMA has retired by accb[2]) ----
+        float* stg = reinterpret_cast<float*>(stages + (e / 3) * STAGE_BYTES + (e % 3) * STG_WARP_BYTES);
+        const int cl = (lane & 7) * 4, rsub = lane >> 3;
+        const int tq = t0 + q * 32 + rsub;
+        const float inv_sqrt2 = 0.70710678118654752440f;
+        // software pipeline over the warp's 8 (g, j) chunks: the global loads of chunk n+1 are issued before chunk n
+        // is processed
+        float4 in[8], inn[8];
+        auto load_inputs = [&](int g, int j, float4* dst) {
+            const int col = j * 32 + cl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int t = tq + 4 * i;
+                if (t < p.T && (g == 0 || !p.first)) {
+                    const float* src = (g == 0 ? p.x : p.skip) + ((long long)b * p.T + t) * C + col;
+                    dst[i] = *reinterpret_cast<const float4*>(src);
+                }
+            }
+        };
+        load_inputs(0, sub, inn);
+#pragma unroll 1
+        for (int n = 0; n < 8; ++n) {
+            const int g = n >> 2, j = 2 * (n & 3) + sub;
+            if ((n & 3) == 0) {
+                mbar_wait(&accb[2 + g], 0);
+                tc_fence_after();
+            }
+            float acc[32];
+            tmem_ld32(taddr + g * BN + j * 32, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) in[i] = inn[i];
+            if (n + 1 < 8) load_inputs((n + 1) >> 2, 2 * ((n + 1) & 3) + sub, inn);
+            const int col = j * 32 + cl;                                      // channel of x / skip
+            const float4 bias = __ldg(reinterpret_cast<const float4*>(p.bo + g * C + col));
+            float4 dsh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g == 0 && p.y_next && p.d_stride == 0) dsh = __ldg(reinterpret_cast<const float4*>(p.dvec + col));
+            tmem_ld_wait();
+            float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) srow[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int t = tq + 4 * i;
+                if (t < p.T) {
+                    const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * STG_LD + cl);
+                    const long long r = (long long)b * p.T + t;
+                    const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+                    if (g == 0) {
+                        const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
+                                                      (in[i].z + o.z) * inv_sqrt2, (in[i].w + o.w) * inv_sqrt2);
+                        *reinterpret_cast<float4*>(p.x + r * C + col) = xn;
+                        if (p.y_next) {
+                            const float4 d = p.d_stride == 0
+                                                 ? dsh
+                                                 : __ldg(reinterpret_cast<const float4*>(p.dvec + (long long)b * p.d_stride + col));
+                            uint2 yo;
+                            yo.x = Half16<BF16>::pack2(xn.x + d.x, xn.y + d.y);
+                            yo.y = Half16<BF16>::pack2(xn.z + d.z, xn.w + d.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.y_next) + r * C + col) = yo;
+                        }
+                    } else {
+                        const float4 s = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
+                        *reinterpret_cast<float4*>(p.skip + r * C + col) = s;
+                        if (p.skip_h) {
+                            uint2 so;
+                            so.x = Half16<BF16>::pack2(s.x, s.y);
+                            so.y = Half16<BF16>::pack2(s.z, s.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.skip_h) + r * C + col) = so;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int BF16>
+static int launch_layer(const LayerP& p, int grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_layer_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_layer_kernel<BF16>, p));
+    return B2S_OK;
+}
+
+}  // namespace wl
+}  // namespace tc
+}  // namespace b2s
+
+using namespace b2s;
+using namespace b2s::tc;
+
+extern "C" int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const void* cond_h, int ld_cond, const void* Wo_h,
+                                    const float* bo, float* x, void* y_next_h, float* skip, void* skip_h,
+                                    const float* dvec_next, int d_stride, int first_layer, int B, int T, int C, int dilation,
+                                    int bf16, void* stream) {
+    B2S_CHECK_ARG(y_h && Wd_h && cond_h && Wo_h && bo && x && skip, "b2s_tc_wavenet_layer: null pointer");
+    if (C != wl::C) {
+        set_error("b2s_tc_wavenet_layer: the fused layer kernel is specialised for %d residual channels (got %d); use "
+                  "b2s_tc_wavenet_gate + b2s_tc_wavenet_out", wl::C, C);
+        return B2S_ERR_UNSUPPORTED;
+    }
+    B2S_CHECK_ARG(y_next_h != y_h, "b2s_tc_wavenet_layer: y_next must not alias y (neighbouring tiles read its halo)");
+    B2S_CHECK_ARG(!y_next_h || (dvec_next && d_stride % 4 == 0 && al16(dvec_next)), "b2s_tc_wavenet_layer: y_next needs dvec_next");
+    B2S_CHECK_ARG(dilation >= 1 && ld_cond % 8 == 0 && al16(cond_h) && al16(y_h) && al16(Wd_h) && al16(Wo_h) && al16(bo) &&
+                      al16(x) && al16(skip) && (!y_next_h || al16(y_next_h)) && (!skip_h || al16(skip_h)),
+                  "b2s_tc_wavenet_layer: bad dilation / alignment");
+    if (B * T == 0) return B2S_OK;
+    wl::LayerP p{};
+    int rc = make_map_act(&p.mapY, y_h, bf16, C, C, T, B, wl::BK, wl::BM);
+    if (rc) return rc;
+    rc = make_map_w(&p.mapWd, Wd_h, bf16, 3 * C, 2 * C, 3 * C, wl::BK, wl::BN);
+    if (rc) return rc;
+    rc = make_map_w(&p.mapWo, Wo_h, bf16, C, 2 * C, C, wl::BK, wl::BN);
+    if (rc) return rc;
+    p.B = B; p.T = T; p.tiles_per_b = ceil_div(T, wl::BM); p.dil = dilation;
+    p.cond = cond_h; p.ldc = ld_cond; p.bo = bo; p.x = x; p.y_next = y_next_h; p.skip = skip; p.skip_h = skip_h;
+    p.dvec = dvec_next; p.d_stride = d_stride; p.first = first_layer;
+    const int grid = B * p.tiles_per_b;
+    return bf16 ? wl::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl::launch_layer<0>(p, grid, (cudaStream_t)stream);
+}

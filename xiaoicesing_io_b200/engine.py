@@ -217,14 +217,15 @@ class WaveNetSessionTC:
         # hoisted conditioner projection of ALL layers: one tensor-core GEMM, 16-bit table [rows, L*2C]
         cond_h = torch.empty((rows, H), device=dev, dtype=hd)
         C.cast_h(cond_bth, cond_h, bf)
-        N = L * 2 * Cc
-        self.cond = torch.empty((rows, N), device=dev, dtype=hd)
-        C.tc_linear(cond_h, H, rows, T, eng.w_cond_h, H, eng.b_cond, N, H, bf, out_h=self.cond, ldoh=N)
+        self.cond = torch.empty((L, rows, 2 * Cc), device=dev, dtype=hd)     # layer-major: one contiguous slab per layer
+        C.tc_cond_table(cond_h, rows, eng.w_cond_h, eng.b_cond, L, 2 * Cc, H, self.cond, bf)
         self.xin_h = torch.empty((rows, eng.MF), device=dev, dtype=hd)
         self.x = torch.empty((rows, Cc), device=dev)
         self.skip = torch.empty((rows, Cc), device=dev)
         self.y_h = torch.empty((rows, Cc), device=dev, dtype=hd)
-        self.z_h = torch.empty((rows, Cc), device=dev, dtype=hd)
+        self.fused = Cc == C.FUSED_LAYER_CHANNELS           # one fused kernel per layer (z never leaves the SM)
+        self.y2_h = torch.empty((rows, Cc), device=dev, dtype=hd) if self.fused else None
+        self.z_h = None if self.fused else torch.empty((rows, Cc), device=dev, dtype=hd)
         self.skip_h = torch.empty((rows, Cc), device=dev, dtype=hd)
         self.h_h = torch.empty((rows, Cc), device=dev, dtype=hd)
 
@@ -241,12 +242,18 @@ class WaveNetSessionTC:
         d0, ds = self._dvec(k, 0)
         C.tc_linear(self.xin_h, MF, rows, T, e.w_in_h, e.w_in_h.shape[1], e.b_in, Cc, MF, bf, act=C.ACT_RELU,
                     out_f32=self.x, ldo=Cc, y_h=self.y_h, ldy=Cc, dvec=d0, d_stride=ds)
-        ldc = L * 2 * Cc
+        ldc = 2 * Cc
+        ya, yb = self.y_h, self.y2_h
         for l in range(L):
-            C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[:, l * 2 * Cc:], ldc, self.z_h, B, T, Cc,
-                              e.dilations[l], bf)
             last = l + 1 == L
             dn, ds = (None, 0) if last else self._dvec(k, l + 1)
+            if self.fused:
+                C.tc_wavenet_layer(ya, e.w_dil_h[l], self.cond[l], ldc, e.w_out_h[l], e.b_out[l], self.x,
+                                   None if last else yb, self.skip, self.skip_h if last else None, dn, ds, l == 0,
+                                   B, T, Cc, e.dilations[l], bf)
+                ya, yb = yb, ya                            # ping-pong: neighbours still read the halo of ya
+                continue
+            C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[l], ldc, self.z_h, B, T, Cc, e.dilations[l], bf)
             C.tc_wavenet_out(self.z_h, e.w_out_h[l], e.b_out[l], self.x, None if last else self.y_h, self.skip,
                              self.skip_h if last else None, dn, ds, l == 0, B, T, Cc, bf)
         C.tc_linear(self.skip_h, Cc, rows, T, e.w_sp_h, Cc, e.b_sp, Cc, Cc, bf, alpha=1.0 / math.sqrt(L),
@@ -255,18 +262,28 @@ class WaveNetSessionTC:
 
     @property
     def launches_per_eval(self) -> int:
-        return 2 + 2 * self.eng.L + 2
+        return 2 + (1 if self.fused else 2) * self.eng.L + 2
 
     def dominant_kernel(self, w=None):
         """(name, algorithmic FLOPs per launch, callable launching it once per layer) for bench.py's roofline."""
         e = self.eng
         B, T, Cc, L = self.B, self.T, e.C, e.L
+        if self.fused:
+            flops = 2.0 * self.rows * 8 * Cc * Cc              # conv 6C^2 + output projection 2C^2 MACs per frame
+            dv = self.dtab[0, :Cc]
+
+            def launch_all():
+                ya, yb = self.y_h, self.y2_h
+                for l in range(L):
+                    C.tc_wavenet_layer(ya, e.w_dil_h[l], self.cond[l], 2 * Cc, e.w_out_h[l], e.b_out[l],
+                                       self.x, yb, self.skip, None, dv, 0, l == 0, B, T, Cc, e.dilations[l], e.bf16)
+                    ya, yb = yb, ya
+            return f'wavenet_layer_kernel<{e.precision}> (b2s_tc_wavenet_layer)', flops, launch_all
         flops = 2.0 * self.rows * (3 * Cc) * (2 * Cc)
 
         def launch_all():
             for l in range(L):
-                C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[:, l * 2 * Cc:], L * 2 * Cc, self.z_h, B, T, Cc,
-                                  e.dilations[l], e.bf16)
+                C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[l], 2 * Cc, self.z_h, B, T, Cc, e.dilations[l], e.bf16)
         return f'tc_gemm_kernel<EPI_GATE,{e.precision}> (b2s_tc_wavenet_gate)', flops, launch_all
 
 
