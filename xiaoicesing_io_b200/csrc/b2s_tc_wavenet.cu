@@ -20,6 +20,8 @@
 // the tail of layer l; dependent global data is only touched after griddepcontrol.wait.
 #include "b2s_tc.cuh"
 
+#include <stdlib.h>
+
 namespace b2s {
 namespace tc {
 namespace wl {
@@ -324,6 +326,322 @@ static int launch_layer(const LayerP& p, int grid, cudaStream_t st) {
 }
 
 }  // namespace wl
+
+// =====================================================================================================================
+// Version 2: 2-CTA cluster, weight tiles multicast, A tiles shared by both N halves.
+//
+// Measured on B200 (profiles/): the L2 slice throughput cap (~6.3 KB / SM-clock chip-wide) bounds version 1, which pulls
+// 1.4 MB of operands per 128-frame tile through L2.  Here
+//   * one pipeline fill = one K slab for BOTH N halves: A [128 x 64] is fetched once (not twice), and
+//   * the two CTAs of a cluster (two neighbouring time tiles) each fetch HALF of every weight tile (128 of its 256
+//     rows) and TMA-multicast it into both CTAs' shared memory,
+// so a CTA pulls 0.7 MB per tile.  Stage = A 16 KB + B(half 0) 32 KB + B(half 1) 32 KB, 2 stages (8 MMAs each).
+// A stage is recycled only when BOTH CTAs' MMAs have consumed it: tcgen05.commit multicasts the arrive to the `empty`
+// barrier (count 2) of both CTAs.
+// =====================================================================================================================
+namespace wl2 {
+
+using wl::ldg_nc_u4;
+using wl::pdl_launch_dependents;
+using wl::pdl_wait;
+using wl::st_shared_u4;
+using wl::LayerP;
+
+constexpr int C = 256;
+constexpr int BM = 128, BK = 64, BN = 256, UK = 16, STAGES = 2, CLUSTER = 2;
+constexpr int A_BYTES = BM * BK * 2;                     // 16 KB
+constexpr int BH_BYTES = (BN / 2) * BK * 2;              // 16 KB: the 128 weight rows one CTA fetches
+constexpr int B_BYTES = BN * BK * 2;                     // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;       // 80 KB
+constexpr int Z_BYTES = BM * C * 2;
+constexpr int G1_KB = 3 * C / BK, G2_KB = C / BK;        // 12, 4
+constexpr int STG_LD = 36;
+constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
+constexpr int SMEM_BYTES = Z_BYTES + STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int NTHREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr uint16_t MASK = (1u << CLUSTER) - 1;
+
+template <int BF16>
+__global__ void __launch_bounds__(NTHREADS, 1) wavenet_layer_cl2_kernel(const __grid_constant__ LayerP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* zs = smem;
+    uint8_t* stages = smem + Z_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* accb = empty + STAGES;                      // [3]: GEMM1 (both halves), GEMM2 residual, GEMM2 skip
+    uint64_t* zready = accb + 3;                          // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zready + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    // tiles_per_b is padded to an even count by the host; a padding tile has t0 >= T (all rows invalid, loads zero-filled)
+    const int b = blockIdx.x / p.tiles_per_b, t0 = (blockIdx.x - b * p.tiles_per_b) * BM;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.mapY);
+        prefetch_tmap(&p.mapWd);
+        prefetch_tmap(&p.mapWo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], CLUSTER);                // one multicast commit from each CTA of the cluster
+        }
+        for (int i = 0; i < 3; ++i) mbar_init(&accb[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&zready[i], EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // the peer's barriers exist before anything is multicast into this CTA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer: 12 conv fills (A + 2 x 2 weight half-tiles), 8 output-projection fills ====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int f = 0; f < G1_KB + 2 * G2_KB; ++f) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (lane == 0) {
+                uint8_t* sa = stages + stage * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                if (f < G1_KB) {
+                    const int kb = f;
+                    const int tap = kb / (C / BK), c0 = (kb - tap * (C / BK)) * BK;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_3d(sa, &p.mapY, &full[stage], c0, t0 + (tap - 1) * p.dil, b);
+                    // this CTA's 128 rows of both weight tiles, multicast to the whole cluster
+                    tma_load_2d_mcast(sb + rank * BH_BYTES, &p.mapWd, &full[stage], kb * BK, rank * (BN / 2), MASK);
+                    tma_load_2d_mcast(sb + B_BYTES + rank * BH_BYTES, &p.mapWd, &full[stage], kb * BK, BN + rank * (BN / 2), MASK);
+                } else {
+                    const int g = (f - G1_KB) / G2_KB, kb = (f - G1_KB) - g * G2_KB;
+                    mbar_expect_tx(&full[stage], B_BYTES);
+                    tma_load_2d_mcast(sb + rank * BH_BYTES, &p.mapWo, &full[stage], kb * BK, g * BN + rank * (BN / 2), MASK);
+                }
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_f16(BM, BN, BF16);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < G1_KB; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(stages + stage * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        umma_ss(tmem_base + h * BN, make_sw128_kmajor_desc(a_addr + k * (UK * 2)),
+                                make_sw128_kmajor_desc(b_addr + h * B_BYTES + k * (UK * 2)), idesc, (kb | k) != 0);
+                umma_commit_mcast(&empty[stage], MASK);
+                if (kb == G1_KB - 1) umma_commit(&accb[0]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t d_tmem = tmem_base + g * BN;
+            for (int kb = 0; kb < G2_KB; ++kb) {
+                if (g == 0 && (kb == 0 || kb == 2)) {
+                    mbar_wait(&zready[kb >> 1], 0);
+                    tc_fence_after();
+                }
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(zs + kb * A_BYTES);
+                    const uint32_t b_addr = smem_u32(stages + stage * STAGE_BYTES) + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        umma_ss(d_tmem, make_sw128_kmajor_desc(a_addr + k * (UK * 2)), make_sw128_kmajor_desc(b_addr + k * (UK * 2)),
+                                idesc, (kb | k) != 0);
+                    umma_commit_mcast(&empty[stage], MASK);
+                    if (kb == G2_KB - 1) umma_commit(&accb[1 + g]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 8 warps, warp e -> lane quarter e&3, chunks j with (j&1) == e>>2 ===========
+        const int e = warp - 4, q = e & 3, sub = e >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        {
+            const int row = q * 32 + lane, t = t0 + row;
+            const bool valid = t < p.T;
+            const uint16_t* crow = reinterpret_cast<const uint16_t*>(p.cond) + ((long long)b * p.T + t) * p.ldc;
+            const uint32_t zrow = smem_u32(zs) + (row >> 3) * 1024 + (row & 7) * 128;
+            const int sw = row & 7;
+            uint4 c[4][4];                                 // rolling cond prefetch: half 0 up front, half 1 as slots free up
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    c[jj][i] = valid ? ldg_nc_u4(crow + (2 * jj + sub) * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
+            mbar_wait(&accb[0], 0);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 2 * jj + sub;
+                    float acc[32];
+                    tmem_ld32(taddr + h * BN + j * 32, acc);
+                    uint4 cc[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cc[i] = c[jj][i];
+                    if (h == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            c[jj][i] = valid ? ldg_nc_u4(crow + BN + j * 32 + 8 * i) : make_uint4(0, 0, 0, 0);
+                    }
+                    tmem_ld_wait();
+                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(cc);
+                    uint32_t zp[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 ca = Half16<BF16>::unpack2(cw[2 * i]), cb = Half16<BF16>::unpack2(cw[2 * i + 1]);
+                        const float z0 = sigmoid_fast(acc[4 * i] + ca.x) * tanh_fast(acc[4 * i + 1] + ca.y);
+                        const float z1 = sigmoid_fast(acc[4 * i + 2] + cb.x) * tanh_fast(acc[4 * i + 3] + cb.y);
+                        zp[i] = valid ? Half16<BF16>::pack2(z0, z1) : 0u;
+                    }
+                    const uint32_t slab = zrow + (2 * h + (j >> 2)) * A_BYTES;
+                    const int c16 = 2 * (j & 3);
+                    st_shared_u4(slab + ((c16 ^ sw) << 4), make_uint4(zp[0], zp[1], zp[2], zp[3]));
+                    st_shared_u4(slab + (((c16 + 1) ^ sw) << 4), make_uint4(zp[4], zp[5], zp[6], zp[7]));
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&zready[h]);
+            }
+        }
+        // ---- EPI2 (staging aliases pipeline memory the output-projection fills never write: the A slot of each stage
+        //      and the second weight tile; every conv MMA has retired by accb[1]) ----
+        const int si = e >> 1;                             // 0..3 within stage (e & 1)
+        float* stg = reinterpret_cast<float*>(stages + (e & 1) * STAGE_BYTES +
+                                              (si < 3 ? si * STG_WARP_BYTES : A_BYTES + B_BYTES));
+        const int cl = (lane & 7) * 4, rsub = lane >> 3;
+        const int tq = t0 + q * 32 + rsub;
+        const float inv_sqrt2 = 0.70710678118654752440f;
+        float4 in[8], inn[8];
+        auto load_inputs = [&](int g, int j, float4* dst) {
+            const int col = j * 32 + cl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int t = tq + 4 * i;
+                if (t < p.T && (g == 0 || !p.first)) {
+                    const float* src = (g == 0 ? p.x : p.skip) + ((long long)b * p.T + t) * C + col;
+                    dst[i] = *reinterpret_cast<const float4*>(src);
+                }
+            }
+        };
+        load_inputs(0, sub, inn);
+#pragma unroll 1
+        for (int n = 0; n < 8; ++n) {
+            const int g = n >> 2, j = 2 * (n & 3) + sub;
+            if ((n & 3) == 0) {
+                mbar_wait(&accb[1 + g], 0);
+                tc_fence_after();
+            }
+            float acc[32];
+            tmem_ld32(taddr + g * BN + j * 32, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) in[i] = inn[i];
+            if (n + 1 < 8) load_inputs((n + 1) >> 2, 2 * ((n + 1) & 3) + sub, inn);
+            const int col = j * 32 + cl;
+            const float4 bias = __ldg(reinterpret_cast<const float4*>(p.bo + g * C + col));
+            float4 dsh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g == 0 && p.y_next && p.d_stride == 0) dsh = __ldg(reinterpret_cast<const float4*>(p.dvec + col));
+            tmem_ld_wait();
+            float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) srow[c2] = make_float4(acc[4 * c2], acc[4 * c2 + 1], acc[4 * c2 + 2], acc[4 * c2 + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int t = tq + 4 * i;
+                if (t < p.T) {
+                    const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * STG_LD + cl);
+                    const long long r = (long long)b * p.T + t;
+                    const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+                    if (g == 0) {
+                        const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
+                                                      (in[i].z + o.z) * inv_sqrt2, (in[i].w + o.w) * inv_sqrt2);
+                        *reinterpret_cast<float4*>(p.x + r * C + col) = xn;
+                        if (p.y_next) {
+                            const float4 d = p.d_stride == 0
+                                                 ? dsh
+                                                 : __ldg(reinterpret_cast<const float4*>(p.dvec + (long long)b * p.d_stride + col));
+                            uint2 yo;
+                            yo.x = Half16<BF16>::pack2(xn.x + d.x, xn.y + d.y);
+                            yo.y = Half16<BF16>::pack2(xn.z + d.z, xn.w + d.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.y_next) + r * C + col) = yo;
+                        }
+                    } else {
+                        const float4 s2 = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
+                        *reinterpret_cast<float4*>(p.skip + r * C + col) = s2;
+                        if (p.skip_h) {
+                            uint2 so;
+                            so.x = Half16<BF16>::pack2(s2.x, s2.y);
+                            so.y = Half16<BF16>::pack2(s2.z, s2.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.skip_h) + r * C + col) = so;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // the peer may still multicast into / arrive on this CTA's shared memory until here
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int BF16>
+static int launch_layer(const LayerP& p, int grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_layer_cl2_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_layer_cl2_kernel<BF16>, p));
+    return B2S_OK;
+}
+
+}  // namespace wl2
 }  // namespace tc
 }  // namespace b2s
 
@@ -346,16 +664,20 @@ extern "C" int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const voi
                       al16(x) && al16(skip) && (!y_next_h || al16(y_next_h)) && (!skip_h || al16(skip_h)),
                   "b2s_tc_wavenet_layer: bad dilation / alignment");
     if (B * T == 0) return B2S_OK;
+    // variant 2 (2-CTA cluster, multicast weights) unless B2S_LAYER_V1 is set in the environment (A/B comparison)
+    static const bool v1 = getenv("B2S_LAYER_V1") != nullptr;
     wl::LayerP p{};
     int rc = make_map_act(&p.mapY, y_h, bf16, C, C, T, B, wl::BK, wl::BM);
     if (rc) return rc;
-    rc = make_map_w(&p.mapWd, Wd_h, bf16, 3 * C, 2 * C, 3 * C, wl::BK, wl::BN);
+    rc = make_map_w(&p.mapWd, Wd_h, bf16, 3 * C, 2 * C, 3 * C, wl::BK, v1 ? wl::BN : wl::BN / 2);
     if (rc) return rc;
-    rc = make_map_w(&p.mapWo, Wo_h, bf16, C, 2 * C, C, wl::BK, wl::BN);
+    rc = make_map_w(&p.mapWo, Wo_h, bf16, C, 2 * C, C, wl::BK, v1 ? wl::BN : wl::BN / 2);
     if (rc) return rc;
     p.B = B; p.T = T; p.tiles_per_b = ceil_div(T, wl::BM); p.dil = dilation;
+    if (!v1) p.tiles_per_b = (p.tiles_per_b + 1) & ~1;          // whole clusters per utterance
     p.cond = cond_h; p.ldc = ld_cond; p.bo = bo; p.x = x; p.y_next = y_next_h; p.skip = skip; p.skip_h = skip_h;
     p.dvec = dvec_next; p.d_stride = d_stride; p.first = first_layer;
     const int grid = B * p.tiles_per_b;
+    if (!v1) return bf16 ? wl2::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl2::launch_layer<0>(p, grid, (cudaStream_t)stream);
     return bf16 ? wl::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl::launch_layer<0>(p, grid, (cudaStream_t)stream);
 }
