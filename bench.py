@@ -358,7 +358,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('B2S_PRECISION', 'fp32'), choices=['fp32', 'bf16', 'fp16'])
+    ap.add_argument('--precision', default=os.environ.get('B2S_PRECISION', 'bf16'), choices=['fp32', 'bf16', 'fp16'])
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
     ap.add_argument('--k-step', type=int, default=None, help='override K_step (debug only; invalidates the metric)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
