@@ -140,6 +140,13 @@ int b2s_tc_linear(const void* A_h, int lda, int rows, int T, const void* W_h, in
 int b2s_tc_cond_table(const void* cond_h, int rows, const void* Wc_h, const float* bc, int L, int N2, int H,
                       void* table_h, int bf16, void* stream);
 
+/* Same GEMM, table written in the TILE/CHUNK-MAJOR layout the fused WaveNet kernels read with fully coalesced 512-byte
+ * warp loads (thread = frame row):  element (layer l, utterance b, frame t, packed column n) lives at
+ *   ((((l*B + b)*tpb + t/128) * (N2/32) + n/32) * 4 + (n%32)/8) * 1024 + (t%128)*8 + n%8        [16-bit elements]
+ * with tpb = ceil(T/128) rounded up to even; size L*B*tpb*128*N2 elements (rows >= T of the last tile are never read). */
+int b2s_tc_cond_table_tiled(const void* cond_h, int B, int T, const void* Wc_h, const float* bc, int L, int N2, int H,
+                            void* table_h, int bf16, void* stream);
+
 /* b2s_wavenet_gate_f32 on the tensor cores: implicit-GEMM dilated conv (3 TMA tiles per K slab at time
  * offsets -d, 0, +d; out-of-bounds zero fill = the per-utterance zero padding), epilogue adds the hoisted
  * 16-bit conditioner projection and applies sigmoid*tanh (wavenet.py:38-42).  C % 64 == 0. */
@@ -161,6 +168,20 @@ int b2s_tc_wavenet_out(const void* z_h, const void* Wo_h, const float* bo, float
 int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const void* cond_h, int ld_cond, const void* Wo_h,
                          const float* bo, float* x, void* y_next_h, float* skip, void* skip_h, const float* dvec_next,
                          int d_stride, int first_layer, int B, int T, int C, int dilation, int bf16, void* stream);
+
+/* The WHOLE residual stack (all L layers, wavenet.py:92-94) as ONE persistent kernel, C = 256: one CTA per 128-frame
+ * tile, every tile resident at once (B * 2*ceil(ceil(T/128)/2) <= b2s_tc_wavenet_stack_max_tiles(), else
+ * B2S_ERR_UNSUPPORTED: split the batch by utterance).  Layer-to-layer hand-off of y between neighbouring tiles goes
+ * through release/acquire flags in `flags` (int32 [B * tiles], must be ZERO at launch) instead of kernel boundaries.
+ *   y0_h      layer 0's input y = x + d_0 (written by the stem); y1_h the ping-pong partner
+ *   Wd_h [L,2C,3C], Wo_h [L,2C,C], bo [L,2C]; cond_h: the table of b2s_tc_cond_table_tiled for THIS call's B and T,
+ *   cond_layer_stride = B*tpb*128*2C elements (ld_cond is ignored)
+ *   dvec: this evaluation's step-embedding row, layer l at dvec + b*d_stride + l*C;  dilations_host: L ints (HOST) */
+int b2s_tc_wavenet_stack_max_tiles(void);
+int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, const void* cond_h, int ld_cond,
+                         int64_t cond_layer_stride, const void* Wo_h, const float* bo, float* x, float* skip, void* skip_h,
+                         const float* dvec, int d_stride, const int* dilations_host, int L, int B, int T, int C, int* flags,
+                         int bf16, void* stream);
 
 /* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
  * down-projection with the residual add into the fp32 stream. */

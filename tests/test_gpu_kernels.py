@@ -245,3 +245,84 @@ def test_tc_cond_table_layer_major(C, kind, hd, eps):
     C.tc_cond_table(cond, rows, W, b, L, N2, H, tab, bf)
     want = (cond.double() @ W.double().t() + b.double()).reshape(rows, L, N2).permute(1, 0, 2)
     assert float((tab.double() - want).abs().max()) < eps * float(want.abs().max())
+
+
+def _tile_cond(cond, B, T, tpb):
+    """[L, B*T, N2] -> the tile/chunk-major layout of b2s_tc_cond_table_tiled (include/b2s.h), built with torch ops."""
+    L, rows, N2 = cond.shape
+    pad = torch.zeros(L, B, tpb * 128, N2, device=cond.device, dtype=cond.dtype)
+    pad[:, :, :T] = cond.reshape(L, B, T, N2)
+    v = pad.reshape(L, B, tpb, 128, N2 // 32, 4, 8)              # l, b, tile, row, chunk, piece, elem
+    return v.permute(0, 1, 2, 4, 5, 3, 6).contiguous()           # l, b, tile, chunk, piece, row, elem
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+def test_tc_cond_table_tiled(C, kind, hd, eps):
+    bf = kind == 'bf16'
+    B, T, H, L, N2 = 3, 300, 256, 4, 512
+    tpb = (-(-T // 128) + 1) & ~1
+    torch.manual_seed(2)
+    cond = torch.randn(B * T, H, device='cuda').to(hd)
+    W = (torch.randn(L * N2, H, device='cuda') / H ** 0.5).to(hd)
+    b = torch.randn(L * N2, device='cuda')
+    tab = torch.zeros(L, B * tpb * 128, N2, device='cuda', dtype=hd)
+    C.tc_cond_table_tiled(cond, B, T, W, b, L, N2, H, tab, bf)
+    want = (cond.double() @ W.double().t() + b.double()).reshape(B * T, L, N2).permute(1, 0, 2)
+    want_t = _tile_cond(want, B, T, tpb).reshape(L, B, tpb, N2 // 32, 4, 128, 8)
+    got = tab.reshape(L, B, tpb, N2 // 32, 4, 128, 8).double()
+    valid = torch.zeros(tpb * 128, dtype=torch.bool, device='cuda')
+    valid[:T] = True
+    m = valid.reshape(1, 1, tpb, 1, 1, 128, 1).expand_as(got)
+    assert float((got[m] - want_t[m]).abs().max()) < eps * float(want.abs().max())
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+def test_tc_stack_matches_per_layer_kernels(C, kind, hd, eps):
+    """The persistent whole-stack kernel (tile-to-tile hand-off through release/acquire flags) must reproduce the
+    sequence of per-layer fused kernels: same operands, same accumulation order -> same bits up to 16-bit y rounding."""
+    bf = kind == 'bf16'
+    Cc, L = 256, 6
+    dil = [1, 2, 4, 8, 16, 1]
+    for (B, T) in [(2, 300), (3, 690), (1, 100), (5, 129)]:
+        rows = B * T
+        torch.manual_seed(B * 1000 + T)
+        y0 = torch.randn(rows, Cc, device='cuda').to(hd)
+        Wd = (torch.randn(L, 2 * Cc, 3 * Cc, device='cuda') / (3 * Cc) ** 0.5).to(hd)
+        Wo = (torch.randn(L, 2 * Cc, Cc, device='cuda') / Cc ** 0.5).to(hd)
+        bo = torch.randn(L, 2 * Cc, device='cuda')
+        cond = torch.randn(L, rows, 2 * Cc, device='cuda').to(hd)
+        x0 = torch.randn(rows, Cc, device='cuda')
+        dvec = torch.randn(B, L * Cc, device='cuda')               # per-utterance step embeddings (d_stride != 0)
+        for per_row in (False, True):
+            ds = L * Cc if per_row else 0
+            # per-layer reference
+            xa, sa = x0.clone(), torch.zeros(rows, Cc, device='cuda')
+            ya, yb = y0.clone(), torch.zeros(rows, Cc, device='cuda', dtype=hd)
+            sha = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+            for l in range(L):
+                last = l == L - 1
+                C.tc_wavenet_layer(ya, Wd[l], cond[l], 2 * Cc, Wo[l], bo[l], xa, None if last else yb, sa, sha if last else None,
+                                   None if last else dvec[0, (l + 1) * Cc:], ds, l == 0, B, T, Cc, dil[l], bf)
+                ya, yb = yb, ya
+            # whole stack
+            xb, sb = x0.clone(), torch.full((rows, Cc), float('nan'), device='cuda')
+            y0b, y1b = y0.clone(), torch.zeros(rows, Cc, device='cuda', dtype=hd)
+            shb = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+            tpb = (-(-T // 128) + 1) & ~1
+            flags = torch.zeros(B * tpb, device='cuda', dtype=torch.int32)
+            tiled = _tile_cond(cond, B, T, tpb)
+            C.tc_wavenet_stack(y0b, y1b, Wd, tiled, 2 * Cc, B * tpb * 128 * 2 * Cc, Wo, bo, xb, sb, shb, dvec, ds, dil, B, T, Cc,
+                               flags, bf)
+            torch.cuda.synchronize()
+            tag = (kind, B, T, per_row)
+            assert int(flags.min()) == L, tag
+            assert torch.equal(xa, xb), (tag, float((xa - xb).abs().max()))
+            assert torch.equal(sa, sb), (tag, float((sa - sb).abs().max()))
+            assert torch.equal(sha, shb), tag
+
+
+def test_tc_stack_rejects_oversized_grid(C):
+    Cc, L, B, T = 256, 2, 40, 690                                    # 240 tiles > 148 SMs
+    z = torch.zeros(8, device='cuda')
+    with pytest.raises(C.B2SError):
+        C.tc_wavenet_stack(z, z[4:], z, z, 2 * Cc, 8, z, z, z, z, None, z, 0, [1, 2], B, T, Cc, z.int(), True)

@@ -32,14 +32,17 @@ _SIGNATURES = {
     'b2s_cast_f32_h': [_vp, _vp, _i64, _i, _vp],
     'b2s_tc_linear': [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp],
     'b2s_tc_cond_table': [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    'b2s_tc_cond_table_tiled': [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_wavenet_gate': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_out': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_layer': [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_tc_wavenet_stack': [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _i, _i, _i, _vp,
+                             _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
 }
 
-EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', *_SIGNATURES]
+EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', 'b2s_tc_wavenet_stack_max_tiles', *_SIGNATURES]
 
 ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU, ACT_SILU = 0, 1, 2, 3, 4
 
@@ -60,6 +63,8 @@ def _load():
     lib.b2s_abi_version.argtypes = []
     lib.b2s_last_error.restype = c_char_p
     lib.b2s_last_error.argtypes = []
+    lib.b2s_tc_wavenet_stack_max_tiles.restype = c_int
+    lib.b2s_tc_wavenet_stack_max_tiles.argtypes = []
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int
@@ -171,6 +176,11 @@ def tc_cond_table(cond_h, rows, Wc_h, bc, L, N2, H, table_h, bf16):
           'b2s_tc_cond_table')
 
 
+def tc_cond_table_tiled(cond_h, B, T, Wc_h, bc, L, N2, H, table_h, bf16):
+    check(lib.b2s_tc_cond_table_tiled(ptr(cond_h), B, T, ptr(Wc_h), ptr(bc), L, N2, H, ptr(table_h), int(bf16),
+                                      stream_ptr()), 'b2s_tc_cond_table_tiled')
+
+
 def tc_wavenet_gate(y_h, Wd_h, cond_h, ld_cond, z_h, B, T, C, dilation, bf16):
     check(lib.b2s_tc_wavenet_gate(ptr(y_h), ptr(Wd_h), ptr(cond_h), ld_cond, ptr(z_h), B, T, C, dilation, int(bf16),
                                   stream_ptr()), 'b2s_tc_wavenet_gate')
@@ -190,6 +200,15 @@ def tc_wavenet_layer(y_h, Wd_h, cond_h, ld_cond, Wo_h, bo, x, y_next_h, skip, sk
     check(lib.b2s_tc_wavenet_layer(ptr(y_h), ptr(Wd_h), ptr(cond_h), ld_cond, ptr(Wo_h), ptr(bo), ptr(x), ptr(y_next_h),
                                    ptr(skip), ptr(skip_h), ptr(dvec_next), d_stride, int(first), B, T, C, dilation,
                                    int(bf16), stream_ptr()), 'b2s_tc_wavenet_layer')
+
+
+def tc_wavenet_stack(y0_h, y1_h, Wd_h, cond_h, ld_cond, cond_layer_stride, Wo_h, bo, x, skip, skip_h, dvec, d_stride,
+                     dilations, B, T, C, flags, bf16):
+    L = len(dilations)
+    dil = (_i * L)(*dilations)
+    check(lib.b2s_tc_wavenet_stack(ptr(y0_h), ptr(y1_h), ptr(Wd_h), ptr(cond_h), ld_cond, cond_layer_stride, ptr(Wo_h),
+                                   ptr(bo), ptr(x), ptr(skip), ptr(skip_h), ptr(dvec), d_stride, dil, L, B, T, C,
+                                   ptr(flags), int(bf16), stream_ptr()), 'b2s_tc_wavenet_stack')
 
 
 def tc_lynx_glu(h_h, W_h, bias, g_h, rows, C, inner, bf16):

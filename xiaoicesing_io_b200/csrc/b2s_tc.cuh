@@ -194,6 +194,24 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem, const CUtensorMap*
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
         : "memory");
 }
+// 3-D multicast variant (weights stacked over layers: coordinates k, n, layer)
+__device__ __forceinline__ void tma_load_3d_mcast(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;" ::"r"(
+            smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// ---- inter-CTA hand-off through global memory (persistent kernels): release / acquire flags + proxy fence ----
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// generic-proxy writes (other SMs' st.global, made visible by release/acquire) -> visible to this thread's TMA loads
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // arrives (once the issuing thread's earlier MMAs retire) on the mbarrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -280,6 +298,24 @@ inline int make_map_w(CUtensorMap* m, const void* base, int bf16, int K, int N, 
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(weights K=%d N=%d ldw=%d) failed with CUresult %d", K, N, ldw, (int)rc);
+        return B2S_ERR_CUDA;
+    }
+    return B2S_OK;
+}
+
+// 16-bit weights stacked over layers [L, N, K] -> 3-D map {K, N, L}, box {box_k, box_rows, 1}
+inline int make_map_w3(CUtensorMap* m, const void* base, int bf16, int K, int N, int L, int box_k, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return B2S_ERR_CUDA; }
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)L};
+    cuuint64_t gstr[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                     const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(stacked weights K=%d N=%d L=%d) failed with CUresult %d", K, N, L, (int)rc);
         return B2S_ERR_CUDA;
     }
     return B2S_OK;

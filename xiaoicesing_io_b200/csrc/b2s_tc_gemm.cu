@@ -47,6 +47,7 @@ struct __align__(64) TcP {
     float* out_f; int ldo;
     void* out_h; int ldoh;
     int oh_blk; long long oh_blk_stride;   // out_h column blocks: block k of oh_blk columns starts at k * oh_blk_stride
+    int oh_tiled, oh_B, oh_tpb;            // out_h in the tile/chunk-major layout of the fused WaveNet kernels (see b2s.h)
     void* y_h; int ldy;
     const float* dvec; int d_stride;
     const void* cond; int ldc;
@@ -138,7 +139,18 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
         if (p.act > ACT_RELU) v = act4_slow(v, p.act);
         if (col + 4 <= p.N) {
             if (p.out_f) *reinterpret_cast<float4*>(p.out_f + r * p.ldo + col) = v;
-            if (p.out_h) store_h4<BF16>(p.out_h, k.oh_off + r * p.ldoh + col, v);
+            if (p.out_h) {
+                if (p.oh_tiled) {
+                    // [l][b][tile][chunk j = (col % N2) / 32][16-byte piece k][row in tile][8 elements]
+                    const int l = col / p.oh_blk, nn = col - l * p.oh_blk;
+                    const int bb = (int)(r / p.T_utt), t = (int)(r - (long long)bb * p.T_utt);
+                    const long long tile = ((long long)l * p.oh_B + bb) * p.oh_tpb + (t >> 7);
+                    const long long idx = ((tile * (p.oh_blk >> 5) + (nn >> 5)) * 4 + ((nn & 31) >> 3)) * 1024 + (t & 127) * 8 + (nn & 7);
+                    store_h4<BF16>(p.out_h, idx, v);
+                } else {
+                    store_h4<BF16>(p.out_h, k.oh_off + r * p.ldoh + col, v);
+                }
+            }
             if (p.y_h) {
                 const float4 d = p.d_stride == 0 ? k.d : __ldg(reinterpret_cast<const float4*>(p.dvec + (long long)b * p.d_stride + col));
                 store_h4<BF16>(p.y_h, r * p.ldy + col, add4(v, d));
@@ -409,6 +421,20 @@ extern "C" int b2s_tc_cond_table(const void* cond_h, int rows, const void* Wc_h,
     if (rc) return rc;
     p.bias = bc; p.alpha = 1.f; p.act = ACT_NONE;
     p.out_h = table_h; p.ldoh = N2; p.oh_blk = N2; p.oh_blk_stride = (long long)rows * N2;
+    return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
+}
+
+extern "C" int b2s_tc_cond_table_tiled(const void* cond_h, int B, int T, const void* Wc_h, const float* bc, int L, int N2,
+                                       int H, void* table_h, int bf16, void* stream) {
+    B2S_CHECK_ARG(cond_h && Wc_h && table_h, "b2s_tc_cond_table_tiled: null pointer");
+    B2S_CHECK_ARG(L > 0 && N2 > 0 && N2 % 32 == 0 && H % 8 == 0, "b2s_tc_cond_table_tiled: bad dims L=%d N2=%d H=%d", L, N2, H);
+    B2S_CHECK_ARG(al16(cond_h) && al16(Wc_h) && al16(table_h), "b2s_tc_cond_table_tiled: misaligned pointer");
+    if (B * T == 0) return B2S_OK;
+    TcP p{};
+    int rc = setup(p, cond_h, H, H, B, T, false, Wc_h, H, L * N2, H, 0, 0, bf16);
+    if (rc) return rc;
+    p.bias = bc; p.alpha = 1.f; p.act = ACT_NONE;
+    p.out_h = table_h; p.oh_blk = N2; p.oh_tiled = 1; p.oh_B = B; p.oh_tpb = (ceil_div(T, 128) + 1) & ~1;
     return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
 }
 

@@ -21,6 +21,7 @@ from typing import Callable, Dict, List, Optional
 import torch
 
 from . import _cabi as C
+from .hparams import hparams
 from .schedules import NOISE0, XSTART, Program, Z
 
 PRECISIONS = ('fp32', 'bf16', 'fp16')
@@ -217,8 +218,8 @@ class WaveNetSessionTC:
         # hoisted conditioner projection of ALL layers: one tensor-core GEMM, 16-bit table [rows, L*2C]
         cond_h = torch.empty((rows, H), device=dev, dtype=hd)
         C.cast_h(cond_bth, cond_h, bf)
-        self.cond = torch.empty((L, rows, 2 * Cc), device=dev, dtype=hd)     # layer-major: one contiguous slab per layer
-        C.tc_cond_table(cond_h, rows, eng.w_cond_h, eng.b_cond, L, 2 * Cc, H, self.cond, bf)
+        self._cond_h, self._hd = cond_h, hd
+        self.cond = None          # built below once the path (stack / per-layer) is known
         self.xin_h = torch.empty((rows, eng.MF), device=dev, dtype=hd)
         self.x = torch.empty((rows, Cc), device=dev)
         self.skip = torch.empty((rows, Cc), device=dev)
@@ -226,6 +227,24 @@ class WaveNetSessionTC:
         self.fused = Cc == C.FUSED_LAYER_CHANNELS           # one fused kernel per layer (z never leaves the SM)
         self.y2_h = torch.empty((rows, Cc), device=dev, dtype=hd) if self.fused else None
         self.z_h = None if self.fused else torch.empty((rows, Cc), device=dev, dtype=hd)
+        # whole-stack persistent kernel: every 128-frame tile of a launch must be resident, so the batch is split by
+        # utterance into groups of `stack_group` (0 = an utterance alone exceeds the SM count -> per-layer kernels)
+        tpb = (-(-T // 128) + 1) & ~1
+        self.stack_group = (C.lib.b2s_tc_wavenet_stack_max_tiles() // tpb) if (self.fused and hparams.get('b2s_stack', True)) else 0
+        self.flags = torch.zeros((B * tpb,), device=dev, dtype=torch.int32) if self.stack_group else None
+        self.tpb = tpb
+        if self.stack_group:
+            # one table per utterance group, in the tile/chunk-major layout the stack kernel reads with coalesced loads
+            self.cond_groups = []
+            for b0 in range(0, B, self.stack_group):
+                nb = min(B, b0 + self.stack_group) - b0
+                tab = torch.empty((L, nb * tpb * 128, 2 * Cc), device=dev, dtype=hd)
+                C.tc_cond_table_tiled(cond_h[b0 * T:], nb, T, eng.w_cond_h, eng.b_cond, L, 2 * Cc, H, tab, bf)
+                self.cond_groups.append(tab)
+        else:
+            self.cond = torch.empty((L, rows, 2 * Cc), device=dev, dtype=hd)     # layer-major: one contiguous slab per layer
+            C.tc_cond_table(cond_h, rows, eng.w_cond_h, eng.b_cond, L, 2 * Cc, H, self.cond, bf)
+        del self._cond_h
         self.skip_h = torch.empty((rows, Cc), device=dev, dtype=hd)
         self.h_h = torch.empty((rows, Cc), device=dev, dtype=hd)
 
@@ -243,8 +262,20 @@ class WaveNetSessionTC:
         C.tc_linear(self.xin_h, MF, rows, T, e.w_in_h, e.w_in_h.shape[1], e.b_in, Cc, MF, bf, act=C.ACT_RELU,
                     out_f32=self.x, ldo=Cc, y_h=self.y_h, ldy=Cc, dvec=d0, d_stride=ds)
         ldc = 2 * Cc
+        if self.stack_group:
+            self.flags.zero_()
+            LC = L * Cc
+            dv = self.dtab[0] if self.per_row_t else self.dtab[k]
+            for gi, b0 in enumerate(range(0, B, self.stack_group)):
+                b1 = min(B, b0 + self.stack_group)
+                r0 = b0 * T
+                tab = self.cond_groups[gi]
+                C.tc_wavenet_stack(self.y_h[r0:], self.y2_h[r0:], e.w_dil_h, tab, ldc, tab.shape[1] * ldc, e.w_out_h,
+                                   e.b_out, self.x[r0:], self.skip[r0:], self.skip_h[r0:],
+                                   dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0, e.dilations,
+                                   b1 - b0, T, Cc, self.flags[b0 * self.tpb:], bf)
         ya, yb = self.y_h, self.y2_h
-        for l in range(L):
+        for l in range(0 if not self.stack_group else L, L):
             last = l + 1 == L
             dn, ds = (None, 0) if last else self._dvec(k, l + 1)
             if self.fused:
@@ -262,12 +293,29 @@ class WaveNetSessionTC:
 
     @property
     def launches_per_eval(self) -> int:
+        if self.stack_group:
+            return 2 + 1 + -(-self.B // self.stack_group) + 2      # cast, stem, flag reset, stack launches, 2 head GEMMs
         return 2 + (1 if self.fused else 2) * self.eng.L + 2
 
     def dominant_kernel(self, w=None):
         """(name, algorithmic FLOPs per launch, callable launching it once per layer) for bench.py's roofline."""
         e = self.eng
         B, T, Cc, L = self.B, self.T, e.C, e.L
+        if self.stack_group:
+            flops = 2.0 * min(self.stack_group, B) * T * 8 * Cc * Cc * L      # the whole residual stack of one group per launch
+            dv = self.dtab[0]
+
+            def launch_all():
+                self.flags.zero_()
+                for gi, b0 in enumerate(range(0, B, self.stack_group)):
+                    b1 = min(B, b0 + self.stack_group)
+                    r0 = b0 * T
+                    tab = self.cond_groups[gi]
+                    C.tc_wavenet_stack(self.y_h[r0:], self.y2_h[r0:], e.w_dil_h, tab, 2 * Cc, tab.shape[1] * 2 * Cc,
+                                       e.w_out_h, e.b_out, self.x[r0:], self.skip[r0:], self.skip_h[r0:], dv, 0, e.dilations,
+                                       b1 - b0, T, Cc, self.flags[b0 * self.tpb:], e.bf16)
+            return (f'wavenet_stack_kernel<{e.precision}> (b2s_tc_wavenet_stack, {L} layers per launch)', flops, launch_all,
+                    -(-B // self.stack_group))
         if self.fused:
             flops = 2.0 * self.rows * 8 * Cc * Cc              # conv 6C^2 + output projection 2C^2 MACs per frame
             dv = self.dtab[0, :Cc]
@@ -278,13 +326,13 @@ class WaveNetSessionTC:
                     C.tc_wavenet_layer(ya, e.w_dil_h[l], self.cond[l], 2 * Cc, e.w_out_h[l], e.b_out[l],
                                        self.x, yb, self.skip, None, dv, 0, l == 0, B, T, Cc, e.dilations[l], e.bf16)
                     ya, yb = yb, ya
-            return f'wavenet_layer_kernel<{e.precision}> (b2s_tc_wavenet_layer)', flops, launch_all
+            return f'wavenet_layer_kernel<{e.precision}> (b2s_tc_wavenet_layer)', flops, launch_all, L
         flops = 2.0 * self.rows * (3 * Cc) * (2 * Cc)
 
         def launch_all():
             for l in range(L):
                 C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[l], 2 * Cc, self.z_h, B, T, Cc, e.dilations[l], e.bf16)
-        return f'tc_gemm_kernel<EPI_GATE,{e.precision}> (b2s_tc_wavenet_gate)', flops, launch_all
+        return f'tc_gemm_kernel<EPI_GATE,{e.precision}> (b2s_tc_wavenet_gate)', flops, launch_all, L
 
 
 # =====================================================================================================
