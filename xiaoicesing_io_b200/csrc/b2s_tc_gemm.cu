@@ -2,11 +2,11 @@
 //
 //   out[rows, N] = epilogue( A[rows, K] . W[N, K]^T )          A, W: bf16 or fp16, fp32 accumulate in TMEM
 //
-// One persistent, warp-specialised kernel (256 threads, 1 CTA / SM):
+// One persistent, warp-specialised kernel (384 threads, 1 CTA / SM):
 //   warp 0    TMA producer   - cp.async.bulk.tensor tiles (128B swizzle) into a 4-stage smem ring
 //   warp 1    MMA issuer     - one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16)
 //   warp 2    TMEM allocator - 512 columns = two 128x256 fp32 accumulators (double buffered)
-//   warps 4-7 epilogue       - tcgen05.ld (32 lanes x 32 columns per warp per step), fused math, global stores;
+//   warps 4-11 epilogue      - tcgen05.ld (32 lanes x 32 columns per warp per step), fused math, global stores;
 //                              the epilogue of tile i overlaps the MMAs of tile i+1
 // Tile 128 (frames) x 256 (output channels) x 64 (K per stage).
 //
@@ -30,10 +30,11 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;          // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;          // 48 KB
 constexpr int STG_LD = 36;                                // floats per staged row: 32 + 4 pad -> conflict-free 128-bit accesses
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;            // one 32x32 fp32 transpose buffer per epilogue warp
+constexpr int EPI_WARPS = 8;                              // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int STG_BYTES = EPI_WARPS * 16 * STG_LD * 4;    // one 16x32 fp32 transpose buffer per epilogue warp (two passes per chunk)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 
 enum Epi : int { EPI_LINEAR = 0, EPI_GATE = 1, EPI_RESSKIP = 2, EPI_SWIGLU = 3, EPI_RESIDUAL = 4 };
 
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);           // one arrival per epilogue warp
+            mbar_init(&tempty[i], EPI_WARPS);   // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -228,6 +229,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+
+    // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -282,9 +287,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int e = warp - 4, q = e & 3, sub = e >> 2;   // TMEM lane quarter q; chunks j with (j & 1) == sub
         int as = 0;
         uint32_t aphase = 0;
+        float* stg = stg_all + e * (16 * STG_LD);
+        const int cl = (lane & 7) * 4, rsub = lane >> 3;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int bt = m_tile / p.tiles_m_per_b, t0 = (m_tile - bt * p.tiles_m_per_b) * BLOCK_M;
@@ -292,41 +299,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
-            float* stg = stg_all + q * (32 * STG_LD);
-            const int cl = (lane & 7) * 4, rsub = lane >> 3;
+            const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
 #pragma unroll 1
-            for (int j = 0; j < BLOCK_N / 32; ++j) {
+            for (int j = sub; j < BLOCK_N / 32; j += 2) {
                 const int col0 = n0 + 32 * j;
                 if (col0 >= p.N) break;
                 float acc[32];
                 tmem_ld32(taddr + j * 32, acc);
-                tmem_ld_wait();
-                // transpose through the warp's private staging tile: thread = row  ->  lane = 4 columns
-                float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) srow[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-                __syncwarp();
                 const int col = col0 + cl;
-                if (col < p.N) {
-                    const EpiConst kc = epilogue_consts<EPI>(p, col);
-                    const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
-                    float4 in[8];
+                const bool colok = col < p.N;
+                EpiConst kc;
+                float4 in[8];
+                if (colok) {
+                    kc = epilogue_consts<EPI>(p, col);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         in[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (tq + 4 * i < p.T) in[i] = epilogue_load<EPI, BF16>(p, (long long)bt * p.T + tq + 4 * i, col);
                     }
-#pragma unroll(EPI == EPI_LINEAR ? 1 : 8)
-                    for (int i = 0; i < 8; ++i) {
-                        const int t = tq + 4 * i;
-                        if (t < p.T) {
-                            const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * STG_LD + cl);
-                            const int b = (p.d_stride != 0 && p.T_utt > 0) ? (bt * p.T + t) / p.T_utt : 0;
-                            epilogue_quad<EPI, BF16>(p, v, in[i], kc, (long long)bt * p.T + t, b, col);
+                }
+                tmem_ld_wait();
+                // transpose through the warp's private 16-row staging tile, two passes: thread = row -> lane = 4 columns
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((lane >> 4) == pass) {
+                        float4* srow = reinterpret_cast<float4*>(stg + (lane & 15) * STG_LD);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) srow[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                    }
+                    __syncwarp();
+                    if (colok) {
+#pragma unroll(EPI == EPI_LINEAR ? 1 : 4)
+                        for (int i2 = 0; i2 < 4; ++i2) {
+                            const int i = 4 * pass + i2;
+                            const int t = tq + 4 * i;
+                            if (t < p.T) {
+                                const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
+                                const int b = (p.d_stride != 0 && p.T_utt > 0) ? (bt * p.T + t) / p.T_utt : 0;
+                                epilogue_quad<EPI, BF16>(p, v, in[i], kc, (long long)bt * p.T + t, b, col);
+                            }
                         }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -353,8 +368,17 @@ static int launch_one(const TcP& p, cudaStream_t st) {
         configured = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    tc_gemm_kernel<EPI, BF16><<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
-    B2S_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BF16>, p));
     return B2S_OK;
 }
 template <int EPI>

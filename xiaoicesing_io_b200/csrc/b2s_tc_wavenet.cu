@@ -856,6 +856,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
         const int cl = (lane & 7) * 4, rsub = lane >> 3;
         const int tq = t0 + q * 32 + rsub;
         const float inv_sqrt2 = 0.70710678118654752440f;
+        // per-lane constants of the coalesced (EPI2) layout
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vmask |= (tq + 4 * i < p.T ? 1u : 0u) << i;
+        const long long rowoff = ((long long)b * p.T + tq) * C + cl;          // element offset of (row 0 of the lane, its 4 columns)
+        float* xrow = p.x + rowoff;
+        float* srow_g = p.skip + rowoff;
+        uint16_t* shrow = reinterpret_cast<uint16_t*>(p.skip_h) + rowoff;
 
 #pragma unroll 1
         for (int l = 0; l < p.L; ++l) {
@@ -905,22 +913,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&zready[h]);
             }
-            // ---- EPI2: coalesced layout through the warp's 16-row staging tile (two passes per 32-row chunk) ----
+            // ---- EPI2: coalesced layout through the warp's 16-row staging tile (two passes per 32-row chunk).
+            //      Row i of the lane is frame tq + 4i: all addresses are (lane base) + (compile-time i) * 4C + (chunk) * 32,
+            //      validity is a precomputed bit mask. ----
             const float* bo = p.bo + (long long)l * 2 * C;
-            const float* dnext = p.dvec + (long long)(l + 1) * C;
-            void* ynext = last ? nullptr : p.ybuf[(l + 1) & 1];
+            const float* dnext = p.dvec + (long long)(l + 1) * C + (long long)b * p.d_stride;
+            uint16_t* ynext = last ? nullptr : reinterpret_cast<uint16_t*>(p.ybuf[(l + 1) & 1]) + rowoff;
             float4 in[8], inn[8];
             auto load_inputs = [&](int g, int j, float4* dst) {
-                const int col = j * 32 + cl;
+                const float* src = (g == 0 ? xrow : srow_g) + j * 32;
+                const bool rd = (g == 0 || !first) && !(p.dbg & 2);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int t = tq + 4 * i;
-                    if (t < p.T && (g == 0 || !first) && !(p.dbg & 2)) {
-                        const float* src = (g == 0 ? p.x : p.skip) + ((long long)b * p.T + t) * C + col;
-                        dst[i] = *reinterpret_cast<const float4*>(src);
-                    }
-                }
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = (rd && (vmask >> i & 1)) ? *reinterpret_cast<const float4*>(src + i * 4 * C) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             load_inputs(0, sub, inn);
 #pragma unroll 1
@@ -937,8 +942,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 if (n + 1 < 8) load_inputs((n + 1) >> 2, 2 * ((n + 1) & 3) + sub, inn);
                 const int col = j * 32 + cl;
                 const float4 bias = __ldg(reinterpret_cast<const float4*>(bo + g * C + col));
-                float4 dsh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g == 0 && ynext && p.d_stride == 0) dsh = __ldg(reinterpret_cast<const float4*>(dnext + col));
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g == 0 && ynext) d = __ldg(reinterpret_cast<const float4*>(dnext + col));
+                float* xo = xrow + j * 32;
+                float* so = srow_g + j * 32;
+                uint16_t* yo = ynext + j * 32;
+                uint16_t* sho = shrow + j * 32;
                 tmem_ld_wait();
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
@@ -949,35 +958,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                             srow[c2] = make_float4(acc[4 * c2], acc[4 * c2 + 1], acc[4 * c2 + 2], acc[4 * c2 + 3]);
                     }
                     __syncwarp();
+                    if (!(p.dbg & 4)) {
 #pragma unroll
-                    for (int i2 = 0; i2 < 4; ++i2) {
-                        const int i = 4 * pass + i2;                            // row 4*i + rsub of the warp's 32
-                        const int t = tq + 4 * i;
-                        if (t < p.T && !(p.dbg & 4)) {
-                            const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
-                            const long long r = (long long)b * p.T + t;
-                            const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
-                            if (g == 0) {
-                                const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
-                                                              (in[i].z + o.z) * inv_sqrt2, (in[i].w + o.w) * inv_sqrt2);
-                                *reinterpret_cast<float4*>(p.x + r * C + col) = xn;
-                                if (ynext) {
-                                    const float4 d = p.d_stride == 0
-                                                         ? dsh
-                                                         : __ldg(reinterpret_cast<const float4*>(dnext + (long long)b * p.d_stride + col));
-                                    uint2 yo;
-                                    yo.x = Half16<BF16>::pack2(xn.x + d.x, xn.y + d.y);
-                                    yo.y = Half16<BF16>::pack2(xn.z + d.z, xn.w + d.w);
-                                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ynext) + r * C + col) = yo;
-                                }
-                            } else {
-                                const float4 s2 = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
-                                *reinterpret_cast<float4*>(p.skip + r * C + col) = s2;
-                                if (last && p.skip_h) {
-                                    uint2 so;
-                                    so.x = Half16<BF16>::pack2(s2.x, s2.y);
-                                    so.y = Half16<BF16>::pack2(s2.z, s2.w);
-                                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.skip_h) + r * C + col) = so;
+                        for (int i2 = 0; i2 < 4; ++i2) {
+                            const int i = 4 * pass + i2;                        // row 4*i + rsub of the warp's 32
+                            if (vmask >> i & 1) {
+                                const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
+                                const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+                                if (g == 0) {
+                                    const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
+                                                                  (in[i].z + o.z) * inv_sqrt2, (in[i].w + o.w) * inv_sqrt2);
+                                    *reinterpret_cast<float4*>(xo + i * 4 * C) = xn;
+                                    if (ynext) {
+                                        uint2 yv;
+                                        yv.x = Half16<BF16>::pack2(xn.x + d.x, xn.y + d.y);
+                                        yv.y = Half16<BF16>::pack2(xn.z + d.z, xn.w + d.w);
+                                        *reinterpret_cast<uint2*>(yo + i * 4 * C) = yv;
+                                    }
+                                } else {
+                                    const float4 s2 = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
+                                    *reinterpret_cast<float4*>(so + i * 4 * C) = s2;
+                                    if (last && p.skip_h) {
+                                        uint2 sv;
+                                        sv.x = Half16<BF16>::pack2(s2.x, s2.y);
+                                        sv.y = Half16<BF16>::pack2(s2.z, s2.w);
+                                        *reinterpret_cast<uint2*>(sho + i * 4 * C) = sv;
+                                    }
                                 }
                             }
                         }
