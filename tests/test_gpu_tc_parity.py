@@ -105,3 +105,60 @@ def test_config5_shape_tensor_core(precision, dev):
     err, scale = _maxabs(out, ref), float(ref.abs().max())
     _report(test='config5_shape_unipc10_C512', precision=precision, max_abs=err, ref_absmax=scale, sigma_w=0.01)
     assert err <= _tol(precision, scale), (precision, err, scale)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+def test_config3_shape_lynxnet_tensor_core(precision, dev):
+    """BASELINE config 3 shape on the tensor cores: rectified-flow Euler 20 with LYNXNet (C=1024 shrunk to 256 so that the
+    oracle finishes in seconds), strong_cond, depthwise k=31."""
+    import xiaoicesing_io_b200 as P
+    from oracle import samplers as OS
+    from oracle import weights as OW
+    cfg = OD.LYNXNetCfg(num_channels=256, num_layers=6, kernel_size=31, strong_cond=True, hidden_size=256)
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, use_shallow_diffusion=False, sampling_algorithm='euler', sampling_steps=20,
+                     infer=False, b2s_precision=precision)
+    bargs = dict(num_layers=6, num_channels=256, kernel_size=31, strong_cond=True)
+    model = P.RectifiedFlow(128, backbone_type='lynxnet', backbone_args=bargs, spec_min=[-12.], spec_max=[0.])
+    sd = OW.make_state_dict(cfg, seed=0, sigma_w=0.01)
+    model.velocity_fn.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(7)
+    B, T = 2, 211
+    condition = torch.randn((B, T, 256), generator=g)
+    noise0 = torch.randn((B, 1, 128, T), generator=g)
+    draws = iter([noise0])
+    model._noise_source = lambda shape: next(draws).to(dev)
+    out = model(condition.to(dev), infer=True).cpu()
+    x = OS.rectified_flow_inference(OD.make_denoiser(sd, cfg), condition.transpose(1, 2), t_start=0.,
+                                    use_shallow=False, algorithm='euler', steps=20, noise0=noise0)
+    ref = OS.denorm_spec(x, torch.tensor(-12.), torch.tensor(0.))
+    err, scale = _maxabs(out, ref), float(ref.abs().max())
+    _report(test='config3_shape_lynx_euler20', precision=precision, max_abs=err, ref_absmax=scale, sigma_w=0.01)
+    assert err <= _tol(precision, scale), (precision, err, scale)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+def test_lynxnet_weak_cond_gelu_single_call(precision, dev):
+    """strong_cond=False: GELU after the input projection (lynxnet.py:142-143), SiLU activation, k=7."""
+    import xiaoicesing_io_b200 as P
+    from oracle import weights as OW
+    cfg = OD.LYNXNetCfg(num_channels=128, num_layers=3, kernel_size=7, strong_cond=False, hidden_size=64, activation='SiLU',
+                        in_dims=64)
+    P.hparams.clear()
+    P.hparams.update(hidden_size=64, b2s_precision=precision)
+    net = P.build_backbone(64, 1, 'lynxnet', dict(num_layers=3, num_channels=128, kernel_size=7, strong_cond=False,
+                                                   activation='SiLU'))
+    sd = OW.make_state_dict(cfg, seed=1, sigma_w=0.05)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    g = torch.Generator().manual_seed(3)
+    B, T = 3, 77
+    spec = torch.randn((B, 1, 64, T), generator=g)
+    cond = torch.randn((B, 64, T), generator=g)
+    t = torch.tensor([500.5])
+    out = net(spec.to(dev), t.to(dev), cond.to(dev)).cpu()
+    ref = OD.make_denoiser(sd, cfg)(spec, t, cond)
+    err, scale = _maxabs(out, ref), float(ref.abs().max())
+    _report(test='lynx_weak_gelu_single_call', precision=precision, max_abs=err, ref_absmax=scale)
+    assert err <= 2e-2 * max(1.0, scale)

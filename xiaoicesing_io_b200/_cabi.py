@@ -40,6 +40,9 @@ _SIGNATURES = {
                              _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    'b2s_lynx_prenorm_h': [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    'b2s_layernorm_h': [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    'b2s_lynx_dwconv_h': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
 }
 
 EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', 'b2s_tc_wavenet_stack_max_tiles', *_SIGNATURES]
@@ -219,3 +222,17 @@ def tc_lynx_glu(h_h, W_h, bias, g_h, rows, C, inner, bf16):
 def tc_linear_residual(p_h, W_h, bias, x, rows, C, inner, bf16):
     check(lib.b2s_tc_linear_residual(ptr(p_h), ptr(W_h), ptr(bias), ptr(x), rows, C, inner, int(bf16), stream_ptr()),
           'b2s_tc_linear_residual')
+
+
+def lynx_prenorm_h(x, cond_h, ld_cond, dvec, d_stride, gamma, beta, h_h, B, T, C, strong, bf16):
+    check(lib.b2s_lynx_prenorm_h(ptr(x), ptr(cond_h), ld_cond, ptr(dvec), d_stride, ptr(gamma), ptr(beta), ptr(h_h), B, T, C,
+                                 int(strong), int(bf16), stream_ptr()), 'b2s_lynx_prenorm_h')
+
+
+def layernorm_h(x, gamma, beta, h_h, rows, C, bf16):
+    check(lib.b2s_layernorm_h(ptr(x), ptr(gamma), ptr(beta), ptr(h_h), rows, C, int(bf16), stream_ptr()), 'b2s_layernorm_h')
+
+
+def lynx_dwconv_h(g_h, Wdw, bias, slope, p_h, B, T, inner, ksize, act, bf16):
+    check(lib.b2s_lynx_dwconv_h(ptr(g_h), ptr(Wdw), ptr(bias), ptr(slope), ptr(p_h), B, T, inner, ksize, act, int(bf16),
+                                stream_ptr()), 'b2s_lynx_dwconv_h')

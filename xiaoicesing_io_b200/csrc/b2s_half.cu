@@ -42,3 +42,172 @@ extern "C" int b2s_cast_f32_h(const float* in, void* out, int64_t n, int bf16, v
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }
+
+// ====================================================================================================
+// LYNXNet layer helpers of the 16-bit path (lynxnet.py:76-87, 52-62): the pointwise convs run on the tensor
+// cores (b2s_tc_lynx_glu / b2s_tc_linear_residual); these two HBM-bound kernels feed them.
+// ====================================================================================================
+namespace b2s {
+
+__device__ __forceinline__ float4 ld_h4(const uint16_t* p, int bf16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a, b;
+    if (bf16) { a = tc::Half16<1>::unpack2(u.x); b = tc::Half16<1>::unpack2(u.y); }
+    else { a = tc::Half16<0>::unpack2(u.x); b = tc::Half16<0>::unpack2(u.y); }
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_h4(uint16_t* p, float4 v, int bf16) {
+    uint2 u;
+    if (bf16) { u.x = tc::Half16<1>::pack2(v.x, v.y); u.y = tc::Half16<1>::pack2(v.z, v.w); }
+    else { u.x = tc::Half16<0>::pack2(v.x, v.y); u.y = tc::Half16<0>::pack2(v.z, v.w); }
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+// One warp per frame row, a lane owns 4 consecutive channels per 128-channel group (16-byte fp32 / 8-byte 16-bit
+// accesses, fully coalesced).  PRE: u = x + cond + d, residual write-back x <- x + cond when strong_cond
+// (front_cond_inject, lynxnet.py:77-84); h = LayerNorm_C(u) * gamma + beta (eps 1e-5) in 16 bits.
+template <bool PRE>
+__global__ void __launch_bounds__(256) layernorm_h_kernel(float* __restrict__ x, const uint16_t* __restrict__ cond, int ld_cond,
+                                                          const float* __restrict__ dvec, int d_stride,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          uint16_t* __restrict__ h, int rows, int T, int C, int strong, int bf16) {
+    extern __shared__ float srow[];                 // [warps][C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= rows) return;
+    float* u = srow + (long long)warp * C;
+    const int b = PRE ? r / T : 0;
+    float sum = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(x + (long long)r * C + c);
+        if (PRE) {
+            const float4 cc = ld_h4(cond + (long long)r * ld_cond + c, bf16);
+            v = make_float4(v.x + cc.x, v.y + cc.y, v.z + cc.z, v.w + cc.w);
+            if (strong) *reinterpret_cast<float4*>(x + (long long)r * C + c) = v;
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dvec + (long long)b * d_stride + c));
+            v = make_float4(v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w);
+        }
+        *reinterpret_cast<float4*>(u + c) = v;
+        sum += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(u + c);
+        const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+        var += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / (float)C + 1e-5f);
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(u + c);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+        st_h4(h + (long long)r * C + c,
+              make_float4((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y, (v.z - mean) * rstd * g.z + bb.z,
+                          (v.w - mean) * rstd * g.w + bb.w), bf16);
+    }
+}
+
+// Depthwise conv along time + bias + activation, 16-bit in / out, fp32 math.  Thread = 2 adjacent channels
+// (4-byte accesses, coalesced across the warp), sliding window over a strip of frames, zero padding per utterance.
+constexpr int DWH_TSTRIP = 32;
+constexpr int DWH_MAXK = 31;
+
+template <int BF16>
+__global__ void __launch_bounds__(128) dwconv_h_kernel(const uint16_t* __restrict__ g, const float* __restrict__ Wdw,
+                                                       const float* __restrict__ bias, const float* __restrict__ slope,
+                                                       uint16_t* __restrict__ p, int T, int inner, int ksize, int act) {
+    const int ch = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (ch >= inner) return;
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.y * DWH_TSTRIP;
+    const int pad = ksize / 2;
+    float w0[DWH_MAXK], w1[DWH_MAXK];
+#pragma unroll
+    for (int k = 0; k < DWH_MAXK; ++k) {
+        w0[k] = k < ksize ? __ldg(Wdw + (long long)ch * ksize + k) : 0.f;
+        w1[k] = k < ksize ? __ldg(Wdw + (long long)(ch + 1) * ksize + k) : 0.f;
+    }
+    const float b0 = __ldg(bias + ch), b1 = __ldg(bias + ch + 1);
+    const float s0 = slope ? __ldg(slope + ch) : 0.f, s1 = slope ? __ldg(slope + ch + 1) : 0.f;
+    const uint16_t* gb = g + (long long)b * T * inner + ch;
+    uint16_t* pb = p + (long long)b * T * inner + ch;
+    float2 win[DWH_MAXK];
+#pragma unroll
+    for (int k = 0; k < DWH_MAXK; ++k) {
+        const int ts = t0 - pad + k;
+        win[k] = (k < ksize && ts >= 0 && ts < T) ? tc::Half16<BF16>::unpack2(*reinterpret_cast<const uint32_t*>(gb + (long long)ts * inner))
+                                                   : make_float2(0.f, 0.f);
+    }
+    for (int i = 0; i < DWH_TSTRIP; ++i) {
+        const int t = t0 + i;
+        if (t >= T) break;
+        float a0 = b0, a1 = b1;
+#pragma unroll
+        for (int k = 0; k < DWH_MAXK; ++k) {
+            a0 = fmaf(w0[k], win[k].x, a0);
+            a1 = fmaf(w1[k], win[k].y, a1);
+        }
+        float o0, o1;
+        if (act == 0) { o0 = a0 >= 0.f ? a0 : s0 * a0; o1 = a1 >= 0.f ? a1 : s1 * a1; }
+        else { o0 = apply_act(a0, act); o1 = apply_act(a1, act); }
+        *reinterpret_cast<uint32_t*>(pb + (long long)t * inner) = tc::Half16<BF16>::pack2(o0, o1);
+#pragma unroll
+        for (int k = 0; k < DWH_MAXK - 1; ++k) win[k] = win[k + 1];
+        const int tn = t + 1 - pad + (ksize - 1);
+        const float2 nv = (tn >= 0 && tn < T) ? tc::Half16<BF16>::unpack2(*reinterpret_cast<const uint32_t*>(gb + (long long)tn * inner))
+                                              : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < DWH_MAXK; ++k)
+            if (k == ksize - 1) win[k] = nv;
+    }
+}
+
+}  // namespace b2s
+
+extern "C" int b2s_lynx_prenorm_h(float* x, const void* cond_h, int ld_cond, const float* dvec, int d_stride,
+                                  const float* gamma, const float* beta, void* h_h, int B, int T, int C, int strong_cond,
+                                  int bf16, void* stream) {
+    B2S_CHECK_ARG(x && cond_h && dvec && gamma && beta && h_h, "b2s_lynx_prenorm_h: null pointer");
+    B2S_CHECK_ARG(C > 0 && C <= 8192 && C % 4 == 0 && ld_cond % 4 == 0 && d_stride % 4 == 0, "b2s_lynx_prenorm_h: C, ld_cond, d_stride must be multiples of 4");
+    const int rows = B * T;
+    if (rows <= 0) return B2S_OK;
+    const int warps = C <= 1024 ? 8 : (C <= 2048 ? 4 : 1);
+    size_t smem = (size_t)warps * C * sizeof(float);
+    layernorm_h_kernel<true><<<ceil_div(rows, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        x, (const uint16_t*)cond_h, ld_cond, dvec, d_stride, gamma, beta, (uint16_t*)h_h, rows, T, C, strong_cond, bf16);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_layernorm_h(const float* x, const float* gamma, const float* beta, void* h_h, int rows, int C, int bf16,
+                               void* stream) {
+    B2S_CHECK_ARG(x && gamma && beta && h_h, "b2s_layernorm_h: null pointer");
+    B2S_CHECK_ARG(C > 0 && C <= 8192 && C % 4 == 0, "b2s_layernorm_h: C must be a multiple of 4");
+    if (rows <= 0) return B2S_OK;
+    const int warps = C <= 1024 ? 8 : (C <= 2048 ? 4 : 1);
+    size_t smem = (size_t)warps * C * sizeof(float);
+    layernorm_h_kernel<false><<<ceil_div(rows, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        const_cast<float*>(x), nullptr, 0, nullptr, 0, gamma, beta, (uint16_t*)h_h, rows, 1, C, 0, bf16);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_lynx_dwconv_h(const void* g_h, const float* Wdw, const float* bias, const float* slope, void* p_h, int B,
+                                 int T, int inner, int ksize, int act, int bf16, void* stream) {
+    B2S_CHECK_ARG(g_h && Wdw && bias && p_h, "b2s_lynx_dwconv_h: null pointer");
+    B2S_CHECK_ARG(ksize >= 1 && ksize <= DWH_MAXK && (ksize & 1), "b2s_lynx_dwconv_h: kernel size must be odd and <= %d", DWH_MAXK);
+    B2S_CHECK_ARG(inner % 2 == 0, "b2s_lynx_dwconv_h: inner must be even");
+    B2S_CHECK_ARG(act != 0 || slope, "b2s_lynx_dwconv_h: PReLU needs slope");
+    B2S_CHECK_ARG(B < 65536, "b2s_lynx_dwconv_h: B too large");
+    if (B <= 0 || T <= 0) return B2S_OK;
+    dim3 grid(ceil_div(inner / 2, 128), ceil_div(T, DWH_TSTRIP), B);
+    if (bf16) dwconv_h_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)g_h, Wdw, bias, slope, (uint16_t*)p_h, T, inner, ksize, act);
+    else dwconv_h_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)g_h, Wdw, bias, slope, (uint16_t*)p_h, T, inner, ksize, act);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}

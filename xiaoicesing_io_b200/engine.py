@@ -346,8 +346,6 @@ class LYNXNetEngine:
     def __init__(self, net, precision: str = 'fp32'):
         if precision not in PRECISIONS:
             raise ValueError(f'unknown precision {precision!r}; available: {PRECISIONS}')
-        if precision != 'fp32':
-            raise C.B2SError("LYNXNet runs on the fp32 path only in this build; set b2s_precision='fp32'")
         self.net = net
         self.precision = precision
         self.C = net.num_channels
@@ -399,6 +397,15 @@ class LYNXNetEngine:
         self.b_down = f(torch.stack([l.convmodule.net[6].bias for l in layers], 0))
         self.norm_g, self.norm_b = f(net.norm.weight), f(net.norm.bias)
         self.w_fin, self.b_fin = f(net.output_projection.weight[:, :, 0]), f(net.output_projection.bias)
+        if self.precision != 'fp32':
+            if self.C % 32 or inner % 32:
+                raise C.B2SError(f'the {self.precision} tensor-core path needs num_channels and num_channels*expansion_factor '
+                                 f"to be multiples of 32 (got {self.C}, {inner}); use b2s_precision='fp32'")
+            hd = C.HALF_DTYPES[self.precision]
+            self.bf16 = self.precision == 'bf16'
+            h = lambda t: t.to(hd).contiguous()
+            self.w_in_h, self.w_cond_h, self.w_up_h = h(self.w_in), h(self.w_cond), h(self.w_up)
+            self.w_down_h, self.w_fin_h = h(self.w_down), h(self.w_fin)
         self._packed_version = v
 
     def step_table(self, t_values):
@@ -425,6 +432,8 @@ class LYNXNetEngine:
         self.pack()
         C.require_cuda(cond_bth, 'cond')
         C.require_cuda(t_values, 't_values')
+        if self.precision != 'fp32':
+            return LYNXNetSessionTC(self, cond_bth, t_values, per_row_t)
         return LYNXNetSession(self, cond_bth, t_values, per_row_t)
 
 
@@ -471,6 +480,63 @@ class LYNXNetSession:
     @property
     def launches_per_eval(self) -> int:
         return 1 + 4 * self.eng.L + 2
+
+
+class LYNXNetSessionTC:
+    """16-bit tensor-core session of LYNXNet (lynxnet.py:128-163): the three pointwise convolutions of every layer and
+    the stem / head run on tcgen05 (SwiGLU and residual-add fused into the GEMM epilogues); LayerNorm and the depthwise
+    k=31 conv are HBM-bound kernels with 16-bit I/O and fp32 math; the residual stream x stays fp32."""
+
+    def __init__(self, eng: LYNXNetEngine, cond_bth, t_values, per_row_t):
+        self.eng = eng
+        B, T, H = cond_bth.shape
+        if H != eng.H:
+            raise C.B2SError(f'condition has {H} channels, backbone expects hidden_size={eng.H}')
+        if per_row_t and t_values.numel() != B:
+            raise C.B2SError('per-row step embedding needs one time value per utterance')
+        if H % 8 or eng.MF % 8:
+            raise C.B2SError(f'the tensor-core path needs hidden_size and in_dims*n_feats to be multiples of 8 '
+                             f'(got {H}, {eng.MF})')
+        self.B, self.T, self.rows = B, T, B * T
+        self.per_row_t = per_row_t
+        dev, hd, bf = eng.device, C.HALF_DTYPES[eng.precision], eng.bf16
+        rows, Cc, L, inner = self.rows, eng.C, eng.L, eng.inner
+        self.dtab = eng.step_table(t_values)
+        cond_h = torch.empty((rows, H), device=dev, dtype=hd)
+        C.cast_h(cond_bth, cond_h, bf)
+        self.cond = torch.empty((L, rows, Cc), device=dev, dtype=hd)             # layer-major hoisted cond projection
+        C.tc_cond_table(cond_h, rows, eng.w_cond_h, eng.b_cond, L, Cc, H, self.cond, bf)
+        self.xin_h = torch.empty((rows, eng.MF), device=dev, dtype=hd)
+        self.x = torch.empty((rows, Cc), device=dev)
+        self.h_h = torch.empty((rows, Cc), device=dev, dtype=hd)
+        self.g_h = torch.empty((rows, inner), device=dev, dtype=hd)
+        self.p_h = torch.empty((rows, inner), device=dev, dtype=hd)
+
+    def _dvec(self, k, l):
+        LC = self.eng.L * self.eng.C
+        if self.per_row_t:
+            return self.dtab[0, l * self.eng.C:], LC
+        return self.dtab[k, l * self.eng.C:], 0
+
+    def eval(self, x_in, k, out):
+        e = self.eng
+        B, T, rows, Cc, L, MF, inner, bf = self.B, self.T, self.rows, e.C, e.L, e.MF, e.inner, e.bf16
+        C.cast_h(x_in, self.xin_h, bf)
+        C.tc_linear(self.xin_h, MF, rows, T, e.w_in_h, MF, e.b_in, Cc, MF, bf,
+                    act=C.ACT_NONE if e.strong else C.ACT_GELU, out_f32=self.x, ldo=Cc)
+        for l in range(L):
+            dv, ds = self._dvec(k, l)
+            C.lynx_prenorm_h(self.x, self.cond[l], Cc, dv, ds, e.ln_g[l], e.ln_b[l], self.h_h, B, T, Cc, e.strong, bf)
+            C.tc_lynx_glu(self.h_h, e.w_up_h[l], e.b_up[l], self.g_h, rows, Cc, inner, bf)
+            C.lynx_dwconv_h(self.g_h, e.w_dw[l], e.b_dw[l], None if e.slope is None else e.slope[l], self.p_h, B, T, inner,
+                            e.ksize, e.act, bf)
+            C.tc_linear_residual(self.p_h, e.w_down_h[l], e.b_down[l], self.x, rows, Cc, inner, bf)
+        C.layernorm_h(self.x, e.norm_g, e.norm_b, self.h_h, rows, Cc, bf)
+        C.tc_linear(self.h_h, Cc, rows, T, e.w_fin_h, Cc, e.b_fin, MF, Cc, bf, out_f32=out, ldo=MF)
+
+    @property
+    def launches_per_eval(self) -> int:
+        return 2 + 4 * self.eng.L + 2
 
 
 # =====================================================================================================
