@@ -40,12 +40,23 @@ WORKLOADS = {
     # name: (B per GPU, T, K_step, sampler)
     'config2': dict(B=16, T=690, k_step=400, layers=20, channels=256, mel=128, hidden=256, cycle=4,
                     desc='shallow DDPM K_step=400 full-step, WaveNet 20x256, 128 mel, B=16 x T=690 per GPU'),
+    # secondary workloads (not the headline; `--workload NAME` for the tables in DESIGN.md)
+    'config3': dict(kind='lynx_reflow', B=64, T=690, k_step=20, layers=6, channels=1024, mel=128, hidden=256, cycle=0,
+                    desc='rectified-flow Euler 20 steps, LYNXNet 6x1024 (E=2, k=31, strong_cond), 128 mel, B=64 x T=690 per GPU'),
+    'config5': dict(kind='wavenet_unipc', B=32, T=690, k_step=20, layers=20, channels=512, mel=128, hidden=256, cycle=4,
+                    desc='UniPC 20 steps, WaveNet 20x512, 128 mel, B=32 x T=690 per GPU'),
+    'config1': dict(kind='wavenet_ddim', B=1, T=690, k_step=20, layers=20, channels=256, mel=128, hidden=256, cycle=4,
+                    desc='DDIM 20 steps (speedup 50), WaveNet 20x256, 128 mel, one 8-s utterance (690 frames)'),
 }
 SIGMA_W = 0.01
 
 
-def flops_per_frame_nfe(L, C, MF):
-    """F_step(WaveNet) = 2*[L*8C^2 + MF*C + C^2 + C*MF]."""
+def flops_per_frame_nfe(L, C, MF, kind='wavenet'):
+    """SURVEY.md section 8d: F_step(WaveNet) = 2*[L*8C^2 + MF*C + C^2 + C*MF];
+    F_step(LYNXNet) = 2*[L*(C*2EC + EC*C + EC*k) + 2*MF*C], E = 2, k = 31."""
+    if kind.startswith('lynx'):
+        E, k = 2, 31
+        return 2 * (L * (C * 2 * E * C + E * C * C + E * C * k) + 2 * MF * C)
     return 2 * (L * 8 * C * C + MF * C + C * C + C * MF)
 
 
@@ -109,7 +120,29 @@ class ClockSampler:
 
 def make_model(w, precision, device, cuda_graph=True):
     import xiaoicesing_io_b200 as P
+    kind = w.get('kind', 'wavenet_ddpm_shallow')
     P.hparams.clear()
+    if kind == 'lynx_reflow':
+        P.hparams.update(hidden_size=w['hidden'], use_shallow_diffusion=False, sampling_algorithm='euler',
+                         sampling_steps=w['k_step'], infer=False, b2s_precision=precision, b2s_cuda_graph=cuda_graph)
+        torch.manual_seed(0)
+        model = P.RectifiedFlow(
+            w['mel'], backbone_type='lynxnet',
+            backbone_args=dict(num_layers=w['layers'], num_channels=w['channels'], kernel_size=31, strong_cond=True),
+            spec_min=[-12.], spec_max=[0.])
+        torch.nn.init.normal_(model.velocity_fn.output_projection.weight, std=SIGMA_W)
+        return model.to(device).eval()
+    if kind in ('wavenet_unipc', 'wavenet_ddim'):
+        P.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=False,
+                         diff_speedup=1000 // w['k_step'], diff_accelerator='unipc' if kind == 'wavenet_unipc' else 'ddim',
+                         infer=False, b2s_precision=precision, b2s_cuda_graph=cuda_graph)
+        torch.manual_seed(0)
+        model = P.GaussianDiffusion(
+            w['mel'], timesteps=1000, k_step=1000, backbone_type='wavenet',
+            backbone_args=dict(num_layers=w['layers'], num_channels=w['channels'], dilation_cycle_length=w['cycle']),
+            spec_min=[-12.], spec_max=[0.])
+        torch.nn.init.normal_(model.denoise_fn.output_projection.weight, std=SIGMA_W)
+        return model.to(device).eval()
     P.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=True,
                      K_step_infer=w['k_step'], diff_speedup=1, diff_accelerator='ddim', infer=False,
                      b2s_precision=precision, b2s_cuda_graph=cuda_graph)
@@ -199,13 +232,15 @@ def dominant_kernel_roofline(model, w, precision, reps=5):
     """Times the dominant kernel of one denoiser evaluation in isolation, at the bench shapes, with CUDA
     events on the launching stream: all L per-layer launches back to back, ``reps`` times."""
     from xiaoicesing_io_b200 import _cabi as C
-    eng = model.denoise_fn._engine()
+    eng = getattr(model, model.backbone_attr)._engine()
     eng.pack()
     dev = eng.device
     B, T, Cc, L = w['B'], w['T'], w['channels'], w['layers']
     cond = torch.randn((B, T, w['hidden']), device=dev)
     tvals = torch.tensor([float(w['k_step'] - 1)], device=dev)
     sess = eng.begin(cond, tvals)
+    if not hasattr(sess, 'dominant_kernel') and not (precision == 'fp32' and hasattr(sess, 'y')):
+        return None                                   # no per-kernel roofline for this backbone / precision
     x_in = torch.randn((B * T, w['mel']), device=dev)
     out = torch.empty_like(x_in)
     sess.eval(x_in, 0, out)                       # fills y / z with realistic values
@@ -268,6 +303,10 @@ def run_b200_arm(args, w):
     nfe = prog.n_nfe
     index = list(range(rank * B, (rank + 1) * B))
 
+    shallow = w.get('kind', 'wavenet_ddpm_shallow') == 'wavenet_ddpm_shallow'
+    if not shallow:
+        src_d = None
+
     def step_resident():
         mel = model(cond_d, src_spec=src_d, infer=True)
         if world > 1:
@@ -276,7 +315,7 @@ def run_b200_arm(args, w):
 
     def step_e2e():
         c = cond_h.to(dev, non_blocking=True)
-        s = src_h.to(dev, non_blocking=True)
+        s = src_h.to(dev, non_blocking=True) if shallow else None
         mel = model(c, src_spec=s, infer=True)
         if world > 1:
             full = gather_mels(mel.contiguous(), index, world * B, dst=0)
@@ -320,18 +359,18 @@ def run_b200_arm(args, w):
     roof = cpu = None
     if rank == 0:
         roof = dominant_kernel_roofline(model, w, args.precision)
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and shallow:
             torch.set_num_threads(os.cpu_count() or 1)
             n_utt, n_nfe = 4, 4
             thr, _ = cpu_sample_throughput(w, model.denoise_fn.state_dict(), n_utt, n_nfe, repeats=3, warmup=1)
             cpu = {'value': thr, 'unit': 'frame*NFE/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                    'sample': f'{n_utt} utterances x {T} frames x first {n_nfe} of {w["k_step"]} ancestral steps, median of 3'}
     if rank == 0:
-        sess_launches = roof.get('launches_per_eval', (1 if args.precision == 'fp32' else 2) + 2 * w['layers'] + 2)
+        sess_launches = (roof or {}).get('launches_per_eval', (1 if args.precision == 'fp32' else 2) + 2 * w['layers'] + 2)
         n_lin = sum(1 for op in prog.ops if op.kind == 'lin')
         n_noise = prog.n_draws
         launches_per_step = nfe * sess_launches + n_lin + n_noise + 2 + 4   # + start transposes + tables
-        F = flops_per_frame_nfe(w['layers'], w['channels'], w['mel'])
+        F = flops_per_frame_nfe(w['layers'], w['channels'], w['mel'], w.get('kind', 'wavenet'))
         p = peaks()
         line = {
             'metric': 'denoised mel-frames x NFE per second', 'value': value, 'unit': 'frame*NFE/s',
@@ -340,11 +379,13 @@ def run_b200_arm(args, w):
             'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'fp16': 'f16'}[args.precision], 'data': 'synthetic',
             'config': {'workload': w['desc'], 'nfe_per_step': nfe, 'global_batch': world * B, 'frames': T,
                        'parallelism': f'utterance-partition x{world}', 'precision': args.precision, 'cuda_graph': not args.no_graph,
-                       'l2': 'working set (hoisted cond table %.0f MB) exceeds the 126 MB L2; no explicit flush'
-                             % (B * T * w['layers'] * 2 * w['channels'] * 4 / 1e6),
+                       'l2': ('hoisted cond table %.0f MB + weights/activations per GPU vs the 126 MB L2; no explicit flush '
+                              '(the table is streamed once per denoiser evaluation)'
+                              % (B * T * w['layers'] * (1 if w.get('kind', '').startswith('lynx') else 2) * w['channels']
+                                 * (4 if args.precision == 'fp32' else 2) / 1e6)),
                        'sigma_w': SIGMA_W},
             'e2e': {'value': e2e_value, 'unit': 'frame*NFE/s', 'ms_per_step': max(e2e_ms, e2e_wall_ms) / args.steps,
-                    'h2d_bytes_per_step': int(cond_h.numel() * 4 + src_h.numel() * 4) * world,
+                    'h2d_bytes_per_step': int(cond_h.numel() * 4 + (src_h.numel() * 4 if shallow else 0)) * world,
                     'd2h_bytes_per_step': int(world * B * T * w['mel'] * 4)},
             'gpu_launches': int(launches_per_step * args.steps),
             'rtf': (ms_total / args.steps * 1e-3) / (world * B * T * 512 / 44100.0),

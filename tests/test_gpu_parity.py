@@ -210,3 +210,33 @@ def test_cuda_graph_replay_equals_eager(dev):
     other = model(cond, src_spec=src, infer=True)
     assert not torch.equal(other, outs[0])
     _sampling.clear_graph_cache()
+
+
+def test_edge_cases_empty_and_tiny_batches(dev):
+    """Edge cases: a single frame, T smaller than every dilation, and an empty batch (no kernel may fault)."""
+    import xiaoicesing_io_b200 as P
+    for precision in ('fp32', 'bf16'):
+        P.hparams.clear()
+        P.hparams.update(hidden_size=256, schedule_type='linear', use_shallow_diffusion=False, diff_speedup=200,
+                         diff_accelerator='ddim', infer=False, b2s_precision=precision, b2s_cuda_graph=False)
+        torch.manual_seed(0)
+        model = P.GaussianDiffusion(128, backbone_type='wavenet',
+                                    backbone_args=dict(num_layers=5, num_channels=256, dilation_cycle_length=5),
+                                    spec_min=[-12.], spec_max=[0.])
+        torch.nn.init.normal_(model.denoise_fn.output_projection.weight, std=0.01)
+        model = model.to(dev).eval()
+        for (B, T) in [(1, 1), (2, 3), (3, 129)]:
+            out = model(torch.randn(B, T, 256, device=dev), infer=True)
+            assert tuple(out.shape) == (B, T, 128) and bool(torch.isfinite(out).all()), (precision, B, T)
+        out = model(torch.randn(0, 7, 256, device=dev), infer=True)
+        assert tuple(out.shape) == (0, 7, 128)
+    P.hparams.pop('b2s_precision', None)
+
+
+def test_cpu_inputs_are_rejected_loudly(dev):
+    """No CPU fallback: a CPU condition tensor raises instead of silently computing somewhere else."""
+    import xiaoicesing_io_b200 as P
+    fx = GU.Fixture('gd_ddim_5')
+    model = PU.build_model(fx, dev)
+    with pytest.raises(P._cabi.B2SError):
+        model(fx['condition'], infer=True)

@@ -82,6 +82,8 @@ class _B2SBackbone(nn.Module):
         if not spec.is_cuda:
             raise C.B2SError('spec must be a CUDA tensor: this backbone has no CPU fallback')
         B, F_, M, T = spec.shape
+        if B * T == 0:
+            return torch.zeros_like(spec, dtype=torch.float32)
         eng = self._engine()
         cond_bth = _time_major_cond(cond.float())
         t = diffusion_step.reshape(-1).to(device=spec.device, dtype=torch.float32).contiguous()

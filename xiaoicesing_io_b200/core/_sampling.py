@@ -156,8 +156,11 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
             return x[:, :, 0, :]                            # [B, T, M]
         return x.permute(0, 2, 1, 3).contiguous()           # [B, F, T, M]
 
+    if B * T == 0:                                          # empty batch / zero frames: nothing to launch
+        return finish(torch.zeros((0, F_ * M), device=device))
+
     graph_key = None
-    if noise_source is None and hparams.get('b2s_cuda_graph', True) and B * T > 0:
+    if noise_source is None and hparams.get('b2s_cuda_graph', True):
         graph_key = (id(backbone), eng._packed_version, eng.precision, _program_key(prog), B, T, F_, M, str(device))
         entry = _GRAPH_CACHE.get(graph_key)
         if entry is not None:
