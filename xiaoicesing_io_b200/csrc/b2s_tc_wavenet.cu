@@ -1040,6 +1040,375 @@ static int launch_stack(const StackP& p, int grid, cudaStream_t st) {
 }
 
 }  // namespace ws
+
+// =====================================================================================================================
+// Version 4: the whole-stack kernel with cta_group::2 MMAs.  The two CTAs of a cluster (neighbouring time tiles) form ONE
+// 256-row MMA: each keeps its own A tile and HALF of every weight tile in shared memory (32 KB per K slab instead of
+// 48 KB: SM ingress, not L2, is what bounds the per-layer GEMMs), only the leader issues tcgen05.mma / commit, both CTAs'
+// TMA loads complete on the LEADER's full barrier, and the leader waits for BOTH CTAs' epilogues (remote mbarrier
+// arrives) before it overwrites TMEM halves or reads the z tiles.
+// =====================================================================================================================
+namespace ws2 {
+
+using ws::StackP;
+using ws::wait_flag;
+
+using wl::ldg_nc_u4;
+using wl::pdl_launch_dependents;
+using wl::pdl_wait;
+using wl::st_shared_u4;
+
+constexpr int C = 256, MAXL = 32;
+constexpr int BM = 128, BK = 64, BN = 256, UK = 16, STAGES = 4, CLUSTER = 2;
+constexpr int A_BYTES = BM * BK * 2, BH_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + BH_BYTES;   // each CTA keeps HALF of B
+constexpr int Z_BYTES = BM * C * 2;
+constexpr int G1_KB = 3 * C / BK, G2_KB = C / BK;
+constexpr int FILLS = 2 * G1_KB + 2 * G2_KB;             // 32 per layer
+constexpr int STG_LD = 36, STG_ROWS = 16;
+constexpr int STG_WARP_BYTES = STG_ROWS * STG_LD * 4;    // 2304: 16-row transpose buffer (two passes per 32-row chunk)
+constexpr int NTHREADS = 384, EPI_WARPS = 8;
+constexpr int SMEM_BYTES = Z_BYTES + STAGES * STAGE_BYTES + EPI_WARPS * STG_WARP_BYTES + 256;   // 231680
+constexpr uint16_t MASK = (1u << CLUSTER) - 1;
+
+template <int BF16>
+__global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_cg2_kernel(const __grid_constant__ StackP p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* zs = smem;
+    uint8_t* stages = smem + Z_BYTES;
+    float* stg_all = reinterpret_cast<float*>(stages + STAGES * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + STAGES * STAGE_BYTES + EPI_WARPS * STG_WARP_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* accb = empty + STAGES;                      // [4]: G1 half 0, G1 half 1, G2 residual, G2 skip
+    uint64_t* zready = accb + 4;                          // [2]
+    uint64_t* tfree = zready + 2;                         // [2]: EPI2 has drained TMEM half h
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tfree + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int b = blockIdx.x / p.tiles_per_b, ti = blockIdx.x - b * p.tiles_per_b, t0 = ti * BM;
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+        printf("b2s: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.mapY[0]);
+        prefetch_tmap(&p.mapY[1]);
+        prefetch_tmap(&p.mapWd);
+        prefetch_tmap(&p.mapWo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);                       // one multicast commit from the leader's MMA thread
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&accb[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&zready[i], EPI_WARPS * CLUSTER);    // the leader's MMA thread waits for BOTH CTAs' epilogues
+            mbar_init(&tfree[i], EPI_WARPS * CLUSTER);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_cg2(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int l = 0; l < p.L; ++l) {
+            const int dil = p.dil[l];
+            if (lane == 0 && l + 1 < p.L && t0 < p.T) {
+                // the next layer's 128 KB slab of the hoisted conditioner projection -> L2 (it streams from HBM once per evaluation)
+                const uint8_t* nxt = reinterpret_cast<const uint8_t*>(p.cond) + ((l + 1) * p.cond_lstride + (long long)blockIdx.x * (BM * 2 * C)) * 2;
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + i * 16384), "r"(16384) : "memory");
+            }
+            for (int f = 0; f < FILLS; ++f) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sa = stages + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    const uint32_t lbar = mapa_u32(&full[stage], 0);          // the LEADER's full barrier collects both CTAs' bytes
+                    if (f < 2 * G1_KB) {
+                        const int h = f / G1_KB, kb = f - h * G1_KB;
+                        const int tap = kb / (C / BK), c0 = (kb - tap * (C / BK)) * BK;
+                        if (rank == 0) mbar_expect_tx(&full[stage], CLUSTER * STAGE_BYTES);
+                        tma_load_3d_cg2(sb, &p.mapWd, lbar, kb * BK, h * BN + rank * (BN / 2), l);
+                        if (f == 0 && l > 0 && t0 < p.T) {
+                            const int* fl = p.flags + b * p.tiles_per_b;
+                            if (ti > 0) wait_flag(fl + ti - 1, l);
+                            wait_flag(fl + ti, l);
+                            if ((ti + 1) * BM < p.T) wait_flag(fl + ti + 1, l);
+                            fence_proxy_async_all();
+                        }
+                        tma_load_3d_cg2(sa, &p.mapY[l & 1], lbar, c0, t0 + (tap - 1) * dil, b);
+                    } else {
+                        const int g = (f - 2 * G1_KB) / G2_KB, kb = (f - 2 * G1_KB) - g * G2_KB;
+                        if (rank == 0) mbar_expect_tx(&full[stage], CLUSTER * BH_BYTES);
+                        tma_load_3d_cg2(sb, &p.mapWo, lbar, kb * BK, g * BN + rank * (BN / 2), l);
+                    }
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA only): M = 256 across the pair =====================
+        const uint32_t idesc = make_idesc_f16(2 * BM, BN, BF16);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int l = 0; l < p.L; ++l) {
+            const uint32_t par = l & 1;
+            for (int h = 0; h < 2; ++h) {
+                if (l > 0) {                                   // EPI2 of the previous layer has drained these columns
+                    mbar_wait(&tfree[h], par ^ 1);
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + h * BN;
+                for (int kb = 0; kb < G1_KB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_u32(stages + stage * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k)
+                            umma_ss_cg2(d_tmem, make_sw128_kmajor_desc(a_addr + k * (UK * 2)), make_sw128_kmajor_desc(b_addr + k * (UK * 2)),
+                                    idesc, (kb | k) != 0);
+                        umma_commit_cg2_mcast(&empty[stage], MASK);
+                        if (kb == G1_KB - 1) umma_commit_cg2_mcast(&accb[h], MASK);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t d_tmem = tmem_base + g * BN;
+                for (int kb = 0; kb < G2_KB; ++kb) {
+                    if (g == 0 && (kb == 0 || kb == 2)) {
+                        mbar_wait(&zready[kb >> 1], par);
+                        tc_fence_after();
+                    }
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_u32(zs + kb * A_BYTES);
+                        const uint32_t b_addr = smem_u32(stages + stage * STAGE_BYTES) + A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k)
+                            umma_ss_cg2(d_tmem, make_sw128_kmajor_desc(a_addr + k * (UK * 2)), make_sw128_kmajor_desc(b_addr + k * (UK * 2)),
+                                    idesc, (kb | k) != 0);
+                        umma_commit_cg2_mcast(&empty[stage], MASK);
+                        if (kb == G2_KB - 1) umma_commit_cg2_mcast(&accb[2 + g], MASK);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 8 warps, warp e -> lane quarter e&3, chunks j with (j&1) == e>>2 ===========
+        const int e = warp - 4, q = e & 3, sub = e >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int row = q * 32 + lane;
+        const bool valid = t0 + row < p.T;
+        const uint32_t zrow = smem_u32(zs) + (row >> 3) * 1024 + (row & 7) * 128;
+        const int sw = row & 7;
+        float* stg = stg_all + e * (STG_ROWS * STG_LD);
+        const int cl = (lane & 7) * 4, rsub = lane >> 3;
+        const int tq = t0 + q * 32 + rsub;
+        const float inv_sqrt2 = 0.70710678118654752440f;
+        // per-lane constants of the coalesced (EPI2) layout
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vmask |= (tq + 4 * i < p.T ? 1u : 0u) << i;
+        const long long rowoff = ((long long)b * p.T + tq) * C + cl;          // element offset of (row 0 of the lane, its 4 columns)
+        float* xrow = p.x + rowoff;
+        float* srow_g = p.skip + rowoff;
+        uint16_t* shrow = reinterpret_cast<uint16_t*>(p.skip_h) + rowoff;
+
+#pragma unroll 1
+        for (int l = 0; l < p.L; ++l) {
+            const uint32_t par = l & 1;
+            const bool first = l == 0, last = l == p.L - 1;
+            // ---- EPI1: thread = frame row; + cond; gate; z -> swizzled smem ----
+            // tile/chunk-major table: (chunk j, 16-byte piece i) of this tile = 128 rows x 16 B contiguous
+            const uint16_t* ctile = reinterpret_cast<const uint16_t*>(p.cond) + l * p.cond_lstride + (long long)blockIdx.x * (BM * 2 * C) + row * 8;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint4 c[4][4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        c[jj][i] = (valid && !(p.dbg & 1)) ? ldg_nc_u4(ctile + ((8 * h + 2 * jj + sub) * 4 + i) * (BM * 8)) : make_uint4(0, 0, 0, 0);
+                mbar_wait(&accb[h], par);
+                tc_fence_after();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 2 * jj + sub;
+                    float acc[32];
+                    tmem_ld32(taddr + h * BN + j * 32, acc);
+                    tmem_ld_wait();
+                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(c[jj]);
+                    uint32_t zp[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 ca = Half16<BF16>::unpack2(cw[2 * i]), cb = Half16<BF16>::unpack2(cw[2 * i + 1]);
+                        float z0, z1;
+                        if (p.dbg & 8) {
+                            z0 = (acc[4 * i] + ca.x) * (acc[4 * i + 1] + ca.y);
+                            z1 = (acc[4 * i + 2] + cb.x) * (acc[4 * i + 3] + cb.y);
+                        } else {
+                            z0 = sigmoid_fast(acc[4 * i] + ca.x) * tanh_fast(acc[4 * i + 1] + ca.y);
+                            z1 = sigmoid_fast(acc[4 * i + 2] + cb.x) * tanh_fast(acc[4 * i + 3] + cb.y);
+                        }
+                        zp[i] = valid ? Half16<BF16>::pack2(z0, z1) : 0u;
+                    }
+                    const uint32_t slab = zrow + (2 * h + (j >> 2)) * A_BYTES;
+                    const int c16 = 2 * (j & 3);
+                    st_shared_u4(slab + ((c16 ^ sw) << 4), make_uint4(zp[0], zp[1], zp[2], zp[3]));
+                    st_shared_u4(slab + (((c16 + 1) ^ sw) << 4), make_uint4(zp[4], zp[5], zp[6], zp[7]));
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(&zready[h], 0));
+            }
+            // ---- EPI2: coalesced layout through the warp's 16-row staging tile (two passes per 32-row chunk).
+            //      Row i of the lane is frame tq + 4i: all addresses are (lane base) + (compile-time i) * 4C + (chunk) * 32,
+            //      validity is a precomputed bit mask. ----
+            const float* bo = p.bo + (long long)l * 2 * C;
+            const float* dnext = p.dvec + (long long)(l + 1) * C + (long long)b * p.d_stride;
+            uint16_t* ynext = last ? nullptr : reinterpret_cast<uint16_t*>(p.ybuf[(l + 1) & 1]) + rowoff;
+            float4 in[8], inn[8];
+            auto load_inputs = [&](int g, int j, float4* dst) {
+                const float* src = (g == 0 ? xrow : srow_g) + j * 32;
+                const bool rd = (g == 0 || !first) && !(p.dbg & 2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = (rd && (vmask >> i & 1)) ? *reinterpret_cast<const float4*>(src + i * 4 * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            load_inputs(0, sub, inn);
+#pragma unroll 1
+            for (int n = 0; n < 8; ++n) {
+                const int g = n >> 2, j = 2 * (n & 3) + sub;
+                if ((n & 3) == 0) {
+                    mbar_wait(&accb[2 + g], par);
+                    tc_fence_after();
+                }
+                float acc[32];
+                tmem_ld32(taddr + g * BN + j * 32, acc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) in[i] = inn[i];
+                if (n + 1 < 8) load_inputs((n + 1) >> 2, 2 * ((n + 1) & 3) + sub, inn);
+                const int col = j * 32 + cl;
+                const float4 bias = __ldg(reinterpret_cast<const float4*>(bo + g * C + col));
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g == 0 && ynext) d = __ldg(reinterpret_cast<const float4*>(dnext + col));
+                float* xo = xrow + j * 32;
+                float* so = srow_g + j * 32;
+                uint16_t* yo = ynext + j * 32;
+                uint16_t* sho = shrow + j * 32;
+                tmem_ld_wait();
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((lane >> 4) == pass) {
+                        float4* srow = reinterpret_cast<float4*>(stg + (lane & 15) * STG_LD);
+#pragma unroll
+                        for (int c2 = 0; c2 < 8; ++c2)
+                            srow[c2] = make_float4(acc[4 * c2], acc[4 * c2 + 1], acc[4 * c2 + 2], acc[4 * c2 + 3]);
+                    }
+                    __syncwarp();
+                    if (!(p.dbg & 4)) {
+#pragma unroll
+                        for (int i2 = 0; i2 < 4; ++i2) {
+                            const int i = 4 * pass + i2;                        // row 4*i + rsub of the warp's 32
+                            if (vmask >> i & 1) {
+                                const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
+                                const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+                                if (g == 0) {
+                                    const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
+                                                                  (in[i].z + o.z) * inv_sqrt2, (in[i].w + o.w) * inv_sqrt2);
+                                    *reinterpret_cast<float4*>(xo + i * 4 * C) = xn;
+                                    if (ynext) {
+                                        uint2 yv;
+                                        yv.x = Half16<BF16>::pack2(xn.x + d.x, xn.y + d.y);
+                                        yv.y = Half16<BF16>::pack2(xn.z + d.z, xn.w + d.w);
+                                        *reinterpret_cast<uint2*>(yo + i * 4 * C) = yv;
+                                    }
+                                } else {
+                                    const float4 s2 = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
+                                    *reinterpret_cast<float4*>(so + i * 4 * C) = s2;
+                                    if (last && p.skip_h) {
+                                        uint2 sv;
+                                        sv.x = Half16<BF16>::pack2(s2.x, s2.y);
+                                        sv.y = Half16<BF16>::pack2(s2.z, s2.w);
+                                        *reinterpret_cast<uint2*>(sho + i * 4 * C) = sv;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if ((n & 3) == 3) {
+                    // this warp has finished TMEM half g of the layer
+                    if (g == 0) __threadfence();                   // y_next stores visible GPU-wide before the flag
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_u32(&tfree[g], 0));
+                    if (g == 0) {
+                        named_bar_sync(1, EPI_WARPS * 32);          // all 8 epilogue warps have stored + fenced
+                        if (e == 0 && lane == 0) st_release_gpu(p.flags + blockIdx.x, l + 1);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, 512);
+    }
+}
+
+template <int BF16>
+static int launch_stack_cg2(const StackP& p, int grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_stack_cg2_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_stack_cg2_kernel<BF16>, p));
+    return B2S_OK;
+}
+
+}  // namespace ws2
 }  // namespace tc
 }  // namespace b2s
 
@@ -1110,6 +1479,7 @@ extern "C" int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, co
     if (rc) return rc;
     rc = make_map_act(&p.mapY[1], y1_h, bf16, C, C, T, B, ws::BK, ws::BM);
     if (rc) return rc;
+    static const bool cg2 = getenv("B2S_STACK_CG2") != nullptr && atoi(getenv("B2S_STACK_CG2")) != 0;
     rc = make_map_w3(&p.mapWd, Wd_h, bf16, 3 * C, 2 * C, L, ws::BK, ws::BN / 2);
     if (rc) return rc;
     rc = make_map_w3(&p.mapWo, Wo_h, bf16, C, 2 * C, L, ws::BK, ws::BN / 2);
@@ -1124,5 +1494,6 @@ extern "C" int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, co
     p.dvec = dvec; p.d_stride = d_stride; p.flags = flags;
     static const int dbg = getenv("B2S_STACK_DBG") ? atoi(getenv("B2S_STACK_DBG")) : 0;
     p.dbg = dbg;
+    if (cg2) return bf16 ? ws2::launch_stack_cg2<1>(p, grid, (cudaStream_t)stream) : ws2::launch_stack_cg2<0>(p, grid, (cudaStream_t)stream);
     return bf16 ? ws::launch_stack<1>(p, grid, (cudaStream_t)stream) : ws::launch_stack<0>(p, grid, (cudaStream_t)stream);
 }
