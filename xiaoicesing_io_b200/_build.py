@@ -24,6 +24,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get('B2S_BUILD_TLOG'):          # profiling build: in-kernel phase timestamps (scripts/stack_timeline.py)
+    NVCC_FLAGS.append('-DB2S_TLOG')
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
         if cand and os.path.exists(cand):

@@ -653,7 +653,7 @@ static int launch_layer(const LayerP& p, int grid, cudaStream_t st) {
 //     epilogue          | EPI1h0(l)  | EPI1h1(l)  |          | EPI2res(l)          | EPI2skip(l) ...
 // Layer l+1 of a tile needs y_{l+1} of its two neighbour tiles (dilation halo).  That hand-off goes through global
 // memory with a release/acquire flag per tile (value = number of finished y buffers) instead of a kernel boundary:
-//     writer  y stores -> __threadfence -> bar.sync(epilogue warps) -> st.release.gpu flag[tile] = l+1
+//     writer  y stores -> bar.sync(epilogue warps) -> one thread: __threadfence, st.release.gpu flag[tile] = l+1
 //     reader  (TMA producer) ld.acquire.gpu spin on flag[tile-1], flag[tile], flag[tile+1] -> fence.proxy.async -> TMA
 // Weight tiles of layer l+1 are requested BEFORE the flag wait, so their latency hides behind the hand-off.
 // TMEM columns are recycled through two more mbarriers (tfree[h]: EPI2 of layer l has drained half h).
@@ -687,7 +687,15 @@ struct __align__(64) StackP {
     const float* dvec; int d_stride;                      // layer l's step embedding at dvec + b*d_stride + l*C
     int* flags;                                           // [B * tiles_per_b], zero before the launch
     int dbg;                                              // profiling experiments only (B2S_STACK_DBG): results are WRONG when != 0
+    unsigned long long* tlog;                             // optional phase timestamps of CTA 2 (B2S_STACK_TLOG): [L][16] globaltimer ns
 };
+
+// phase timestamps of CTA 2 for scripts/stack_timeline.py; compiled in only with -DB2S_TLOG (B2S_BUILD_TLOG=1 python _build.py)
+#ifdef B2S_TLOG
+#define TLOG(slot) do { if (p.tlog && blockIdx.x == 2 && lane == 0) p.tlog[l * 16 + (slot)] = globaltimer_ns(); } while (0)
+#else
+#define TLOG(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void wait_flag(const int* f, int want) {
     if (ld_acquire_gpu(f) >= want) return;
@@ -780,6 +788,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                             if ((ti + 1) * BM < p.T) wait_flag(fl + ti + 1, l);
                             fence_proxy_async_all();
                         }
+                        if (f == 0) TLOG(0);                               // neighbours' y ready, first A load issued
                         tma_load_3d(sa, &p.mapY[l & 1], &full[stage], c0, t0 + (tap - 1) * dil, b);
                     } else {
                         const int g = (f - 2 * G1_KB) / G2_KB, kb = (f - 2 * G1_KB) - g * G2_KB;
@@ -807,6 +816,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 for (int kb = 0; kb < G1_KB; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    if (kb == 0) TLOG(1 + h);                              // first K slab of G1 half h has landed
                     if (lane == 0) {
                         const uint32_t a_addr = smem_u32(stages + stage * STAGE_BYTES), b_addr = a_addr + A_BYTES;
 #pragma unroll
@@ -882,6 +892,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                         c[jj][i] = (valid && !(p.dbg & 1)) ? ldg_nc_u4(ctile + ((8 * h + 2 * jj + sub) * 4 + i) * (BM * 8)) : make_uint4(0, 0, 0, 0);
                 mbar_wait(&accb[h], par);
                 tc_fence_after();
+                if (e == 0) TLOG(3 + 2 * h);                              // G1 half h complete
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = 2 * jj + sub;
@@ -912,6 +923,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&zready[h]);
+                if (e == 0) TLOG(4 + 2 * h);                              // EPI1 half h done (this warp)
             }
             // ---- EPI2: coalesced layout through the warp's 16-row staging tile (two passes per 32-row chunk).
             //      Row i of the lane is frame tq + 4i: all addresses are (lane base) + (compile-time i) * 4C + (chunk) * 32,
@@ -934,6 +946,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 if ((n & 3) == 0) {
                     mbar_wait(&accb[2 + g], par);
                     tc_fence_after();
+                    if (e == 0) TLOG(7 + 2 * g);                          // G2 half g complete
                 }
                 float acc[32];
                 tmem_ld32(taddr + g * BN + j * 32, acc);
@@ -990,16 +1003,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                     }
                     __syncwarp();
                 }
+                if (e == 0 && n < 4) TLOG(11 + n);                          // EPI2-res chunk n of this warp stored
                 if ((n & 3) == 3) {
                     // this warp has finished TMEM half g of the layer
-                    if (g == 0) __threadfence();                   // y_next stores visible GPU-wide before the flag
+                    if (e == 0 && g == 0) TLOG(15);                         // this warp's last residual chunk stored
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tfree[g]);
                     if (g == 0) {
-                        named_bar_sync(1, EPI_WARPS * 32);          // all 8 epilogue warps have stored + fenced
-                        if (e == 0 && lane == 0) st_release_gpu(p.flags + blockIdx.x, l + 1);
+                        // hand-off: every epilogue thread has issued its y_next stores -> CTA barrier -> ONE thread makes them
+                        // visible GPU-wide (the fence is cumulative over the barrier) and releases the tile flag
+                        named_bar_sync(1, EPI_WARPS * 32);
+                        if (e == 0 && lane == 0) {
+                            __threadfence();
+                            st_release_gpu(p.flags + blockIdx.x, l + 1);
+                        }
                     }
+                    if (e == 0) TLOG(8 + 2 * g);                          // EPI2 half g done, flag released
                 }
             }
         }
@@ -1149,6 +1169,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_cg2_kernel(const __
                             if ((ti + 1) * BM < p.T) wait_flag(fl + ti + 1, l);
                             fence_proxy_async_all();
                         }
+                        if (f == 0) TLOG(0);
                         tma_load_3d_cg2(sa, &p.mapY[l & 1], lbar, c0, t0 + (tap - 1) * dil, b);
                     } else {
                         const int g = (f - 2 * G1_KB) / G2_KB, kb = (f - 2 * G1_KB) - g * G2_KB;
@@ -1176,6 +1197,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_cg2_kernel(const __
                 for (int kb = 0; kb < G1_KB; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    if (kb == 0) TLOG(1 + h);
                     if (lane == 0) {
                         const uint32_t a_addr = smem_u32(stages + stage * STAGE_BYTES), b_addr = a_addr + A_BYTES;
 #pragma unroll
@@ -1251,6 +1273,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_cg2_kernel(const __
                         c[jj][i] = (valid && !(p.dbg & 1)) ? ldg_nc_u4(ctile + ((8 * h + 2 * jj + sub) * 4 + i) * (BM * 8)) : make_uint4(0, 0, 0, 0);
                 mbar_wait(&accb[h], par);
                 tc_fence_after();
+                if (e == 0) TLOG(3 + 2 * h);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = 2 * jj + sub;
@@ -1281,6 +1304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_cg2_kernel(const __
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(mapa_u32(&zready[h], 0));
+                if (e == 0) TLOG(4 + 2 * h);
             }
             // ---- EPI2: coalesced layout through the warp's 16-row staging tile (two passes per 32-row chunk).
             //      Row i of the lane is frame tq + 4i: all addresses are (lane base) + (compile-time i) * 4C + (chunk) * 32,
@@ -1303,6 +1327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_cg2_kernel(const __
                 if ((n & 3) == 0) {
                     mbar_wait(&accb[2 + g], par);
                     tc_fence_after();
+                    if (e == 0) TLOG(7 + 2 * g);
                 }
                 float acc[32];
                 tmem_ld32(taddr + g * BN + j * 32, acc);
@@ -1361,14 +1386,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_cg2_kernel(const __
                 }
                 if ((n & 3) == 3) {
                     // this warp has finished TMEM half g of the layer
-                    if (g == 0) __threadfence();                   // y_next stores visible GPU-wide before the flag
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(mapa_u32(&tfree[g], 0));
                     if (g == 0) {
-                        named_bar_sync(1, EPI_WARPS * 32);          // all 8 epilogue warps have stored + fenced
-                        if (e == 0 && lane == 0) st_release_gpu(p.flags + blockIdx.x, l + 1);
+                        // hand-off: every epilogue thread has issued its y_next stores -> CTA barrier -> ONE thread makes them
+                        // visible GPU-wide (the fence is cumulative over the barrier) and releases the tile flag
+                        named_bar_sync(1, EPI_WARPS * 32);
+                        if (e == 0 && lane == 0) {
+                            __threadfence();
+                            st_release_gpu(p.flags + blockIdx.x, l + 1);
+                        }
                     }
+                    if (e == 0) TLOG(8 + 2 * g);
                 }
             }
         }
@@ -1449,6 +1479,10 @@ extern "C" int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const voi
     return bf16 ? wl::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl::launch_layer<0>(p, grid, (cudaStream_t)stream);
 }
 
+static unsigned long long* g_tlog = nullptr;
+/* profiling hook (not part of the product API): device buffer [L][16] of globaltimer ns, or NULL to switch off */
+extern "C" void b2s_debug_set_stack_tlog(void* buf) { g_tlog = (unsigned long long*)buf; }
+
 extern "C" int b2s_tc_wavenet_stack_max_tiles(void) { return num_sms(); }
 
 extern "C" int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, const void* cond_h, int ld_cond,
@@ -1494,6 +1528,7 @@ extern "C" int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, co
     p.dvec = dvec; p.d_stride = d_stride; p.flags = flags;
     static const int dbg = getenv("B2S_STACK_DBG") ? atoi(getenv("B2S_STACK_DBG")) : 0;
     p.dbg = dbg;
+    p.tlog = g_tlog;
     if (cg2) return bf16 ? ws2::launch_stack_cg2<1>(p, grid, (cudaStream_t)stream) : ws2::launch_stack_cg2<0>(p, grid, (cudaStream_t)stream);
     return bf16 ? ws::launch_stack<1>(p, grid, (cudaStream_t)stream) : ws::launch_stack<0>(p, grid, (cudaStream_t)stream);
 }
