@@ -162,3 +162,40 @@ def test_lynxnet_weak_cond_gelu_single_call(precision, dev):
     err, scale = _maxabs(out, ref), float(ref.abs().max())
     _report(test='lynx_weak_gelu_single_call', precision=precision, max_abs=err, ref_absmax=scale)
     assert err <= 2e-2 * max(1.0, scale)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+@pytest.mark.parametrize('acc', ['dpm-solver', 'unipc'])
+def test_config4_variance_predictors_tensor_core(acc, precision, dev):
+    """BASELINE config 4 on the tensor cores: the multi-variance predictor (2 curves x 24 repeat bins = 48 packed bins,
+    WaveNet 10 x 192, configs/variance.yaml:95-100) under DPM-Solver++ / UniPC 10 steps.  C = 192 runs the two-kernel
+    tensor-core path (N = 384 is not a multiple of the 256-column tile, K = 48 < 64, N = 48 output bins)."""
+    import xiaoicesing_io_b200 as P
+    from oracle import samplers as OS
+    from oracle import weights as OW
+    cfg = OD.WaveNetCfg(in_dims=24, n_feats=2, num_layers=10, num_channels=192, dilation_cycle_length=4, hidden_size=256)
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, schedule_type='linear', use_shallow_diffusion=False, diff_speedup=100,
+                     diff_accelerator=acc, infer=False, b2s_precision=precision)
+    model = P.MultiVarianceDiffusion(ranges=[(-96., -12.), (-96., -20.)], clamps=[(-96., -12.), (-96., -20.)], repeat_bins=24,
+                                     backbone_type='wavenet',
+                                     backbone_args=dict(num_layers=10, num_channels=192, dilation_cycle_length=4))
+    sd = OW.make_state_dict(cfg, seed=0, sigma_w=0.01)
+    model.denoise_fn.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(21)
+    B, T = 3, 257
+    cond = torch.randn((B, 256, T), generator=g)
+    noise0 = torch.randn((B, 2, 24, T), generator=g)
+    draws = iter([noise0])
+    model._noise_source = lambda shape: next(draws).to(dev)
+    x = model.inference(cond.to(dev), B, None, dev).cpu()                      # normalised [B, F, T, M]
+    sch = OS.DiffusionSchedule(1000, 'linear')
+    ref = OS.gaussian_diffusion_inference(OD.make_denoiser(sd, cfg), sch, cond, k_step=1000, timesteps=1000, use_shallow=False,
+                                          K_step_infer=1000, speedup=100, accelerator=acc, noise0=noise0, x_start=None,
+                                          step_noise=[])
+    assert tuple(x.shape) == tuple(ref.shape)
+    err, scale = _maxabs(x, ref), float(ref.abs().max())
+    _report(test='config4_multivariance_10', sampler=acc, precision=precision, max_abs_normalised=err, ref_absmax=scale)
+    # normalised units: the de-normalisation slope of these curves is (vmax - vmin) / 2 = 42 and 38 per unit
+    assert err <= (2e-4 * scale if precision == 'bf16' else 5e-5 * max(scale, 1.0)), (acc, precision, err, scale)
