@@ -273,9 +273,20 @@ def dominant_kernel_roofline(model, w, precision, reps=5):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (reps * n_launch)
+    # DRAM traffic of one launch from the committed `ncu --set full` capture of the SAME kernel at the SAME shapes
+    traffic = None
+    prof = os.path.join(ROOT, 'profiles', 'r01_ncu_full_wavenet_stack.csv')
+    if 'wavenet_stack_kernel' in name and os.path.exists(prof) and (B, T, Cc, L) == (16, 690, 256, 20):
+        try:
+            import csv
+            vals = {r[0]: (r[1], float(r[2])) for r in csv.reader(open(prof)) if len(r) >= 3 and r[0].startswith('dram__bytes')}
+            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            traffic = sum(v * scale[u] for u, v in vals.values())
+        except Exception:                                   # noqa: BLE001
+            traffic = None
     achieved = flops / (ms * 1e-3) / 1e12
     return {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': p['bf16_burst'], 'unit': 'TFLOP/s',
-            'frac': achieved / p['bf16_burst'], 'traffic': None, 'avg_launch_ms': ms,
+            'frac': achieved / p['bf16_burst'], 'traffic': traffic, 'avg_launch_ms': ms,
             'flops_per_launch': flops, 'peak_source': p['source'], 'launches_per_eval': sess.launches_per_eval,
             'note': 'algorithmic FLOPs of the launch / avg CUDA-event duration of the launches replayed back to back as a CUDA graph'}
 
