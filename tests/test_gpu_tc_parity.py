@@ -199,3 +199,30 @@ def test_config4_variance_predictors_tensor_core(acc, precision, dev):
     _report(test='config4_multivariance_10', sampler=acc, precision=precision, max_abs_normalised=err, ref_absmax=scale)
     # normalised units: the de-normalisation slope of these curves is (vmax - vmin) / 2 = 42 and 38 per unit
     assert err <= (2e-4 * scale if precision == 'bf16' else 5e-5 * max(scale, 1.0)), (acc, precision, err, scale)
+
+
+def _bf16_backbone(dev, stack, L=4):
+    import xiaoicesing_io_b200 as P
+    from oracle import weights as OW
+    cfg = OD.WaveNetCfg(num_layers=L, num_channels=256, dilation_cycle_length=4)
+    P.hparams.clear()
+    P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision='bf16', b2s_stack=stack)
+    net = P.build_backbone(cfg.in_dims, 1, 'wavenet', dict(num_layers=L, num_channels=256, dilation_cycle_length=4))
+    net.load_state_dict(OW.make_state_dict(cfg, seed=0, sigma_w=0.01), strict=True)
+    return net.to(dev).eval()
+
+
+@pytest.mark.parametrize('B,T', [(30, 690), (5, 129), (1, 19500)])
+def test_stack_kernel_grouping_and_fallback_match_per_layer_path(B, T, dev):
+    """The whole-stack kernel needs every tile resident: batches with more tiles than SMs are split by utterance into
+    several launches (B=30 x 690 -> 2 groups), and an utterance that alone exceeds the SM count (19500 frames = 154 tiles)
+    falls back to the per-layer kernels.  All of them must agree with the per-layer path bit for bit, also with one
+    diffusion step per utterance (d_stride != 0)."""
+    g = torch.Generator().manual_seed(B * 7 + T)
+    spec = torch.randn((B, 1, 128, T), generator=g).to(dev)
+    cond = torch.randn((B, 256, T), generator=g).to(dev)
+    for t in (torch.tensor([437.0]), torch.arange(B, dtype=torch.float32) * 13 + 5):
+        a = _bf16_backbone(dev, stack=True)(spec, t.to(dev), cond)
+        b = _bf16_backbone(dev, stack=False)(spec, t.to(dev), cond)
+        assert bool(torch.isfinite(a).all())
+        assert torch.equal(a, b), (B, T, float((a - b).abs().max()))

@@ -265,7 +265,7 @@ class WaveNetSessionTC:
         if self.stack_group:
             self.flags.zero_()
             LC = L * Cc
-            dv = self.dtab[0] if self.per_row_t else self.dtab[k]
+            dv = self.dtab.reshape(-1) if self.per_row_t else self.dtab[k]     # per-row: utterance b's row starts at b * L*C
             for gi, b0 in enumerate(range(0, B, self.stack_group)):
                 b1 = min(B, b0 + self.stack_group)
                 r0 = b0 * T
