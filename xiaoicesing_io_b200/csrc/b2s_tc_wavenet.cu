@@ -932,12 +932,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
             const float* dnext = p.dvec + (long long)(l + 1) * C + (long long)b * p.d_stride;
             uint16_t* ynext = last ? nullptr : reinterpret_cast<uint16_t*>(p.ybuf[(l + 1) & 1]) + rowoff;
             float4 in[8], inn[8];
+            float4 biasn, dn;                       // bias / step-embedding quads of the NEXT chunk (L1 is ~0 KB here: every
+                                                    // __ldg is an L2 round trip, so they are prefetched with the inputs)
             auto load_inputs = [&](int g, int j, float4* dst) {
                 const float* src = (g == 0 ? xrow : srow_g) + j * 32;
                 const bool rd = (g == 0 || !first) && !(p.dbg & 2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     dst[i] = (rd && (vmask >> i & 1)) ? *reinterpret_cast<const float4*>(src + i * 4 * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+                biasn = __ldg(reinterpret_cast<const float4*>(bo + g * C + j * 32 + cl));
+                dn = (g == 0 && ynext) ? __ldg(reinterpret_cast<const float4*>(dnext + j * 32 + cl)) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             load_inputs(0, sub, inn);
 #pragma unroll 1
@@ -952,11 +956,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 tmem_ld32(taddr + g * BN + j * 32, acc);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) in[i] = inn[i];
+                const float4 bias = biasn, d = dn;
                 if (n + 1 < 8) load_inputs((n + 1) >> 2, 2 * ((n + 1) & 3) + sub, inn);
-                const int col = j * 32 + cl;
-                const float4 bias = __ldg(reinterpret_cast<const float4*>(bo + g * C + col));
-                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g == 0 && ynext) d = __ldg(reinterpret_cast<const float4*>(dnext + col));
                 float* xo = xrow + j * 32;
                 float* so = srow_g + j * 32;
                 uint16_t* yo = ynext + j * 32;
@@ -981,8 +982,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                                 if (g == 0) {
                                     const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
                                                                   (in[i].z + o.z) * inv_sqrt2, (in[i].w + o.w) * inv_sqrt2);
-                                    *reinterpret_cast<float4*>(xo + i * 4 * C) = xn;
-                                    if (ynext) {
+                                    if (!(p.dbg & 32)) *reinterpret_cast<float4*>(xo + i * 4 * C) = xn;
+                                    if (ynext && !(p.dbg & 64)) {
                                         uint2 yv;
                                         yv.x = Half16<BF16>::pack2(xn.x + d.x, xn.y + d.y);
                                         yv.y = Half16<BF16>::pack2(xn.z + d.z, xn.w + d.w);
@@ -990,7 +991,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                                     }
                                 } else {
                                     const float4 s2 = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
-                                    *reinterpret_cast<float4*>(so + i * 4 * C) = s2;
+                                    if (!(p.dbg & 32)) *reinterpret_cast<float4*>(so + i * 4 * C) = s2;
                                     if (last && p.skip_h) {
                                         uint2 sv;
                                         sv.x = Half16<BF16>::pack2(s2.x, s2.y);
