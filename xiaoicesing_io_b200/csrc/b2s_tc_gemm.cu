@@ -22,6 +22,8 @@
 //   SWIGLU   g = out * silu(gate)  (interleaved)             RESIDUAL   x <- x + acc + b
 #include "b2s_tc.cuh"
 
+#include <stdlib.h>
+
 namespace b2s {
 namespace tc {
 
@@ -53,6 +55,7 @@ struct __align__(64) TcP {
     const float* dvec; int d_stride;
     const void* cond; int ldc;
     float* x; float* skip; void* skip_h; int C; int first;
+    int cg2;                   // 1: cta_group::2 kernel (tiles_m_per_b even, weight map box = 128 rows)
 };
 
 // ---- 16-bit helpers --------------------------------------------------------------------------------
@@ -359,6 +362,186 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     }
 }
 
+// ---- the same kernel with cta_group::2 MMAs (the default) ----------------------------------------------------
+// Two CTAs of a cluster take two neighbouring M tiles of the same N tile and form ONE 256-row MMA: each CTA keeps its own
+// A tile and HALF of the B tile (128 of its 256 rows), so a K slab costs 32 KB of shared memory per CTA instead of 48 KB
+// (6 pipeline stages instead of 4, and half the L2 traffic for the weights: scripts/tc_probe.py showed the single-CTA
+// mainloop sitting on the 6.3 KB/clk L2 slice cap).  Only the leader issues tcgen05.mma / commit; both CTAs' TMA loads
+// complete on the leader's full barrier; both CTAs' epilogue warps arrive on the leader's tempty barrier.
+constexpr int STAGES2 = 6;
+constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;       // 16 KB
+constexpr int STAGE2_BYTES = A_BYTES + BH_BYTES;            // 32 KB
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + STG_BYTES + 1024 + 256;
+
+template <int EPI, int BF16>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_constant__ TcP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* stg_all = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES + STG_BYTES);
+    uint64_t* empty = full + STAGES2;
+    uint64_t* tfull = empty + STAGES2;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;      // a cluster walks over (M-tile pair, N tile)
+    const int num_pt = (p.B * p.tiles_m_per_b / 2) * p.tiles_n;      // tiles_m_per_b is even (host)
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.mapA);
+        prefetch_tmap(&p.mapW);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES2; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 2 * EPI_WARPS);   // one arrival per epilogue warp of BOTH CTAs (on the leader's barrier)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_cg2(tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int pt = pair; pt < num_pt; pt += npairs) {
+            const int n_tile = pt % p.tiles_n, m_tile = 2 * (pt / p.tiles_n) + rank;
+            const int b = m_tile / p.tiles_m_per_b, t0 = (m_tile - b * p.tiles_m_per_b) * BLOCK_M;
+            const int n0 = n_tile * BLOCK_N;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sa = smem + stage * STAGE2_BYTES;
+                    const uint32_t lbar = mapa_u32(&full[stage], 0);
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+                    const int tap = kb / p.kb_per_tap;
+                    const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
+                    tma_load_3d_cg2(sa, &p.mapA, lbar, c0, t0 + (tap - 1) * p.dil, b);
+                    tma_load_2d_cg2(sa + A_BYTES, &p.mapW, lbar, kb * BLOCK_K, n0 + rank * (BLOCK_N / 2));
+                }
+                __syncwarp();
+                if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA): M = 256 across the pair =====================
+        const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N, BF16);
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int pt = pair; pt < num_pt; pt += npairs) {
+            mbar_wait(&tempty[as], aphase ^ 1);          // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_ss_cg2(d_tmem, make_sw128_kmajor_desc(a_addr + k * (UMMA_K * 2)),
+                                make_sw128_kmajor_desc(b_addr + k * (UMMA_K * 2)), idesc, (kb | k) != 0);
+                    }
+                    umma_commit_cg2_mcast(&empty[stage], 3);                       // frees the smem slot in BOTH CTAs
+                    if (kb == p.num_kb - 1) umma_commit_cg2_mcast(&tfull[as], 3);  // accumulator complete, both CTAs
+                }
+                __syncwarp();
+                if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+            }
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int e = warp - 4, q = e & 3, sub = e >> 2;   // TMEM lane quarter q; chunks j with (j & 1) == sub
+        int as = 0;
+        uint32_t aphase = 0;
+        float* stg = stg_all + e * (16 * STG_LD);
+        const int cl = (lane & 7) * 4, rsub = lane >> 3;
+        for (int pt = pair; pt < num_pt; pt += npairs) {
+            const int n_tile = pt % p.tiles_n, m_tile = 2 * (pt / p.tiles_n) + rank;
+            const int bt = m_tile / p.tiles_m_per_b, t0 = (m_tile - bt * p.tiles_m_per_b) * BLOCK_M;
+            const int n0 = n_tile * BLOCK_N;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+            const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
+#pragma unroll 1
+            for (int j = sub; j < BLOCK_N / 32; j += 2) {
+                const int col0 = n0 + 32 * j;
+                if (col0 >= p.N) break;
+                float acc[32];
+                tmem_ld32(taddr + j * 32, acc);
+                const int col = col0 + cl;
+                const bool colok = col < p.N;
+                EpiConst kc;
+                float4 in[8];
+                if (colok) {
+                    kc = epilogue_consts<EPI>(p, col);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        in[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tq + 4 * i < p.T) in[i] = epilogue_load<EPI, BF16>(p, (long long)bt * p.T + tq + 4 * i, col);
+                    }
+                }
+                tmem_ld_wait();
+                // transpose through the warp's private 16-row staging tile, two passes: thread = row -> lane = 4 columns
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((lane >> 4) == pass) {
+                        float4* srow = reinterpret_cast<float4*>(stg + (lane & 15) * STG_LD);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) srow[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                    }
+                    __syncwarp();
+                    if (colok) {
+#pragma unroll(EPI == EPI_LINEAR ? 1 : 4)
+                        for (int i2 = 0; i2 < 4; ++i2) {
+                            const int i = 4 * pass + i2;
+                            const int t = tq + 4 * i;
+                            if (t < p.T) {
+                                const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
+                                const int b = (p.d_stride != 0 && p.T_utt > 0) ? (bt * p.T + t) / p.T_utt : 0;
+                                epilogue_quad<EPI, BF16>(p, v, in[i], kc, (long long)bt * p.T + t, b, col);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---- host side (tensor-map builders live in b2s_tc.cuh) ------------------------------------------------
 template <int EPI, int BF16>
 static int launch_one(const TcP& p, cudaStream_t st) {
@@ -366,6 +549,31 @@ static int launch_one(const TcP& p, cudaStream_t st) {
     if (!configured) {
         B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
+    }
+    if (p.cg2) {
+        static bool configured2 = false;
+        if (!configured2) {
+            B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_cg2_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+            configured2 = true;
+        }
+        const int num_pt = (p.B * p.tiles_m_per_b / 2) * p.tiles_n;
+        const int pairs = num_pt < num_sms() / 2 ? num_pt : num_sms() / 2;
+        cudaLaunchConfig_t cfg2{};
+        cfg2.gridDim = dim3(2 * pairs);
+        cfg2.blockDim = dim3(NTHREADS);
+        cfg2.dynamicSmemBytes = SMEM2_BYTES;
+        cfg2.stream = st;
+        cudaLaunchAttribute attr2[2];
+        attr2[0].id = cudaLaunchAttributeClusterDimension;
+        attr2[0].val.clusterDim.x = 2;
+        attr2[0].val.clusterDim.y = 1;
+        attr2[0].val.clusterDim.z = 1;
+        attr2[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr2[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg2.attrs = attr2;
+        cfg2.numAttrs = 2;
+        B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg2, tc_gemm_cg2_kernel<EPI, BF16>, p));
+        return B2S_OK;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     cudaLaunchConfig_t cfg{};
@@ -393,7 +601,9 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     const int Bm = per_utt ? B : 1, Tm = per_utt ? T : B * T;
     int rc = make_map_act(&p.mapA, A, bf16, a_cols, lda, Tm, Bm, BLOCK_K, BLOCK_M);
     if (rc) return rc;
-    rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, BLOCK_N);
+    static const bool cg1 = getenv("B2S_GEMM_CG1") != nullptr;      // A/B switch: the single-CTA kernel
+    p.cg2 = cg1 ? 0 : 1;
+    rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, p.cg2 ? BLOCK_N / 2 : BLOCK_N);
     if (rc) return rc;
     p.B = Bm; p.T = Tm; p.T_utt = T;
     p.N = N;
@@ -401,6 +611,7 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     p.kb_per_tap = kb_per_tap > 0 ? kb_per_tap : p.num_kb;
     p.dil = dil;
     p.tiles_m_per_b = ceil_div(Tm, BLOCK_M);
+    if (p.cg2) p.tiles_m_per_b = (p.tiles_m_per_b + 1) & ~1;       // whole CTA pairs; a padding tile has no valid row
     p.tiles_n = ceil_div(N, BLOCK_N);
     p.num_tiles = Bm * p.tiles_m_per_b * p.tiles_n;
     return B2S_OK;
