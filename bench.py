@@ -420,6 +420,8 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('B2S_PRECISION', 'bf16'), choices=['fp32', 'bf16', 'fp16'])
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
     ap.add_argument('--k-step', type=int, default=None, help='override K_step (debug only; invalidates the metric)')
+    ap.add_argument('--batch', type=int, default=None, help='override utterances per GPU (sweeps only; not the headline config)')
+    ap.add_argument('--frames', type=int, default=None, help='override frames per utterance (sweeps only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the captured CUDA graph')
     args = ap.parse_args()
@@ -427,6 +429,10 @@ def main():
     if args.k_step:
         w['k_step'] = args.k_step
         w['desc'] += f' [DEBUG K_step={args.k_step}]'
+    if args.batch or args.frames:
+        w['B'] = args.batch or w['B']
+        w['T'] = args.frames or w['T']
+        w['desc'] += f' [SWEEP OVERRIDE B={w["B"]} T={w["T"]}]'
     if args.impl == 'reference':
         run_reference_arm(args, w)
     else:
