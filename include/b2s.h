@@ -192,12 +192,13 @@ int b2s_tc_linear_residual(const void* p_h, const void* W_h, const float* bias, 
 
 /* 16-bit LYNXNet layer helpers (HBM-bound): fused (x + cond + d) -> residual write-back -> LayerNorm with 16-bit
  * cond table in / 16-bit h out (lynxnet.py:76-84, 54), plain LayerNorm (lynxnet.py:151), depthwise conv + activation
- * with 16-bit in / out and fp32 math (lynxnet.py:57-58).  Same argument meaning as the _f32 entry points. */
+ * with 16-bit in / out and fp32 math (lynxnet.py:57-58).  Same argument meaning as the _f32 entry points, except that
+ * b2s_lynx_dwconv_h takes the depthwise weights K-MAJOR: WdwT [ksize][inner] (coalesced loads). */
 int b2s_lynx_prenorm_h(float* x, const void* cond_h, int ld_cond, const float* dvec, int d_stride, const float* gamma,
                        const float* beta, void* h_h, int B, int T, int C, int strong_cond, int bf16, void* stream);
 int b2s_layernorm_h(const float* x, const float* gamma, const float* beta, void* h_h, int rows, int C, int bf16,
                     void* stream);
-int b2s_lynx_dwconv_h(const void* g_h, const float* Wdw, const float* bias, const float* slope, void* p_h, int B, int T,
+int b2s_lynx_dwconv_h(const void* g_h, const float* WdwT, const float* bias, const float* slope, void* p_h, int B, int T,
                       int inner, int ksize, int act, int bf16, void* stream);
 
 #ifdef __cplusplus

@@ -112,59 +112,92 @@ __global__ void __launch_bounds__(256) layernorm_h_kernel(float* __restrict__ x,
     }
 }
 
-// Depthwise conv along time + bias + activation, 16-bit in / out, fp32 math.  Thread = 2 adjacent channels
-// (4-byte accesses, coalesced across the warp), sliding window over a strip of frames, zero padding per utterance.
-constexpr int DWH_TSTRIP = 32;
-constexpr int DWH_MAXK = 31;
+// Depthwise conv along time + bias + activation, 16-bit in / out, fp32 math (lynxnet.py:57-58).
+// Thread = 2 adjacent channels (4-byte accesses, a warp reads 128 contiguous bytes per frame), one block = 256 channels x
+// a strip of DWH_STRIP frames of one utterance.  Per iteration a thread produces G = 8 consecutive output frames from a
+// register window of K+7 input frames (8 x 2 independent FMA chains), then shifts the window by 8 (7.5 moves per output)
+// and takes the 8 new frames that were requested one iteration earlier (memory-level parallelism).  The loop body is
+// ~700 instructions: an earlier version unrolled K-fold (11.5 k instructions) and was instruction-cache bound.
+// Weights are K-MAJOR [K][inner] so that they load coalesced.
+// SiLU / ReLU variants go through ONE out-of-line call (PReLU, the default, is inline): keeps the unrolled body small
+__device__ __noinline__ float2 act2_slow(float2 v, int act) { return make_float2(apply_act(v.x, act), apply_act(v.y, act)); }
 
-template <int BF16>
-__global__ void __launch_bounds__(128) dwconv_h_kernel(const uint16_t* __restrict__ g, const float* __restrict__ Wdw,
-                                                       const float* __restrict__ bias, const float* __restrict__ slope,
-                                                       uint16_t* __restrict__ p, int T, int inner, int ksize, int act) {
+constexpr int DWH_MAXK = 31;
+constexpr int DWH_G = 8;
+constexpr int DWH_STRIP = 128;
+
+template <int K, int BF16>
+__global__ void __launch_bounds__(128, 2) dwconv_h_kernel(const uint16_t* __restrict__ g, const float* __restrict__ WdwT,
+                                                          const float* __restrict__ bias, const float* __restrict__ slope,
+                                                          uint16_t* __restrict__ p, int T, int inner, int act) {
     const int ch = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (ch >= inner) return;
+    constexpr int PAD = K / 2, G = DWH_G, W = K + G - 1;
     const int b = blockIdx.z;
-    const int t0 = blockIdx.y * DWH_TSTRIP;
-    const int pad = ksize / 2;
-    float w0[DWH_MAXK], w1[DWH_MAXK];
+    const int t_begin = blockIdx.y * DWH_STRIP;
+    const int t_end = min(T, t_begin + DWH_STRIP);
+    float2 w[K];
 #pragma unroll
-    for (int k = 0; k < DWH_MAXK; ++k) {
-        w0[k] = k < ksize ? __ldg(Wdw + (long long)ch * ksize + k) : 0.f;
-        w1[k] = k < ksize ? __ldg(Wdw + (long long)(ch + 1) * ksize + k) : 0.f;
-    }
-    const float b0 = __ldg(bias + ch), b1 = __ldg(bias + ch + 1);
-    const float s0 = slope ? __ldg(slope + ch) : 0.f, s1 = slope ? __ldg(slope + ch + 1) : 0.f;
+    for (int k = 0; k < K; ++k) w[k] = __ldg(reinterpret_cast<const float2*>(WdwT + (long long)k * inner + ch));
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + ch));
+    const float2 sl = slope ? __ldg(reinterpret_cast<const float2*>(slope + ch)) : make_float2(0.f, 0.f);
     const uint16_t* gb = g + (long long)b * T * inner + ch;
     uint16_t* pb = p + (long long)b * T * inner + ch;
-    float2 win[DWH_MAXK];
+    auto fetch = [&](int s) -> uint32_t {
+        return (s >= 0 && s < T) ? __ldg(reinterpret_cast<const uint32_t*>(gb + (long long)s * inner)) : 0u;
+    };
+    // window: win[i] = input frame (t0 - PAD + i) for the current group of outputs t0 .. t0+G-1
+    float2 win[W];
 #pragma unroll
-    for (int k = 0; k < DWH_MAXK; ++k) {
-        const int ts = t0 - pad + k;
-        win[k] = (k < ksize && ts >= 0 && ts < T) ? tc::Half16<BF16>::unpack2(*reinterpret_cast<const uint32_t*>(gb + (long long)ts * inner))
-                                                   : make_float2(0.f, 0.f);
-    }
-    for (int i = 0; i < DWH_TSTRIP; ++i) {
-        const int t = t0 + i;
-        if (t >= T) break;
-        float a0 = b0, a1 = b1;
+    for (int i = 0; i < W; ++i) win[i] = tc::Half16<BF16>::unpack2(fetch(t_begin - PAD + i));
+    uint32_t nxt[G];
 #pragma unroll
-        for (int k = 0; k < DWH_MAXK; ++k) {
-            a0 = fmaf(w0[k], win[k].x, a0);
-            a1 = fmaf(w1[k], win[k].y, a1);
+    for (int j = 0; j < G; ++j) nxt[j] = fetch(t_begin - PAD + W + j);
+#pragma unroll 1
+    for (int t0 = t_begin; t0 < t_end; t0 += G) {
+        uint32_t cur[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) cur[j] = nxt[j];
+        if (t0 + G < t_end) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) nxt[j] = fetch(t0 + G - PAD + W + j);
         }
-        float o0, o1;
-        if (act == 0) { o0 = a0 >= 0.f ? a0 : s0 * a0; o1 = a1 >= 0.f ? a1 : s1 * a1; }
-        else { o0 = apply_act(a0, act); o1 = apply_act(a1, act); }
-        *reinterpret_cast<uint32_t*>(pb + (long long)t * inner) = tc::Half16<BF16>::pack2(o0, o1);
+        float2 acc[G];
 #pragma unroll
-        for (int k = 0; k < DWH_MAXK - 1; ++k) win[k] = win[k + 1];
-        const int tn = t + 1 - pad + (ksize - 1);
-        const float2 nv = (tn >= 0 && tn < T) ? tc::Half16<BF16>::unpack2(*reinterpret_cast<const uint32_t*>(gb + (long long)tn * inner))
-                                              : make_float2(0.f, 0.f);
+        for (int j = 0; j < G; ++j) acc[j] = bb;
 #pragma unroll
-        for (int k = 0; k < DWH_MAXK; ++k)
-            if (k == ksize - 1) win[k] = nv;
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                acc[j].x = fmaf(w[k].x, win[j + k].x, acc[j].x);
+                acc[j].y = fmaf(w[k].y, win[j + k].y, acc[j].y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            if (t0 + j < t_end) {
+                float o0, o1;
+                if (act == 0) { o0 = acc[j].x >= 0.f ? acc[j].x : sl.x * acc[j].x; o1 = acc[j].y >= 0.f ? acc[j].y : sl.y * acc[j].y; }
+                else { const float2 o = act2_slow(acc[j], act); o0 = o.x; o1 = o.y; }
+                *reinterpret_cast<uint32_t*>(pb + (long long)(t0 + j) * inner) = tc::Half16<BF16>::pack2(o0, o1);
+            }
+        }
+        // slide the window by G frames
+#pragma unroll
+        for (int i = 0; i < W - G; ++i) win[i] = win[i + G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) win[W - G + j] = tc::Half16<BF16>::unpack2(cur[j]);
     }
+}
+
+template <int K>
+static int launch_dwconv_h(const void* g_h, const float* WdwT, const float* bias, const float* slope, void* p_h, int B, int T,
+                           int inner, int act, int bf16, cudaStream_t st) {
+    dim3 grid(ceil_div(inner / 2, 128), ceil_div(T, DWH_STRIP), B);
+    if (bf16) dwconv_h_kernel<K, 1><<<grid, 128, 0, st>>>((const uint16_t*)g_h, WdwT, bias, slope, (uint16_t*)p_h, T, inner, act);
+    else dwconv_h_kernel<K, 0><<<grid, 128, 0, st>>>((const uint16_t*)g_h, WdwT, bias, slope, (uint16_t*)p_h, T, inner, act);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
 }
 
 }  // namespace b2s
@@ -197,17 +230,21 @@ extern "C" int b2s_layernorm_h(const float* x, const float* gamma, const float* 
     return B2S_OK;
 }
 
-extern "C" int b2s_lynx_dwconv_h(const void* g_h, const float* Wdw, const float* bias, const float* slope, void* p_h, int B,
+extern "C" int b2s_lynx_dwconv_h(const void* g_h, const float* WdwT, const float* bias, const float* slope, void* p_h, int B,
                                  int T, int inner, int ksize, int act, int bf16, void* stream) {
-    B2S_CHECK_ARG(g_h && Wdw && bias && p_h, "b2s_lynx_dwconv_h: null pointer");
+    B2S_CHECK_ARG(g_h && WdwT && bias && p_h, "b2s_lynx_dwconv_h: null pointer");
     B2S_CHECK_ARG(ksize >= 1 && ksize <= DWH_MAXK && (ksize & 1), "b2s_lynx_dwconv_h: kernel size must be odd and <= %d", DWH_MAXK);
     B2S_CHECK_ARG(inner % 2 == 0, "b2s_lynx_dwconv_h: inner must be even");
     B2S_CHECK_ARG(act != 0 || slope, "b2s_lynx_dwconv_h: PReLU needs slope");
     B2S_CHECK_ARG(B < 65536, "b2s_lynx_dwconv_h: B too large");
     if (B <= 0 || T <= 0) return B2S_OK;
-    dim3 grid(ceil_div(inner / 2, 128), ceil_div(T, DWH_TSTRIP), B);
-    if (bf16) dwconv_h_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)g_h, Wdw, bias, slope, (uint16_t*)p_h, T, inner, ksize, act);
-    else dwconv_h_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>((const uint16_t*)g_h, Wdw, bias, slope, (uint16_t*)p_h, T, inner, ksize, act);
-    B2S_CHECK_LAUNCH();
-    return B2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ksize) {          // the window ring is a compile-time structure: one instantiation per (odd) kernel size
+#define B2S_DW_CASE(KK) case KK: return launch_dwconv_h<KK>(g_h, WdwT, bias, slope, p_h, B, T, inner, act, bf16, st);
+        B2S_DW_CASE(1) B2S_DW_CASE(3) B2S_DW_CASE(5) B2S_DW_CASE(7) B2S_DW_CASE(9) B2S_DW_CASE(11) B2S_DW_CASE(13) B2S_DW_CASE(15)
+        B2S_DW_CASE(17) B2S_DW_CASE(19) B2S_DW_CASE(21) B2S_DW_CASE(23) B2S_DW_CASE(25) B2S_DW_CASE(27) B2S_DW_CASE(29) B2S_DW_CASE(31)
+#undef B2S_DW_CASE
+    }
+    set_error("b2s_lynx_dwconv_h: unsupported kernel size %d", ksize);
+    return B2S_ERR_UNSUPPORTED;
 }

@@ -406,6 +406,7 @@ class LYNXNetEngine:
             h = lambda t: t.to(hd).contiguous()
             self.w_in_h, self.w_cond_h, self.w_up_h = h(self.w_in), h(self.w_cond), h(self.w_up)
             self.w_down_h, self.w_fin_h = h(self.w_down), h(self.w_fin)
+            self.w_dw_t = self.w_dw.transpose(1, 2).contiguous()          # [L, k, inner]: k-major for coalesced loads
         self._packed_version = v
 
     def step_table(self, t_values):
@@ -528,7 +529,7 @@ class LYNXNetSessionTC:
             dv, ds = self._dvec(k, l)
             C.lynx_prenorm_h(self.x, self.cond[l], Cc, dv, ds, e.ln_g[l], e.ln_b[l], self.h_h, B, T, Cc, e.strong, bf)
             C.tc_lynx_glu(self.h_h, e.w_up_h[l], e.b_up[l], self.g_h, rows, Cc, inner, bf)
-            C.lynx_dwconv_h(self.g_h, e.w_dw[l], e.b_dw[l], None if e.slope is None else e.slope[l], self.p_h, B, T, inner,
+            C.lynx_dwconv_h(self.g_h, e.w_dw_t[l], e.b_dw[l], None if e.slope is None else e.slope[l], self.p_h, B, T, inner,
                             e.ksize, e.act, bf)
             C.tc_linear_residual(self.p_h, e.w_down_h[l], e.b_down[l], self.x, rows, Cc, inner, bf)
         C.layernorm_h(self.x, e.norm_g, e.norm_b, self.h_h, rows, Cc, bf)
