@@ -183,6 +183,18 @@ int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, const void* c
                          const float* dvec, int d_stride, const int* dilations_host, int L, int B, int T, int C, int* flags,
                          int bf16, void* stream);
 
+/* ONE launch per denoiser evaluation (wavenet.py:75-107 without the step-embedding MLP, which is hoisted into the step
+ * table): b2s_tc_wavenet_stack plus, inside the same persistent kernel, the stem x = relu(W_in x_in + b_in), y_0 = x + d_0
+ * (wavenet.py:86-88, :36) before the first layer and the head out = W_fin relu(W_sp skip/sqrt(L) + b_sp) + b_fin
+ * (wavenet.py:96-99) after the last one (the skip sum and the hidden tile go through shared memory, never through HBM).
+ *   xin_h [B*T, MF] 16-bit sampler state; Win_h [C, ld_win >= MF]; Wsp_h [C, C]; Wfin_h [MF, C]; out [B*T, MF] fp32.
+ * MF = in_dims * n_feats, a multiple of 8, <= 256.  Same residency rule as b2s_tc_wavenet_stack. */
+int b2s_tc_wavenet_denoiser(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, void* y0_h, void* y1_h,
+                            const void* Wd_h, const void* cond_h, int64_t cond_layer_stride, const void* Wo_h, const float* bo,
+                            float* x, float* skip, const float* dvec, int d_stride, const int* dilations_host, int L,
+                            const void* Wsp_h, const float* b_sp, const void* Wfin_h, const float* b_fin, float* out, int B, int T,
+                            int C, int* flags, int bf16, void* stream);
+
 /* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
  * down-projection with the residual add into the fp32 stream. */
 int b2s_tc_lynx_glu(const void* h_h, const void* W_h, const float* bias, void* g_h, int rows, int C, int inner, int bf16,

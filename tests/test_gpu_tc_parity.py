@@ -201,13 +201,13 @@ def test_config4_variance_predictors_tensor_core(acc, precision, dev):
     assert err <= (2e-4 * scale if precision == 'bf16' else 5e-5 * max(scale, 1.0)), (acc, precision, err, scale)
 
 
-def _bf16_backbone(dev, stack, L=4):
+def _bf16_backbone(dev, stack, L=4, fuse_io=False, in_dims=128, n_feats=1):
     import xiaoicesing_io_b200 as P
     from oracle import weights as OW
-    cfg = OD.WaveNetCfg(num_layers=L, num_channels=256, dilation_cycle_length=4)
+    cfg = OD.WaveNetCfg(in_dims=in_dims, n_feats=n_feats, num_layers=L, num_channels=256, dilation_cycle_length=4)
     P.hparams.clear()
-    P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision='bf16', b2s_stack=stack)
-    net = P.build_backbone(cfg.in_dims, 1, 'wavenet', dict(num_layers=L, num_channels=256, dilation_cycle_length=4))
+    P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision='bf16', b2s_stack=stack, b2s_fuse_io=fuse_io)
+    net = P.build_backbone(cfg.in_dims, n_feats, 'wavenet', dict(num_layers=L, num_channels=256, dilation_cycle_length=4))
     net.load_state_dict(OW.make_state_dict(cfg, seed=0, sigma_w=0.01), strict=True)
     return net.to(dev).eval()
 
@@ -226,3 +226,18 @@ def test_stack_kernel_grouping_and_fallback_match_per_layer_path(B, T, dev):
         b = _bf16_backbone(dev, stack=False)(spec, t.to(dev), cond)
         assert bool(torch.isfinite(a).all())
         assert torch.equal(a, b), (B, T, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize('B,T,in_dims,n_feats', [(16, 690, 128, 1), (30, 300, 128, 1), (3, 257, 64, 1), (2, 130, 24, 2), (1, 50, 128, 1)])
+def test_one_launch_denoiser_matches_separate_stem_and_head(B, T, in_dims, n_feats, dev):
+    """b2s_fuse_io: stem and head run inside the persistent stack kernel (one launch per evaluation).  Same operands, same
+    accumulation order -> the result must equal the stem GEMM + stack kernel + two head GEMMs bit for bit, for 128 / 64 /
+    48 packed bins, several utterance groups and per-utterance diffusion steps."""
+    g = torch.Generator().manual_seed(B * 11 + T)
+    spec = torch.randn((B, n_feats, in_dims, T), generator=g).to(dev)
+    cond = torch.randn((B, 256, T), generator=g).to(dev)
+    for t in (torch.tensor([437.0]), torch.arange(B, dtype=torch.float32) * 13 + 5):
+        a = _bf16_backbone(dev, True, fuse_io=True, in_dims=in_dims, n_feats=n_feats)(spec, t.to(dev), cond)
+        b = _bf16_backbone(dev, True, fuse_io=False, in_dims=in_dims, n_feats=n_feats)(spec, t.to(dev), cond)
+        assert bool(torch.isfinite(a).all())
+        assert torch.equal(a, b), (B, T, in_dims, float((a - b).abs().max()))

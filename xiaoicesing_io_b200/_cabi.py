@@ -38,6 +38,8 @@ _SIGNATURES = {
     'b2s_tc_wavenet_layer': [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_stack': [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _i, _i, _i, _vp,
                              _i, _vp],
+    'b2s_tc_wavenet_denoiser': [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i,
+                                _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_lynx_prenorm_h': [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -212,6 +214,16 @@ def tc_wavenet_stack(y0_h, y1_h, Wd_h, cond_h, ld_cond, cond_layer_stride, Wo_h,
     check(lib.b2s_tc_wavenet_stack(ptr(y0_h), ptr(y1_h), ptr(Wd_h), ptr(cond_h), ld_cond, cond_layer_stride, ptr(Wo_h),
                                    ptr(bo), ptr(x), ptr(skip), ptr(skip_h), ptr(dvec), d_stride, dil, L, B, T, C,
                                    ptr(flags), int(bf16), stream_ptr()), 'b2s_tc_wavenet_stack')
+
+
+def tc_wavenet_denoiser(xin_h, MF, Win_h, ld_win, b_in, y0_h, y1_h, Wd_h, cond_h, cond_layer_stride, Wo_h, bo, x, skip, dvec,
+                        d_stride, dilations, Wsp_h, b_sp, Wfin_h, b_fin, out, B, T, C, flags, bf16):
+    L = len(dilations)
+    dil = (_i * L)(*dilations)
+    check(lib.b2s_tc_wavenet_denoiser(ptr(xin_h), MF, ptr(Win_h), ld_win, ptr(b_in), ptr(y0_h), ptr(y1_h), ptr(Wd_h), ptr(cond_h),
+                                      cond_layer_stride, ptr(Wo_h), ptr(bo), ptr(x), ptr(skip), ptr(dvec), d_stride, dil, L,
+                                      ptr(Wsp_h), ptr(b_sp), ptr(Wfin_h), ptr(b_fin), ptr(out), B, T, C, ptr(flags), int(bf16),
+                                      stream_ptr()), 'b2s_tc_wavenet_denoiser')
 
 
 def tc_lynx_glu(h_h, W_h, bias, g_h, rows, C, inner, bf16):

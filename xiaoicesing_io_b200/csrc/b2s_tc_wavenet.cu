@@ -20,6 +20,7 @@
 // the tail of layer l; dependent global data is only touched after griddepcontrol.wait.
 #include "b2s_tc.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 
 namespace b2s {
@@ -688,6 +689,13 @@ struct __align__(64) StackP {
     int* flags;                                           // [B * tiles_per_b], zero before the launch
     int dbg;                                              // profiling experiments only (B2S_STACK_DBG): results are WRONG when != 0
     unsigned long long* tlog;                             // optional phase timestamps of CTA 2 (B2S_STACK_TLOG): [L][16] globaltimer ns
+    // ---- whole denoiser in one launch (fuse = 1): stem (input projection, wavenet.py:86-88) before the stack and head
+    //      (skip sum -> skip_projection -> ReLU -> output_projection, wavenet.py:96-99) after it
+    int fuse, MF, kb_in;                                  // MF = in_dims * n_feats; kb_in = K slabs of the stem GEMM
+    CUtensorMap mapXin, mapWin, mapWsp, mapWfin;
+    const float* b_in; const float* b_sp; const float* b_fin;
+    float alpha_head;                                     // 1 / sqrt(L)
+    float* out;                                           // [rows, MF] fp32
 };
 
 // phase timestamps of CTA 2 for scripts/stack_timeline.py; compiled in only with -DB2S_TLOG (B2S_BUILD_TLOG=1 python _build.py)
@@ -720,7 +728,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
     uint64_t* accb = empty + STAGES;                      // [4]: G1 half 0, G1 half 1, G2 residual, G2 skip
     uint64_t* zready = accb + 4;                          // [2]
     uint64_t* tfree = zready + 2;                         // [2]: EPI2 has drained TMEM half h
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tfree + 2);
+    uint64_t* stemb = tfree + 2;                          // stem accumulator complete
+    uint64_t* stemfree = stemb + 1;                       // stem epilogue has drained TMEM columns [0,256)
+    uint64_t* hz = stemfree + 1;                          // [2]: head operand tiles (skip sum, hidden) are in the z buffer
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hz + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -735,6 +746,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
         prefetch_tmap(&p.mapY[1]);
         prefetch_tmap(&p.mapWd);
         prefetch_tmap(&p.mapWo);
+        if (p.fuse) {
+            prefetch_tmap(&p.mapXin);
+            prefetch_tmap(&p.mapWin);
+            prefetch_tmap(&p.mapWsp);
+            prefetch_tmap(&p.mapWfin);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -745,7 +762,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
         for (int i = 0; i < 2; ++i) {
             mbar_init(&zready[i], EPI_WARPS);
             mbar_init(&tfree[i], EPI_WARPS);
+            mbar_init(&hz[i], EPI_WARPS);
         }
+        mbar_init(stemb, 1);
+        mbar_init(stemfree, EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -762,6 +782,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
+        if (p.fuse) {                                       // stem: A = x_in tile, B = input_projection weights
+            for (int kb = 0; kb < p.kb_in; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sa = stages + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_2d_mcast(sa + A_BYTES + rank * BH_BYTES, &p.mapWin, &full[stage], kb * BK, rank * (BN / 2), MASK);
+                    tma_load_3d(sa, &p.mapXin, &full[stage], kb * BK, t0, b);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
         for (int l = 0; l < p.L; ++l) {
             const int dil = p.dil[l];
             if (lane == 0 && l + 1 < p.L && t0 < p.T) {
@@ -780,12 +813,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                         const int tap = kb / (C / BK), c0 = (kb - tap * (C / BK)) * BK;
                         mbar_expect_tx(&full[stage], STAGE_BYTES);
                         tma_load_3d_mcast(sb + rank * BH_BYTES, &p.mapWd, &full[stage], kb * BK, h * BN + rank * (BN / 2), l, MASK);
-                        if (f == 0 && l > 0 && t0 < p.T) {
+                        if (f == 0 && l + p.fuse > 0 && t0 < p.T) {
                             // y_l of this tile and of its neighbours (dilation halo) must be complete
                             const int* fl = p.flags + b * p.tiles_per_b;
-                            if (ti > 0) wait_flag(fl + ti - 1, l);
-                            wait_flag(fl + ti, l);
-                            if ((ti + 1) * BM < p.T) wait_flag(fl + ti + 1, l);
+                            const int want = l + p.fuse;         // number of finished y buffers (the stem's y_0 counts when fused)
+                            if (ti > 0) wait_flag(fl + ti - 1, want);
+                            wait_flag(fl + ti, want);
+                            if ((ti + 1) * BM < p.T) wait_flag(fl + ti + 1, want);
                             fence_proxy_async_all();
                         }
                         if (f == 0) TLOG(0);                               // neighbours' y ready, first A load issued
@@ -800,16 +834,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (p.fuse) {                                       // head: skip_projection then output_projection weights (B only)
+            for (int i = 0; i < 2 * G2_KB; ++i) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sb = stages + stage * STAGE_BYTES + A_BYTES;
+                    mbar_expect_tx(&full[stage], B_BYTES);
+                    tma_load_2d_mcast(sb + rank * BH_BYTES, i < G2_KB ? &p.mapWsp : &p.mapWfin, &full[stage], (i % G2_KB) * BK,
+                                      rank * (BN / 2), MASK);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = make_idesc_f16(BM, BN, BF16);
         int stage = 0;
         uint32_t phase = 0;
+        auto mma_block = [&](uint32_t d_tmem, uint32_t a_addr, int kb, uint64_t* done) {
+            // one K slab (4 MMAs of K = 16) with the B operand of the current stage; frees the stage, optionally signals `done`
+            if (lane == 0) {
+                const uint32_t b_addr = smem_u32(stages + stage * STAGE_BYTES) + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k)
+                    umma_ss(d_tmem, make_sw128_kmajor_desc(a_addr + k * (UK * 2)), make_sw128_kmajor_desc(b_addr + k * (UK * 2)), idesc,
+                            (kb | k) != 0);
+                umma_commit_mcast(&empty[stage], MASK);
+                if (done) umma_commit(done);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        if (p.fuse) {                                       // stem GEMM -> TMEM columns [0,256)
+            for (int kb = 0; kb < p.kb_in; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                mma_block(tmem_base, smem_u32(stages + stage * STAGE_BYTES), kb, kb == p.kb_in - 1 ? stemb : nullptr);
+            }
+        }
         for (int l = 0; l < p.L; ++l) {
             const uint32_t par = l & 1;
             for (int h = 0; h < 2; ++h) {
                 if (l > 0) {                                   // EPI2 of the previous layer has drained these columns
                     mbar_wait(&tfree[h], par ^ 1);
+                    tc_fence_after();
+                } else if (p.fuse && h == 0) {                 // the stem epilogue has drained columns [0,256)
+                    mbar_wait(stemfree, 0);
                     tc_fence_after();
                 }
                 const uint32_t d_tmem = tmem_base + h * BN;
@@ -854,6 +925,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 }
             }
         }
+        if (p.fuse) {
+            // head GEMMs, A operand = the z buffer: skip sum (written by the last layer's EPI2-skip) then the hidden tile
+            const uint32_t plast = (p.L - 1) & 1, pl = p.L & 1;
+            (void)pl;
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(&tfree[g], plast);                // the last layer's EPI2 has drained this TMEM half
+                mbar_wait(&hz[g], 0);                       // and the A tile is in shared memory
+                tc_fence_after();
+                for (int kb = 0; kb < G2_KB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    mma_block(tmem_base + g * BN, smem_u32(zs + kb * A_BYTES), kb, kb == G2_KB - 1 ? &accb[g] : nullptr);
+                }
+            }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue: 8 warps, warp e -> lane quarter e&3, chunks j with (j&1) == e>>2 ===========
         const int e = warp - 4, q = e & 3, sub = e >> 2;
@@ -874,6 +960,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
         float* xrow = p.x + rowoff;
         float* srow_g = p.skip + rowoff;
         uint16_t* shrow = reinterpret_cast<uint16_t*>(p.skip_h) + rowoff;
+
+        // z-buffer address of this lane's 4 channels (coalesced layout) for row 4i + rsub of the warp: used by the fused head
+        auto z_addr_quad = [&](int i, int col) -> uint32_t {
+            const int rt = q * 32 + 4 * i + rsub;
+            return smem_u32(zs) + (col >> 6) * A_BYTES + (rt >> 3) * 1024 + (rt & 7) * 128 + ((((col & 63) >> 3) ^ (rt & 7)) << 4) + (col & 4) * 2;
+        };
+        if (p.fuse) {
+            // ---- stem epilogue: x = relu(acc + b_in) (fp32), y_0 = x + d_0 (16-bit), then the tile flag ----
+            const float* d0 = p.dvec + (long long)b * p.d_stride;
+            uint16_t* y0 = reinterpret_cast<uint16_t*>(p.ybuf[0]) + rowoff;
+            mbar_wait(stemb, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 2 * jj + sub, col = j * 32 + cl;
+                float acc[32];
+                tmem_ld32(taddr + j * 32, acc);
+                const float4 bias = __ldg(reinterpret_cast<const float4*>(p.b_in + col));
+                const float4 d = __ldg(reinterpret_cast<const float4*>(d0 + col));
+                tmem_ld_wait();
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((lane >> 4) == pass) {
+                        float4* srow = reinterpret_cast<float4*>(stg + (lane & 15) * STG_LD);
+#pragma unroll
+                        for (int c2 = 0; c2 < 8; ++c2)
+                            srow[c2] = make_float4(acc[4 * c2], acc[4 * c2 + 1], acc[4 * c2 + 2], acc[4 * c2 + 3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2) {
+                        const int i = 4 * pass + i2;
+                        if (vmask >> i & 1) {
+                            const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
+                            const float4 xv = make_float4(fmaxf(v.x + bias.x, 0.f), fmaxf(v.y + bias.y, 0.f), fmaxf(v.z + bias.z, 0.f),
+                                                          fmaxf(v.w + bias.w, 0.f));
+                            *reinterpret_cast<float4*>(xrow + j * 32 + i * 4 * C) = xv;
+                            uint2 yv;
+                            yv.x = Half16<BF16>::pack2(xv.x + d.x, xv.y + d.y);
+                            yv.y = Half16<BF16>::pack2(xv.z + d.z, xv.w + d.w);
+                            *reinterpret_cast<uint2*>(y0 + j * 32 + i * 4 * C) = yv;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stemfree);
+            named_bar_sync(1, EPI_WARPS * 32);
+            if (e == 0 && lane == 0) {
+                __threadfence();
+                st_release_gpu(p.flags + blockIdx.x, 1);
+            }
+        }
 
 #pragma unroll 1
         for (int l = 0; l < p.L; ++l) {
@@ -992,11 +1133,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                                 } else {
                                     const float4 s2 = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
                                     if (!(p.dbg & 32)) *reinterpret_cast<float4*>(so + i * 4 * C) = s2;
-                                    if (last && p.skip_h) {
+                                    if (last && (p.skip_h || p.fuse)) {
                                         uint2 sv;
                                         sv.x = Half16<BF16>::pack2(s2.x, s2.y);
                                         sv.y = Half16<BF16>::pack2(s2.z, s2.w);
-                                        *reinterpret_cast<uint2*>(sho + i * 4 * C) = sv;
+                                        if (p.fuse) {       // the head GEMM's A operand: straight into the (now idle) z buffer
+                                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(z_addr_quad(i, j * 32 + cl)), "r"(sv.x), "r"(sv.y) : "memory");
+                                        } else {
+                                            *reinterpret_cast<uint2*>(sho + i * 4 * C) = sv;
+                                        }
                                     }
                                 }
                             }
@@ -1017,10 +1162,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                         named_bar_sync(1, EPI_WARPS * 32);
                         if (e == 0 && lane == 0) {
                             __threadfence();
-                            st_release_gpu(p.flags + blockIdx.x, l + 1);
+                            st_release_gpu(p.flags + blockIdx.x, l + 1 + p.fuse);
                         }
+                    } else if (last && p.fuse) {
+                        fence_proxy_async_smem();                   // skip-sum tile (generic-proxy writes) -> tensor core
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&hz[0]);
                     }
                     if (e == 0) TLOG(8 + 2 * g);                          // EPI2 half g done, flag released
+                }
+            }
+        }
+        if (p.fuse) {
+            const uint32_t pl = p.L & 1;
+            // ---- EPI3 (thread = frame row): hidden = relu(alpha * acc + b_sp) -> 16-bit, back into the z buffer ----
+            mbar_wait(&accb[0], pl);
+            tc_fence_after();
+#pragma unroll 1
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 2 * jj + sub;
+                float acc[32];
+                tmem_ld32(taddr + j * 32, acc);
+                float4 bs[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bs[i] = __ldg(reinterpret_cast<const float4*>(p.b_sp + j * 32 + 4 * i));
+                tmem_ld_wait();
+                uint32_t hp[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float h0 = fmaxf(fmaf(p.alpha_head, acc[4 * i], bs[i].x), 0.f), h1 = fmaxf(fmaf(p.alpha_head, acc[4 * i + 1], bs[i].y), 0.f);
+                    const float h2 = fmaxf(fmaf(p.alpha_head, acc[4 * i + 2], bs[i].z), 0.f), h3 = fmaxf(fmaf(p.alpha_head, acc[4 * i + 3], bs[i].w), 0.f);
+                    hp[2 * i] = valid ? Half16<BF16>::pack2(h0, h1) : 0u;
+                    hp[2 * i + 1] = valid ? Half16<BF16>::pack2(h2, h3) : 0u;
+                }
+                // 32 hidden channels [32j, +32) of this row: K slab j/2, 16-byte chunks 4(j%2) .. 4(j%2)+3
+                const uint32_t slab = zrow + (j >> 1) * A_BYTES;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                    st_shared_u4(slab + (((4 * (j & 1) + c4) ^ sw) << 4), make_uint4(hp[4 * c4], hp[4 * c4 + 1], hp[4 * c4 + 2], hp[4 * c4 + 3]));
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hz[1]);
+            // ---- EPI4 (coalesced layout): out = acc + b_fin -> fp32 [rows, MF] ----
+            mbar_wait(&accb[1], pl);
+            tc_fence_after();
+            float* orow = p.out + ((long long)b * p.T + tq) * p.MF + cl;
+#pragma unroll 1
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 2 * jj + sub, col = j * 32 + cl;
+                if (j * 32 >= p.MF) break;
+                float acc[32];
+                tmem_ld32(taddr + BN + j * 32, acc);
+                const float4 bias = col < p.MF ? __ldg(reinterpret_cast<const float4*>(p.b_fin + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                tmem_ld_wait();
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((lane >> 4) == pass) {
+                        float4* srow = reinterpret_cast<float4*>(stg + (lane & 15) * STG_LD);
+#pragma unroll
+                        for (int c2 = 0; c2 < 8; ++c2)
+                            srow[c2] = make_float4(acc[4 * c2], acc[4 * c2 + 1], acc[4 * c2 + 2], acc[4 * c2 + 3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2) {
+                        const int i = 4 * pass + i2;
+                        if ((vmask >> i & 1) && col < p.MF) {
+                            const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
+                            *reinterpret_cast<float4*>(orow + j * 32 + (long long)i * 4 * p.MF) =
+                                make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -1486,10 +1701,15 @@ extern "C" void b2s_debug_set_stack_tlog(void* buf) { g_tlog = (unsigned long lo
 
 extern "C" int b2s_tc_wavenet_stack_max_tiles(void) { return num_sms(); }
 
-extern "C" int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, const void* cond_h, int ld_cond,
-                                    int64_t cond_layer_stride, const void* Wo_h, const float* bo, float* x, float* skip,
-                                    void* skip_h, const float* dvec, int d_stride, const int* dilations_host, int L, int B,
-                                    int T, int C, int* flags, int bf16, void* stream) {
+struct DenoiserIO {            // stem / head operands of b2s_tc_wavenet_denoiser (all NULL for the plain stack)
+    const void* xin_h; int MF; const void* Win_h; int ld_win; const float* b_in;
+    const void* Wsp_h; const float* b_sp; const void* Wfin_h; const float* b_fin; float* out;
+};
+
+static int stack_impl(void* y0_h, void* y1_h, const void* Wd_h, const void* cond_h, int ld_cond, int64_t cond_layer_stride,
+                      const void* Wo_h, const float* bo, float* x, float* skip, void* skip_h, const float* dvec, int d_stride,
+                      const int* dilations_host, int L, int B, int T, int C, int* flags, int bf16, void* stream,
+                      const DenoiserIO* io) {
     B2S_CHECK_ARG(y0_h && y1_h && Wd_h && cond_h && Wo_h && bo && x && skip && dvec && dilations_host && flags,
                   "b2s_tc_wavenet_stack: null pointer");
     if (C != ws::C) {
@@ -1527,9 +1747,46 @@ extern "C" int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, co
     p.cond = cond_h; p.ldc = ld_cond; p.cond_lstride = cond_layer_stride; p.bo = bo;
     p.x = x; p.ybuf[0] = y0_h; p.ybuf[1] = y1_h; p.skip = skip; p.skip_h = skip_h;
     p.dvec = dvec; p.d_stride = d_stride; p.flags = flags;
+    if (io) {
+        B2S_CHECK_ARG(io->xin_h && io->Win_h && io->b_in && io->Wsp_h && io->b_sp && io->Wfin_h && io->b_fin && io->out,
+                      "b2s_tc_wavenet_denoiser: null pointer");
+        B2S_CHECK_ARG(io->MF > 0 && io->MF <= ws::BN && io->MF % 8 == 0 && io->ld_win % 8 == 0,
+                      "b2s_tc_wavenet_denoiser: in_dims*n_feats must be a multiple of 8 and <= %d (got %d)", ws::BN, io->MF);
+        B2S_CHECK_ARG(al16(io->xin_h) && al16(io->Win_h) && al16(io->b_in) && al16(io->Wsp_h) && al16(io->b_sp) && al16(io->Wfin_h) &&
+                          al16(io->b_fin) && al16(io->out), "b2s_tc_wavenet_denoiser: misaligned pointer");
+        p.fuse = 1; p.MF = io->MF; p.kb_in = ceil_div(io->MF, ws::BK);
+        rc = make_map_act(&p.mapXin, io->xin_h, bf16, io->MF, io->MF, T, B, ws::BK, ws::BM);
+        if (rc) return rc;
+        rc = make_map_w(&p.mapWin, io->Win_h, bf16, io->MF, C, io->ld_win, ws::BK, ws::BN / 2);
+        if (rc) return rc;
+        rc = make_map_w(&p.mapWsp, io->Wsp_h, bf16, C, C, C, ws::BK, ws::BN / 2);
+        if (rc) return rc;
+        rc = make_map_w(&p.mapWfin, io->Wfin_h, bf16, C, io->MF, C, ws::BK, ws::BN / 2);
+        if (rc) return rc;
+        p.b_in = io->b_in; p.b_sp = io->b_sp; p.b_fin = io->b_fin; p.out = io->out;
+        p.alpha_head = 1.0f / sqrtf((float)L);
+    }
     static const int dbg = getenv("B2S_STACK_DBG") ? atoi(getenv("B2S_STACK_DBG")) : 0;
     p.dbg = dbg;
     p.tlog = g_tlog;
-    if (cg2) return bf16 ? ws2::launch_stack_cg2<1>(p, grid, (cudaStream_t)stream) : ws2::launch_stack_cg2<0>(p, grid, (cudaStream_t)stream);
+    if (cg2 && !io) return bf16 ? ws2::launch_stack_cg2<1>(p, grid, (cudaStream_t)stream) : ws2::launch_stack_cg2<0>(p, grid, (cudaStream_t)stream);
     return bf16 ? ws::launch_stack<1>(p, grid, (cudaStream_t)stream) : ws::launch_stack<0>(p, grid, (cudaStream_t)stream);
+}
+
+extern "C" int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, const void* cond_h, int ld_cond,
+                                    int64_t cond_layer_stride, const void* Wo_h, const float* bo, float* x, float* skip,
+                                    void* skip_h, const float* dvec, int d_stride, const int* dilations_host, int L, int B,
+                                    int T, int C, int* flags, int bf16, void* stream) {
+    return stack_impl(y0_h, y1_h, Wd_h, cond_h, ld_cond, cond_layer_stride, Wo_h, bo, x, skip, skip_h, dvec, d_stride,
+                      dilations_host, L, B, T, C, flags, bf16, stream, nullptr);
+}
+
+extern "C" int b2s_tc_wavenet_denoiser(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, void* y0_h,
+                                       void* y1_h, const void* Wd_h, const void* cond_h, int64_t cond_layer_stride,
+                                       const void* Wo_h, const float* bo, float* x, float* skip, const float* dvec, int d_stride,
+                                       const int* dilations_host, int L, const void* Wsp_h, const float* b_sp, const void* Wfin_h,
+                                       const float* b_fin, float* out, int B, int T, int C, int* flags, int bf16, void* stream) {
+    DenoiserIO io{xin_h, MF, Win_h, ld_win, b_in, Wsp_h, b_sp, Wfin_h, b_fin, out};
+    return stack_impl(y0_h, y1_h, Wd_h, cond_h, 2 * C, cond_layer_stride, Wo_h, bo, x, skip, nullptr, dvec, d_stride, dilations_host,
+                      L, B, T, C, flags, bf16, stream, &io);
 }

@@ -258,6 +258,20 @@ class WaveNetSessionTC:
         e = self.eng
         B, T, rows, Cc, L, MF, bf = self.B, self.T, self.rows, e.C, e.L, e.MF, e.bf16
         C.cast_h(x_in, self.xin_h, bf)
+        if self.stack_group and hparams.get('b2s_fuse_io', True) and MF <= 256:
+            # ONE launch per utterance group: stem + residual stack + head inside the persistent kernel
+            self.flags.zero_()
+            LC = L * Cc
+            dv = self.dtab.reshape(-1) if self.per_row_t else self.dtab[k]
+            for gi, b0 in enumerate(range(0, B, self.stack_group)):
+                b1 = min(B, b0 + self.stack_group)
+                r0 = b0 * T
+                tab = self.cond_groups[gi]
+                C.tc_wavenet_denoiser(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, self.y_h[r0:], self.y2_h[r0:],
+                                      e.w_dil_h, tab, tab.shape[1] * 2 * Cc, e.w_out_h, e.b_out, self.x[r0:], self.skip[r0:],
+                                      dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0, e.dilations,
+                                      e.w_sp_h, e.b_sp, e.w_fin_h, e.b_fin, out[r0:], b1 - b0, T, Cc, self.flags[b0 * self.tpb:], bf)
+            return
         d0, ds = self._dvec(k, 0)
         C.tc_linear(self.xin_h, MF, rows, T, e.w_in_h, e.w_in_h.shape[1], e.b_in, Cc, MF, bf, act=C.ACT_RELU,
                     out_f32=self.x, ldo=Cc, y_h=self.y_h, ldy=Cc, dvec=d0, d_stride=ds)
@@ -293,6 +307,8 @@ class WaveNetSessionTC:
 
     @property
     def launches_per_eval(self) -> int:
+        if self.stack_group and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256:
+            return 2 + -(-self.B // self.stack_group)              # cast, flag reset, one denoiser launch per utterance group
         if self.stack_group:
             return 2 + 1 + -(-self.B // self.stack_group) + 2      # cast, stem, flag reset, stack launches, 2 head GEMMs
         return 2 + (1 if self.fused else 2) * self.eng.L + 2
