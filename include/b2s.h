@@ -124,6 +124,8 @@ int b2s_linear_residual_f32(const float* p, const float* W, const float* bias, f
 
 /* out = fp32 -> 16-bit cast (feeds the TMA-staged A operands; n elements) */
 int b2s_cast_f32_h(const float* in, void* out_h, int64_t n, int bf16, void* stream);
+/* same, and zeroes `flags[0..n_flags)` (the tile flags of b2s_tc_wavenet_stack / _denoiser) in the same launch */
+int b2s_cast_f32_h_reset(const float* in, void* out_h, int64_t n, int* flags, int n_flags, int bf16, void* stream);
 
 /* Same contract as b2s_linear_f32 with 16-bit A [rows, K] / W [N, K]:
  *   v = act(alpha * A.W^T + bias);  out_f32 (nullable) <- v;  out_h (nullable) <- v;

@@ -30,6 +30,7 @@ _SIGNATURES = {
     'b2s_linear_residual_f32': [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     # 16-bit tensor-core path
     'b2s_cast_f32_h': [_vp, _vp, _i64, _i, _vp],
+    'b2s_cast_f32_h_reset': [_vp, _vp, _i64, _vp, _i, _i, _vp],
     'b2s_tc_linear': [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp],
     'b2s_tc_cond_table': [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_cond_table_tiled': [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
@@ -165,8 +166,13 @@ def linear_residual(p, W, bias, x, rows, C, inner):
 HALF_DTYPES = {'bf16': torch.bfloat16, 'fp16': torch.float16}
 
 
-def cast_h(inp, out, bf16):
-    check(lib.b2s_cast_f32_h(ptr(inp), ptr(out), inp.numel(), int(bf16), stream_ptr()), 'b2s_cast_f32_h')
+def cast_h(inp, out, bf16, reset_flags=None):
+    """fp32 -> 16-bit cast; ``reset_flags`` (int32 tensor) is zeroed in the same launch."""
+    if reset_flags is None:
+        check(lib.b2s_cast_f32_h(ptr(inp), ptr(out), inp.numel(), int(bf16), stream_ptr()), 'b2s_cast_f32_h')
+    else:
+        check(lib.b2s_cast_f32_h_reset(ptr(inp), ptr(out), inp.numel(), ptr(reset_flags), reset_flags.numel(), int(bf16),
+                                       stream_ptr()), 'b2s_cast_f32_h_reset')
 
 
 def tc_linear(A, lda, rows, T, W, ldw, bias, N, K, bf16, alpha=1.0, act=ACT_NONE, out_f32=None, ldo=0, out_h=None,

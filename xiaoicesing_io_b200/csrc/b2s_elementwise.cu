@@ -1,6 +1,7 @@
 // HBM-bound helper kernels of the sampling path: layout transposes, the sampler update
 // (linear combination), the sinusoidal step embedding, LayerNorm(+cond/step add) and the LYNXNet
 // depthwise convolution.  All fp32, vectorised, grid sized from the problem (grid-stride where useful).
+#include <stdlib.h>
 #include "b2s_common.cuh"
 
 #include <string.h>
@@ -48,6 +49,9 @@ struct LinCombArgs {
 
 template <int NS>
 __global__ void __launch_bounds__(256) lincomb_kernel(const LinCombArgs a) {
+    // programmatic dependent launch: overlap this kernel's launch with the tail of its predecessor
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     float c[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) c[i] = __ldg(a.coef + i);
@@ -215,18 +219,28 @@ extern "C" int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host
     a.dst = dst; a.coef = coef; a.n_src = n_src; a.n = n; a.n4 = n / 4;
     long long want = (a.n4 + 255) / 256;
     int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const bool ew_pdl = getenv("B2S_EW_PDL") != nullptr && atoi(getenv("B2S_EW_PDL")) != 0;
+    cfg.numAttrs = ew_pdl ? 1 : 0;
+    cudaError_t err;
     switch (n_src) {
-        case 1: lincomb_kernel<1><<<blocks, 256, 0, st>>>(a); break;
-        case 2: lincomb_kernel<2><<<blocks, 256, 0, st>>>(a); break;
-        case 3: lincomb_kernel<3><<<blocks, 256, 0, st>>>(a); break;
-        case 4: lincomb_kernel<4><<<blocks, 256, 0, st>>>(a); break;
-        case 5: lincomb_kernel<5><<<blocks, 256, 0, st>>>(a); break;
-        case 6: lincomb_kernel<6><<<blocks, 256, 0, st>>>(a); break;
-        case 7: lincomb_kernel<7><<<blocks, 256, 0, st>>>(a); break;
-        default: lincomb_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+        case 1: err = cudaLaunchKernelEx(&cfg, lincomb_kernel<1>, a); break;
+        case 2: err = cudaLaunchKernelEx(&cfg, lincomb_kernel<2>, a); break;
+        case 3: err = cudaLaunchKernelEx(&cfg, lincomb_kernel<3>, a); break;
+        case 4: err = cudaLaunchKernelEx(&cfg, lincomb_kernel<4>, a); break;
+        case 5: err = cudaLaunchKernelEx(&cfg, lincomb_kernel<5>, a); break;
+        case 6: err = cudaLaunchKernelEx(&cfg, lincomb_kernel<6>, a); break;
+        case 7: err = cudaLaunchKernelEx(&cfg, lincomb_kernel<7>, a); break;
+        default: err = cudaLaunchKernelEx(&cfg, lincomb_kernel<8>, a); break;
     }
-    B2S_CHECK_LAUNCH();
+    B2S_CHECK_CUDA(err);
     return B2S_OK;
 }
 

@@ -1,11 +1,18 @@
 // 16-bit side of the elementwise helpers: fp32 -> bf16/fp16 casts that feed the TMA-staged
 // tensor-core operands (HBM-bound, vectorised, grid-stride).
+#include <stdlib.h>
 #include "b2s_tc.cuh"
 
 namespace b2s {
 
 template <int BF16>
-__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n) {
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n,
+                                                   int* __restrict__ zero, int nzero) {
+    // programmatic dependent launch: this kernel may start while its predecessor drains; nothing is read before the wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // optional: reset the tile flags of the persistent denoiser kernel that consumes `out` (saves a memset launch)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = 0;
     const long long n8 = n >> 3;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
@@ -29,17 +36,39 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 
 using namespace b2s;
 
+static int cast_impl(const float* in, void* out, int64_t n, int* zero, int nzero, int bf16, void* stream);
+
 extern "C" int b2s_cast_f32_h(const float* in, void* out, int64_t n, int bf16, void* stream) {
+    return cast_impl(in, out, n, nullptr, 0, bf16, stream);
+}
+
+extern "C" int b2s_cast_f32_h_reset(const float* in, void* out, int64_t n, int* flags, int n_flags, int bf16, void* stream) {
+    B2S_CHECK_ARG(n_flags == 0 || flags, "b2s_cast_f32_h_reset: null flags");
+    return cast_impl(in, out, n, flags, n_flags, bf16, stream);
+}
+
+static int cast_impl(const float* in, void* out, int64_t n, int* zero, int nzero, int bf16, void* stream) {
     B2S_CHECK_ARG(n >= 0 && (n == 0 || (in && out)), "b2s_cast_f32_h: null pointer");
     B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                   "b2s_cast_f32_h: pointers must be 16B aligned");
-    if (n == 0) return B2S_OK;
+    if (n == 0 && nzero == 0) return B2S_OK;
     long long blocks = ((n >> 3) + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (bf16) cast_kernel<1><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, (uint16_t*)out, n);
-    else cast_kernel<0><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, (uint16_t*)out, n);
-    B2S_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const bool ew_pdl = getenv("B2S_EW_PDL") != nullptr && atoi(getenv("B2S_EW_PDL")) != 0;
+    cfg.numAttrs = ew_pdl ? 1 : 0;
+    uint16_t* o = (uint16_t*)out;
+    long long nn = n;
+    if (bf16) B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cast_kernel<1>, in, o, nn, zero, nzero));
+    else B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cast_kernel<0>, in, o, nn, zero, nzero));
     return B2S_OK;
 }
 

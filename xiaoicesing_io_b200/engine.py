@@ -257,10 +257,9 @@ class WaveNetSessionTC:
     def eval(self, x_in: torch.Tensor, k: int, out: torch.Tensor):
         e = self.eng
         B, T, rows, Cc, L, MF, bf = self.B, self.T, self.rows, e.C, e.L, e.MF, e.bf16
-        C.cast_h(x_in, self.xin_h, bf)
+        C.cast_h(x_in, self.xin_h, bf, reset_flags=self.flags)       # also re-arms the tile flags of the persistent kernel
         if self.stack_group and hparams.get('b2s_fuse_io', True) and MF <= 256:
             # ONE launch per utterance group: stem + residual stack + head inside the persistent kernel
-            self.flags.zero_()
             LC = L * Cc
             dv = self.dtab.reshape(-1) if self.per_row_t else self.dtab[k]
             for gi, b0 in enumerate(range(0, B, self.stack_group)):
@@ -277,7 +276,6 @@ class WaveNetSessionTC:
                     out_f32=self.x, ldo=Cc, y_h=self.y_h, ldy=Cc, dvec=d0, d_stride=ds)
         ldc = 2 * Cc
         if self.stack_group:
-            self.flags.zero_()
             LC = L * Cc
             dv = self.dtab.reshape(-1) if self.per_row_t else self.dtab[k]     # per-row: utterance b's row starts at b * L*C
             for gi, b0 in enumerate(range(0, B, self.stack_group)):
@@ -308,9 +306,9 @@ class WaveNetSessionTC:
     @property
     def launches_per_eval(self) -> int:
         if self.stack_group and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256:
-            return 2 + -(-self.B // self.stack_group)              # cast, flag reset, one denoiser launch per utterance group
+            return 1 + -(-self.B // self.stack_group)              # cast (+ flag reset), one denoiser launch per utterance group
         if self.stack_group:
-            return 2 + 1 + -(-self.B // self.stack_group) + 2      # cast, stem, flag reset, stack launches, 2 head GEMMs
+            return 1 + 1 + -(-self.B // self.stack_group) + 2      # cast (+ flag reset), stem, stack launches, 2 head GEMMs
         return 2 + (1 if self.fused else 2) * self.eng.L + 2
 
     def dominant_kernel(self, w=None):
