@@ -307,8 +307,9 @@ def run_b200_arm(args, w):
 
     model = make_model(w, args.precision, dev, cuda_graph=not args.no_graph)
     if args.fuse_io is not None:
-        import xiaoicesing_io_b200 as _P
-        _P.hparams['b2s_fuse_io'] = bool(args.fuse_io)
+        P.hparams['b2s_fuse_io'] = bool(args.fuse_io)
+    if args.overlap_noise is not None:
+        P.hparams['b2s_overlap_noise'] = bool(args.overlap_noise)
     cond_h, src_h = synth_inputs(w, seed=1000 + rank)          # every rank owns its utterances (weak scaling)
     cond_h, src_h = cond_h.pin_memory(), src_h.pin_memory()
     cond_d, src_d = cond_h.to(dev), src_h.to(dev)
@@ -427,6 +428,7 @@ def main():
     ap.add_argument('--frames', type=int, default=None, help='override frames per utterance (sweeps only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--fuse-io', type=int, default=None, help='override hparams b2s_fuse_io (A/B switch)')
+    ap.add_argument('--overlap-noise', type=int, default=None, help='override hparams b2s_overlap_noise (A/B switch)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the captured CUDA graph')
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

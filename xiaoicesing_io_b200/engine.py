@@ -578,15 +578,37 @@ class CompiledProgram:
 def run_program(cp: CompiledProgram, session, bufs: Dict[str, torch.Tensor],
                 draw_noise: Optional[Callable[[int, torch.Tensor], None]] = None) -> torch.Tensor:
     """Executes the program.  ``bufs`` maps buffer names to [B*T, MF] fp32 device tensors (NOISE0 /
-    XSTART pre-filled by the caller); ``draw_noise(j, dst)`` fills ``dst`` with the j-th per-step draw."""
+    XSTART pre-filled by the caller); ``draw_noise(j, dst)`` fills ``dst`` with the j-th per-step draw.
+
+    A per-step noise draw that directly follows a denoiser evaluation (ancestral sampling, ddpm.py:149-156) does not depend
+    on it: it is issued on a side stream BEFORE the evaluation is launched and joined before the update that consumes it,
+    so the draw + layout change overlap the persistent denoiser kernel (which leaves SMs idle at small batches).  The
+    draws keep their call order, so the random stream - and the result - are unchanged; under CUDA-graph capture the
+    fork / join becomes a parallel branch of the graph."""
     prog = cp.prog
-    for op, off in zip(prog.ops, cp.offsets):
+    ops = prog.ops
+    main = torch.cuda.current_stream()
+    side = None
+    hoisted = set()
+    for i, (op, off) in enumerate(zip(ops, cp.offsets)):
         if op.kind == 'nfe':
+            nxt = ops[i + 1] if i + 1 < len(ops) else None
+            joined = False
+            if (nxt is not None and nxt.kind == 'noise' and nxt.dst not in (op.src, op.dst) and hparams.get('b2s_overlap_noise', True)):
+                if side is None:
+                    side = torch.cuda.Stream(device=bufs[op.dst].device)
+                side.wait_stream(main)                      # earlier readers of the noise buffer are done
+                with torch.cuda.stream(side):
+                    draw_noise(nxt.draw, bufs[nxt.dst])
+                hoisted.add(i + 1)
+                joined = True
             session.eval(bufs[op.src], op.t_index, bufs[op.dst])
+            if joined:
+                main.wait_stream(side)
         elif op.kind == 'lin':
             n = len(op.terms)
             C.lincomb(bufs[op.dst], [bufs[b] for b, _ in op.terms], cp.coef[off:off + n])
-        else:
+        elif i not in hoisted:
             draw_noise(op.draw, bufs[op.dst])
     return bufs[prog.result]
 
