@@ -310,6 +310,9 @@ def run_b200_arm(args, w):
         P.hparams['b2s_fuse_io'] = bool(args.fuse_io)
     if args.overlap_noise is not None:
         P.hparams['b2s_overlap_noise'] = bool(args.overlap_noise)
+    for kv in args.hparam or []:
+        k, v = kv.split('=', 1)
+        P.hparams[k] = json.loads(v)
     cond_h, src_h = synth_inputs(w, seed=1000 + rank)          # every rank owns its utterances (weak scaling)
     cond_h, src_h = cond_h.pin_memory(), src_h.pin_memory()
     cond_d, src_d = cond_h.to(dev), src_h.to(dev)
@@ -384,7 +387,11 @@ def run_b200_arm(args, w):
         sess_launches = (roof or {}).get('launches_per_eval', (1 if args.precision == 'fp32' else 2) + 2 * w['layers'] + 2)
         n_lin = sum(1 for op in prog.ops if op.kind == 'lin')
         n_noise = prog.n_draws
-        launches_per_step = nfe * sess_launches + n_lin + n_noise + 2 + 4   # + start transposes + tables
+        # 16-bit path: an update that feeds the next evaluation writes the 16-bit input itself (no cast launch there)
+        n_precast = 0 if (args.precision == 'fp32' or not P.hparams.get('b2s_fuse_cast', True)) else sum(
+            1 for i, op in enumerate(prog.ops)
+            if op.kind == 'nfe' and i > 0 and prog.ops[i - 1].kind == 'lin' and prog.ops[i - 1].dst == op.src)
+        launches_per_step = nfe * sess_launches - n_precast + n_lin + n_noise + 2 + 4   # + start transposes + tables
         F = flops_per_frame_nfe(w['layers'], w['channels'], w['mel'], w.get('kind', 'wavenet'))
         p = peaks()
         line = {
@@ -429,6 +436,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--fuse-io', type=int, default=None, help='override hparams b2s_fuse_io (A/B switch)')
     ap.add_argument('--overlap-noise', type=int, default=None, help='override hparams b2s_overlap_noise (A/B switch)')
+    ap.add_argument('--hparam', action='append', help='extra hparams entry key=json (A/B switches, e.g. b2s_fuse_cast=false)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the captured CUDA graph')
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

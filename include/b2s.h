@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2S_ABI_VERSION 2
+#define B2S_ABI_VERSION 3
 
 #define B2S_OK 0
 #define B2S_ERR_INVALID_ARGUMENT (-1)
@@ -62,6 +62,12 @@ int b2s_transpose_f32(const float* in, float* out, int batch, int rows, int cols
  * ---------------------------------------------------------------------------------------------- */
 int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host, const float* coef, int n_src,
                             int64_t n, void* stream);
+
+/* Same update, and in the same launch: out_h [n] = dst rounded to bf16 (bf16 != 0) or fp16 - the 16-bit A operand the
+ * tensor-core denoiser reads next (ddpm.py:149-156 feeds x' straight back into denoise_fn, :141) - and flags[0..n_flags)
+ * = 0, re-arming the tile flags of the persistent denoiser kernel (replaces b2s_cast_f32_h_reset after an update). */
+int b2s_sampler_lincomb_f32_h(float* dst, const float* const* srcs_host, const float* coef, int n_src, int64_t n,
+                              void* out_h, int bf16, int* flags, int n_flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Step embedding:  SinusoidalPosEmb (common_layers.py:266-278)

@@ -63,7 +63,7 @@ def sinusoidal_pos_emb(t: torch.Tensor, dim: int, dtype) -> torch.Tensor:
     """
     half = dim // 2
     k = math.log(10000) / (half - 1)
-    freq = torch.exp(torch.arange(half) * -k)            # fp32, as the reference
+    freq = torch.exp(torch.arange(half, device=t.device) * -k)            # fp32, as the reference
     if dtype == torch.float64:
         emb = t.to(torch.float64)[:, None] * freq.to(torch.float64)[None, :]
     else:

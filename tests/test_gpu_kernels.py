@@ -42,6 +42,32 @@ def test_lincomb(C, n):
     srcs[0].copy_(keep)
 
 
+@pytest.mark.parametrize('n', [4, 1023, 4096 + 3, 16 * 690 * 128])
+@pytest.mark.parametrize('bf16', [True, False])
+def test_lincomb_h_equals_lincomb_then_cast(C, n, bf16):
+    """The fused update (+ 16-bit copy + flag reset) is bit-identical to the update followed by b2s_cast_f32_h_reset."""
+    hd = torch.bfloat16 if bf16 else torch.float16
+    srcs = [torch.randn(n, device='cuda') for _ in range(3)]
+    coef = torch.tensor([0.75, -1.5, 0.031], device='cuda')
+    want = torch.empty(n, device='cuda')
+    C.lincomb(want, srcs, coef)
+    want_h = torch.empty(n, device='cuda', dtype=hd)
+    flags_a = torch.full((37,), 5, device='cuda', dtype=torch.int32)
+    C.cast_h(want, want_h, bf16, reset_flags=flags_a)
+    got = torch.empty(n, device='cuda')
+    got_h = torch.full((n,), 9.0, device='cuda', dtype=hd)
+    flags_b = torch.full((37,), 5, device='cuda', dtype=torch.int32)
+    C.lincomb_h(got, srcs, coef, got_h, bf16, reset_flags=flags_b)
+    assert torch.equal(got, want)
+    assert torch.equal(got_h.view(torch.int16), want_h.view(torch.int16))
+    assert int(flags_a.abs().sum()) == 0 and int(flags_b.abs().sum()) == 0
+    # dst aliases a source (the ancestral update x <- a x + b eps + c z)
+    keep = srcs[0].clone()
+    C.lincomb_h(srcs[0], srcs, coef, got_h, bf16)
+    assert torch.equal(srcs[0], want) and torch.equal(got_h.view(torch.int16), want_h.view(torch.int16))
+    srcs[0].copy_(keep)
+
+
 def test_lincomb_rejects_too_many_sources(C):
     x = torch.zeros(16, device='cuda')
     with pytest.raises(C.B2SError):

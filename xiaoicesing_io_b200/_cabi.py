@@ -19,6 +19,7 @@ _vp, _i, _f, _i64 = c_void_p, c_int, c_float, c_int64
 _SIGNATURES = {
     'b2s_transpose_f32': [_vp, _vp, _i, _i, _i, _vp],
     'b2s_sampler_lincomb_f32': [_vp, ctypes.POINTER(_vp), _vp, _i, _i64, _vp],
+    'b2s_sampler_lincomb_f32_h': [_vp, ctypes.POINTER(_vp), _vp, _i, _i64, _vp, _i, _vp, _i, _vp],
     'b2s_sinusoid_f32': [_vp, _vp, _i, _i, _vp],
     'b2s_linear_f32': [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _i, _i, _vp],
     'b2s_wavenet_gate_f32': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
@@ -118,6 +119,14 @@ def lincomb(dst, srcs, coef_dev):
     arr = (_vp * len(srcs))(*[s.data_ptr() for s in srcs])
     check(lib.b2s_sampler_lincomb_f32(ptr(dst), arr, ptr(coef_dev), len(srcs), dst.numel(), stream_ptr()),
           'b2s_sampler_lincomb_f32')
+
+
+def lincomb_h(dst, srcs, coef_dev, out_h, bf16, reset_flags=None):
+    """lincomb + the 16-bit copy of dst the tensor-core denoiser reads next (+ tile-flag reset), one launch."""
+    arr = (_vp * len(srcs))(*[s.data_ptr() for s in srcs])
+    nf = 0 if reset_flags is None else reset_flags.numel()
+    check(lib.b2s_sampler_lincomb_f32_h(ptr(dst), arr, ptr(coef_dev), len(srcs), dst.numel(), ptr(out_h), int(bf16),
+                                        ptr(reset_flags), nf, stream_ptr()), 'b2s_sampler_lincomb_f32_h')
 
 
 def sinusoid(t, out, n, dim):

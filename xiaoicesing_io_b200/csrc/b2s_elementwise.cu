@@ -45,7 +45,17 @@ struct LinCombArgs {
     int n_src;
     long long n4;     // number of float4 groups
     long long n;      // total elements
+    uint16_t* out_h;  // optional 16-bit copy of dst (the denoiser's A operand), else null
+    int bf16;
+    int* zero;        // optional tile flags of the persistent denoiser kernel to re-arm
+    int nzero;
 };
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b, int bf16) {
+    if (bf16) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 
 template <int NS>
 __global__ void __launch_bounds__(256) lincomb_kernel(const LinCombArgs a) {
@@ -56,6 +66,7 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LinCombArgs a) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) c[i] = __ldg(a.coef + i);
     const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nzero; i += (int)stride) a.zero[i] = 0;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n4; idx += stride) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -67,6 +78,12 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LinCombArgs a) {
             acc.w = fmaf(c[i], v.w, acc.w);
         }
         *reinterpret_cast<float4*>(a.dst + idx * 4) = acc;
+        if (a.out_h) {
+            uint2 h;
+            h.x = pack_h2(acc.x, acc.y, a.bf16);
+            h.y = pack_h2(acc.z, acc.w, a.bf16);
+            *reinterpret_cast<uint2*>(a.out_h + idx * 4) = h;
+        }
     }
     // scalar tail (n % 4)
     if (blockIdx.x == 0 && threadIdx.x < (a.n - a.n4 * 4)) {
@@ -75,6 +92,7 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LinCombArgs a) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) acc = fmaf(c[i], a.src[i][idx], acc);
         a.dst[idx] = acc;
+        if (a.out_h) a.out_h[idx] = (uint16_t)(pack_h2(acc, 0.f, a.bf16) & 0xFFFFu);
     }
 }
 
@@ -204,19 +222,22 @@ extern "C" int b2s_transpose_f32(const float* in, float* out, int batch, int row
     return B2S_OK;
 }
 
-extern "C" int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host, const float* coef, int n_src,
-                                       int64_t n, void* stream) {
-    B2S_CHECK_ARG(n_src >= 1 && n_src <= 8, "b2s_sampler_lincomb_f32: n_src must be in [1, 8] (got %d)", n_src);
+static int lincomb_impl(const char* who, float* dst, const float* const* srcs_host, const float* coef, int n_src, int64_t n,
+                        void* out_h, int bf16, int* flags, int n_flags, void* stream) {
+    B2S_CHECK_ARG(n_src >= 1 && n_src <= 8, "%s: n_src must be in [1, 8] (got %d)", who, n_src);
     if (n <= 0) return B2S_OK;
-    B2S_CHECK_ARG(dst && srcs_host && coef, "b2s_sampler_lincomb_f32: null pointer");
+    B2S_CHECK_ARG(dst && srcs_host && coef, "%s: null pointer", who);
     LinCombArgs a{};
     for (int i = 0; i < n_src; ++i) {
         B2S_CHECK_ARG(srcs_host[i] && (reinterpret_cast<uintptr_t>(srcs_host[i]) & 15) == 0,
-                      "b2s_sampler_lincomb_f32: src %d null or not 16B aligned", i);
+                      "%s: src %d null or not 16B aligned", who, i);
         a.src[i] = srcs_host[i];
     }
-    B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "b2s_sampler_lincomb_f32: dst not 16B aligned");
+    B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "%s: dst not 16B aligned", who);
+    B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(out_h) & 7) == 0, "%s: out_h not 8B aligned", who);
+    B2S_CHECK_ARG(n_flags == 0 || flags, "%s: null flags", who);
     a.dst = dst; a.coef = coef; a.n_src = n_src; a.n = n; a.n4 = n / 4;
+    a.out_h = (uint16_t*)out_h; a.bf16 = bf16; a.zero = flags; a.nzero = n_flags;
     long long want = (a.n4 + 255) / 256;
     int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
     cudaLaunchConfig_t cfg{};
@@ -242,6 +263,17 @@ extern "C" int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host
     }
     B2S_CHECK_CUDA(err);
     return B2S_OK;
+}
+
+extern "C" int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host, const float* coef, int n_src,
+                                       int64_t n, void* stream) {
+    return lincomb_impl("b2s_sampler_lincomb_f32", dst, srcs_host, coef, n_src, n, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int b2s_sampler_lincomb_f32_h(float* dst, const float* const* srcs_host, const float* coef, int n_src, int64_t n,
+                                         void* out_h, int bf16, int* flags, int n_flags, void* stream) {
+    B2S_CHECK_ARG(out_h || n <= 0, "b2s_sampler_lincomb_f32_h: null out_h");
+    return lincomb_impl("b2s_sampler_lincomb_f32_h", dst, srcs_host, coef, n_src, n, out_h, bf16, flags, n_flags, stream);
 }
 
 extern "C" int b2s_sinusoid_f32(const float* t, float* out, int n, int dim, void* stream) {

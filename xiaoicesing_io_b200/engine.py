@@ -254,10 +254,16 @@ class WaveNetSessionTC:
             return self.dtab[0, l * self.eng.C:], LC
         return self.dtab[k, l * self.eng.C:], 0
 
-    def eval(self, x_in: torch.Tensor, k: int, out: torch.Tensor):
+    def half_sink(self):
+        """(16-bit input buffer, tile flags, bf16): a sampler update that produces the next denoiser input can write its
+        16-bit copy (and re-arm the flags) itself - ``eval(..., precast=True)`` then skips the cast launch."""
+        return self.xin_h, self.flags, self.eng.bf16
+
+    def eval(self, x_in: torch.Tensor, k: int, out: torch.Tensor, precast: bool = False):
         e = self.eng
         B, T, rows, Cc, L, MF, bf = self.B, self.T, self.rows, e.C, e.L, e.MF, e.bf16
-        C.cast_h(x_in, self.xin_h, bf, reset_flags=self.flags)       # also re-arms the tile flags of the persistent kernel
+        if not precast:
+            C.cast_h(x_in, self.xin_h, bf, reset_flags=self.flags)   # also re-arms the tile flags of the persistent kernel
         if self.stack_group and hparams.get('b2s_fuse_io', True) and MF <= 256:
             # ONE launch per utterance group: stem + residual stack + head inside the persistent kernel
             LC = L * Cc
@@ -533,10 +539,14 @@ class LYNXNetSessionTC:
             return self.dtab[0, l * self.eng.C:], LC
         return self.dtab[k, l * self.eng.C:], 0
 
-    def eval(self, x_in, k, out):
+    def half_sink(self):
+        return self.xin_h, None, self.eng.bf16
+
+    def eval(self, x_in, k, out, precast: bool = False):
         e = self.eng
         B, T, rows, Cc, L, MF, inner, bf = self.B, self.T, self.rows, e.C, e.L, e.MF, e.inner, e.bf16
-        C.cast_h(x_in, self.xin_h, bf)
+        if not precast:
+            C.cast_h(x_in, self.xin_h, bf)
         C.tc_linear(self.xin_h, MF, rows, T, e.w_in_h, MF, e.b_in, Cc, MF, bf,
                     act=C.ACT_NONE if e.strong else C.ACT_GELU, out_f32=self.x, ldo=Cc)
         for l in range(L):
@@ -590,6 +600,9 @@ def run_program(cp: CompiledProgram, session, bufs: Dict[str, torch.Tensor],
     main = torch.cuda.current_stream()
     side = None
     hoisted = set()
+    # 16-bit sessions: the update that produces the next denoiser input also writes its 16-bit copy (one launch less per NFE)
+    sink = session.half_sink() if (hasattr(session, 'half_sink') and hparams.get('b2s_fuse_cast', True)) else None
+    precast = set()
     for i, (op, off) in enumerate(zip(ops, cp.offsets)):
         if op.kind == 'nfe':
             nxt = ops[i + 1] if i + 1 < len(ops) else None
@@ -602,12 +615,20 @@ def run_program(cp: CompiledProgram, session, bufs: Dict[str, torch.Tensor],
                     draw_noise(nxt.draw, bufs[nxt.dst])
                 hoisted.add(i + 1)
                 joined = True
-            session.eval(bufs[op.src], op.t_index, bufs[op.dst])
+            if i in precast:
+                session.eval(bufs[op.src], op.t_index, bufs[op.dst], precast=True)
+            else:
+                session.eval(bufs[op.src], op.t_index, bufs[op.dst])
             if joined:
                 main.wait_stream(side)
         elif op.kind == 'lin':
             n = len(op.terms)
-            C.lincomb(bufs[op.dst], [bufs[b] for b, _ in op.terms], cp.coef[off:off + n])
+            nxt = ops[i + 1] if i + 1 < len(ops) else None
+            if sink is not None and nxt is not None and nxt.kind == 'nfe' and nxt.src == op.dst:
+                C.lincomb_h(bufs[op.dst], [bufs[b] for b, _ in op.terms], cp.coef[off:off + n], sink[0], sink[2], reset_flags=sink[1])
+                precast.add(i + 1)
+            else:
+                C.lincomb(bufs[op.dst], [bufs[b] for b, _ in op.terms], cp.coef[off:off + n])
         elif i not in hoisted:
             draw_noise(op.draw, bufs[op.dst])
     return bufs[prog.result]
