@@ -191,6 +191,22 @@ int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, const void* c
                          const float* dvec, int d_stride, const int* dilations_host, int L, int B, int T, int C, int* flags,
                          int bf16, void* stream);
 
+/* The residual stack with the GEMMs TRANSPOSED (channels on the tensor-core M axis, frames on N), C = 256: the frame tile
+ * NT is 32, 48, 64 or 80 instead of 128, so a small batch still fills the SMs (16 x 690 frames = 144 tiles of 80); the fp32
+ * residual stream lives in registers and the skip sum in TMEM for all L layers (wavenet.py:33-48, 92-96).
+ *   tiles      b2s_tc_wavenet_stack_t_tiles(B, T, NT) = B * ceil(T / NT) rounded up to even; must be <= ..._max_tiles()
+ *   Wd_h       [L, 2C, 3C] rows in BLOCK-PLANAR order: row 256h + 128g + c = (g ? filter : gate) of channel 128h + c
+ *   cond_t     b2s_tc_cond_retile() of the layer-major table [L, B*T, 2C] computed with the same row order
+ *   Wo_h, bo   [L, 2C, C], [L, 2C] in the reference's order (residual | skip)
+ *   x          [B*T, C] fp32 stem output (read once); y0_h = x + d_0 (16-bit) on entry, y1_h its ping-pong partner
+ *   skip_h     out: sum over layers of the skip outputs (+ biases), 16-bit [B*T, C]  (the head divides by sqrt(L))
+ *   flags      int32 [tiles], ZERO at launch;  dilations (HOST) <= min(16, NT) */
+int b2s_tc_wavenet_stack_t_tiles(int B, int T, int NT);
+int b2s_tc_cond_retile(const void* table_h, int L, int B, int T, int n2, int NT, void* out_h, void* stream);
+int b2s_tc_wavenet_stack_t(void* y0_h, void* y1_h, const void* Wd_h, const void* cond_t, const void* Wo_h, const float* bo,
+                           const float* x, void* skip_h, const float* dvec, int d_stride, const int* dilations_host, int L,
+                           int B, int T, int C, int NT, int* flags, int bf16, void* stream);
+
 /* ONE launch per denoiser evaluation (wavenet.py:75-107 without the step-embedding MLP, which is hoisted into the step
  * table): b2s_tc_wavenet_stack plus, inside the same persistent kernel, the stem x = relu(W_in x_in + b_in), y_0 = x + d_0
  * (wavenet.py:86-88, :36) before the first layer and the head out = W_fin relu(W_sp skip/sqrt(L) + b_sp) + b_fin

@@ -22,6 +22,15 @@ C.lib.b2s_debug_set_stack_tlog(ctypes.c_void_p(tlog.data_ptr()))
 sess.eval(x_in, 0, out); torch.cuda.synchronize()
 C.lib.b2s_debug_set_stack_tlog(None)
 t = tlog.cpu().reshape(20, 16).double()
+if getattr(sess, 'tgroups', None):
+    names = ['W pre issued', 'own EPI2 seen', 'flags+Y issued', 'Y landed', 'G1b0 issued', 'G1b1 issued', 'G1b2 issued', 'G1b3 issued',
+             'G2res issued', 'G2skip issued', 'G1h0 done', 'G1h1 done', 'EPI1h0 done', 'EPI1h1 done', 'G2res done', 'EPI2+flag']
+    t0 = t[2, 0]
+    print('layer ' + ' '.join(f'{n[:13]:>14s}' for n in names))
+    for l in range(2, 9):
+        print(f'{l:5d} ' + ' '.join(f'{(t[l, i] - t0) / 1e3:14.2f}' for i in range(len(names))))
+    print('per-layer period (us):', [(float(t[l + 1, 15] - t[l, 15]) / 1e3) for l in range(2, 12)])
+    sys.exit(0)
 names = ['y ready/A issued', 'G1h0 1st slab', 'G1h1 1st slab', 'G1h0 done', 'EPI1h0 done', 'G1h1 done', 'EPI1h1 done',
          'G2res done', 'EPI2res done+flag', 'G2skip done', 'EPI2skip done', 'res chunk0', 'res chunk1', 'res chunk2', 'res chunk3',
          'after fence']

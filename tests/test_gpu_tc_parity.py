@@ -201,13 +201,13 @@ def test_config4_variance_predictors_tensor_core(acc, precision, dev):
     assert err <= (2e-4 * scale if precision == 'bf16' else 5e-5 * max(scale, 1.0)), (acc, precision, err, scale)
 
 
-def _bf16_backbone(dev, stack, L=4, fuse_io=False, in_dims=128, n_feats=1):
+def _bf16_backbone(dev, stack, L=4, fuse_io=False, in_dims=128, n_feats=1, stack_t=False, cycle=4, precision='bf16'):
     import xiaoicesing_io_b200 as P
     from oracle import weights as OW
-    cfg = OD.WaveNetCfg(in_dims=in_dims, n_feats=n_feats, num_layers=L, num_channels=256, dilation_cycle_length=4)
+    cfg = OD.WaveNetCfg(in_dims=in_dims, n_feats=n_feats, num_layers=L, num_channels=256, dilation_cycle_length=cycle)
     P.hparams.clear()
-    P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision='bf16', b2s_stack=stack, b2s_fuse_io=fuse_io)
-    net = P.build_backbone(cfg.in_dims, n_feats, 'wavenet', dict(num_layers=L, num_channels=256, dilation_cycle_length=4))
+    P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision=precision, b2s_stack=stack, b2s_fuse_io=fuse_io, b2s_stack_t=stack_t)
+    net = P.build_backbone(cfg.in_dims, n_feats, 'wavenet', dict(num_layers=L, num_channels=256, dilation_cycle_length=cycle))
     net.load_state_dict(OW.make_state_dict(cfg, seed=0, sigma_w=0.01), strict=True)
     return net.to(dev).eval()
 
@@ -241,3 +241,24 @@ def test_one_launch_denoiser_matches_separate_stem_and_head(B, T, in_dims, n_fea
         b = _bf16_backbone(dev, True, fuse_io=False, in_dims=in_dims, n_feats=n_feats)(spec, t.to(dev), cond)
         assert bool(torch.isfinite(a).all())
         assert torch.equal(a, b), (B, T, in_dims, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize('B,T,L,cycle', [(2, 300, 4, 4), (16, 690, 20, 4), (3, 81, 5, 5), (1, 40, 3, 2), (5, 129, 6, 4), (7, 1000, 4, 4)])
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+def test_transposed_stack_matches_row_stack(B, T, L, cycle, precision, dev):
+    """b2s_stack_t: the residual stack with channels on the tensor-core M axis and 32..80-frame tiles on N (x in registers,
+    skip sum in TMEM).  Same operands as the 128-row stack kernel; only the fp32 summation order of the skip path differs
+    (one TMEM accumulator over all layers instead of a per-layer fp32 add), so the outputs agree to fp32 rounding of the
+    16-bit head inputs.  Shapes: one launch with 144 tiles of 80 (config 2), odd tile counts (dummy CTA), dilation 16
+    (cycle 5), tiles shorter than one frame tile, per-utterance diffusion steps."""
+    g = torch.Generator().manual_seed(B * 5 + T)
+    spec = torch.randn((B, 1, 128, T), generator=g).to(dev)
+    cond = torch.randn((B, 256, T), generator=g).to(dev)
+    for t in (torch.tensor([437.0]), torch.arange(B, dtype=torch.float32) * 13 + 5):
+        net = _bf16_backbone(dev, stack=True, L=L, stack_t='always', cycle=cycle, precision=precision)
+        a = net(spec, t.to(dev), cond)
+        b = _bf16_backbone(dev, stack=True, L=L, stack_t=False, cycle=cycle, precision=precision)(spec, t.to(dev), cond)
+        assert bool(torch.isfinite(a).all())
+        scale = float(b.abs().max())
+        err = float((a - b).abs().max())
+        assert err <= 4e-3 * scale, (B, T, L, err, scale)

@@ -40,6 +40,9 @@ _SIGNATURES = {
     'b2s_tc_wavenet_layer': [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_stack': [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _i, _i, _i, _vp,
                              _i, _vp],
+    'b2s_tc_wavenet_stack_t_tiles': [_i, _i, _i],
+    'b2s_tc_cond_retile': [_vp, _i, _i, _i, _i, _i, _vp, _vp],
+    'b2s_tc_wavenet_stack_t': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _i, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_wavenet_denoiser': [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i,
                                 _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -229,6 +232,18 @@ def tc_wavenet_stack(y0_h, y1_h, Wd_h, cond_h, ld_cond, cond_layer_stride, Wo_h,
     check(lib.b2s_tc_wavenet_stack(ptr(y0_h), ptr(y1_h), ptr(Wd_h), ptr(cond_h), ld_cond, cond_layer_stride, ptr(Wo_h),
                                    ptr(bo), ptr(x), ptr(skip), ptr(skip_h), ptr(dvec), d_stride, dil, L, B, T, C,
                                    ptr(flags), int(bf16), stream_ptr()), 'b2s_tc_wavenet_stack')
+
+
+def tc_cond_retile(table_h, L, B, T, n2, NT, out_h):
+    check(lib.b2s_tc_cond_retile(ptr(table_h), L, B, T, n2, NT, ptr(out_h), stream_ptr()), 'b2s_tc_cond_retile')
+
+
+def tc_wavenet_stack_t(y0_h, y1_h, Wd_h, cond_t, Wo_h, bo, x, skip_h, dvec, d_stride, dilations, B, T, C, NT, flags, bf16):
+    L = len(dilations)
+    dil = (_i * L)(*dilations)
+    check(lib.b2s_tc_wavenet_stack_t(ptr(y0_h), ptr(y1_h), ptr(Wd_h), ptr(cond_t), ptr(Wo_h), ptr(bo), ptr(x), ptr(skip_h),
+                                     ptr(dvec), d_stride, dil, L, B, T, C, NT, ptr(flags), int(bf16), stream_ptr()),
+          'b2s_tc_wavenet_stack_t')
 
 
 def tc_wavenet_denoiser(xin_h, MF, Win_h, ld_win, b_in, y0_h, y1_h, Wd_h, cond_h, cond_layer_stride, Wo_h, bo, x, skip, dvec,

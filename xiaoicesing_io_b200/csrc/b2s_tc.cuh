@@ -172,6 +172,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// K-major SWIZZLE_128B descriptor whose start address is NOT 1024-byte aligned (a window that starts `r` rows into a
+// TMA-written slab): `base_offset` is the descriptor's [49,52) field
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc_bo(uint32_t smem_addr, uint32_t base_offset) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_offset & 7u) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // thread-block clusters: multicast TMA, multicast tcgen05.commit, cluster barrier

@@ -1695,7 +1695,7 @@ extern "C" int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const voi
     return bf16 ? wl::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl::launch_layer<0>(p, grid, (cudaStream_t)stream);
 }
 
-static unsigned long long* g_tlog = nullptr;
+unsigned long long* g_tlog = nullptr;      // shared with b2s_tc_wavenet_t.cu
 /* profiling hook (not part of the product API): device buffer [L][16] of globaltimer ns, or NULL to switch off */
 extern "C" void b2s_debug_set_stack_tlog(void* buf) { g_tlog = (unsigned long long*)buf; }
 

@@ -98,6 +98,20 @@ class WaveNetEngine:
             self.w_in_h = h(_pad_cols(self.w_in, 8))
             self.w_cond_h, self.w_dil_h, self.w_out_h = h(self.w_cond), h(self.w_dil), h(self.w_out)
             self.w_sp_h, self.w_fin_h = h(self.w_sp), h(self.w_fin)
+            self.w_dil_t_h = self.w_cond_t_h = self.b_cond_t = None
+            if Cc == C.FUSED_LAYER_CHANNELS:
+                # transposed stack kernel (b2s_tc_wavenet_stack_t): row 256h + 128g + c = (g ? filter : gate) of channel 128h + c,
+                # i.e. gate and filter of a channel land on the same TMEM lane of two neighbouring accumulator blocks
+                n = torch.arange(2 * Cc, device=dev)
+                perm_t = 128 * (n // 256) + (n % 128) + Cc * ((n % 256) // 128)
+                wc_t, bc_t, wd_t = [], [], []
+                for l in layers:
+                    wc_t.append(l.conditioner_projection.weight[:, :, 0][perm_t])
+                    bc_t.append((l.conditioner_projection.bias + l.dilated_conv.bias)[perm_t])
+                    wd_t.append(l.dilated_conv.weight[perm_t].permute(0, 2, 1).reshape(2 * Cc, 3 * Cc))
+                self.w_cond_t_h = h(f(torch.cat(wc_t, 0)))
+                self.b_cond_t = f(torch.cat(bc_t, 0))
+                self.w_dil_t_h = h(f(torch.stack(wd_t, 0)))
         self._packed_version = v
 
     # -- per-call tables ---------------------------------------------------------------------------
@@ -233,7 +247,10 @@ class WaveNetSessionTC:
         self.stack_group = (C.lib.b2s_tc_wavenet_stack_max_tiles() // tpb) if (self.fused and hparams.get('b2s_stack', True)) else 0
         self.flags = torch.zeros((B * tpb,), device=dev, dtype=torch.int32) if self.stack_group else None
         self.tpb = tpb
-        if self.stack_group:
+        self.tgroups = self._plan_transposed(cond_h) if (self.stack_group and hparams.get('b2s_stack_t', False)) else None
+        if self.tgroups:
+            self.flags = torch.zeros((max(B * tpb, sum(g[4] for g in self.tgroups)),), device=dev, dtype=torch.int32)
+        if self.stack_group and not self.tgroups:
             # one table per utterance group, in the tile/chunk-major layout the stack kernel reads with coalesced loads
             self.cond_groups = []
             for b0 in range(0, B, self.stack_group):
@@ -241,7 +258,7 @@ class WaveNetSessionTC:
                 tab = torch.empty((L, nb * tpb * 128, 2 * Cc), device=dev, dtype=hd)
                 C.tc_cond_table_tiled(cond_h[b0 * T:], nb, T, eng.w_cond_h, eng.b_cond, L, 2 * Cc, H, tab, bf)
                 self.cond_groups.append(tab)
-        else:
+        elif not self.tgroups:
             self.cond = torch.empty((L, rows, 2 * Cc), device=dev, dtype=hd)     # layer-major: one contiguous slab per layer
             C.tc_cond_table(cond_h, rows, eng.w_cond_h, eng.b_cond, L, 2 * Cc, H, self.cond, bf)
         del self._cond_h
@@ -254,6 +271,42 @@ class WaveNetSessionTC:
             return self.dtab[0, l * self.eng.C:], LC
         return self.dtab[k, l * self.eng.C:], 0
 
+    T_TILES = (32, 48, 64, 80)
+
+    def _plan_transposed(self, cond_h):
+        """Utterance groups for the transposed stack kernel (``b2s_stack_t``, OFF by default; frame tiles of 32..80 instead of
+        128, so a small batch occupies every SM): [(b0, b1, NT, retiled cond table, tiles, flag offset)] or None.
+        Every tile of a launch must be resident.  ``True``: only when the whole batch fits ONE launch; ``'always'``: any batch.
+        Measured: a tcgen05 SS-mode instruction costs the same ~128 cycles for N = 48 .. 80 as for
+        N = 256 (the 128 x 16 A slice is re-read from shared memory every instruction), so the 4x larger instruction count of
+        this formulation makes it SLOWER than the 128-row kernel despite 144 busy SMs (18.0 vs 20.8 M frame*NFE/s)."""
+        e = self.eng
+        B, T, Cc, L, H, bf = self.B, self.T, e.C, e.L, e.H, e.bf16
+        if e.w_dil_t_h is None or max(e.dilations) > 16:
+            return None
+        cap = C.lib.b2s_tc_wavenet_stack_max_tiles()
+        tiles = lambda nb, nt: C.lib.b2s_tc_wavenet_stack_t_tiles(nb, T, nt)
+        per = max(nb for nb in range(0, B + 1) if tiles(nb, self.T_TILES[-1]) <= cap)     # utterances per launch at the largest tile
+        if per == 0 or (per < B and hparams.get('b2s_stack_t', False) != 'always'):
+            return None
+        hd = C.HALF_DTYPES[e.precision]
+        dev = cond_h.device
+        groups, f0 = [], 0
+        for b0 in range(0, B, per):
+            b1 = min(B, b0 + per)
+            nb = b1 - b0
+            nt = next(t for t in self.T_TILES if t >= max(e.dilations) and tiles(nb, t) <= cap)
+            nt = int(hparams.get('b2s_stack_t_tile', nt))
+            n_tiles = tiles(nb, nt)
+            tmp = torch.empty((L, nb * T, 2 * Cc), device=dev, dtype=hd)
+            C.tc_cond_table(cond_h[b0 * T:], nb * T, e.w_cond_t_h, e.b_cond_t, L, 2 * Cc, H, tmp, bf)
+            tab = torch.empty((L * n_tiles * nt * 2 * Cc,), device=dev, dtype=hd)
+            C.tc_cond_retile(tmp, L, nb, T, 2 * Cc, nt, tab)
+            del tmp
+            groups.append((b0, b1, nt, tab, n_tiles, f0))
+            f0 += n_tiles
+        return groups
+
     def half_sink(self):
         """(16-bit input buffer, tile flags, bf16): a sampler update that produces the next denoiser input can write its
         16-bit copy (and re-arm the flags) itself - ``eval(..., precast=True)`` then skips the cast launch."""
@@ -264,6 +317,21 @@ class WaveNetSessionTC:
         B, T, rows, Cc, L, MF, bf = self.B, self.T, self.rows, e.C, e.L, e.MF, e.bf16
         if not precast:
             C.cast_h(x_in, self.xin_h, bf, reset_flags=self.flags)   # also re-arms the tile flags of the persistent kernel
+        if self.tgroups:
+            LC = L * Cc
+            d0, ds = self._dvec(k, 0)
+            C.tc_linear(self.xin_h, MF, rows, T, e.w_in_h, e.w_in_h.shape[1], e.b_in, Cc, MF, bf, act=C.ACT_RELU,
+                        out_f32=self.x, ldo=Cc, y_h=self.y_h, ldy=Cc, dvec=d0, d_stride=ds)
+            dv = self.dtab.reshape(-1) if self.per_row_t else self.dtab[k]
+            for (b0, b1, nt, tab, n_tiles, f0) in self.tgroups:
+                r0 = b0 * T
+                C.tc_wavenet_stack_t(self.y_h[r0:], self.y2_h[r0:], e.w_dil_t_h, tab, e.w_out_h, e.b_out, self.x[r0:],
+                                     self.skip_h[r0:], dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
+                                     e.dilations, b1 - b0, T, Cc, nt, self.flags[f0:], bf)
+            C.tc_linear(self.skip_h, Cc, rows, T, e.w_sp_h, Cc, e.b_sp, Cc, Cc, bf, alpha=1.0 / math.sqrt(L),
+                        act=C.ACT_RELU, out_h=self.h_h, ldoh=Cc)
+            C.tc_linear(self.h_h, Cc, rows, T, e.w_fin_h, Cc, e.b_fin, MF, Cc, bf, out_f32=out, ldo=MF)
+            return
         if self.stack_group and hparams.get('b2s_fuse_io', True) and MF <= 256:
             # ONE launch per utterance group: stem + residual stack + head inside the persistent kernel
             LC = L * Cc
@@ -311,6 +379,8 @@ class WaveNetSessionTC:
 
     @property
     def launches_per_eval(self) -> int:
+        if self.tgroups:
+            return 1 + 1 + len(self.tgroups) + 2                   # cast, stem, transposed stack launches, 2 head GEMMs
         if self.stack_group and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256:
             return 1 + -(-self.B // self.stack_group)              # cast (+ flag reset), one denoiser launch per utterance group
         if self.stack_group:
@@ -321,6 +391,19 @@ class WaveNetSessionTC:
         """(name, algorithmic FLOPs per launch, callable launching it once per layer) for bench.py's roofline."""
         e = self.eng
         B, T, Cc, L = self.B, self.T, e.C, e.L
+        if self.tgroups:
+            b0, b1, nt, tab, n_tiles, f0 = self.tgroups[0]
+            flops = 2.0 * (b1 - b0) * T * 8 * Cc * Cc * L
+            dv = self.dtab[0]
+
+            def launch_all():
+                self.flags.zero_()
+                for (b0, b1, nt, tab, n_tiles, f0) in self.tgroups:
+                    r0 = b0 * T
+                    C.tc_wavenet_stack_t(self.y_h[r0:], self.y2_h[r0:], e.w_dil_t_h, tab, e.w_out_h, e.b_out, self.x[r0:],
+                                         self.skip_h[r0:], dv, 0, e.dilations, b1 - b0, T, Cc, nt, self.flags[f0:], e.bf16)
+            return (f'wavenet_stack_t_kernel<{nt}, {e.precision}> (b2s_tc_wavenet_stack_t, {L} layers per launch, {n_tiles} tiles of {nt} frames)',
+                    flops, launch_all, len(self.tgroups))
         if self.stack_group:
             flops = 2.0 * min(self.stack_group, B) * T * 8 * Cc * Cc * L      # the whole residual stack of one group per launch
             dv = self.dtab[0]
