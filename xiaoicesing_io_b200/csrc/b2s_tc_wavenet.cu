@@ -22,6 +22,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace b2s {
 namespace tc {
@@ -1072,33 +1073,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
             const float* bo = p.bo + (long long)l * 2 * C;
             const float* dnext = p.dvec + (long long)(l + 1) * C + (long long)b * p.d_stride;
             uint16_t* ynext = last ? nullptr : reinterpret_cast<uint16_t*>(p.ybuf[(l + 1) & 1]) + rowoff;
-            float4 in[8], inn[8];
-            float4 biasn, dn;                       // bias / step-embedding quads of the NEXT chunk (L1 is ~0 KB here: every
-                                                    // __ldg is an L2 round trip, so they are prefetched with the inputs)
-            auto load_inputs = [&](int g, int j, float4* dst) {
+            // Eight chunk bodies (4 residual, 4 skip), each specialised at compile time on the half it drains and fully
+            // unrolled: the loop used to carry both halves, the profiling switches and a register copy of the prefetched inputs
+            // in ONE body of ~800 SASS instructions per 32x32 chunk, and two warps per scheduler made EPI2 instruction-issue bound.
+            // Inputs of chunk n+1 (x or skip rows, bias and step-embedding quads: L1 is ~0 KB here, every load is an L2 round
+            // trip) are requested while chunk n's TMEM load is in flight, alternating between two register buffers.
+            float4 bufA[8], bufB[8];
+            float4 cbA, cdA, cbB, cdB;
+            auto load_inputs = [&](int g, int j, float4* dst, float4& cb, float4& cd) {
                 const float* src = (g == 0 ? xrow : srow_g) + j * 32;
-                const bool rd = (g == 0 || !first) && !(p.dbg & 2);
+                const bool rd = (g == 0 || !first);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     dst[i] = (rd && (vmask >> i & 1)) ? *reinterpret_cast<const float4*>(src + i * 4 * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-                biasn = __ldg(reinterpret_cast<const float4*>(bo + g * C + j * 32 + cl));
-                dn = (g == 0 && ynext) ? __ldg(reinterpret_cast<const float4*>(dnext + j * 32 + cl)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cb = __ldg(reinterpret_cast<const float4*>(bo + g * C + j * 32 + cl));
+                cd = (g == 0 && ynext) ? __ldg(reinterpret_cast<const float4*>(dnext + j * 32 + cl)) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
-            load_inputs(0, sub, inn);
-#pragma unroll 1
-            for (int n = 0; n < 8; ++n) {
-                const int g = n >> 2, j = 2 * (n & 3) + sub;
-                if ((n & 3) == 0) {
-                    mbar_wait(&accb[2 + g], par);
-                    tc_fence_after();
-                    if (e == 0) TLOG(7 + 2 * g);                          // G2 half g complete
-                }
+            auto chunk = [&](auto gtag, int j, const float4* in, const float4 bias, const float4 d, auto&& prefetch_next) {
+                constexpr int g = decltype(gtag)::value;
                 float acc[32];
                 tmem_ld32(taddr + g * BN + j * 32, acc);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) in[i] = inn[i];
-                const float4 bias = biasn, d = dn;
-                if (n + 1 < 8) load_inputs((n + 1) >> 2, 2 * ((n + 1) & 3) + sub, inn);
+                prefetch_next();
                 float* xo = xrow + j * 32;
                 float* so = srow_g + j * 32;
                 uint16_t* yo = ynext + j * 32;
@@ -1113,35 +1108,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                             srow[c2] = make_float4(acc[4 * c2], acc[4 * c2 + 1], acc[4 * c2 + 2], acc[4 * c2 + 3]);
                     }
                     __syncwarp();
-                    if (!(p.dbg & 4)) {
 #pragma unroll
-                        for (int i2 = 0; i2 < 4; ++i2) {
-                            const int i = 4 * pass + i2;                        // row 4*i + rsub of the warp's 32
-                            if (vmask >> i & 1) {
-                                const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
-                                const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
-                                if (g == 0) {
-                                    const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
-                                                                  (in[i].z + o.z) * inv_sqrt2, (in[i].w + o.w) * inv_sqrt2);
-                                    if (!(p.dbg & 32)) *reinterpret_cast<float4*>(xo + i * 4 * C) = xn;
-                                    if (ynext && !(p.dbg & 64)) {
-                                        uint2 yv;
-                                        yv.x = Half16<BF16>::pack2(xn.x + d.x, xn.y + d.y);
-                                        yv.y = Half16<BF16>::pack2(xn.z + d.z, xn.w + d.w);
-                                        *reinterpret_cast<uint2*>(yo + i * 4 * C) = yv;
-                                    }
-                                } else {
-                                    const float4 s2 = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
-                                    if (!(p.dbg & 32)) *reinterpret_cast<float4*>(so + i * 4 * C) = s2;
-                                    if (last && (p.skip_h || p.fuse)) {
-                                        uint2 sv;
-                                        sv.x = Half16<BF16>::pack2(s2.x, s2.y);
-                                        sv.y = Half16<BF16>::pack2(s2.z, s2.w);
-                                        if (p.fuse) {       // the head GEMM's A operand: straight into the (now idle) z buffer
-                                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(z_addr_quad(i, j * 32 + cl)), "r"(sv.x), "r"(sv.y) : "memory");
-                                        } else {
-                                            *reinterpret_cast<uint2*>(sho + i * 4 * C) = sv;
-                                        }
+                    for (int i2 = 0; i2 < 4; ++i2) {
+                        const int i = 4 * pass + i2;                        // row 4*i + rsub of the warp's 32
+                        if (vmask >> i & 1) {
+                            const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
+                            const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+                            if (g == 0) {
+                                const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
+                                                              (in[i].z + o.z) * inv_sqrt2, (in[i].w + o.w) * inv_sqrt2);
+                                *reinterpret_cast<float4*>(xo + i * 4 * C) = xn;
+                                if (ynext) {
+                                    uint2 yv;
+                                    yv.x = Half16<BF16>::pack2(xn.x + d.x, xn.y + d.y);
+                                    yv.y = Half16<BF16>::pack2(xn.z + d.z, xn.w + d.w);
+                                    *reinterpret_cast<uint2*>(yo + i * 4 * C) = yv;
+                                }
+                            } else {
+                                const float4 s2 = make_float4(o.x + in[i].x, o.y + in[i].y, o.z + in[i].z, o.w + in[i].w);
+                                *reinterpret_cast<float4*>(so + i * 4 * C) = s2;
+                                if (last && (p.skip_h || p.fuse)) {
+                                    uint2 sv;
+                                    sv.x = Half16<BF16>::pack2(s2.x, s2.y);
+                                    sv.y = Half16<BF16>::pack2(s2.z, s2.w);
+                                    if (p.fuse) {       // the head GEMM's A operand: straight into the (now idle) z buffer
+                                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(z_addr_quad(i, j * 32 + cl)), "r"(sv.x), "r"(sv.y) : "memory");
+                                    } else {
+                                        *reinterpret_cast<uint2*>(sho + i * 4 * C) = sv;
                                     }
                                 }
                             }
@@ -1149,29 +1142,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                     }
                     __syncwarp();
                 }
-                if (e == 0 && n < 4) TLOG(11 + n);                          // EPI2-res chunk n of this warp stored
-                if ((n & 3) == 3) {
-                    // this warp has finished TMEM half g of the layer
-                    if (e == 0 && g == 0) TLOG(15);                         // this warp's last residual chunk stored
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tfree[g]);
-                    if (g == 0) {
-                        // hand-off: every epilogue thread has issued its y_next stores -> CTA barrier -> ONE thread makes them
-                        // visible GPU-wide (the fence is cumulative over the barrier) and releases the tile flag
-                        named_bar_sync(1, EPI_WARPS * 32);
-                        if (e == 0 && lane == 0) {
-                            __threadfence();
-                            st_release_gpu(p.flags + blockIdx.x, l + 1 + p.fuse);
-                        }
-                    } else if (last && p.fuse) {
-                        fence_proxy_async_smem();                   // skip-sum tile (generic-proxy writes) -> tensor core
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&hz[0]);
-                    }
-                    if (e == 0) TLOG(8 + 2 * g);                          // EPI2 half g done, flag released
-                }
+            };
+            using G0 = std::integral_constant<int, 0>;
+            using G1 = std::integral_constant<int, 1>;
+            load_inputs(0, sub, bufA, cbA, cdA);
+            // ---- residual half ----
+            mbar_wait(&accb[2], par);
+            tc_fence_after();
+            if (e == 0) TLOG(7);                                        // G2 residual half complete
+            chunk(G0{}, sub, bufA, cbA, cdA, [&] { load_inputs(0, 2 + sub, bufB, cbB, cdB); });
+            if (e == 0) TLOG(11);
+            chunk(G0{}, 2 + sub, bufB, cbB, cdB, [&] { load_inputs(0, 4 + sub, bufA, cbA, cdA); });
+            if (e == 0) TLOG(12);
+            chunk(G0{}, 4 + sub, bufA, cbA, cdA, [&] { load_inputs(0, 6 + sub, bufB, cbB, cdB); });
+            if (e == 0) TLOG(13);
+            chunk(G0{}, 6 + sub, bufB, cbB, cdB, [&] { load_inputs(1, sub, bufA, cbA, cdA); });
+            if (e == 0) TLOG(14);
+            if (e == 0) TLOG(15);                                       // this warp's last residual chunk stored
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tfree[0]);
+            // hand-off: every epilogue thread has issued its y_next stores -> CTA barrier -> ONE thread publishes the tile flag.
+            // st.release.gpu is itself a GPU-scope release fence, cumulative over the barrier: no separate __threadfence().
+            named_bar_sync(1, EPI_WARPS * 32);
+            if (e == 0 && lane == 0) st_release_gpu(p.flags + blockIdx.x, l + 1 + p.fuse);
+            if (e == 0) TLOG(8);                                        // EPI2 residual half done, flag released
+            // ---- skip half (overlaps GEMM1 of the next layer) ----
+            mbar_wait(&accb[3], par);
+            tc_fence_after();
+            if (e == 0) TLOG(9);                                        // G2 skip half complete
+            chunk(G1{}, sub, bufA, cbA, cdA, [&] { load_inputs(1, 2 + sub, bufB, cbB, cdB); });
+            chunk(G1{}, 2 + sub, bufB, cbB, cdB, [&] { load_inputs(1, 4 + sub, bufA, cbA, cdA); });
+            chunk(G1{}, 4 + sub, bufA, cbA, cdA, [&] { load_inputs(1, 6 + sub, bufB, cbB, cdB); });
+            chunk(G1{}, 6 + sub, bufB, cbB, cdB, [] {});
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tfree[1]);
+            if (last && p.fuse) {
+                fence_proxy_async_smem();                   // skip-sum tile (generic-proxy writes) -> tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hz[0]);
             }
+            if (e == 0) TLOG(10);                                       // EPI2 skip half done
         }
         if (p.fuse) {
             const uint32_t pl = p.L & 1;
