@@ -58,6 +58,14 @@ __device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
 __device__ __forceinline__ void st_shared_u4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -666,6 +674,8 @@ using wl::ldg_nc_u4;
 using wl::pdl_launch_dependents;
 using wl::pdl_wait;
 using wl::st_shared_u4;
+using wl::st_shared_f4;
+using wl::ld_shared_f4;
 
 constexpr int C = 256, MAXL = 32;
 constexpr int BM = 128, BK = 64, BN = 256, UK = 16, STAGES = 3, CLUSTER = 2;
@@ -1080,39 +1090,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
             // trip) are requested while chunk n's TMEM load is in flight, alternating between two register buffers.
             float4 bufA[8], bufB[8];
             float4 cbA, cdA, cbB, cdB;
-            auto load_inputs = [&](int g, int j, float4* dst, float4& cb, float4& cd) {
-                const float* src = (g == 0 ? xrow : srow_g) + j * 32;
+            // chunk j = 2 * JJ + sub: `sub` is folded into the base pointers so that every address below is base + immediate
+            const float* xs_ = xrow + sub * 32;
+            const float* ss_ = srow_g + sub * 32;
+            uint16_t* ys_ = ynext ? ynext + sub * 32 : nullptr;
+            uint16_t* shs_ = shrow + sub * 32;
+            const float* bos_ = bo + sub * 32 + cl;
+            const float* dns_ = dnext + sub * 32 + cl;
+            const uint32_t tsub = taddr + sub * 32;
+            const uint32_t stg_w = smem_u32(stg) + (lane & 15) * (STG_LD * 4);          // this lane's staging row (its pass)
+            const uint32_t stg_r = smem_u32(stg) + (rsub * STG_LD + cl) * 4;             // coalesced read-back: + i2 * 4 rows
+            auto load_inputs = [&](auto gtag, auto jtag, float4* dst, float4& cb, float4& cd) {
+                constexpr int g = decltype(gtag)::value, JJ = decltype(jtag)::value;
+                const float* src = (g == 0 ? xs_ : ss_) + JJ * 64;
                 const bool rd = (g == 0 || !first);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     dst[i] = (rd && (vmask >> i & 1)) ? *reinterpret_cast<const float4*>(src + i * 4 * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-                cb = __ldg(reinterpret_cast<const float4*>(bo + g * C + j * 32 + cl));
-                cd = (g == 0 && ynext) ? __ldg(reinterpret_cast<const float4*>(dnext + j * 32 + cl)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cb = __ldg(reinterpret_cast<const float4*>(bos_ + g * C + JJ * 64));
+                cd = (g == 0 && ynext) ? __ldg(reinterpret_cast<const float4*>(dns_ + JJ * 64)) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
-            auto chunk = [&](auto gtag, int j, const float4* in, const float4 bias, const float4 d, auto&& prefetch_next) {
-                constexpr int g = decltype(gtag)::value;
+            auto chunk = [&](auto gtag, auto jtag, const float4* in, const float4 bias, const float4 d, auto&& prefetch_next) {
+                constexpr int g = decltype(gtag)::value, JJ = decltype(jtag)::value;
                 float acc[32];
-                tmem_ld32(taddr + g * BN + j * 32, acc);
+                tmem_ld32(tsub + g * BN + JJ * 64, acc);
                 prefetch_next();
-                float* xo = xrow + j * 32;
-                float* so = srow_g + j * 32;
-                uint16_t* yo = ynext + j * 32;
-                uint16_t* sho = shrow + j * 32;
+                float* xo = const_cast<float*>(xs_) + JJ * 64;
+                float* so = const_cast<float*>(ss_) + JJ * 64;
+                uint16_t* yo = ys_ + JJ * 64;
+                uint16_t* sho = shs_ + JJ * 64;
                 tmem_ld_wait();
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     if ((lane >> 4) == pass) {
-                        float4* srow = reinterpret_cast<float4*>(stg + (lane & 15) * STG_LD);
 #pragma unroll
                         for (int c2 = 0; c2 < 8; ++c2)
-                            srow[c2] = make_float4(acc[4 * c2], acc[4 * c2 + 1], acc[4 * c2 + 2], acc[4 * c2 + 3]);
+                            st_shared_f4(stg_w + c2 * 16, acc[4 * c2], acc[4 * c2 + 1], acc[4 * c2 + 2], acc[4 * c2 + 3]);
                     }
                     __syncwarp();
 #pragma unroll
                     for (int i2 = 0; i2 < 4; ++i2) {
                         const int i = 4 * pass + i2;                        // row 4*i + rsub of the warp's 32
                         if (vmask >> i & 1) {
-                            const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
+                            const float4 v = ld_shared_f4(stg_r + i2 * (4 * STG_LD * 4));
                             const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
                             if (g == 0) {
                                 const float4 xn = make_float4((in[i].x + o.x) * inv_sqrt2, (in[i].y + o.y) * inv_sqrt2,
@@ -1132,7 +1152,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                                     sv.x = Half16<BF16>::pack2(s2.x, s2.y);
                                     sv.y = Half16<BF16>::pack2(s2.z, s2.w);
                                     if (p.fuse) {       // the head GEMM's A operand: straight into the (now idle) z buffer
-                                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(z_addr_quad(i, j * 32 + cl)), "r"(sv.x), "r"(sv.y) : "memory");
+                                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(z_addr_quad(i, (2 * JJ + sub) * 32 + cl)), "r"(sv.x), "r"(sv.y) : "memory");
                                     } else {
                                         *reinterpret_cast<uint2*>(sho + i * 4 * C) = sv;
                                     }
@@ -1145,18 +1165,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
             };
             using G0 = std::integral_constant<int, 0>;
             using G1 = std::integral_constant<int, 1>;
-            load_inputs(0, sub, bufA, cbA, cdA);
+            using J0 = std::integral_constant<int, 0>;
+            using J1 = std::integral_constant<int, 1>;
+            using J2 = std::integral_constant<int, 2>;
+            using J3 = std::integral_constant<int, 3>;
+            load_inputs(G0{}, J0{}, bufA, cbA, cdA);
             // ---- residual half ----
             mbar_wait(&accb[2], par);
             tc_fence_after();
             if (e == 0) TLOG(7);                                        // G2 residual half complete
-            chunk(G0{}, sub, bufA, cbA, cdA, [&] { load_inputs(0, 2 + sub, bufB, cbB, cdB); });
+            chunk(G0{}, J0{}, bufA, cbA, cdA, [&] { load_inputs(G0{}, J1{}, bufB, cbB, cdB); });
             if (e == 0) TLOG(11);
-            chunk(G0{}, 2 + sub, bufB, cbB, cdB, [&] { load_inputs(0, 4 + sub, bufA, cbA, cdA); });
+            chunk(G0{}, J1{}, bufB, cbB, cdB, [&] { load_inputs(G0{}, J2{}, bufA, cbA, cdA); });
             if (e == 0) TLOG(12);
-            chunk(G0{}, 4 + sub, bufA, cbA, cdA, [&] { load_inputs(0, 6 + sub, bufB, cbB, cdB); });
+            chunk(G0{}, J2{}, bufA, cbA, cdA, [&] { load_inputs(G0{}, J3{}, bufB, cbB, cdB); });
             if (e == 0) TLOG(13);
-            chunk(G0{}, 6 + sub, bufB, cbB, cdB, [&] { load_inputs(1, sub, bufA, cbA, cdA); });
+            chunk(G0{}, J3{}, bufB, cbB, cdB, [&] { load_inputs(G1{}, J0{}, bufA, cbA, cdA); });
             if (e == 0) TLOG(14);
             if (e == 0) TLOG(15);                                       // this warp's last residual chunk stored
             tc_fence_before();
@@ -1171,10 +1195,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
             mbar_wait(&accb[3], par);
             tc_fence_after();
             if (e == 0) TLOG(9);                                        // G2 skip half complete
-            chunk(G1{}, sub, bufA, cbA, cdA, [&] { load_inputs(1, 2 + sub, bufB, cbB, cdB); });
-            chunk(G1{}, 2 + sub, bufB, cbB, cdB, [&] { load_inputs(1, 4 + sub, bufA, cbA, cdA); });
-            chunk(G1{}, 4 + sub, bufA, cbA, cdA, [&] { load_inputs(1, 6 + sub, bufB, cbB, cdB); });
-            chunk(G1{}, 6 + sub, bufB, cbB, cdB, [] {});
+            chunk(G1{}, J0{}, bufA, cbA, cdA, [&] { load_inputs(G1{}, J1{}, bufB, cbB, cdB); });
+            chunk(G1{}, J1{}, bufB, cbB, cdB, [&] { load_inputs(G1{}, J2{}, bufA, cbA, cdA); });
+            chunk(G1{}, J2{}, bufA, cbA, cdA, [&] { load_inputs(G1{}, J3{}, bufB, cbB, cdB); });
+            chunk(G1{}, J3{}, bufB, cbB, cdB, [] {});
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tfree[1]);
