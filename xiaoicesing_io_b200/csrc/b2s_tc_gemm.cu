@@ -299,10 +299,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int bt = m_tile / p.tiles_m_per_b, t0 = (m_tile - bt * p.tiles_m_per_b) * BLOCK_M;
             const int n0 = n_tile * BLOCK_N;
+            const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
+            // per-chunk inputs (cond / x / skip rows of the lane, bias and step-embedding quads) are requested ONE CHUNK AHEAD -
+            // the first chunk's before the accumulator wait - so their L2 / HBM latency hides behind the TMEM drain of the
+            // previous chunk (ncu: the GATE / RESSKIP epilogues were long-scoreboard bound, tensor pipe 46 % / 18 % active)
+            EpiConst kcn;
+            float4 inn[8];
+            bool okn = false;
+            auto load_chunk = [&](int j) {
+                const int col = n0 + 32 * j + cl;
+                okn = col < p.N;
+                if (okn) {
+                    kcn = epilogue_consts<EPI>(p, col);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        inn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tq + 4 * i < p.T) inn[i] = epilogue_load<EPI, BF16>(p, (long long)bt * p.T + tq + 4 * i, col);
+                    }
+                }
+            };
+            if (n0 + 32 * sub < p.N) load_chunk(sub);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
-            const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
 #pragma unroll 1
             for (int j = sub; j < BLOCK_N / 32; j += 2) {
                 const int col0 = n0 + 32 * j;
@@ -310,17 +329,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                 float acc[32];
                 tmem_ld32(taddr + j * 32, acc);
                 const int col = col0 + cl;
-                const bool colok = col < p.N;
-                EpiConst kc;
+                const bool colok = okn;
+                const EpiConst kc = kcn;
                 float4 in[8];
-                if (colok) {
-                    kc = epilogue_consts<EPI>(p, col);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        in[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (tq + 4 * i < p.T) in[i] = epilogue_load<EPI, BF16>(p, (long long)bt * p.T + tq + 4 * i, col);
-                    }
-                }
+                for (int i = 0; i < 8; ++i) in[i] = inn[i];
+                if (j + 2 < BLOCK_N / 32 && col0 + 64 < p.N) load_chunk(j + 2);
                 tmem_ld_wait();
                 // transpose through the warp's private 16-row staging tile, two passes: thread = row -> lane = 4 columns
 #pragma unroll
