@@ -279,9 +279,14 @@ def dominant_kernel_roofline(model, w, precision, reps=5):
     if 'wavenet_stack_kernel' in name and os.path.exists(prof) and (B, T, Cc, L) == (16, 690, 256, 20):
         try:
             import csv
-            vals = {r[0]: (r[1], float(r[2])) for r in csv.reader(open(prof)) if len(r) >= 3 and r[0].startswith('dram__bytes')}
+            rows = list(csv.reader(open(prof)))
             scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-            traffic = sum(v * scale[u] for u, v in vals.values())
+            if rows and 'dram__bytes_read.sum' in rows[0]:      # `ncu --page raw --csv`: header row, unit row, one row per launch
+                cols = [rows[0].index(k) for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum')]
+                traffic = sum(float(rows[2][c].replace(',', '')) * scale[rows[1][c]] for c in cols)
+            else:                                               # one metric per row: name, unit, value
+                vals = {r[0]: (r[1], float(r[2])) for r in rows if len(r) >= 3 and r[0].startswith('dram__bytes')}
+                traffic = sum(v * scale[u] for u, v in vals.values())
         except Exception:                                   # noqa: BLE001
             traffic = None
     achieved = flops / (ms * 1e-3) / 1e12
