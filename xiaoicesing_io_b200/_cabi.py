@@ -62,7 +62,7 @@ class B2SError(RuntimeError):
 
 
 def _load():
-    path = _build.LIB_PATH
+    path = os.environ.get('B2S_LIB', _build.LIB_PATH)       # B2S_LIB: A/B measurements of two builds on the same GPU box
     if not os.path.exists(path):
         raise ImportError(
             f'{path} is missing: the CUDA extension has not been built.  Run '
