@@ -397,6 +397,11 @@ def run_b200_arm(args, w):
             1 for i, op in enumerate(prog.ops)
             if op.kind == 'nfe' and i > 0 and prog.ops[i - 1].kind == 'lin' and prog.ops[i - 1].dst == op.src)
         launches_per_step = nfe * sess_launches - n_precast + n_lin + n_noise + 2 + 4   # + start transposes + tables
+        if not args.no_graph:
+            from xiaoicesing_io_b200.core import _sampling as _S
+            counted = [g.n_launches for g in _S._GRAPH_CACHE.values() if hasattr(g, 'n_launches')]
+            if counted:
+                launches_per_step = counted[-1]          # counted while the replayed graph was captured
         F = flops_per_frame_nfe(w['layers'], w['channels'], w['mel'], w.get('kind', 'wavenet'))
         p = peaks()
         line = {

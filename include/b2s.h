@@ -219,6 +219,22 @@ int b2s_tc_wavenet_denoiser(const void* xin_h, int MF, const void* Win_h, int ld
                             const void* Wsp_h, const float* b_sp, const void* Wfin_h, const float* b_fin, float* out, int B, int T,
                             int C, int* flags, int bf16, void* stream);
 
+/* b2s_tc_wavenet_denoiser + the sampler update that consumes its output, in the same launch (ancestral / DDIM-type steps,
+ * ddpm.py:149-167): x' = sum_i coef[i] * src_i for n_terms <= 3 terms in the order given, where srcs_host[i] == NULL stands
+ * for THIS evaluation's output (eps_hat) and the other sources are fp32 [B*T, MF] buffers (the state x, the step's noise);
+ * same fma order as b2s_sampler_lincomb_f32, so results are bit-identical to evaluation + update as two launches.
+ * x_out (fp32, may alias a source) and x_out_h (16-bit: the next evaluation's xin_h; may alias this launch's xin_h - a tile
+ * only overwrites the rows it alone has read) receive x'; the evaluation's output itself is not stored.
+ * flags_next: the tile flags of the NEXT launch (or NULL): zeroed here, so consecutive launches alternate two flag buffers
+ * and need no reset kernel in between. */
+int b2s_tc_wavenet_denoiser_update(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, void* y0_h,
+                                   void* y1_h, const void* Wd_h, const void* cond_h, int64_t cond_layer_stride, const void* Wo_h,
+                                   const float* bo, float* x, float* skip, const float* dvec, int d_stride,
+                                   const int* dilations_host, int L, const void* Wsp_h, const float* b_sp, const void* Wfin_h,
+                                   const float* b_fin, int B, int T, int C, int* flags, int* flags_next, int n_terms,
+                                   const float* const* srcs_host, const float* coef, float* x_out, void* x_out_h, int bf16,
+                                   void* stream);
+
 /* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
  * down-projection with the residual add into the fp32 stream. */
 int b2s_tc_lynx_glu(const void* h_h, const void* W_h, const float* bias, void* g_h, int rows, int C, int inner, int bf16,

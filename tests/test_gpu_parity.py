@@ -215,18 +215,20 @@ def test_cuda_graph_replay_equals_eager(dev):
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 @pytest.mark.parametrize('graph', [False, True])
 def test_launch_structure_switches_do_not_change_results(precision, graph, dev):
-    """``b2s_overlap_noise`` (per-step noise draws on a side stream, a parallel branch of the captured graph) and
-    ``b2s_fuse_cast`` (the sampler update writes the 16-bit denoiser input itself) only change WHICH launches run WHERE:
+    """``b2s_overlap_noise`` (per-step noise draws on a side stream, a parallel branch of the captured graph),
+    ``b2s_fuse_cast`` (the sampler update writes the 16-bit denoiser input itself) and ``b2s_fuse_update`` (the update runs
+    inside the whole-denoiser launch; bf16 / fp16 sessions only) only change WHICH launches run WHERE:
     seeded ancestral sampling must give bit-identical mels with the switches on and off, eagerly and from a graph replay
     (same draw order on the default generator, same arithmetic)."""
     import xiaoicesing_io_b200 as P
     from xiaoicesing_io_b200.core import _sampling
     outs = []
-    for overlap, fuse_cast in [(True, True), (False, True), (True, False), (False, False)]:
+    for overlap, fuse_cast, fuse_update in [(True, True, True), (False, True, True), (True, True, False), (False, True, False),
+                                           (True, False, False), (False, False, False)]:
         P.hparams.clear()
         P.hparams.update(hidden_size=256, schedule_type='linear', use_shallow_diffusion=True, K_step_infer=9, diff_speedup=1,
                          infer=False, b2s_precision=precision, b2s_cuda_graph=graph, b2s_overlap_noise=overlap,
-                         b2s_fuse_cast=fuse_cast)
+                         b2s_fuse_cast=fuse_cast, b2s_fuse_update=fuse_update)
         torch.manual_seed(0)
         model = P.GaussianDiffusion(128, k_step=9, backbone_type='wavenet',
                                     backbone_args=dict(num_layers=4, num_channels=256, dilation_cycle_length=4),

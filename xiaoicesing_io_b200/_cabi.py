@@ -45,6 +45,8 @@ _SIGNATURES = {
     'b2s_tc_wavenet_stack_t': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _i, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_wavenet_denoiser': [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i,
                                 _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    'b2s_tc_wavenet_denoiser_update': [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i,
+                                       _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, ctypes.POINTER(_vp), _vp, _vp, _vp, _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_lynx_prenorm_h': [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -86,7 +88,12 @@ lib = _load()
 LIB_PATH = _build.LIB_PATH
 
 
+N_CALLS = 0     # successful kernel-launching C-ABI calls so far (every entry point launches exactly one kernel)
+
+
 def check(rc: int, what: str = ''):
+    global N_CALLS
+    N_CALLS += 1
     if rc != 0:
         raise B2SError(f'{what} failed (code {rc}): {lib.b2s_last_error().decode()}')
 
@@ -232,6 +239,20 @@ def tc_wavenet_stack(y0_h, y1_h, Wd_h, cond_h, ld_cond, cond_layer_stride, Wo_h,
     check(lib.b2s_tc_wavenet_stack(ptr(y0_h), ptr(y1_h), ptr(Wd_h), ptr(cond_h), ld_cond, cond_layer_stride, ptr(Wo_h),
                                    ptr(bo), ptr(x), ptr(skip), ptr(skip_h), ptr(dvec), d_stride, dil, L, B, T, C,
                                    ptr(flags), int(bf16), stream_ptr()), 'b2s_tc_wavenet_stack')
+
+
+def tc_wavenet_denoiser_update(xin_h, MF, Win_h, ld_win, b_in, y0_h, y1_h, Wd_h, cond_h, cond_layer_stride, Wo_h, bo, x, skip, dvec,
+                               d_stride, dilations, Wsp_h, b_sp, Wfin_h, b_fin, B, T, C, flags, flags_next, srcs, coef, x_out,
+                               x_out_h, bf16):
+    """srcs: fp32 tensors or None (None = this evaluation's output), in term order; coef: device fp32 view of len(srcs)."""
+    L = len(dilations)
+    dil = (_i * L)(*dilations)
+    arr = (_vp * len(srcs))(*[None if t is None else t.data_ptr() for t in srcs])
+    check(lib.b2s_tc_wavenet_denoiser_update(ptr(xin_h), MF, ptr(Win_h), ld_win, ptr(b_in), ptr(y0_h), ptr(y1_h), ptr(Wd_h),
+                                             ptr(cond_h), cond_layer_stride, ptr(Wo_h), ptr(bo), ptr(x), ptr(skip), ptr(dvec),
+                                             d_stride, dil, L, ptr(Wsp_h), ptr(b_sp), ptr(Wfin_h), ptr(b_fin), B, T, C, ptr(flags),
+                                             ptr(flags_next), len(srcs), arr, ptr(coef), ptr(x_out), ptr(x_out_h), int(bf16),
+                                             stream_ptr()), 'b2s_tc_wavenet_denoiser_update')
 
 
 def tc_cond_retile(table_h, L, B, T, n2, NT, out_h):

@@ -707,6 +707,15 @@ struct __align__(64) StackP {
     const float* b_in; const float* b_sp; const float* b_fin;
     float alpha_head;                                     // 1 / sqrt(L)
     float* out;                                           // [rows, MF] fp32
+    // ---- sampler update inside the head epilogue (upd_n > 0): x' = sum_i coef[i] * src_i, src_i = upd_src[i] or, where
+    //      upd_src[i] is NULL, this evaluation's output; x' -> upd_x (fp32, may alias a source) and upd_xh (16-bit: the
+    //      next evaluation's input).  `out` is not written then.
+    int upd_n;
+    const float* upd_src[3];
+    const float* upd_coef;
+    float* upd_x;
+    void* upd_xh;
+    int* flags_next;                                      // the NEXT launch's tile flags: every CTA zeroes its own entry
 };
 
 // phase timestamps of CTA 2 for scripts/stack_timeline.py; compiled in only with -DB2S_TLOG (B2S_BUILD_TLOG=1 python _build.py)
@@ -786,8 +795,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    pdl_launch_dependents();
+    // The dependent launch is released LATE (when the epilogue warps reach the head, see below): released here, the next
+    // denoiser launch of a fused-update step would park its CTAs on the SMs this grid leaves idle and starve the side-stream
+    // noise kernels that are supposed to run there meanwhile (measured: 2 % slower).
     pdl_wait();
+    if (threadIdx.x == 64 && p.flags_next) p.flags_next[blockIdx.x] = 0;     // re-arm the next launch (it starts after this grid ends)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -1209,6 +1221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
             }
             if (e == 0) TLOG(10);                                       // EPI2 skip half done
         }
+        pdl_launch_dependents();
         if (p.fuse) {
             const uint32_t pl = p.L & 1;
             // ---- EPI3 (thread = frame row): hidden = relu(alpha * acc + b_sp) -> 16-bit, back into the z buffer ----
@@ -1244,7 +1257,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
             // ---- EPI4 (coalesced layout): out = acc + b_fin -> fp32 [rows, MF] ----
             mbar_wait(&accb[1], pl);
             tc_fence_after();
-            float* orow = p.out + ((long long)b * p.T + tq) * p.MF + cl;
+            const long long orow_off = ((long long)b * p.T + tq) * p.MF + cl;
+            float uc[3] = {0.f, 0.f, 0.f};
+            for (int n = 0; n < p.upd_n; ++n) uc[n] = __ldg(p.upd_coef + n);
+            // the (at most two) buffer operands of the update: all 8 rows of a chunk are requested BEFORE the first store - the
+            // destination aliases a source, so loads issued after a store would be serialised behind it
+            const float* upA = nullptr;
+            const float* upB = nullptr;
+            for (int n = 0; n < p.upd_n; ++n)
+                if (p.upd_src[n]) { if (!upA) upA = p.upd_src[n]; else upB = p.upd_src[n]; }
 #pragma unroll 1
             for (int jj = 0; jj < 4; ++jj) {
                 const int j = 2 * jj + sub, col = j * 32 + cl;
@@ -1252,6 +1273,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 float acc[32];
                 tmem_ld32(taddr + BN + j * 32, acc);
                 const float4 bias = col < p.MF ? __ldg(reinterpret_cast<const float4*>(p.b_fin + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 preA[8], preB[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const long long off = orow_off + j * 32 + (long long)i * 4 * p.MF;
+                    const bool okr = (vmask >> i & 1) && col < p.MF;
+                    preA[i] = (upA && okr) ? *reinterpret_cast<const float4*>(upA + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    preB[i] = (upB && okr) ? *reinterpret_cast<const float4*>(upB + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
@@ -1267,8 +1296,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                         const int i = 4 * pass + i2;
                         if ((vmask >> i & 1) && col < p.MF) {
                             const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
-                            *reinterpret_cast<float4*>(orow + j * 32 + (long long)i * 4 * p.MF) =
-                                make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+                            const float4 o = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+                            const long long off = orow_off + j * 32 + (long long)i * 4 * p.MF;
+                            if (p.upd_n == 0) {
+                                *reinterpret_cast<float4*>(p.out + off) = o;
+                            } else {
+                                // same operation order as lincomb_kernel: acc = 0; acc = fma(c_i, src_i, acc) in term order
+                                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                                bool usedA = false;
+                                for (int n = 0; n < p.upd_n; ++n) {
+                                    const float c = uc[n];
+                                    float4 sv = o;
+                                    if (p.upd_src[n]) { sv = usedA ? preB[i] : preA[i]; usedA = true; }
+                                    u.x = fmaf(c, sv.x, u.x);
+                                    u.y = fmaf(c, sv.y, u.y);
+                                    u.z = fmaf(c, sv.z, u.z);
+                                    u.w = fmaf(c, sv.w, u.w);
+                                }
+                                *reinterpret_cast<float4*>(p.upd_x + off) = u;
+                                uint2 h;
+                                h.x = Half16<BF16>::pack2(u.x, u.y);
+                                h.y = Half16<BF16>::pack2(u.z, u.w);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.upd_xh) + off) = h;
+                            }
                         }
                     }
                     __syncwarp();
@@ -1740,6 +1790,7 @@ extern "C" int b2s_tc_wavenet_stack_max_tiles(void) { return num_sms(); }
 struct DenoiserIO {            // stem / head operands of b2s_tc_wavenet_denoiser (all NULL for the plain stack)
     const void* xin_h; int MF; const void* Win_h; int ld_win; const float* b_in;
     const void* Wsp_h; const float* b_sp; const void* Wfin_h; const float* b_fin; float* out;
+    int upd_n; const float* upd_src[3]; const float* upd_coef; float* upd_x; void* upd_xh; int* flags_next;
 };
 
 static int stack_impl(void* y0_h, void* y1_h, const void* Wd_h, const void* cond_h, int ld_cond, int64_t cond_layer_stride,
@@ -1784,12 +1835,19 @@ static int stack_impl(void* y0_h, void* y1_h, const void* Wd_h, const void* cond
     p.x = x; p.ybuf[0] = y0_h; p.ybuf[1] = y1_h; p.skip = skip; p.skip_h = skip_h;
     p.dvec = dvec; p.d_stride = d_stride; p.flags = flags;
     if (io) {
-        B2S_CHECK_ARG(io->xin_h && io->Win_h && io->b_in && io->Wsp_h && io->b_sp && io->Wfin_h && io->b_fin && io->out,
+        B2S_CHECK_ARG(io->xin_h && io->Win_h && io->b_in && io->Wsp_h && io->b_sp && io->Wfin_h && io->b_fin && (io->out || io->upd_n > 0),
                       "b2s_tc_wavenet_denoiser: null pointer");
+        B2S_CHECK_ARG(io->upd_n >= 0 && io->upd_n <= 3, "b2s_tc_wavenet_denoiser_update: 1 <= n_terms <= 3 (got %d)", io->upd_n);
+        if (io->upd_n > 0) {
+            B2S_CHECK_ARG(io->upd_coef && io->upd_x && io->upd_xh && al16(io->upd_x) && al16(io->upd_xh),
+                          "b2s_tc_wavenet_denoiser_update: null or misaligned update operand");
+            for (int i = 0; i < io->upd_n; ++i)
+                B2S_CHECK_ARG(al16(io->upd_src[i]), "b2s_tc_wavenet_denoiser_update: misaligned source %d", i);
+        }
         B2S_CHECK_ARG(io->MF > 0 && io->MF <= ws::BN && io->MF % 8 == 0 && io->ld_win % 8 == 0,
                       "b2s_tc_wavenet_denoiser: in_dims*n_feats must be a multiple of 8 and <= %d (got %d)", ws::BN, io->MF);
         B2S_CHECK_ARG(al16(io->xin_h) && al16(io->Win_h) && al16(io->b_in) && al16(io->Wsp_h) && al16(io->b_sp) && al16(io->Wfin_h) &&
-                          al16(io->b_fin) && al16(io->out), "b2s_tc_wavenet_denoiser: misaligned pointer");
+                          al16(io->b_fin) && (!io->out || al16(io->out)), "b2s_tc_wavenet_denoiser: misaligned pointer");
         p.fuse = 1; p.MF = io->MF; p.kb_in = ceil_div(io->MF, ws::BK);
         rc = make_map_act(&p.mapXin, io->xin_h, bf16, io->MF, io->MF, T, B, ws::BK, ws::BM);
         if (rc) return rc;
@@ -1800,6 +1858,8 @@ static int stack_impl(void* y0_h, void* y1_h, const void* Wd_h, const void* cond
         rc = make_map_w(&p.mapWfin, io->Wfin_h, bf16, C, io->MF, C, ws::BK, ws::BN / 2);
         if (rc) return rc;
         p.b_in = io->b_in; p.b_sp = io->b_sp; p.b_fin = io->b_fin; p.out = io->out;
+        p.upd_n = io->upd_n; p.upd_coef = io->upd_coef; p.upd_x = io->upd_x; p.upd_xh = io->upd_xh; p.flags_next = io->flags_next;
+        for (int i = 0; i < 3; ++i) p.upd_src[i] = i < io->upd_n ? io->upd_src[i] : nullptr;
         p.alpha_head = 1.0f / sqrtf((float)L);
     }
     static const int dbg = getenv("B2S_STACK_DBG") ? atoi(getenv("B2S_STACK_DBG")) : 0;
@@ -1822,7 +1882,22 @@ extern "C" int b2s_tc_wavenet_denoiser(const void* xin_h, int MF, const void* Wi
                                        const void* Wo_h, const float* bo, float* x, float* skip, const float* dvec, int d_stride,
                                        const int* dilations_host, int L, const void* Wsp_h, const float* b_sp, const void* Wfin_h,
                                        const float* b_fin, float* out, int B, int T, int C, int* flags, int bf16, void* stream) {
-    DenoiserIO io{xin_h, MF, Win_h, ld_win, b_in, Wsp_h, b_sp, Wfin_h, b_fin, out};
+    DenoiserIO io{xin_h, MF, Win_h, ld_win, b_in, Wsp_h, b_sp, Wfin_h, b_fin, out, 0, {nullptr, nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr};
+    return stack_impl(y0_h, y1_h, Wd_h, cond_h, 2 * C, cond_layer_stride, Wo_h, bo, x, skip, nullptr, dvec, d_stride, dilations_host,
+                      L, B, T, C, flags, bf16, stream, &io);
+}
+
+extern "C" int b2s_tc_wavenet_denoiser_update(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, void* y0_h,
+                                              void* y1_h, const void* Wd_h, const void* cond_h, int64_t cond_layer_stride,
+                                              const void* Wo_h, const float* bo, float* x, float* skip, const float* dvec, int d_stride,
+                                              const int* dilations_host, int L, const void* Wsp_h, const float* b_sp, const void* Wfin_h,
+                                              const float* b_fin, int B, int T, int C, int* flags, int* flags_next, int n_terms,
+                                              const float* const* srcs_host, const float* coef, float* x_out, void* x_out_h, int bf16,
+                                              void* stream) {
+    B2S_CHECK_ARG(n_terms >= 1 && n_terms <= 3 && srcs_host, "b2s_tc_wavenet_denoiser_update: 1 <= n_terms <= 3 (got %d)", n_terms);
+    DenoiserIO io{xin_h, MF, Win_h, ld_win, b_in, Wsp_h, b_sp, Wfin_h, b_fin, nullptr, n_terms, {nullptr, nullptr, nullptr}, coef, x_out, x_out_h,
+                  flags_next};
+    for (int i = 0; i < n_terms; ++i) io.upd_src[i] = srcs_host[i];
     return stack_impl(y0_h, y1_h, Wd_h, cond_h, 2 * C, cond_layer_stride, Wo_h, bo, x, skip, nullptr, dvec, d_stride, dilations_host,
                       L, B, T, C, flags, bf16, stream, &io);
 }

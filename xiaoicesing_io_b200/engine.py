@@ -250,6 +250,7 @@ class WaveNetSessionTC:
         self.tgroups = self._plan_transposed(cond_h) if (self.stack_group and hparams.get('b2s_stack_t', False)) else None
         if self.tgroups:
             self.flags = torch.zeros((max(B * tpb, sum(g[4] for g in self.tgroups)),), device=dev, dtype=torch.int32)
+        self.flags_alt = torch.zeros_like(self.flags) if self.flags is not None else None
         if self.stack_group and not self.tgroups:
             # one table per utterance group, in the tile/chunk-major layout the stack kernel reads with coalesced loads
             self.cond_groups = []
@@ -308,9 +309,34 @@ class WaveNetSessionTC:
         return groups
 
     def half_sink(self):
-        """(16-bit input buffer, tile flags, bf16): a sampler update that produces the next denoiser input can write its
-        16-bit copy (and re-arm the flags) itself - ``eval(..., precast=True)`` then skips the cast launch."""
+        """(16-bit input buffer, tile flags of the NEXT evaluation, bf16): a sampler update that produces the next denoiser
+        input can write its 16-bit copy (and re-arm the flags) itself - ``eval(..., precast=True)`` then skips the cast."""
         return self.xin_h, self.flags, self.eng.bf16
+
+    @property
+    def can_fuse_update(self) -> bool:
+        return bool(self.stack_group) and not self.tgroups and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256
+
+    def eval_update(self, x_in, k, srcs, coef, x_dst, precast=False):
+        """One launch: denoiser evaluation + ``x_dst <- sum coef[i] * srcs[i]`` (``None`` in srcs = the evaluation's output),
+        the 16-bit copy of x_dst for the next evaluation, and the next launch's tile flags re-armed (two flag buffers alternate)."""
+        e = self.eng
+        B, T, Cc, L, MF, bf = self.B, self.T, e.C, e.L, e.MF, e.bf16
+        if not precast:
+            C.cast_h(x_in, self.xin_h, bf, reset_flags=self.flags)
+        LC = L * Cc
+        dv = self.dtab.reshape(-1) if self.per_row_t else self.dtab[k]
+        for gi, b0 in enumerate(range(0, B, self.stack_group)):
+            b1 = min(B, b0 + self.stack_group)
+            r0 = b0 * T
+            tab = self.cond_groups[gi]
+            C.tc_wavenet_denoiser_update(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, self.y_h[r0:], self.y2_h[r0:],
+                                         e.w_dil_h, tab, tab.shape[1] * 2 * Cc, e.w_out_h, e.b_out, self.x[r0:], self.skip[r0:],
+                                         dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0, e.dilations,
+                                         e.w_sp_h, e.b_sp, e.w_fin_h, e.b_fin, b1 - b0, T, Cc, self.flags[b0 * self.tpb:],
+                                         self.flags_alt[b0 * self.tpb:], [None if t is None else t[r0:] for t in srcs], coef,
+                                         x_dst[r0:], self.xin_h[r0:], bf)
+        self.flags, self.flags_alt = self.flags_alt, self.flags
 
     def eval(self, x_in: torch.Tensor, k: int, out: torch.Tensor, precast: bool = False):
         e = self.eng
@@ -668,35 +694,113 @@ class CompiledProgram:
         self.n_lin = sum(1 for op in prog.ops if op.kind == 'lin')
 
 
+def _fusable_update(prog: Program, i: int):
+    """ops[i] is an nfe.  Returns (index of the step's noise op or None, index of the lin op) when the update that follows
+    can run inside the denoiser launch: ``x <- c0 x + c1 eps_hat (+ c2 z)`` written back to the evaluation's own input
+    buffer (ancestral and DDIM-type steps, ddpm.py:149-167), with eps_hat not needed by anything else."""
+    ops = prog.ops
+    nfe = ops[i]
+    j, noise = i + 1, None
+    if j < len(ops) and ops[j].kind == 'noise':
+        noise, j = j, j + 1
+    if j >= len(ops) or ops[j].kind != 'lin':
+        return None
+    lin = ops[j]
+    names = [b for b, _ in lin.terms]
+    if lin.dst != nfe.src or nfe.dst not in names or len(names) > 3 or len(set(names)) != len(names):
+        return None
+    zname = ops[noise].dst if noise is not None else None
+    if zname in (nfe.src, nfe.dst) or any(b not in (nfe.src, nfe.dst, zname) for b in names):
+        return None
+    for op in ops[j + 1:]:                      # eps_hat is never materialised: nobody may read it afterwards
+        reads = [op.src] if op.kind == 'nfe' else ([b for b, _ in op.terms] if op.kind == 'lin' else [])
+        if nfe.dst in reads:
+            return None
+        if op.dst == nfe.dst:
+            break
+    else:
+        if prog.result == nfe.dst:
+            return None
+    return noise, j
+
+
 def run_program(cp: CompiledProgram, session, bufs: Dict[str, torch.Tensor],
                 draw_noise: Optional[Callable[[int, torch.Tensor], None]] = None) -> torch.Tensor:
     """Executes the program.  ``bufs`` maps buffer names to [B*T, MF] fp32 device tensors (NOISE0 /
     XSTART pre-filled by the caller); ``draw_noise(j, dst)`` fills ``dst`` with the j-th per-step draw.
 
-    A per-step noise draw that directly follows a denoiser evaluation (ancestral sampling, ddpm.py:149-156) does not depend
-    on it: it is issued on a side stream BEFORE the evaluation is launched and joined before the update that consumes it,
-    so the draw + layout change overlap the persistent denoiser kernel (which leaves SMs idle at small batches).  The
-    draws keep their call order, so the random stream - and the result - are unchanged; under CUDA-graph capture the
-    fork / join becomes a parallel branch of the graph."""
+    Launch structure (none of it changes a result bit - ``test_launch_structure_switches_do_not_change_results``):
+    * ``b2s_fuse_update`` (OFF by default): an evaluation followed by ``x <- c0 x + c1 eps_hat (+ c2 z)`` is ONE launch - the
+      update runs in the head epilogue of the whole-denoiser kernel, which also writes the next evaluation's 16-bit input and
+      re-arms the next launch's tile flags; an ancestral step is then one kernel on the critical path.  Measured 1 % SLOWER
+      than the separate update launch (the update's operand loads are a latency chain in 96 CTAs' tails, the separate kernel
+      streams them on all 148 SMs in 6 us), so it stays a tested switch.
+    * ``b2s_overlap_noise``: per-step noise draws run on a side stream, concurrently with a denoiser launch that does not
+      need them (the draw of step s+1 during the fused launch of step s, into the other of two noise buffers).  The draws keep
+      their call order, so the random stream is unchanged; under CUDA-graph capture the fork / join is a parallel branch.
+    * ``b2s_fuse_cast``: any other update that feeds an evaluation writes its 16-bit input itself."""
     prog = cp.prog
     ops = prog.ops
+    dev = bufs[prog.result].device
     main = torch.cuda.current_stream()
     side = None
-    hoisted = set()
-    # 16-bit sessions: the update that produces the next denoiser input also writes its 16-bit copy (one launch less per NFE)
-    sink = session.half_sink() if (hasattr(session, 'half_sink') and hparams.get('b2s_fuse_cast', True)) else None
-    precast = set()
+    overlap = hparams.get('b2s_overlap_noise', True)
+    use_sink = hasattr(session, 'half_sink') and hparams.get('b2s_fuse_cast', True)
+    fuse_upd = hparams.get('b2s_fuse_update', False) and getattr(session, 'can_fuse_update', False)
+    done, precast = set(), set()
+    pre_drawn: Dict[int, torch.Tensor] = {}     # noise op index -> buffer being filled on the side stream
+    zb, zflip = None, 0
     for i, (op, off) in enumerate(zip(ops, cp.offsets)):
+        if i in done:
+            continue
         if op.kind == 'nfe':
+            fus = _fusable_update(prog, i) if fuse_upd else None
+            if fus is not None:
+                ni, j = fus
+                lin = ops[j]
+                zsel = None
+                if ni is not None:
+                    if zb is None:
+                        bufs['__noise_alt'] = torch.empty_like(bufs[ops[ni].dst])
+                        zb = [bufs[ops[ni].dst], bufs['__noise_alt']]
+                    if ni in pre_drawn:
+                        zsel = pre_drawn.pop(ni)
+                        main.wait_stream(side)
+                    else:
+                        zsel, zflip = zb[zflip], zflip ^ 1
+                        draw_noise(ops[ni].draw, zsel)
+                    done.add(ni)
+                srcs = [None if b == op.dst else (zsel if (ni is not None and b == ops[ni].dst) else bufs[b]) for b, _ in lin.terms]
+                ev = None
+                if overlap:
+                    ev = torch.cuda.Event()
+                    ev.record(main)                     # everything before this launch (the reader of the other noise buffer) is done
+                n = len(lin.terms)
+                session.eval_update(bufs[op.src], op.t_index, srcs, cp.coef[cp.offsets[j]:cp.offsets[j] + n], bufs[lin.dst],
+                                    precast=i in precast)
+                done.add(j)
+                k = j + 1
+                if k < len(ops) and ops[k].kind == 'nfe' and ops[k].src == lin.dst:
+                    precast.add(k)
+                    f2 = _fusable_update(prog, k) if overlap else None
+                    if f2 is not None and f2[0] is not None and zb is not None:
+                        if side is None:
+                            side = torch.cuda.Stream(device=dev)
+                        ztarget, zflip = zb[zflip], zflip ^ 1
+                        side.wait_event(ev)
+                        with torch.cuda.stream(side):
+                            draw_noise(ops[f2[0]].draw, ztarget)
+                        pre_drawn[f2[0]] = ztarget
+                continue
             nxt = ops[i + 1] if i + 1 < len(ops) else None
             joined = False
-            if (nxt is not None and nxt.kind == 'noise' and nxt.dst not in (op.src, op.dst) and hparams.get('b2s_overlap_noise', True)):
+            if nxt is not None and nxt.kind == 'noise' and nxt.dst not in (op.src, op.dst) and overlap:
                 if side is None:
-                    side = torch.cuda.Stream(device=bufs[op.dst].device)
+                    side = torch.cuda.Stream(device=dev)
                 side.wait_stream(main)                      # earlier readers of the noise buffer are done
                 with torch.cuda.stream(side):
                     draw_noise(nxt.draw, bufs[nxt.dst])
-                hoisted.add(i + 1)
+                done.add(i + 1)
                 joined = True
             if i in precast:
                 session.eval(bufs[op.src], op.t_index, bufs[op.dst], precast=True)
@@ -707,12 +811,13 @@ def run_program(cp: CompiledProgram, session, bufs: Dict[str, torch.Tensor],
         elif op.kind == 'lin':
             n = len(op.terms)
             nxt = ops[i + 1] if i + 1 < len(ops) else None
-            if sink is not None and nxt is not None and nxt.kind == 'nfe' and nxt.src == op.dst:
-                C.lincomb_h(bufs[op.dst], [bufs[b] for b, _ in op.terms], cp.coef[off:off + n], sink[0], sink[2], reset_flags=sink[1])
+            if use_sink and nxt is not None and nxt.kind == 'nfe' and nxt.src == op.dst:
+                xin_h, flags, bf = session.half_sink()
+                C.lincomb_h(bufs[op.dst], [bufs[b] for b, _ in op.terms], cp.coef[off:off + n], xin_h, bf, reset_flags=flags)
                 precast.add(i + 1)
             else:
                 C.lincomb(bufs[op.dst], [bufs[b] for b, _ in op.terms], cp.coef[off:off + n])
-        elif i not in hoisted:
+        else:
             draw_noise(op.draw, bufs[op.dst])
     return bufs[prog.result]
 
