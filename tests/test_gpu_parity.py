@@ -69,7 +69,7 @@ def test_sampling_vs_reference_fixture(name, dev):
         assert _maxabs(o, r) <= tol, (name, _maxabs(o, r), float(r.abs().max()))
 
 
-def _oracle_and_product(cfg, hp, sampler_kw, B, T, dev, seed=1234, sigma_w=0.01, n_draws=1, src=False):
+def _oracle_and_product(cfg, hp, sampler_kw, B, T, dev, seed=1234, sigma_w=0.01, n_draws=1, src=False, oracle_on_gpu=False):
     import xiaoicesing_io_b200 as P
     P.hparams.clear()
     P.hparams.update(hidden_size=cfg.hidden_size, schedule_type='linear', infer=False, **hp)
@@ -92,12 +92,27 @@ def _oracle_and_product(cfg, hp, sampler_kw, B, T, dev, seed=1234, sigma_w=0.01,
         x_start = OS.norm_spec(src_spec, torch.tensor(-12.), torch.tensor(0.)).transpose(-2, -1)[:, None]
     use_shallow = hp.get('use_shallow_diffusion', False)
     k_step = sampler_kw.get('k_step', 1000) if use_shallow else sampler_kw.get('timesteps', 1000)
-    x = OS.gaussian_diffusion_inference(
-        OD.make_denoiser(sd, cfg), sch, condition.transpose(1, 2), k_step=k_step,
-        timesteps=sampler_kw.get('timesteps', 1000), use_shallow=use_shallow,
-        K_step_infer=hp.get('K_step_infer', k_step), speedup=hp['diff_speedup'],
-        accelerator=hp.get('diff_accelerator', 'ddim'), noise0=draws[0], x_start=x_start, step_noise=draws[1:])
-    ref = OS.denorm_spec(x, torch.tensor(-12.), torch.tensor(0.))
+    denoise, to = OD.make_denoiser(sd, cfg), (lambda t: t)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    if oracle_on_gpu:
+        # the oracle is plain torch code over a state dict: with its tensors on the GPU (TF32 off) it is a strict-fp32 truth
+        # that finishes FULL-SIZE batches in seconds (the CPU oracle needs minutes for 16 x 690 frames)
+        sd_gpu = {k: v.to(dev) for k, v in sd.items()}
+        denoise = lambda x, t, c: OD.wavenet_forward(sd_gpu, cfg, x, t.to(dev), c)
+        to = lambda t: t.to(dev)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            x = OS.gaussian_diffusion_inference(
+                denoise, sch, to(condition.transpose(1, 2)), k_step=k_step,
+                timesteps=sampler_kw.get('timesteps', 1000), use_shallow=use_shallow,
+                K_step_infer=hp.get('K_step_infer', k_step), speedup=hp['diff_speedup'],
+                accelerator=hp.get('diff_accelerator', 'ddim'), noise0=to(draws[0]),
+                x_start=None if x_start is None else to(x_start), step_noise=[to(d) for d in draws[1:]])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    ref = OS.denorm_spec(x.cpu(), torch.tensor(-12.), torch.tensor(0.))
     return out, ref
 
 
@@ -110,6 +125,23 @@ def test_config1_full_size_wavenet_20x256(acc, dev):
     err = _maxabs(out, ref)
     print(f'config1 {acc}: max-abs {err:.3e}, |mel|max {float(ref.abs().max()):.1f}')
     assert err <= FP32_TOL
+
+
+@pytest.mark.parametrize('K', [8, 400])
+@pytest.mark.parametrize('precision,tol', [('fp32', FP32_TOL), ('bf16', 2e-2), ('fp16', 2e-2)])
+def test_config2_full_batch_against_gpu_oracle(precision, tol, K, dev):
+    """BASELINE config 2 at its FULL size: 16 utterances x 690 frames, WaveNet 20x256, shallow ancestral sampling with
+    per-step noise, K = 8 and the headline's K_step = 400.  The oracle runs on the GPU in strict fp32 (TF32 off) on the
+    same pre-drawn noise (401 draws of [16, 1, 128, 690] for K = 400)."""
+    cfg = OD.WaveNetCfg()
+    out, ref = _oracle_and_product(
+        cfg, dict(use_shallow_diffusion=True, K_step_infer=K, diff_speedup=1, b2s_precision=precision), dict(k_step=K),
+        16, 690, dev, n_draws=K + 1, src=True, oracle_on_gpu=True)
+    import xiaoicesing_io_b200 as P
+    P.hparams.pop('b2s_precision', None)
+    err = _maxabs(out, ref)
+    print(f'config2 full batch ddpm K={K} {precision}: max-abs {err:.3e}, |mel|max {float(ref.abs().max()):.1f}')
+    assert err <= tol
 
 
 def test_config2_shape_shallow_ddpm_ragged_T(dev):
