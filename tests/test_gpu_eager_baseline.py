@@ -109,3 +109,100 @@ def test_full_size_parity_and_eager_baseline(dev):
         json.dump(report, f, indent=1)
     print(json.dumps(report))
     assert ms['product_bf16_call'] < ms['eager_autocast_bf16'], ms
+
+
+def _strict_fp32():
+    class _Ctx:
+        def __enter__(self):
+            self.old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+
+        def __exit__(self, *a):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.old
+    return _Ctx()
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-3), ('bf16', 2e-2), ('fp16', 2e-2)])
+def test_config3_full_width_lynxnet_against_gpu_oracle(precision, tol, dev):
+    """BASELINE config 3 at the full model width: rectified-flow Euler 20 steps, LYNXNet 6 x 1024 (expansion 2, depthwise k = 31,
+    strong_cond), 16 utterances x 690 frames, against the oracle on the GPU in strict fp32."""
+    import xiaoicesing_io_b200 as P
+    from oracle import samplers as OS
+    cfg = OD.LYNXNetCfg(num_channels=1024, num_layers=6, kernel_size=31, strong_cond=True, hidden_size=256)
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, use_shallow_diffusion=False, sampling_algorithm='euler', sampling_steps=20, infer=False,
+                     b2s_precision=precision)
+    model = P.RectifiedFlow(128, backbone_type='lynxnet', backbone_args=dict(num_layers=6, num_channels=1024, kernel_size=31,
+                                                                             strong_cond=True),
+                            spec_min=[-12.], spec_max=[0.])
+    sd = OW.make_state_dict(cfg, seed=0, sigma_w=0.01)
+    model.velocity_fn.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(7)
+    Bc, Tc = 16, 690
+    condition = torch.randn((Bc, Tc, 256), generator=g)
+    noise0 = torch.randn((Bc, 1, 128, Tc), generator=g)
+    draws = iter([noise0])
+    model._noise_source = lambda shape: next(draws).to(dev)
+    out = model(condition.to(dev), infer=True).cpu()
+    P.hparams.pop('b2s_precision', None)
+    sd_gpu = {k: v.to(dev) for k, v in sd.items()}
+    velocity = lambda x, t, c: OD.lynxnet_forward(sd_gpu, cfg, x, t.to(dev), c)
+    with _strict_fp32(), torch.no_grad():
+        x = OS.rectified_flow_inference(velocity, condition.transpose(1, 2).to(dev), t_start=0., use_shallow=False,
+                                        algorithm='euler', steps=20, noise0=noise0.to(dev))
+    ref = OS.denorm_spec(x.cpu(), torch.tensor(-12.), torch.tensor(0.))
+    err, scale = float((out - ref).abs().max()), float(ref.abs().max())
+    msg = f'config3 full width euler-20 {precision}: max-abs {err:.3e}, |mel|max {scale:.1f}'
+    if precision == 'bf16':
+        # yardstick: torch's own bf16 autocast of the same network on the same inputs.  At C = 1024 (K = 1024 / 2048 contractions
+        # of 8-bit-mantissa activations, 6 layers x 20 Euler steps from noise) bf16 itself does not reach 2e-2 absolute; the
+        # product has to be at least as good as autocast (it keeps the residual stream, LayerNorm and sampler state in fp32).
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+            xa = OS.rectified_flow_inference(velocity, condition.transpose(1, 2).to(dev), t_start=0., use_shallow=False,
+                                             algorithm='euler', steps=20, noise0=noise0.to(dev))
+        err_ac = float((OS.denorm_spec(xa.float().cpu(), torch.tensor(-12.), torch.tensor(0.)) - ref).abs().max())
+        msg += f'; torch autocast(bf16) of the oracle: {err_ac:.3e}'
+        tol = max(tol, err_ac)
+    print(msg)
+    assert err <= tol, (precision, err, scale)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'fp16'])
+def test_config5_full_width_wavenet512_against_gpu_oracle(precision, dev):
+    """BASELINE config 5 at the full model width: UniPC 20 steps from noise, WaveNet 20 x 512, 8 utterances x 690 frames,
+    against the oracle on the GPU in strict fp32.  From-noise sampling under random init reaches |mel| ~ 300, so the 16-bit
+    bounds are the documented relative ones (tests/test_gpu_tc_parity.py)."""
+    import xiaoicesing_io_b200 as P
+    from oracle import samplers as OS
+    cfg = OD.WaveNetCfg(num_channels=512)
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, schedule_type='linear', use_shallow_diffusion=False, diff_speedup=50,
+                     diff_accelerator='unipc', infer=False, b2s_precision=precision)
+    model = P.GaussianDiffusion(128, backbone_type='wavenet',
+                                backbone_args=dict(num_layers=20, num_channels=512, dilation_cycle_length=4),
+                                spec_min=[-12.], spec_max=[0.])
+    sd = OW.make_state_dict(cfg, seed=0, sigma_w=0.01)
+    model.denoise_fn.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(9)
+    Bc, Tc = 8, 690
+    condition = torch.randn((Bc, Tc, 256), generator=g)
+    noise0 = torch.randn((Bc, 1, 128, Tc), generator=g)
+    draws = iter([noise0])
+    model._noise_source = lambda shape: next(draws).to(dev)
+    out = model(condition.to(dev), infer=True).cpu()
+    P.hparams.pop('b2s_precision', None)
+    sd_gpu = {k: v.to(dev) for k, v in sd.items()}
+    denoise = lambda x, t, c: OD.wavenet_forward(sd_gpu, cfg, x, t.to(dev), c)
+    sch = OS.DiffusionSchedule(1000, 'linear')
+    with _strict_fp32(), torch.no_grad():
+        x = OS.gaussian_diffusion_inference(denoise, sch, condition.transpose(1, 2).to(dev), k_step=1000, timesteps=1000,
+                                            use_shallow=False, K_step_infer=1000, speedup=50, accelerator='unipc',
+                                            noise0=noise0.to(dev))
+    ref = OS.denorm_spec(x.cpu(), torch.tensor(-12.), torch.tensor(0.))
+    err, scale = float((out - ref).abs().max()), float(ref.abs().max())
+    print(f'config5 full width unipc-20 {precision}: max-abs {err:.3e}, |mel|max {scale:.1f}')
+    tol = 1e-3 if precision == 'fp32' else (2e-4 * scale if (precision == 'bf16' and scale > 64.0) else 2e-2)
+    assert err <= tol, (precision, err, scale)
