@@ -241,13 +241,20 @@ int b2s_tc_lynx_glu(const void* h_h, const void* W_h, const float* bias, void* g
                     void* stream);
 int b2s_tc_linear_residual(const void* p_h, const void* W_h, const float* bias, float* x, int rows, int C, int inner,
                            int bf16, void* stream);
+/* Same, plus the NEXT layer's front_cond_inject (strong_cond, lynxnet.py:77-82): x <- (x + W p + b) + cond_next, cond_next a
+ * 16-bit [rows, ld_cond] slab of the hoisted conditioner projection.  The next b2s_lynx_prenorm_h is then called with
+ * cond_h = NULL (it only adds the step embedding) and neither reads the table nor writes x back.  Bit-identical to the
+ * unfolded sequence. */
+int b2s_tc_linear_residual_cond(const void* p_h, const void* W_h, const float* bias, float* x, const void* cond_next_h,
+                                int ld_cond, int rows, int C, int inner, int bf16, void* stream);
 
 /* 16-bit LYNXNet layer helpers (HBM-bound): fused (x + cond + d) -> residual write-back -> LayerNorm with 16-bit
  * cond table in / 16-bit h out (lynxnet.py:76-84, 54), plain LayerNorm (lynxnet.py:151), depthwise conv + activation
  * with 16-bit in / out and fp32 math (lynxnet.py:57-58).  Same argument meaning as the _f32 entry points, except that
  * b2s_lynx_dwconv_h takes the depthwise weights K-MAJOR: WdwT [ksize][inner] (coalesced loads). */
-int b2s_lynx_prenorm_h(float* x, const void* cond_h, int ld_cond, const float* dvec, int d_stride, const float* gamma,
-                       const float* beta, void* h_h, int B, int T, int C, int strong_cond, int bf16, void* stream);
+int b2s_lynx_prenorm_h(float* x, const void* cond_h /* may be NULL: cond already folded in */, int ld_cond, const float* dvec,
+                       int d_stride, const float* gamma, const float* beta, void* h_h, int B, int T, int C, int strong_cond,
+                       int bf16, void* stream);
 int b2s_layernorm_h(const float* x, const float* gamma, const float* beta, void* h_h, int rows, int C, int bf16,
                     void* stream);
 int b2s_lynx_dwconv_h(const void* g_h, const float* WdwT, const float* bias, const float* slope, void* p_h, int B, int T,

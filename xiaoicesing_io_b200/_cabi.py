@@ -48,6 +48,7 @@ _SIGNATURES = {
     'b2s_tc_wavenet_denoiser_update': [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i,
                                        _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, ctypes.POINTER(_vp), _vp, _vp, _vp, _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    'b2s_tc_linear_residual_cond': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_lynx_prenorm_h': [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_layernorm_h': [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
@@ -285,6 +286,11 @@ def tc_lynx_glu(h_h, W_h, bias, g_h, rows, C, inner, bf16):
 def tc_linear_residual(p_h, W_h, bias, x, rows, C, inner, bf16):
     check(lib.b2s_tc_linear_residual(ptr(p_h), ptr(W_h), ptr(bias), ptr(x), rows, C, inner, int(bf16), stream_ptr()),
           'b2s_tc_linear_residual')
+
+
+def tc_linear_residual_cond(p_h, W_h, bias, x, cond_next_h, ld_cond, rows, C, inner, bf16):
+    check(lib.b2s_tc_linear_residual_cond(ptr(p_h), ptr(W_h), ptr(bias), ptr(x), ptr(cond_next_h), ld_cond, rows, C, inner,
+                                          int(bf16), stream_ptr()), 'b2s_tc_linear_residual_cond')
 
 
 def lynx_prenorm_h(x, cond_h, ld_cond, dvec, d_stride, gamma, beta, h_h, B, T, C, strong, bf16):

@@ -110,9 +110,11 @@ __global__ void __launch_bounds__(256) layernorm_h_kernel(float* __restrict__ x,
     for (int c = lane * 4; c < C; c += 128) {
         float4 v = *reinterpret_cast<const float4*>(x + (long long)r * C + c);
         if (PRE) {
-            const float4 cc = ld_h4(cond + (long long)r * ld_cond + c, bf16);
-            v = make_float4(v.x + cc.x, v.y + cc.y, v.z + cc.z, v.w + cc.w);
-            if (strong) *reinterpret_cast<float4*>(x + (long long)r * C + c) = v;
+            if (cond) {          // NULL: the cond add was folded into the previous layer's residual epilogue (b2s_tc_linear_residual_cond)
+                const float4 cc = ld_h4(cond + (long long)r * ld_cond + c, bf16);
+                v = make_float4(v.x + cc.x, v.y + cc.y, v.z + cc.z, v.w + cc.w);
+                if (strong) *reinterpret_cast<float4*>(x + (long long)r * C + c) = v;
+            }
             const float4 d = __ldg(reinterpret_cast<const float4*>(dvec + (long long)b * d_stride + c));
             v = make_float4(v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w);
         }
@@ -234,7 +236,7 @@ static int launch_dwconv_h(const void* g_h, const float* WdwT, const float* bias
 extern "C" int b2s_lynx_prenorm_h(float* x, const void* cond_h, int ld_cond, const float* dvec, int d_stride,
                                   const float* gamma, const float* beta, void* h_h, int B, int T, int C, int strong_cond,
                                   int bf16, void* stream) {
-    B2S_CHECK_ARG(x && cond_h && dvec && gamma && beta && h_h, "b2s_lynx_prenorm_h: null pointer");
+    B2S_CHECK_ARG(x && dvec && gamma && beta && h_h, "b2s_lynx_prenorm_h: null pointer");
     B2S_CHECK_ARG(C > 0 && C <= 8192 && C % 4 == 0 && ld_cond % 4 == 0 && d_stride % 4 == 0, "b2s_lynx_prenorm_h: C, ld_cond, d_stride must be multiples of 4");
     const int rows = B * T;
     if (rows <= 0) return B2S_OK;

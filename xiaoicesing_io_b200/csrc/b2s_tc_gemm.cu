@@ -133,7 +133,7 @@ __device__ __forceinline__ float4 epilogue_load(const TcP& p, long long r, int c
 
 template <int EPI, int BF16>
 __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 in, const EpiConst& k, long long r, int b,
-                                              int col) {
+                                              int col, const uint2* pre_cond = nullptr) {
     if (EPI == EPI_LINEAR) {
         // ReLU / identity inline (the hot cases: stem, head, cond table); Mish / GELU / SiLU through ONE
         // out-of-line call so the unrolled epilogue stays small enough for the instruction cache
@@ -178,7 +178,15 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
         store_h2<BF16>(p.out_h, r * p.ldoh + (col >> 1), (acc.x + k.bias.x) * (g0 * sigmoid_fast(g0)),
                        (acc.z + k.bias.z) * (g1 * sigmoid_fast(g1)));
     } else if (EPI == EPI_RESIDUAL) {
-        *reinterpret_cast<float4*>(p.x + r * p.C + col) = add4(in, add4(acc, k.bias));
+        float4 xn = add4(in, add4(acc, k.bias));
+        if (p.cond) {
+            // strong_cond LYNXNet: the NEXT layer's front_cond_inject (x += cond_proj(cond), lynxnet.py:77-82) folded into this
+            // layer's residual epilogue, so the next LayerNorm kernel neither reads the cond table nor writes x back
+            const uint2 c = pre_cond ? *pre_cond : ldg_nc_u2(reinterpret_cast<const uint16_t*>(p.cond) + r * p.ldc + col);
+            const float2 c0 = Half16<BF16>::unpack2(c.x), c1 = Half16<BF16>::unpack2(c.y);
+            xn = add4(xn, make_float4(c0.x, c0.y, c1.x, c1.y));
+        }
+        *reinterpret_cast<float4*>(p.x + r * p.C + col) = xn;
     } else {   // EPI_RESSKIP: reference column order, [0, C) residual, [C, 2C) skip
         const float inv_sqrt2 = 0.70710678118654752440f;
         const float4 o = add4(acc, k.bias);
@@ -305,6 +313,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             // previous chunk (ncu: the GATE / RESSKIP epilogues were long-scoreboard bound, tensor pipe 46 % / 18 % active)
             EpiConst kcn;
             float4 inn[8];
+            uint2 cnn[8];                                   // EPI_RESIDUAL with a folded cond add: the next layer's cond quads
+            const bool fold = EPI == EPI_RESIDUAL && p.cond != nullptr;
             bool okn = false;
             auto load_chunk = [&](int j) {
                 const int col = n0 + 32 * j + cl;
@@ -314,7 +324,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         inn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (tq + 4 * i < p.T) inn[i] = epilogue_load<EPI, BF16>(p, (long long)bt * p.T + tq + 4 * i, col);
+                        cnn[i] = make_uint2(0u, 0u);
+                        if (tq + 4 * i < p.T) {
+                            const long long r = (long long)bt * p.T + tq + 4 * i;
+                            inn[i] = epilogue_load<EPI, BF16>(p, r, col);
+                            if (fold) cnn[i] = ldg_nc_u2(reinterpret_cast<const uint16_t*>(p.cond) + r * p.ldc + col);
+                        }
                     }
                 }
             };
@@ -332,8 +347,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                 const bool colok = okn;
                 const EpiConst kc = kcn;
                 float4 in[8];
+                uint2 cn[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) in[i] = inn[i];
+                for (int i = 0; i < 8; ++i) { in[i] = inn[i]; cn[i] = cnn[i]; }
                 if (j + 2 < BLOCK_N / 32 && col0 + 64 < p.N) load_chunk(j + 2);
                 tmem_ld_wait();
                 // transpose through the warp's private 16-row staging tile, two passes: thread = row -> lane = 4 columns
@@ -492,10 +508,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
             const int n_tile = pt % p.tiles_n, m_tile = 2 * (pt / p.tiles_n) + rank;
             const int bt = m_tile / p.tiles_m_per_b, t0 = (m_tile - bt * p.tiles_m_per_b) * BLOCK_M;
             const int n0 = n_tile * BLOCK_N;
+            const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
+            // per-chunk inputs (cond / x / skip rows of the lane, bias and step-embedding quads) are requested ONE CHUNK AHEAD -
+            // the first chunk's before the accumulator wait - so their L2 / HBM latency hides behind the TMEM drain of the
+            // previous chunk (ncu: the GATE / RESSKIP epilogues were long-scoreboard bound, tensor pipe 46 % / 18 % active)
+            EpiConst kcn;
+            float4 inn[8];
+            uint2 cnn[8];                                   // EPI_RESIDUAL with a folded cond add: the next layer's cond quads
+            const bool fold = EPI == EPI_RESIDUAL && p.cond != nullptr;
+            bool okn = false;
+            auto load_chunk = [&](int j) {
+                const int col = n0 + 32 * j + cl;
+                okn = col < p.N;
+                if (okn) {
+                    kcn = epilogue_consts<EPI>(p, col);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        inn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        cnn[i] = make_uint2(0u, 0u);
+                        if (tq + 4 * i < p.T) {
+                            const long long r = (long long)bt * p.T + tq + 4 * i;
+                            inn[i] = epilogue_load<EPI, BF16>(p, r, col);
+                            if (fold) cnn[i] = ldg_nc_u2(reinterpret_cast<const uint16_t*>(p.cond) + r * p.ldc + col);
+                        }
+                    }
+                }
+            };
+            if (n0 + 32 * sub < p.N) load_chunk(sub);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
-            const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
 #pragma unroll 1
             for (int j = sub; j < BLOCK_N / 32; j += 2) {
                 const int col0 = n0 + 32 * j;
@@ -503,17 +545,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                 float acc[32];
                 tmem_ld32(taddr + j * 32, acc);
                 const int col = col0 + cl;
-                const bool colok = col < p.N;
-                EpiConst kc;
+                const bool colok = okn;
+                const EpiConst kc = kcn;
                 float4 in[8];
-                if (colok) {
-                    kc = epilogue_consts<EPI>(p, col);
+                uint2 cn[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        in[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (tq + 4 * i < p.T) in[i] = epilogue_load<EPI, BF16>(p, (long long)bt * p.T + tq + 4 * i, col);
-                    }
-                }
+                for (int i = 0; i < 8; ++i) { in[i] = inn[i]; cn[i] = cnn[i]; }
+                if (j + 2 < BLOCK_N / 32 && col0 + 64 < p.N) load_chunk(j + 2);
                 tmem_ld_wait();
                 // transpose through the warp's private 16-row staging tile, two passes: thread = row -> lane = 4 columns
 #pragma unroll
@@ -532,7 +570,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                             if (t < p.T) {
                                 const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i2 + rsub) * STG_LD + cl);
                                 const int b = (p.d_stride != 0 && p.T_utt > 0) ? (bt * p.T + t) / p.T_utt : 0;
-                                epilogue_quad<EPI, BF16>(p, v, in[i], kc, (long long)bt * p.T + t, b, col);
+                                epilogue_quad<EPI, BF16>(p, v, in[i], kc, (long long)bt * p.T + t, b, col, fold ? &cn[i] : nullptr);
                             }
                         }
                     }
@@ -730,15 +768,28 @@ extern "C" int b2s_tc_lynx_glu(const void* h_h, const void* W_h, const float* bi
     return launch<EPI_SWIGLU>(p, bf16, (cudaStream_t)stream);
 }
 
-extern "C" int b2s_tc_linear_residual(const void* p_h, const void* W_h, const float* bias, float* x, int rows, int C,
-                                      int inner, int bf16, void* stream) {
+static int linear_residual_impl(const void* p_h, const void* W_h, const float* bias, float* x, const void* cond_next_h, int ld_cond,
+                                int rows, int C, int inner, int bf16, void* stream) {
     B2S_CHECK_ARG(p_h && W_h && bias && x, "b2s_tc_linear_residual: null pointer");
     B2S_CHECK_ARG(C % 32 == 0 && inner % 8 == 0, "b2s_tc_linear_residual: bad dims C=%d inner=%d", C, inner);
     B2S_CHECK_ARG(al16(p_h) && al16(W_h) && al16(bias) && al16(x), "b2s_tc_linear_residual: misaligned pointer");
+    B2S_CHECK_ARG(!cond_next_h || (ld_cond % 4 == 0 && (reinterpret_cast<uintptr_t>(cond_next_h) & 7) == 0),
+                  "b2s_tc_linear_residual_cond: cond table must be 8-byte aligned with ld_cond %% 4 == 0");
     if (rows == 0) return B2S_OK;
     TcP p{};
     int rc = setup(p, p_h, inner, inner, 1, rows, false, W_h, inner, C, inner, 0, 0, bf16);
     if (rc) return rc;
-    p.bias = bias; p.x = x; p.C = C;
+    p.bias = bias; p.x = x; p.C = C; p.cond = cond_next_h; p.ldc = ld_cond;
     return launch<EPI_RESIDUAL>(p, bf16, (cudaStream_t)stream);
+}
+
+extern "C" int b2s_tc_linear_residual(const void* p_h, const void* W_h, const float* bias, float* x, int rows, int C,
+                                      int inner, int bf16, void* stream) {
+    return linear_residual_impl(p_h, W_h, bias, x, nullptr, 0, rows, C, inner, bf16, stream);
+}
+
+extern "C" int b2s_tc_linear_residual_cond(const void* p_h, const void* W_h, const float* bias, float* x, const void* cond_next_h,
+                                           int ld_cond, int rows, int C, int inner, int bf16, void* stream) {
+    B2S_CHECK_ARG(cond_next_h, "b2s_tc_linear_residual_cond: null cond table");
+    return linear_residual_impl(p_h, W_h, bias, x, cond_next_h, ld_cond, rows, C, inner, bf16, stream);
 }

@@ -658,13 +658,20 @@ class LYNXNetSessionTC:
             C.cast_h(x_in, self.xin_h, bf)
         C.tc_linear(self.xin_h, MF, rows, T, e.w_in_h, MF, e.b_in, Cc, MF, bf,
                     act=C.ACT_NONE if e.strong else C.ACT_GELU, out_f32=self.x, ldo=Cc)
+        # strong_cond: layer l+1's front_cond_inject (x += cond_{l+1}) rides on layer l's residual epilogue, so only the first
+        # LayerNorm kernel reads the cond table and writes x back (halves the HBM traffic of the other L-1)
+        fold = bool(e.strong) and hparams.get('b2s_lynx_fold_cond', True)
         for l in range(L):
             dv, ds = self._dvec(k, l)
-            C.lynx_prenorm_h(self.x, self.cond[l], Cc, dv, ds, e.ln_g[l], e.ln_b[l], self.h_h, B, T, Cc, e.strong, bf)
+            C.lynx_prenorm_h(self.x, None if (fold and l > 0) else self.cond[l], Cc, dv, ds, e.ln_g[l], e.ln_b[l], self.h_h, B, T, Cc,
+                             e.strong, bf)
             C.tc_lynx_glu(self.h_h, e.w_up_h[l], e.b_up[l], self.g_h, rows, Cc, inner, bf)
             C.lynx_dwconv_h(self.g_h, e.w_dw_t[l], e.b_dw[l], None if e.slope is None else e.slope[l], self.p_h, B, T, inner,
                             e.ksize, e.act, bf)
-            C.tc_linear_residual(self.p_h, e.w_down_h[l], e.b_down[l], self.x, rows, Cc, inner, bf)
+            if fold and l + 1 < L:
+                C.tc_linear_residual_cond(self.p_h, e.w_down_h[l], e.b_down[l], self.x, self.cond[l + 1], Cc, rows, Cc, inner, bf)
+            else:
+                C.tc_linear_residual(self.p_h, e.w_down_h[l], e.b_down[l], self.x, rows, Cc, inner, bf)
         C.layernorm_h(self.x, e.norm_g, e.norm_b, self.h_h, rows, Cc, bf)
         C.tc_linear(self.h_h, Cc, rows, T, e.w_fin_h, Cc, e.b_fin, MF, Cc, bf, out_f32=out, ldo=MF)
 
