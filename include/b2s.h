@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2S_ABI_VERSION 3
+#define B2S_ABI_VERSION 4
 
 #define B2S_OK 0
 #define B2S_ERR_INVALID_ARGUMENT (-1)

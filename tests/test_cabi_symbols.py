@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.lib.b2s_abi_version() == 3
+    assert lib.lib.b2s_abi_version() == 4
 
 
 def test_argument_validation_needs_no_gpu(lib):
