@@ -35,6 +35,8 @@ _SIGNATURES = {
     'b2s_tc_linear': [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp],
     'b2s_tc_cond_table': [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_cond_table_tiled': [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    'b2s_tc_wavenet_gate_ld': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_tc_wavenet_res': [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_gate': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_out': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_layer': [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -254,6 +256,16 @@ def tc_wavenet_denoiser_update(xin_h, MF, Win_h, ld_win, b_in, y0_h, y1_h, Wd_h,
                                              d_stride, dil, L, ptr(Wsp_h), ptr(b_sp), ptr(Wfin_h), ptr(b_fin), B, T, C, ptr(flags),
                                              ptr(flags_next), len(srcs), arr, ptr(coef), ptr(x_out), ptr(x_out_h), int(bf16),
                                              stream_ptr()), 'b2s_tc_wavenet_denoiser_update')
+
+
+def tc_wavenet_gate_ld(y_h, Wd_h, cond_h, ld_cond, z_h, ld_z, B, T, C, dilation, bf16):
+    check(lib.b2s_tc_wavenet_gate_ld(ptr(y_h), ptr(Wd_h), ptr(cond_h), ld_cond, ptr(z_h), ld_z, B, T, C, dilation, int(bf16),
+                                     stream_ptr()), 'b2s_tc_wavenet_gate_ld')
+
+
+def tc_wavenet_res(z_h, ld_z, Wres_h, b_res, x, y_next_h, dvec_next, d_stride, B, T, C, bf16):
+    check(lib.b2s_tc_wavenet_res(ptr(z_h), ld_z, ptr(Wres_h), ptr(b_res), ptr(x), ptr(y_next_h), ptr(dvec_next), d_stride, B, T, C,
+                                 int(bf16), stream_ptr()), 'b2s_tc_wavenet_res')
 
 
 def tc_cond_retile(table_h, L, B, T, n2, NT, out_h):

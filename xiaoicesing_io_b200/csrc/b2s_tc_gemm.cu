@@ -725,18 +725,38 @@ extern "C" int b2s_tc_cond_table_tiled(const void* cond_h, int B, int T, const v
     return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
 }
 
-extern "C" int b2s_tc_wavenet_gate(const void* y_h, const void* Wd_h, const void* cond_h, int ld_cond, void* z_h, int B,
-                                   int T, int C, int dilation, int bf16, void* stream) {
+extern "C" int b2s_tc_wavenet_gate_ld(const void* y_h, const void* Wd_h, const void* cond_h, int ld_cond, void* z_h, int ld_z,
+                                      int B, int T, int C, int dilation, int bf16, void* stream) {
     B2S_CHECK_ARG(y_h && Wd_h && cond_h && z_h, "b2s_tc_wavenet_gate: null pointer");
     B2S_CHECK_ARG(C % 64 == 0, "b2s_tc_wavenet_gate: the tensor-core path needs residual channels %% 64 == 0 (C=%d)", C);
-    B2S_CHECK_ARG(dilation >= 1 && ld_cond % 8 == 0 && al16(cond_h) && al16(y_h) && al16(z_h) && al16(Wd_h),
-                  "b2s_tc_wavenet_gate: bad dilation / alignment");
+    B2S_CHECK_ARG(dilation >= 1 && ld_cond % 8 == 0 && ld_z >= C && ld_z % 8 == 0 && al16(cond_h) && al16(y_h) && al16(z_h) && al16(Wd_h),
+                  "b2s_tc_wavenet_gate: bad dilation / leading dimension / alignment");
     if (B * T == 0) return B2S_OK;
     TcP p{};
     int rc = setup(p, y_h, C, C, B, T, true, Wd_h, 3 * C, 2 * C, 3 * C, C / BLOCK_K, dilation, bf16);
     if (rc) return rc;
-    p.cond = cond_h; p.ldc = ld_cond; p.out_h = z_h; p.ldoh = C;
+    p.cond = cond_h; p.ldc = ld_cond; p.out_h = z_h; p.ldoh = ld_z;
     return launch<EPI_GATE>(p, bf16, (cudaStream_t)stream);
+}
+
+extern "C" int b2s_tc_wavenet_gate(const void* y_h, const void* Wd_h, const void* cond_h, int ld_cond, void* z_h, int B,
+                                   int T, int C, int dilation, int bf16, void* stream) {
+    return b2s_tc_wavenet_gate_ld(y_h, Wd_h, cond_h, ld_cond, z_h, C, B, T, C, dilation, bf16, stream);
+}
+
+extern "C" int b2s_tc_wavenet_res(const void* z_h, int ld_z, const void* Wres_h, const float* b_res, float* x, void* y_next_h,
+                                  const float* dvec_next, int d_stride, int B, int T, int C, int bf16, void* stream) {
+    B2S_CHECK_ARG(z_h && Wres_h && b_res && x, "b2s_tc_wavenet_res: null pointer");
+    B2S_CHECK_ARG(C % 64 == 0 && ld_z >= C && ld_z % 8 == 0, "b2s_tc_wavenet_res: bad C=%d / ld_z=%d", C, ld_z);
+    B2S_CHECK_ARG(!y_next_h || (dvec_next && d_stride % 4 == 0 && al16(dvec_next)), "b2s_tc_wavenet_res: y_next needs dvec_next");
+    B2S_CHECK_ARG(al16(z_h) && al16(Wres_h) && al16(b_res) && al16(x), "b2s_tc_wavenet_res: misaligned pointer");
+    if (B * T == 0) return B2S_OK;
+    TcP p{};
+    int rc = setup(p, z_h, ld_z, C, B, T, false, Wres_h, C, C, C, 0, 0, bf16);     // N = C: the residual rows only
+    if (rc) return rc;
+    p.bias = b_res; p.x = x; p.y_h = y_next_h; p.ldy = C; p.C = C;
+    p.dvec = dvec_next; p.d_stride = d_stride;
+    return launch<EPI_RESSKIP>(p, bf16, (cudaStream_t)stream);
 }
 
 extern "C" int b2s_tc_wavenet_out(const void* z_h, const void* Wo_h, const float* bo, float* x, void* y_next_h,

@@ -98,6 +98,11 @@ class WaveNetEngine:
             self.w_in_h = h(_pad_cols(self.w_in, 8))
             self.w_cond_h, self.w_dil_h, self.w_out_h = h(self.w_cond), h(self.w_dil), h(self.w_out)
             self.w_sp_h, self.w_fin_h = h(self.w_sp), h(self.w_fin)
+            # deferred skip sum (two-kernel path): residual rows per layer, all skip rows as ONE [C, L*C] matrix (K = l*C + k)
+            self.w_res_h = h(self.w_out[:, :Cc, :])
+            self.b_res = self.b_out[:, :Cc].contiguous()
+            self.w_skipcat_h = h(self.w_out[:, Cc:, :].permute(1, 0, 2).reshape(Cc, L * Cc))
+            self.b_skip_sum = self.b_out[:, Cc:].sum(0).contiguous()
             self.w_dil_t_h = self.w_cond_t_h = self.b_cond_t = None
             if Cc == C.FUSED_LAYER_CHANNELS:
                 # transposed stack kernel (b2s_tc_wavenet_stack_t): row 256h + 128g + c = (g ? filter : gate) of channel 128h + c,
@@ -263,6 +268,9 @@ class WaveNetSessionTC:
             self.cond = torch.empty((L, rows, 2 * Cc), device=dev, dtype=hd)     # layer-major: one contiguous slab per layer
             C.tc_cond_table(cond_h, rows, eng.w_cond_h, eng.b_cond, L, 2 * Cc, H, self.cond, bf)
         del self._cond_h
+        # two-kernel path: the L skip outputs are summed by ONE K = L*C GEMM after the last layer (no per-layer fp32 skip RMW)
+        self.defer_skip = (not self.fused) and hparams.get('b2s_defer_skip', True) and rows * L * Cc * 2 <= 8e9
+        self.z_all = torch.empty((rows, L * Cc), device=dev, dtype=hd) if self.defer_skip else None
         self.skip_h = torch.empty((rows, Cc), device=dev, dtype=hd)
         self.h_h = torch.empty((rows, Cc), device=dev, dtype=hd)
 
@@ -396,9 +404,16 @@ class WaveNetSessionTC:
                                    B, T, Cc, e.dilations[l], bf)
                 ya, yb = yb, ya                            # ping-pong: neighbours still read the halo of ya
                 continue
+            if self.defer_skip:
+                zl = self.z_all[:, l * Cc:]
+                C.tc_wavenet_gate_ld(self.y_h, e.w_dil_h[l], self.cond[l], ldc, zl, L * Cc, B, T, Cc, e.dilations[l], bf)
+                C.tc_wavenet_res(zl, L * Cc, e.w_res_h[l], e.b_res[l], self.x, None if last else self.y_h, dn, ds, B, T, Cc, bf)
+                continue
             C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[l], ldc, self.z_h, B, T, Cc, e.dilations[l], bf)
             C.tc_wavenet_out(self.z_h, e.w_out_h[l], e.b_out[l], self.x, None if last else self.y_h, self.skip,
                              self.skip_h if last else None, dn, ds, l == 0, B, T, Cc, bf)
+        if self.defer_skip:
+            C.tc_linear(self.z_all, L * Cc, rows, T, e.w_skipcat_h, L * Cc, e.b_skip_sum, Cc, L * Cc, bf, out_h=self.skip_h, ldoh=Cc)
         C.tc_linear(self.skip_h, Cc, rows, T, e.w_sp_h, Cc, e.b_sp, Cc, Cc, bf, alpha=1.0 / math.sqrt(L),
                     act=C.ACT_RELU, out_h=self.h_h, ldoh=Cc)
         C.tc_linear(self.h_h, Cc, rows, T, e.w_fin_h, Cc, e.b_fin, MF, Cc, bf, out_f32=out, ldo=MF)
@@ -411,7 +426,7 @@ class WaveNetSessionTC:
             return 1 + -(-self.B // self.stack_group)              # cast (+ flag reset), one denoiser launch per utterance group
         if self.stack_group:
             return 1 + 1 + -(-self.B // self.stack_group) + 2      # cast (+ flag reset), stem, stack launches, 2 head GEMMs
-        return 2 + (1 if self.fused else 2) * self.eng.L + 2
+        return 2 + (1 if self.fused else 2) * self.eng.L + 2 + (1 if self.defer_skip else 0)
 
     def dominant_kernel(self, w=None):
         """(name, algorithmic FLOPs per launch, callable launching it once per layer) for bench.py's roofline."""
