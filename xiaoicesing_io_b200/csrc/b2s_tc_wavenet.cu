@@ -698,7 +698,7 @@ struct __align__(64) StackP {
     float* x; void* ybuf[2]; float* skip; void* skip_h;
     const float* dvec; int d_stride;                      // layer l's step embedding at dvec + b*d_stride + l*C
     int* flags;                                           // [B * tiles_per_b], zero before the launch
-    int dbg;                                              // profiling experiments only (B2S_STACK_DBG): results are WRONG when != 0
+    int dbg;                                              // (profiling switches of earlier rounds; no longer read by this kernel)
     unsigned long long* tlog;                             // optional phase timestamps of CTA 2 (B2S_STACK_TLOG): [L][16] globaltimer ns
     // ---- whole denoiser in one launch (fuse = 1): stem (input projection, wavenet.py:86-88) before the stack and head
     //      (skip sum -> skip_projection -> ReLU -> output_projection, wavenet.py:96-99) after it
@@ -1053,7 +1053,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
                 for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        c[jj][i] = (valid && !(p.dbg & 1)) ? ldg_nc_u4(ctile + ((8 * h + 2 * jj + sub) * 4 + i) * (BM * 8)) : make_uint4(0, 0, 0, 0);
+                        c[jj][i] = valid ? ldg_nc_u4(ctile + ((8 * h + 2 * jj + sub) * 4 + i) * (BM * 8)) : make_uint4(0, 0, 0, 0);
                 mbar_wait(&accb[h], par);
                 tc_fence_after();
                 if (e == 0) TLOG(3 + 2 * h);                              // G1 half h complete
@@ -1068,14 +1068,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float2 ca = Half16<BF16>::unpack2(cw[2 * i]), cb = Half16<BF16>::unpack2(cw[2 * i + 1]);
-                        float z0, z1;
-                        if (p.dbg & 8) {
-                            z0 = (acc[4 * i] + ca.x) * (acc[4 * i + 1] + ca.y);
-                            z1 = (acc[4 * i + 2] + cb.x) * (acc[4 * i + 3] + cb.y);
-                        } else {
-                            z0 = sigmoid_fast(acc[4 * i] + ca.x) * tanh_fast(acc[4 * i + 1] + ca.y);
-                            z1 = sigmoid_fast(acc[4 * i + 2] + cb.x) * tanh_fast(acc[4 * i + 3] + cb.y);
-                        }
+                        const float z0 = sigmoid_fast(acc[4 * i] + ca.x) * tanh_fast(acc[4 * i + 1] + ca.y);
+                        const float z1 = sigmoid_fast(acc[4 * i + 2] + cb.x) * tanh_fast(acc[4 * i + 3] + cb.y);
                         zp[i] = valid ? Half16<BF16>::pack2(z0, z1) : 0u;
                     }
                     const uint32_t slab = zrow + (2 * h + (j >> 2)) * A_BYTES;
