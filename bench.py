@@ -432,7 +432,23 @@ def run_b200_arm(args, w):
         dist.destroy_process_group()
 
 
+def _ensure_built():
+    """libb2s.so is git-ignored: build it when it is missing (local rank 0 builds, the other ranks wait for the file)."""
+    lib = os.path.join(ROOT, 'xiaoicesing_io_b200', 'libb2s.so')
+    if os.path.exists(lib):
+        return
+    if int(os.environ.get('LOCAL_RANK', '0')) == 0:
+        import __graft_entry__ as entry
+        entry._build_module().build()
+    else:
+        t0 = time.time()
+        while not os.path.exists(lib) and time.time() - t0 < 900:
+            time.sleep(1.0)
+        time.sleep(2.0)
+
+
 def main():
+    _ensure_built()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
