@@ -45,6 +45,9 @@ WORKLOADS = {
                     desc='rectified-flow Euler 20 steps, LYNXNet 6x1024 (E=2, k=31, strong_cond), 128 mel, B=64 x T=690 per GPU'),
     'config5': dict(kind='wavenet_unipc', B=32, T=690, k_step=20, layers=20, channels=512, mel=128, hidden=256, cycle=4,
                     desc='UniPC 20 steps, WaveNet 20x512, 128 mel, B=32 x T=690 per GPU'),
+    'config4': dict(kind='wavenet_variance', B=64, T=690, k_step=10, layers=10, channels=192, mel=48, out=2, hidden=256, cycle=4,
+                    desc='variance multi-predictor (energy + breathiness, 2 x 24 repeat bins), DPM-Solver++ 10 steps, WaveNet 10x192, '
+                         'B=64 x T=690 per GPU'),
     'config1': dict(kind='wavenet_ddim', B=1, T=690, k_step=20, layers=20, channels=256, mel=128, hidden=256, cycle=4,
                     desc='DDIM 20 steps (speedup 50), WaveNet 20x256, 128 mel, one 8-s utterance (690 frames)'),
 }
@@ -131,6 +134,18 @@ def make_model(w, precision, device, cuda_graph=True):
             backbone_args=dict(num_layers=w['layers'], num_channels=w['channels'], kernel_size=31, strong_cond=True),
             spec_min=[-12.], spec_max=[0.])
         torch.nn.init.normal_(model.velocity_fn.output_projection.weight, std=SIGMA_W)
+        return model.to(device).eval()
+    if kind == 'wavenet_variance':
+        # configs/variance.yaml:95-100: MultiVarianceDiffusion over 2 curves x 24 repeat bins, WaveNet 10 x 192
+        P.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=False,
+                         diff_speedup=1000 // w['k_step'], diff_accelerator='dpm-solver', infer=False, b2s_precision=precision,
+                         b2s_cuda_graph=cuda_graph)
+        torch.manual_seed(0)
+        model = P.MultiVarianceDiffusion(ranges=[(-96., -12.), (-96., -20.)], clamps=[(-96., -12.), (-96., -20.)], repeat_bins=24,
+                                         backbone_type='wavenet',
+                                         backbone_args=dict(num_layers=w['layers'], num_channels=w['channels'],
+                                                            dilation_cycle_length=w['cycle']))
+        torch.nn.init.normal_(model.denoise_fn.output_projection.weight, std=SIGMA_W)
         return model.to(device).eval()
     if kind in ('wavenet_unipc', 'wavenet_ddim'):
         P.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=False,
@@ -330,8 +345,12 @@ def run_b200_arm(args, w):
     if not shallow:
         src_d = None
 
+    variance = w.get('kind') == 'wavenet_variance'
+    n_out = w.get('out', w['mel'])
+    run = (lambda c, s: torch.stack(model(c, infer=True), -1)) if variance else (lambda c, s: model(c, src_spec=s, infer=True))
+
     def step_resident():
-        mel = model(cond_d, src_spec=src_d, infer=True)
+        mel = run(cond_d, src_d)
         if world > 1:
             gather_mels(mel.contiguous(), index, world * B, dst=0)     # the ONLY exchange: final mel gather
         return mel
@@ -339,7 +358,7 @@ def run_b200_arm(args, w):
     def step_e2e():
         c = cond_h.to(dev, non_blocking=True)
         s = src_h.to(dev, non_blocking=True) if shallow else None
-        mel = model(c, src_spec=s, infer=True)
+        mel = run(c, s)
         if world > 1:
             full = gather_mels(mel.contiguous(), index, world * B, dst=0)
             return full.cpu() if full is not None else None
@@ -418,7 +437,7 @@ def run_b200_arm(args, w):
                        'sigma_w': SIGMA_W},
             'e2e': {'value': e2e_value, 'unit': 'frame*NFE/s', 'ms_per_step': max(e2e_ms, e2e_wall_ms) / args.steps,
                     'h2d_bytes_per_step': int(cond_h.numel() * 4 + (src_h.numel() * 4 if shallow else 0)) * world,
-                    'd2h_bytes_per_step': int(world * B * T * w['mel'] * 4)},
+                    'd2h_bytes_per_step': int(world * B * T * n_out * 4)},
             'gpu_launches': int(launches_per_step * args.steps),
             'rtf': (ms_total / args.steps * 1e-3) / (world * B * T * 512 / 44100.0),
             'tflops_algorithmic': value * F / 1e12,
