@@ -168,15 +168,20 @@ int b2s_tc_wavenet_out(const void* z_h, const void* Wo_h, const float* bo, float
                        int bf16, void* stream);
 
 /* Deferred skip sum (channel widths without a fused stack kernel, e.g. C = 512 / 192): the L skip outputs are never
- * accumulated layer by layer.  b2s_tc_wavenet_gate_ld writes z_l into column block l of ONE [rows, ld_z = L*C] buffer,
- * b2s_tc_wavenet_res applies only the residual rows of output_projection (wavenet.py:44-48: x <- (x + W_res z + b)/sqrt(2),
- * y_next = x + d_next), and after the last layer a single b2s_tc_linear with K = L*C computes
- * sum_l W_skip,l z_l (wavenet.py:96) - the same FLOPs, but no fp32 skip read-modify-write per layer and half the columns in
- * every per-layer GEMM. */
+ * accumulated layer by layer.  Every layer's z_l is kept (b2s_tc_wavenet_gate into slab l of a [L][rows][C] buffer, or
+ * b2s_tc_wavenet_gate_ld into column block l of a [rows, ld_z = L*C] one), b2s_tc_wavenet_res applies only the residual rows of
+ * output_projection (wavenet.py:44-48: x <- (x + W_res z + b)/sqrt(2), y_next = x + d_next), and after the last layer ONE GEMM
+ * with K = L*C (b2s_tc_skip_sum, or b2s_tc_linear on the [rows, L*C] layout) computes sum_l W_skip,l z_l (wavenet.py:96) - the
+ * same FLOPs, but no fp32 skip read-modify-write per layer and half the columns in every per-layer GEMM. */
 int b2s_tc_wavenet_gate_ld(const void* y_h, const void* Wd_h, const void* cond_h, int ld_cond, void* z_h, int ld_z, int B, int T,
                            int C, int dilation, int bf16, void* stream);
 int b2s_tc_wavenet_res(const void* z_h, int ld_z, const void* Wres_h, const float* b_res, float* x, void* y_next_h,
                        const float* dvec_next, int d_stride, int B, int T, int C, int bf16, void* stream);
+/* The deferred skip GEMM over a LAYER-MAJOR z buffer [L][rows][C] (every layer's z rows stay contiguous, as the gate GEMM
+ * writes them): out_h [rows, C] = sum_l z_l W_skip,l^T + bias, Wcat_h [C, L*C] with column l*C + k = W_skip,l[:, k]; the K loop
+ * walks a 3-D tensor map {C, rows, L}. */
+int b2s_tc_skip_sum(const void* z_all_h, const void* Wcat_h, const float* bias, void* out_h, int rows, int C, int L, int bf16,
+                    void* stream);
 
 /* ONE fused kernel per WaveNet residual layer (wavenet.py:33-48), residual channels C = 256:
  * dilated conv (implicit GEMM) -> + hoisted cond -> sigmoid*tanh -> z kept in shared memory -> output projection

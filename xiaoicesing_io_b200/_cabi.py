@@ -36,6 +36,7 @@ _SIGNATURES = {
     'b2s_tc_cond_table': [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_cond_table_tiled': [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     'b2s_tc_wavenet_gate_ld': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_tc_skip_sum': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_res': [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_gate': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_wavenet_out': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
@@ -266,6 +267,10 @@ def tc_wavenet_gate_ld(y_h, Wd_h, cond_h, ld_cond, z_h, ld_z, B, T, C, dilation,
 def tc_wavenet_res(z_h, ld_z, Wres_h, b_res, x, y_next_h, dvec_next, d_stride, B, T, C, bf16):
     check(lib.b2s_tc_wavenet_res(ptr(z_h), ld_z, ptr(Wres_h), ptr(b_res), ptr(x), ptr(y_next_h), ptr(dvec_next), d_stride, B, T, C,
                                  int(bf16), stream_ptr()), 'b2s_tc_wavenet_res')
+
+
+def tc_skip_sum(z_all_h, Wcat_h, bias, out_h, rows, C, L, bf16):
+    check(lib.b2s_tc_skip_sum(ptr(z_all_h), ptr(Wcat_h), ptr(bias), ptr(out_h), rows, C, L, int(bf16), stream_ptr()), 'b2s_tc_skip_sum')
 
 
 def tc_cond_retile(table_h, L, B, T, n2, NT, out_h):

@@ -56,6 +56,7 @@ struct __align__(64) TcP {
     const void* cond; int ldc;
     float* x; float* skip; void* skip_h; int C; int first;
     int cg2;                   // 1: cta_group::2 kernel (tiles_m_per_b even, weight map box = 128 rows)
+    int k_layered;             // 1: K block group g = kb / kb_per_tap selects the THIRD coordinate of the A map (A = [L][rows][C], K = L*C)
 };
 
 // ---- 16-bit helpers --------------------------------------------------------------------------------
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
-                    tma_load_3d(sa, &p.mapA, &full[stage], c0, t0 + (tap - 1) * p.dil, b);
+                    tma_load_3d(sa, &p.mapA, &full[stage], c0, t0 + (tap - 1) * p.dil, p.k_layered ? tap : b);
                     tma_load_2d(sa + A_BYTES, &p.mapW, &full[stage], kb * BLOCK_K, n0);
                 }
                 __syncwarp();
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
-                    tma_load_3d_cg2(sa, &p.mapA, lbar, c0, t0 + (tap - 1) * p.dil, b);
+                    tma_load_3d_cg2(sa, &p.mapA, lbar, c0, t0 + (tap - 1) * p.dil, p.k_layered ? tap : b);
                     tma_load_2d_cg2(sa + A_BYTES, &p.mapW, lbar, kb * BLOCK_K, n0 + rank * (BLOCK_N / 2));
                 }
                 __syncwarp();
@@ -773,6 +774,24 @@ extern "C" int b2s_tc_wavenet_out(const void* z_h, const void* Wo_h, const float
     p.bias = bo; p.x = x; p.y_h = y_next_h; p.ldy = C; p.skip = skip; p.skip_h = skip_h; p.C = C;
     p.dvec = dvec_next; p.d_stride = d_stride; p.first = first_layer;
     return launch<EPI_RESSKIP>(p, bf16, (cudaStream_t)stream);
+}
+
+extern "C" int b2s_tc_skip_sum(const void* z_all_h, const void* Wcat_h, const float* bias, void* out_h, int rows, int C, int L,
+                               int bf16, void* stream) {
+    B2S_CHECK_ARG(z_all_h && Wcat_h && bias && out_h, "b2s_tc_skip_sum: null pointer");
+    B2S_CHECK_ARG(C % 64 == 0 && L >= 1, "b2s_tc_skip_sum: needs C %% 64 == 0 (C=%d) and L >= 1", C);
+    B2S_CHECK_ARG(al16(z_all_h) && al16(Wcat_h) && al16(bias) && al16(out_h), "b2s_tc_skip_sum: misaligned pointer");
+    if (rows == 0) return B2S_OK;
+    TcP p{};
+    // tiling of a flat [rows, L*C] x [L*C, C] GEMM; the A map is 3-D {C, rows, L} so that K block kb reads layer kb / (C/64)
+    int rc = setup(p, z_all_h, C, C, 1, rows, false, Wcat_h, L * C, C, L * C, C / BLOCK_K, 0, bf16);
+    if (rc) return rc;
+    rc = make_map_act(&p.mapA, z_all_h, bf16, C, C, rows, L, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+    p.k_layered = 1;
+    p.dil = 0;
+    p.bias = bias; p.alpha = 1.0f; p.act = ACT_NONE; p.out_h = out_h; p.ldoh = C;
+    return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
 }
 
 extern "C" int b2s_tc_lynx_glu(const void* h_h, const void* W_h, const float* bias, void* g_h, int rows, int C, int inner,

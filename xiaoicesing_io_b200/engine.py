@@ -270,7 +270,7 @@ class WaveNetSessionTC:
         del self._cond_h
         # two-kernel path: the L skip outputs are summed by ONE K = L*C GEMM after the last layer (no per-layer fp32 skip RMW)
         self.defer_skip = (not self.fused) and hparams.get('b2s_defer_skip', True) and rows * L * Cc * 2 <= 8e9
-        self.z_all = torch.empty((rows, L * Cc), device=dev, dtype=hd) if self.defer_skip else None
+        self.z_all = torch.empty((L, rows, Cc), device=dev, dtype=hd) if self.defer_skip else None     # layer-major: contiguous rows per layer
         self.skip_h = torch.empty((rows, Cc), device=dev, dtype=hd)
         self.h_h = torch.empty((rows, Cc), device=dev, dtype=hd)
 
@@ -405,15 +405,15 @@ class WaveNetSessionTC:
                 ya, yb = yb, ya                            # ping-pong: neighbours still read the halo of ya
                 continue
             if self.defer_skip:
-                zl = self.z_all[:, l * Cc:]
-                C.tc_wavenet_gate_ld(self.y_h, e.w_dil_h[l], self.cond[l], ldc, zl, L * Cc, B, T, Cc, e.dilations[l], bf)
-                C.tc_wavenet_res(zl, L * Cc, e.w_res_h[l], e.b_res[l], self.x, None if last else self.y_h, dn, ds, B, T, Cc, bf)
+                zl = self.z_all[l]
+                C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[l], ldc, zl, B, T, Cc, e.dilations[l], bf)
+                C.tc_wavenet_res(zl, Cc, e.w_res_h[l], e.b_res[l], self.x, None if last else self.y_h, dn, ds, B, T, Cc, bf)
                 continue
             C.tc_wavenet_gate(self.y_h, e.w_dil_h[l], self.cond[l], ldc, self.z_h, B, T, Cc, e.dilations[l], bf)
             C.tc_wavenet_out(self.z_h, e.w_out_h[l], e.b_out[l], self.x, None if last else self.y_h, self.skip,
                              self.skip_h if last else None, dn, ds, l == 0, B, T, Cc, bf)
         if self.defer_skip:
-            C.tc_linear(self.z_all, L * Cc, rows, T, e.w_skipcat_h, L * Cc, e.b_skip_sum, Cc, L * Cc, bf, out_h=self.skip_h, ldoh=Cc)
+            C.tc_skip_sum(self.z_all, e.w_skipcat_h, e.b_skip_sum, self.skip_h, rows, Cc, L, bf)
         C.tc_linear(self.skip_h, Cc, rows, T, e.w_sp_h, Cc, e.b_sp, Cc, Cc, bf, alpha=1.0 / math.sqrt(L),
                     act=C.ACT_RELU, out_h=self.h_h, ldoh=Cc)
         C.tc_linear(self.h_h, Cc, rows, T, e.w_fin_h, Cc, e.b_fin, MF, Cc, bf, out_f32=out, ldo=MF)
