@@ -450,10 +450,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
+        // EPI_GATE: the hoisted conditioner-projection rows of a tile stream from HBM once per evaluation; ncu showed the epilogue
+        // warps waiting on them (long scoreboard) although they are requested one chunk ahead.  The producer asks L2 for the rows
+        // of the tile AFTER the current one (and of the first tile at kernel start), a whole mainloop before the epilogue needs them.
+        auto prefetch_cond = [&](int pt2) {
+            if (EPI != EPI_GATE || p.cond == nullptr || pt2 >= num_pt || lane != 0) return;
+            const int m2 = 2 * (pt2 / p.tiles_n) + rank;
+            const int b2 = m2 / p.tiles_m_per_b, t2 = (m2 - b2 * p.tiles_m_per_b) * BLOCK_M;
+            const int nrows = min(BLOCK_M, p.T - t2);
+            if (b2 >= p.B || nrows <= 0) return;
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(p.cond) + ((long long)b2 * p.T + t2) * p.ldc * 2;
+            const int bytes = nrows * p.ldc * 2;                      // full rows: contiguous, a multiple of 16 bytes
+            for (int off = 0; off < bytes; off += 16384) {
+                const int n = min(16384, bytes - off);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(n) : "memory");
+            }
+        };
+        // (the same prefetch for the fp32 residual-stream rows of the x-updating epilogues was measured: 1-2 % slower)
+        prefetch_cond(pair);
         for (int pt = pair; pt < num_pt; pt += npairs) {
             const int n_tile = pt % p.tiles_n, m_tile = 2 * (pt / p.tiles_n) + rank;
             const int b = m_tile / p.tiles_m_per_b, t0 = (m_tile - b * p.tiles_m_per_b) * BLOCK_M;
             const int n0 = n_tile * BLOCK_N;
+            prefetch_cond(pt + npairs);
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 if (lane == 0) {
