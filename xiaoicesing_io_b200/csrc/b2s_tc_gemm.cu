@@ -56,6 +56,7 @@ struct __align__(64) TcP {
     const void* cond; int ldc;
     float* x; float* skip; void* skip_h; int C; int first;
     int cg2;                   // 1: cta_group::2 kernel (tiles_m_per_b even, weight map box = 128 rows)
+    int bn;                    // N tile of the cta_group::2 kernel: 256, or 192 when N is a multiple of 192 but not of 256 (C = 192 models)
     int k_layered;             // 1: K block group g = kb / kb_per_tap selects the THIRD coordinate of the A map (A = [L][rows][C], K = L*C)
 };
 
@@ -471,18 +472,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
         for (int pt = pair; pt < num_pt; pt += npairs) {
             const int n_tile = pt % p.tiles_n, m_tile = 2 * (pt / p.tiles_n) + rank;
             const int b = m_tile / p.tiles_m_per_b, t0 = (m_tile - b * p.tiles_m_per_b) * BLOCK_M;
-            const int n0 = n_tile * BLOCK_N;
+            const int n0 = n_tile * p.bn;
             prefetch_cond(pt + npairs);
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 if (lane == 0) {
                     uint8_t* sa = smem + stage * STAGE2_BYTES;
                     const uint32_t lbar = mapa_u32(&full[stage], 0);
-                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + (p.bn / 2) * BLOCK_K * 2));
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
                     tma_load_3d_cg2(sa, &p.mapA, lbar, c0, t0 + (tap - 1) * p.dil, p.k_layered ? tap : b);
-                    tma_load_2d_cg2(sa + A_BYTES, &p.mapW, lbar, kb * BLOCK_K, n0 + rank * (BLOCK_N / 2));
+                    tma_load_2d_cg2(sa + A_BYTES, &p.mapW, lbar, kb * BLOCK_K, n0 + rank * (p.bn / 2));
                 }
                 __syncwarp();
                 if (++stage == STAGES2) { stage = 0; phase ^= 1; }
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
         }
     } else if (warp == 1 && rank == 0) {
         // ===================== MMA issuer (leader CTA): M = 256 across the pair =====================
-        const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N, BF16);
+        const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, p.bn, BF16);
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
         for (int pt = pair; pt < num_pt; pt += npairs) {
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
         for (int pt = pair; pt < num_pt; pt += npairs) {
             const int n_tile = pt % p.tiles_n, m_tile = 2 * (pt / p.tiles_n) + rank;
             const int bt = m_tile / p.tiles_m_per_b, t0 = (m_tile - bt * p.tiles_m_per_b) * BLOCK_M;
-            const int n0 = n_tile * BLOCK_N;
+            const int n0 = n_tile * p.bn;
             const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
             // per-chunk inputs (cond / x / skip rows of the lane, bias and step-embedding quads) are requested ONE CHUNK AHEAD -
             // the first chunk's before the accumulator wait - so their L2 / HBM latency hides behind the TMEM drain of the
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
-            for (int j = sub; j < BLOCK_N / 32; j += 2) {
+            for (int j = sub; j < p.bn / 32; j += 2) {
                 const int col0 = n0 + 32 * j;
                 if (col0 >= p.N) break;
                 float acc[32];
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                 uint2 cn[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { in[i] = inn[i]; cn[i] = cnn[i]; }
-                if (j + 2 < BLOCK_N / 32 && col0 + 64 < p.N) load_chunk(j + 2);
+                if (j + 2 < p.bn / 32 && col0 + 64 < p.N) load_chunk(j + 2);
                 tmem_ld_wait();
                 // transpose through the warp's private 16-row staging tile, two passes: thread = row -> lane = 4 columns
 #pragma unroll
@@ -675,7 +676,8 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     if (rc) return rc;
     static const bool cg1 = getenv("B2S_GEMM_CG1") != nullptr;      // A/B switch: the single-CTA kernel
     p.cg2 = cg1 ? 0 : 1;
-    rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, p.cg2 ? BLOCK_N / 2 : BLOCK_N);
+    p.bn = (p.cg2 && N % 192 == 0 && N % 256 != 0) ? 192 : BLOCK_N;      // no half-empty second tile for the C = 192 models
+    rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, p.cg2 ? p.bn / 2 : BLOCK_N);
     if (rc) return rc;
     p.B = Bm; p.T = Tm; p.T_utt = T;
     p.N = N;
@@ -684,7 +686,7 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     p.dil = dil;
     p.tiles_m_per_b = ceil_div(Tm, BLOCK_M);
     if (p.cg2) p.tiles_m_per_b = (p.tiles_m_per_b + 1) & ~1;       // whole CTA pairs; a padding tile has no valid row
-    p.tiles_n = ceil_div(N, BLOCK_N);
+    p.tiles_n = ceil_div(N, p.bn);
     p.num_tiles = Bm * p.tiles_m_per_b * p.tiles_n;
     return B2S_OK;
 }
