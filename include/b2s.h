@@ -251,6 +251,28 @@ int b2s_tc_wavenet_denoiser_update(const void* xin_h, int MF, const void* Win_h,
                                    const float* const* srcs_host, const float* coef, float* x_out, void* x_out_h, int bf16,
                                    void* stream);
 
+/* Third design of the whole-stack kernel (round 2; csrc/b2s_tc_wavenet3.cu), C = 256, dilations <= b2s_tc_wavenet_stack3_halo():
+ * stem + all L residual layers in ONE persistent launch of cta_group::2 pairs (two neighbouring 128-frame tiles form one 256-row
+ * MMA).  The layer input y stays RESIDENT in shared memory (only 16 edge rows per side travel through yedge0_h / yedge1_h and the
+ * tile flags), the fp32 residual stream stays in TMEM (wavenet.py:47-48 folded into the accumulator: Wres_h carries 2^(l/2)), and
+ * the skip half of output_projection is deferred: every layer's gated tile z_l is TMA-stored to z_all_h [L][rows][C]
+ * (z_layer_stride elements between layers) for ONE b2s_tc_skip_sum afterwards (wavenet.py:96).
+ *   xin_h [B*T, MF] 16-bit; Win_h [C, ld_win]; b_in [C]; Wd_h [L,2C,3C] (gate/filter interleaved rows, column = tap*C + c)
+ *   cond_h: table of b2s_tc_cond_table_tiled for THIS B and T; cond_layer_stride = B*tpb*128*2C elements
+ *   Wres_h [L,C,C]: 2^(l/2) * output_projection.weight[:C];  bsum [L,C] fp32: sum_{k<l} 2^(k/2) * output_projection.bias_k[:C]
+ *   dvec: this evaluation's step-embedding row, layer l at dvec + b*d_stride + l*C;  dilations_host: L ints (HOST)
+ *   yedge0_h, yedge1_h: 16-bit [B*T, C] scratch (only the first / last 16 rows of every 128-frame tile are touched)
+ *   flags: int32 [B * tiles], ZERO at launch.  Every tile must be resident: checked against cudaOccupancyMaxActiveClusters. */
+int b2s_tc_wavenet_stack3_halo(void);
+/* tiles (2*ceil(ceil(T/128)/2) per utterance) ONE launch can hold on the current device for utterances of T frames: cluster size =
+ * the largest of 8, 6, 4, 2 dividing the tiles per utterance (halo rows inside a cluster go through distributed shared memory), as
+ * many clusters as cudaOccupancyMaxActiveClusters reports.  The host splits larger batches by utterance. */
+int b2s_tc_wavenet_stack3_max_tiles(int T, int bf16);
+int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
+                          const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum, const float* dvec,
+                          int d_stride, const int* dilations_host, int L, void* yedge0_h, void* yedge1_h, void* z_all_h,
+                          int64_t z_layer_stride, int B, int T, int C, int* flags, int bf16, void* stream);
+
 /* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
  * down-projection with the residual add into the fp32 stream. */
 int b2s_tc_lynx_glu(const void* h_h, const void* W_h, const float* bias, void* g_h, int rows, int C, int inner, int bf16,

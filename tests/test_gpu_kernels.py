@@ -352,3 +352,76 @@ def test_tc_stack_rejects_oversized_grid(C):
     z = torch.zeros(8, device='cuda')
     with pytest.raises(C.B2SError):
         C.tc_wavenet_stack(z, z[4:], z, z, 2 * Cc, 8, z, z, z, z, None, z, 0, [1, 2], B, T, Cc, z.int(), True)
+
+
+def _stack3_reference(xin, Win, b_in, Wd, cond, Wres3, bres, dvec, dil, B, T, hd, per_row):
+    """fp64 restatement of wavenet.py:86-96 on the SAME 16-bit operands, with y and z rounded to 16 bits where the kernel
+    rounds them.  Returns (z of every layer [L, rows, C], final x)."""
+    L, C2, _ = Wd.shape
+    Cc = C2 // 2
+    rows = B * T
+    r16 = lambda t: t.to(hd).double()
+    x = torch.relu(xin.double() @ Win.double().t() + b_in.double())
+    zs = []
+    for l in range(L):
+        d = (dvec[:, l * Cc:(l + 1) * Cc] if per_row else dvec[:1, l * Cc:(l + 1) * Cc]).double()
+        y = r16((x.reshape(B, T, Cc) + d[:, None, :]).float()).reshape(B, T, Cc)
+        pre = cond[l].double().reshape(B, T, C2).clone()
+        for tap in range(3):
+            sh = (tap - 1) * dil[l]
+            ys = torch.zeros_like(y)
+            if sh < 0:
+                ys[:, -sh:] = y[:, :T + sh]
+            elif sh > 0:
+                ys[:, :T - sh] = y[:, sh:]
+            else:
+                ys = y
+            pre += ys @ Wd[l, :, tap * Cc:(tap + 1) * Cc].double().t()
+        z = r16((torch.sigmoid(pre[..., 0::2]) * torch.tanh(pre[..., 1::2])).float()).reshape(rows, Cc)
+        zs.append(z)
+        w = Wres3[l].double() / 2.0 ** (0.5 * l)
+        x = (x + z @ w.t() + bres[l].double()) / 2 ** 0.5
+    return torch.stack(zs, 0), x
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+def test_tc_stack3_against_fp64(C, kind, hd, eps):
+    """Third whole-stack kernel (cta_group::2 pairs, resident y tile with halo, residual stream in TMEM, z tiles TMA-stored
+    for the deferred skip GEMM): every layer's z against an fp64 restatement on the same 16-bit operands."""
+    bf = kind == 'bf16'
+    Cc, L, MF = 256, 6, 128
+    dil = [1, 2, 4, 8, 16, 1]
+    for (B, T) in [(2, 300), (3, 690), (1, 100), (5, 129), (1, 128), (2, 261), (1, 1292)]:
+        rows = B * T
+        torch.manual_seed(B * 1000 + T)
+        xin = torch.randn(rows, MF, device='cuda').to(hd)
+        Win = (torch.randn(Cc, MF, device='cuda') / MF ** 0.5).to(hd)
+        b_in = torch.randn(Cc, device='cuda') * 0.1
+        Wd = (torch.randn(L, 2 * Cc, 3 * Cc, device='cuda') / (3 * Cc) ** 0.5).to(hd)
+        Wres = torch.randn(L, Cc, Cc, device='cuda') / Cc ** 0.5
+        bres = torch.randn(L, Cc, device='cuda') * 0.1
+        sc = 2.0 ** (0.5 * torch.arange(L, device='cuda', dtype=torch.float64))
+        Wres3 = (Wres.double() * sc[:, None, None]).float().to(hd)
+        b3 = bres.double() * sc[:, None]
+        bsum = (torch.cumsum(b3, 0) - b3).float().contiguous()
+        cond = torch.randn(L, rows, 2 * Cc, device='cuda').to(hd)
+        dvec = torch.randn(B, L * Cc, device='cuda')
+        tpb = (-(-T // 128) + 1) & ~1
+        tiled = _tile_cond(cond, B, T, tpb)
+        for per_row in (False, True):
+            ds = L * Cc if per_row else 0
+            flags = torch.zeros(B * tpb, device='cuda', dtype=torch.int32)
+            ye0 = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+            ye1 = torch.zeros(rows, Cc, device='cuda', dtype=hd)
+            z_all = torch.full((L, rows, Cc), float('nan'), device='cuda', dtype=hd)
+            C.tc_wavenet_stack3(xin, MF, Win, MF, b_in, Wd, tiled, B * tpb * 128 * 2 * Cc, Wres3, bsum, dvec, ds, dil, ye0, ye1,
+                                z_all, rows * Cc, B, T, Cc, flags, bf)
+            torch.cuda.synchronize()
+            z_want, _ = _stack3_reference(xin, Win, b_in, Wd, cond, Wres3, bres, dvec, dil, B, T, hd, per_row)
+            tag = (kind, B, T, per_row)
+            assert int(flags.max()) <= L, (tag, flags.tolist())     # only tiles at a cluster boundary inside an utterance publish
+            assert bool(torch.isfinite(z_all.float()).all()), tag
+            errs = [float((z_all[l].double() - z_want[l]).abs().max()) for l in range(L)]
+            print('stack3', tag, ['%.1e' % v for v in errs])
+            # z in (-1, 1); one 16-bit rounding of y moves a pre-activation by ~eps * |y| * sqrt(3C) * |w| ~ a few eps
+            assert max(errs) < 24 * eps, (tag, errs)

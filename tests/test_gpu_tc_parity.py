@@ -201,12 +201,13 @@ def test_config4_variance_predictors_tensor_core(acc, precision, dev):
     assert err <= (2e-4 * scale if precision == 'bf16' else 5e-5 * max(scale, 1.0)), (acc, precision, err, scale)
 
 
-def _bf16_backbone(dev, stack, L=4, fuse_io=False, in_dims=128, n_feats=1, stack_t=False, cycle=4, precision='bf16'):
+def _bf16_backbone(dev, stack, L=4, fuse_io=False, in_dims=128, n_feats=1, stack_t=False, cycle=4, precision='bf16', stack3=False):
     import xiaoicesing_io_b200 as P
     from oracle import weights as OW
     cfg = OD.WaveNetCfg(in_dims=in_dims, n_feats=n_feats, num_layers=L, num_channels=256, dilation_cycle_length=cycle)
     P.hparams.clear()
-    P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision=precision, b2s_stack=stack, b2s_fuse_io=fuse_io, b2s_stack_t=stack_t)
+    P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision=precision, b2s_stack=stack, b2s_fuse_io=fuse_io, b2s_stack_t=stack_t,
+                     b2s_stack3=stack3)
     net = P.build_backbone(cfg.in_dims, n_feats, 'wavenet', dict(num_layers=L, num_channels=256, dilation_cycle_length=cycle))
     net.load_state_dict(OW.make_state_dict(cfg, seed=0, sigma_w=0.01), strict=True)
     return net.to(dev).eval()
@@ -226,6 +227,30 @@ def test_stack_kernel_grouping_and_fallback_match_per_layer_path(B, T, dev):
         b = _bf16_backbone(dev, stack=False)(spec, t.to(dev), cond)
         assert bool(torch.isfinite(a).all())
         assert torch.equal(a, b), (B, T, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+@pytest.mark.parametrize('B,T,L,cycle,in_dims,n_feats', [(30, 690, 4, 4, 128, 1), (5, 129, 6, 4, 128, 1), (16, 690, 20, 4, 128, 1),
+                                                        (3, 257, 5, 5, 64, 1), (2, 130, 4, 4, 24, 2), (1, 1292, 4, 4, 128, 1),
+                                                        (40, 345, 4, 4, 128, 1)])
+def test_stack3_matches_per_layer_path(B, T, L, cycle, in_dims, n_feats, precision, dev):
+    """The third whole-stack kernel (b2s_stack3, the default: cta_group::2 pairs, y resident in shared memory, residual stream in
+    TMEM, halo rows through distributed shared memory, deferred skip GEMM) against the per-layer kernels: same 16-bit operands,
+    but the fp32 residual stream is carried as 2^(l/2)-scaled accumulator, so the two agree to 16-bit rounding of y, not bit for
+    bit.  Shapes: several launches per batch (30 x 690, 40 x 345), clusters of 6 / 4 / 2 tiles, an utterance spanning two
+    clusters (1292 frames), dilation 16 (cycle 5), 64 and 48 packed bins, per-utterance diffusion steps."""
+    g = torch.Generator().manual_seed(B * 7 + T)
+    spec = torch.randn((B, n_feats, in_dims, T), generator=g).to(dev)
+    cond = torch.randn((B, 256, T), generator=g).to(dev)
+    eps = 2 ** -8 if precision == 'bf16' else 2 ** -11
+    for t in (torch.tensor([437.0]), torch.arange(B, dtype=torch.float32) * 13 + 5):
+        net = _bf16_backbone(dev, stack=True, L=L, cycle=cycle, in_dims=in_dims, n_feats=n_feats, precision=precision, stack3=True)
+        a = net(spec, t.to(dev), cond)
+        b = _bf16_backbone(dev, stack=False, L=L, cycle=cycle, in_dims=in_dims, n_feats=n_feats, precision=precision)(spec, t.to(dev), cond)
+        assert bool(torch.isfinite(a).all())
+        scale = float(b.abs().max())
+        err = float((a - b).abs().max())
+        assert err <= 4 * eps * scale, (B, T, L, precision, err, scale)
 
 
 @pytest.mark.parametrize('B,T,in_dims,n_feats', [(16, 690, 128, 1), (30, 300, 128, 1), (3, 257, 64, 1), (2, 130, 24, 2), (1, 50, 128, 1)])

@@ -13,8 +13,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB_PATH = os.path.join(HERE, 'libb2s.so')
-OBJ_DIR = os.path.join(HERE, 'csrc', '_obj')
+LIB_PATH = os.path.join(HERE, os.environ.get('B2S_LIB_OUT', 'libb2s.so'))      # B2S_LIB_OUT: side builds (profiling variants)
+OBJ_DIR = os.path.join(HERE, 'csrc', '_obj' + ('_tlog' if os.environ.get('B2S_BUILD_TLOG') else ''))
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

@@ -103,6 +103,14 @@ class WaveNetEngine:
             self.b_res = self.b_out[:, :Cc].contiguous()
             self.w_skipcat_h = h(self.w_out[:, Cc:, :].permute(1, 0, 2).reshape(Cc, L * Cc))
             self.b_skip_sum = self.b_out[:, Cc:].sum(0).contiguous()
+            # third stack kernel (b2s_tc_wavenet_stack3): the residual stream lives in TMEM as X_l = 2^(l/2) x_l - (bias terms),
+            # so layer l's residual rows carry 2^(l/2) and the biases become one exclusive prefix sum per layer
+            sc = 2.0 ** (0.5 * torch.arange(L, device=dev, dtype=torch.float64))
+            w_res3 = self.w_out[:, :Cc, :].double() * sc[:, None, None]
+            b_res3 = self.b_out[:, :Cc].double() * sc[:, None]
+            self.w_res3_h = h(w_res3.float())
+            self.bsum3 = (torch.cumsum(b_res3, 0) - b_res3).float().contiguous()              # [L, C]: sum over k < l
+            self.res3_ok = bool(torch.isfinite(self.w_res3_h.float()).all())                  # fp16 range (2^(l/2) <= 2^15.5 at L = 32)
             self.w_dil_t_h = self.w_cond_t_h = self.b_cond_t = None
             if Cc == C.FUSED_LAYER_CHANNELS:
                 # transposed stack kernel (b2s_tc_wavenet_stack_t): row 256h + 128g + c = (g ? filter : gate) of channel 128h + c,
@@ -250,6 +258,14 @@ class WaveNetSessionTC:
         # utterance into groups of `stack_group` (0 = an utterance alone exceeds the SM count -> per-layer kernels)
         tpb = (-(-T // 128) + 1) & ~1
         self.stack_group = (C.lib.b2s_tc_wavenet_stack_max_tiles() // tpb) if (self.fused and hparams.get('b2s_stack', True)) else 0
+        # third stack kernel (default): resident y tile (halo <= 16 rows), residual stream in TMEM, deferred skip sum; its launch
+        # capacity comes from cudaOccupancyMaxActiveClusters for the cluster size it will use for this T
+        self.stack3 = False
+        if (self.stack_group and hparams.get('b2s_stack3', True) and not hparams.get('b2s_stack_t', False) and eng.res3_ok
+                and max(eng.dilations) <= C.lib.b2s_tc_wavenet_stack3_halo() and eng.MF <= 256):
+            g3 = C.lib.b2s_tc_wavenet_stack3_max_tiles(T, int(bf)) // tpb
+            if g3 > 0:
+                self.stack3, self.stack_group = True, g3
         self.flags = torch.zeros((B * tpb,), device=dev, dtype=torch.int32) if self.stack_group else None
         self.tpb = tpb
         self.tgroups = self._plan_transposed(cond_h) if (self.stack_group and hparams.get('b2s_stack_t', False)) else None
@@ -270,7 +286,7 @@ class WaveNetSessionTC:
         del self._cond_h
         # two-kernel path: the L skip outputs are summed by ONE K = L*C GEMM after the last layer (no per-layer fp32 skip RMW)
         self.defer_skip = (not self.fused) and hparams.get('b2s_defer_skip', True) and rows * L * Cc * 2 <= 8e9
-        self.z_all = torch.empty((L, rows, Cc), device=dev, dtype=hd) if self.defer_skip else None     # layer-major: contiguous rows per layer
+        self.z_all = torch.empty((L, rows, Cc), device=dev, dtype=hd) if (self.defer_skip or self.stack3) else None     # layer-major: contiguous rows per layer
         self.skip_h = torch.empty((rows, Cc), device=dev, dtype=hd)
         self.h_h = torch.empty((rows, Cc), device=dev, dtype=hd)
 
@@ -323,7 +339,7 @@ class WaveNetSessionTC:
 
     @property
     def can_fuse_update(self) -> bool:
-        return bool(self.stack_group) and not self.tgroups and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256
+        return bool(self.stack_group) and not self.tgroups and not self.stack3 and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256
 
     def eval_update(self, x_in, k, srcs, coef, x_dst, precast=False):
         """One launch: denoiser evaluation + ``x_dst <- sum coef[i] * srcs[i]`` (``None`` in srcs = the evaluation's output),
@@ -362,6 +378,24 @@ class WaveNetSessionTC:
                 C.tc_wavenet_stack_t(self.y_h[r0:], self.y2_h[r0:], e.w_dil_t_h, tab, e.w_out_h, e.b_out, self.x[r0:],
                                      self.skip_h[r0:], dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
                                      e.dilations, b1 - b0, T, Cc, nt, self.flags[f0:], bf)
+            C.tc_linear(self.skip_h, Cc, rows, T, e.w_sp_h, Cc, e.b_sp, Cc, Cc, bf, alpha=1.0 / math.sqrt(L),
+                        act=C.ACT_RELU, out_h=self.h_h, ldoh=Cc)
+            C.tc_linear(self.h_h, Cc, rows, T, e.w_fin_h, Cc, e.b_fin, MF, Cc, bf, out_f32=out, ldo=MF)
+            return
+        if self.stack3:
+            # stem + residual stack in ONE launch per utterance group (z_l of every layer -> z_all), then the deferred skip GEMM
+            # (K = L*C) and the two head GEMMs
+            LC = L * Cc
+            dv = self.dtab.reshape(-1) if self.per_row_t else self.dtab[k]
+            for gi, b0 in enumerate(range(0, B, self.stack_group)):
+                b1 = min(B, b0 + self.stack_group)
+                r0 = b0 * T
+                tab = self.cond_groups[gi]
+                C.tc_wavenet_stack3(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
+                                    e.w_res3_h, e.bsum3, dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
+                                    e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, b1 - b0, T, Cc,
+                                    self.flags[b0 * self.tpb:], bf)
+            C.tc_skip_sum(self.z_all, e.w_skipcat_h, e.b_skip_sum, self.skip_h, rows, Cc, L, bf)
             C.tc_linear(self.skip_h, Cc, rows, T, e.w_sp_h, Cc, e.b_sp, Cc, Cc, bf, alpha=1.0 / math.sqrt(L),
                         act=C.ACT_RELU, out_h=self.h_h, ldoh=Cc)
             C.tc_linear(self.h_h, Cc, rows, T, e.w_fin_h, Cc, e.b_fin, MF, Cc, bf, out_f32=out, ldo=MF)
@@ -422,6 +456,8 @@ class WaveNetSessionTC:
     def launches_per_eval(self) -> int:
         if self.tgroups:
             return 1 + 1 + len(self.tgroups) + 2                   # cast, stem, transposed stack launches, 2 head GEMMs
+        if self.stack3:
+            return 1 + -(-self.B // self.stack_group) + 3          # cast (+ flag reset), stack launches, skip GEMM, 2 head GEMMs
         if self.stack_group and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256:
             return 1 + -(-self.B // self.stack_group)              # cast (+ flag reset), one denoiser launch per utterance group
         if self.stack_group:
@@ -445,6 +481,24 @@ class WaveNetSessionTC:
                                          self.skip_h[r0:], dv, 0, e.dilations, b1 - b0, T, Cc, nt, self.flags[f0:], e.bf16)
             return (f'wavenet_stack_t_kernel<{nt}, {e.precision}> (b2s_tc_wavenet_stack_t, {L} layers per launch, {n_tiles} tiles of {nt} frames)',
                     flops, launch_all, len(self.tgroups))
+        if self.stack3:
+            # algorithmic FLOPs of this launch: stem + conv (6C^2) + residual half of the output projection (C^2; the last layer's
+            # is not needed) per frame; the skip half runs in the deferred b2s_tc_skip_sum launch
+            nb = min(self.stack_group, B)
+            flops = 2.0 * nb * T * (e.MF * Cc + L * 6 * Cc * Cc + (L - 1) * Cc * Cc)
+            dv = self.dtab[0]
+
+            def launch_all():
+                self.flags.zero_()
+                for gi, b0 in enumerate(range(0, B, self.stack_group)):
+                    b1 = min(B, b0 + self.stack_group)
+                    r0 = b0 * T
+                    tab = self.cond_groups[gi]
+                    C.tc_wavenet_stack3(self.xin_h[r0:], e.MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
+                                        e.w_res3_h, e.bsum3, dv, 0, e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:],
+                                        self.rows * Cc, b1 - b0, T, Cc, self.flags[b0 * self.tpb:], e.bf16)
+            return (f'wavenet_stack3_kernel<{e.precision}> (b2s_tc_wavenet_stack3: stem + {L} layers per launch, skip sum deferred)',
+                    flops, launch_all, -(-B // self.stack_group))
         if self.stack_group:
             flops = 2.0 * min(self.stack_group, B) * T * 8 * Cc * Cc * L      # the whole residual stack of one group per launch
             dv = self.dtab[0]
