@@ -273,6 +273,22 @@ int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_h, int ld_w
                           int d_stride, const int* dilations_host, int L, void* yedge0_h, void* yedge1_h, void* z_all_h,
                           int64_t z_layer_stride, int B, int T, int C, int* flags, int bf16, void* stream);
 
+/* b2s_tc_wavenet_stack3 plus, INSIDE the same launch, the deferred skip sum and the head (wavenet.py:96-99): behind the layer tiles
+ * the grid carries one CTA pair per four tiles (on the SMs a 16 x 690-frame batch leaves idle) that accumulates
+ * S = sum_l z_l Wskip_l^T in TMEM as soon as the layer tiles publish their z tiles (zflags), then out = W_fin relu(W_sp (S + bss) /
+ * sqrt(L) + b_sp) + b_fin.  One launch per denoiser evaluation.
+ *   Wskip_h [L,C,C] = output_projection.weight[C:2C] per layer; bss [C] = sum_l output_projection.bias_l[C:2C]
+ *   Wsp_h [C,C], b_sp [C]; Wfin_h [MF,C], b_fin [MF]; out [B*T, MF] fp32; MF a multiple of 16
+ *   flags, zflags: int32 [B * tiles] each, ZERO at launch
+ * b2s_tc_wavenet_denoiser3_max_utterances(T, bf16): utterances of T frames one launch can hold (0: use b2s_tc_wavenet_stack3). */
+int b2s_tc_wavenet_denoiser3_max_utterances(int T, int bf16);
+int b2s_tc_wavenet_denoiser3(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
+                             const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum, const float* dvec,
+                             int d_stride, const int* dilations_host, int L, void* yedge0_h, void* yedge1_h, void* z_all_h,
+                             int64_t z_layer_stride, const void* Wskip_h, const float* bss, const void* Wsp_h, const float* b_sp,
+                             const void* Wfin_h, const float* b_fin, float* out, int B, int T, int C, int* flags, int* zflags,
+                             int bf16, void* stream);
+
 /* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
  * down-projection with the residual add into the fp32 stream. */
 int b2s_tc_lynx_glu(const void* h_h, const void* W_h, const float* bias, void* g_h, int rows, int C, int inner, int bf16,

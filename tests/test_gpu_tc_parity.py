@@ -201,13 +201,14 @@ def test_config4_variance_predictors_tensor_core(acc, precision, dev):
     assert err <= (2e-4 * scale if precision == 'bf16' else 5e-5 * max(scale, 1.0)), (acc, precision, err, scale)
 
 
-def _bf16_backbone(dev, stack, L=4, fuse_io=False, in_dims=128, n_feats=1, stack_t=False, cycle=4, precision='bf16', stack3=False):
+def _bf16_backbone(dev, stack, L=4, fuse_io=False, in_dims=128, n_feats=1, stack_t=False, cycle=4, precision='bf16', stack3=False,
+                   head3=True):
     import xiaoicesing_io_b200 as P
     from oracle import weights as OW
     cfg = OD.WaveNetCfg(in_dims=in_dims, n_feats=n_feats, num_layers=L, num_channels=256, dilation_cycle_length=cycle)
     P.hparams.clear()
     P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision=precision, b2s_stack=stack, b2s_fuse_io=fuse_io, b2s_stack_t=stack_t,
-                     b2s_stack3=stack3)
+                     b2s_stack3=stack3, b2s_stack3_head=head3)
     net = P.build_backbone(cfg.in_dims, n_feats, 'wavenet', dict(num_layers=L, num_channels=256, dilation_cycle_length=cycle))
     net.load_state_dict(OW.make_state_dict(cfg, seed=0, sigma_w=0.01), strict=True)
     return net.to(dev).eval()
@@ -251,6 +252,11 @@ def test_stack3_matches_per_layer_path(B, T, L, cycle, in_dims, n_feats, precisi
         scale = float(b.abs().max())
         err = float((a - b).abs().max())
         assert err <= 4 * eps * scale, (B, T, L, precision, err, scale)
+        # the skip sum + head on extra CTAs of the same launch (default) against the three separate GEMM launches: same operands,
+        # same accumulation order
+        c = _bf16_backbone(dev, stack=True, L=L, cycle=cycle, in_dims=in_dims, n_feats=n_feats, precision=precision, stack3=True,
+                           head3=False)(spec, t.to(dev), cond)
+        assert float((a - c).abs().max()) <= 0.25 * eps * scale, (B, T, L, precision, float((a - c).abs().max()), scale)
 
 
 @pytest.mark.parametrize('B,T,in_dims,n_feats', [(16, 690, 128, 1), (30, 300, 128, 1), (3, 257, 64, 1), (2, 130, 24, 2), (1, 50, 128, 1)])

@@ -52,6 +52,8 @@ _SIGNATURES = {
                                        _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, ctypes.POINTER(_vp), _vp, _vp, _vp, _i, _vp],
     'b2s_tc_wavenet_stack3': [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _i64,
                               _i, _i, _i, _vp, _i, _vp],
+    'b2s_tc_wavenet_denoiser3': [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _i64,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual_cond': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -60,7 +62,7 @@ _SIGNATURES = {
     'b2s_lynx_dwconv_h': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
 }
 
-EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', 'b2s_tc_wavenet_stack_max_tiles', 'b2s_tc_wavenet_stack3_halo', 'b2s_tc_wavenet_stack3_max_tiles', *_SIGNATURES]
+EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', 'b2s_tc_wavenet_stack_max_tiles', 'b2s_tc_wavenet_stack3_halo', 'b2s_tc_wavenet_stack3_max_tiles', 'b2s_tc_wavenet_denoiser3_max_utterances', *_SIGNATURES]
 
 ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU, ACT_SILU = 0, 1, 2, 3, 4
 
@@ -87,6 +89,8 @@ def _load():
     lib.b2s_tc_wavenet_stack3_halo.argtypes = []
     lib.b2s_tc_wavenet_stack3_max_tiles.restype = c_int
     lib.b2s_tc_wavenet_stack3_max_tiles.argtypes = [c_int, c_int]
+    lib.b2s_tc_wavenet_denoiser3_max_utterances.restype = c_int
+    lib.b2s_tc_wavenet_denoiser3_max_utterances.argtypes = [c_int, c_int]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int
@@ -309,6 +313,18 @@ def tc_wavenet_stack3(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_s
                                     ptr(Wres_h), ptr(bsum), ptr(dvec), d_stride, dil, L, ptr(yedge0_h), ptr(yedge1_h),
                                     ptr(z_all_h), z_layer_stride, B, T, C, ptr(flags), int(bf16), stream_ptr()),
           'b2s_tc_wavenet_stack3')
+
+
+def tc_wavenet_denoiser3(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations,
+                         yedge0_h, yedge1_h, z_all_h, z_layer_stride, Wskip_h, bss, Wsp_h, b_sp, Wfin_h, b_fin, out, B, T, C, flags,
+                         zflags, bf16):
+    L = len(dilations)
+    dil = (_i * L)(*dilations)
+    check(lib.b2s_tc_wavenet_denoiser3(ptr(xin_h), MF, ptr(Win_h), ld_win, ptr(b_in), ptr(Wd_h), ptr(cond_h), cond_layer_stride,
+                                       ptr(Wres_h), ptr(bsum), ptr(dvec), d_stride, dil, L, ptr(yedge0_h), ptr(yedge1_h),
+                                       ptr(z_all_h), z_layer_stride, ptr(Wskip_h), ptr(bss), ptr(Wsp_h), ptr(b_sp), ptr(Wfin_h),
+                                       ptr(b_fin), ptr(out), B, T, C, ptr(flags), ptr(zflags), int(bf16), stream_ptr()),
+          'b2s_tc_wavenet_denoiser3')
 
 
 def tc_lynx_glu(h_h, W_h, bias, g_h, rows, C, inner, bf16):

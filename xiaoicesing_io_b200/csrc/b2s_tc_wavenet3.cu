@@ -55,6 +55,13 @@ struct __align__(64) Stack3P {
     const float* dvec; int d_stride;                      // step embedding of layer m at dvec + b*d_stride + m*C
     int* flags;                                           // [B * tiles_per_b], zero before the launch
     unsigned long long* tlog;                             // optional phase timestamps (B2S_TLOG builds)
+    // ---- fused skip sum + head (wavenet.py:96-99) on the CTAs behind the layer tiles (fuse_head = 1): blocks [n_layer_ctas, grid)
+    //      accumulate S = sum_l z_l Wskip_l^T in TMEM as the z tiles are published (zflags[tile] = completed half-tile stores), then
+    //      out = W_fin relu(W_sp (S + bss) / sqrt(L) + b_sp) + b_fin
+    int n_layer_ctas, fuse_head;
+    CUtensorMap mapWskip, mapWsp, mapWfin;
+    const float* bss; const float* b_sp; const float* b_fin; float alpha; float* out;
+    int* zflags;                                          // [B * tiles_per_b], zero before the launch
 };
 
 #ifdef B2S_TLOG
@@ -106,6 +113,13 @@ __device__ __forceinline__ void tma_load_3d_cg2_a(uint32_t smem_addr, const CUte
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
             smem_addr),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2_a(uint32_t smem_addr, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_addr),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_cg2_a(uint32_t smem_addr, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
@@ -170,6 +184,246 @@ __device__ __forceinline__ void wait_flag3(const int* f, int want) {
             printf("b2s: stack3 tile flag timeout (block %d want %d have %d)\n", blockIdx.x, want, ld_acquire_gpu(f));
             __trap();
         }
+    }
+}
+
+// =====================================================================================================================
+// Skip-sum / head role (wavenet.py:96-99) of the CTAs behind the layer tiles.  A pair owns FOUR tiles: slot s in {0,1} of CTA r is
+// tile 4*pair + 2s + r; one cta_group::2 MMA covers the two tiles of a slot.  S_s = sum_l z_l Wskip_l^T accumulates in TMEM columns
+// [256 s, +256) over all layers (z tiles arrive through zflags), then per slot: (S + bss) -> 16-bit tile in shared memory ->
+// skip_projection -> relu(alpha acc + b_sp) -> 16-bit tile -> output_projection -> + b_fin -> out (fp32).
+// Shared memory: [0, 64K) head operand tile (4 swizzled K slabs), then 5 stages of {A 16 KB, B 16 KB}.
+// A kernel of its own (clusters of 2, any number of pairs, no co-residency requirement) launched behind the layer kernel with
+// programmatic dependent launch: it starts on the SMs the layer tiles leave idle (52 of 148 at 16 x 690 frames) once every layer
+// CTA is resident, and follows the layer kernel through the z-tile flags.
+// =====================================================================================================================
+constexpr int SK_STAGES = 5, SK_STAGE_BYTES = 32768, SK_HBUF = 65536;
+
+constexpr int SK_SMEM_BYTES = SK_HBUF + SK_STAGES * SK_STAGE_BYTES + 256;
+
+template <int BF16>
+__global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __grid_constant__ Stack3P p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + SK_HBUF + SK_STAGES * SK_STAGE_BYTES);
+    uint64_t* empty = full + SK_STAGES;
+    uint64_t* sfull = empty + SK_STAGES;       // [2] skip sum of slot s complete          (commit, both CTAs)
+    uint64_t* hready = sfull + 2;              // [2] head operand tile written, both CTAs (leader, 16)
+    uint64_t* hfull0 = hready + 2;             //     skip_projection accumulator complete (commit, both CTAs)
+    uint64_t* hfull1 = hfull0 + 1;             //     output_projection accumulator complete
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hfull1 + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank() & 1u, lead = 0;
+    const uint16_t pmask = 3;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.mapZ);
+        prefetch_tmap(&p.mapWskip);
+        prefetch_tmap(&p.mapWsp);
+        prefetch_tmap(&p.mapWfin);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < SK_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sfull[i], 1);
+            mbar_init(&hready[i], EPI_WARPS * CLUSTER);
+        }
+        mbar_init(hfull0, 1);
+        mbar_init(hfull1, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_cg2(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+#ifdef B2S_TLOG
+    if (p.tlog && blockIdx.x == 0 && threadIdx.x == 0) p.tlog[MAXL * 16 + 4] = globaltimer_ns();
+#endif
+    // NO griddepcontrol.wait: this kernel is released while the layer kernel runs and follows its z tiles through zflags
+    // (release / acquire); everything else it reads (weights, biases) was written before the layer kernel was launched.
+    const int L = p.L, MF = p.MF;
+    const int pairidx = (int)blockIdx.x >> 1;
+    int gt[2], tb[2], tt0[2];
+    bool ok[2], okp[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        gt[s] = 4 * pairidx + 2 * s + (int)rank;
+        const int gp = 4 * pairidx + 2 * s + 1 - (int)rank;
+        tb[s] = gt[s] / p.tiles_per_b;
+        tt0[s] = (gt[s] - tb[s] * p.tiles_per_b) * BM;
+        ok[s] = gt[s] < p.n_layer_ctas && tt0[s] < p.T;
+        okp[s] = gp < p.n_layer_ctas && (gp % p.tiles_per_b) * BM < p.T;
+    }
+    const uint32_t hb_a = smem_u32(smem), st_a = hb_a + SK_HBUF;
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            auto advance = [&] { if (++stage == SK_STAGES) { stage = 0; phase ^= 1; } };
+            for (int l = 0; l < L; ++l)
+                for (int half = 0; half < 2; ++half)
+                    for (int s = 0; s < 2; ++s)
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const int kb = 2 * half + kk;
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            const uint32_t lb = mapa_u32(&full[stage], lead);
+                            if (rank == 0) mbar_expect_tx(&full[stage], 2 * 16384 + (ok[s] ? 16384 : 0) + (okp[s] ? 16384 : 0));
+                            tma_load_3d_cg2_a(st_a + stage * SK_STAGE_BYTES + 16384, &p.mapWskip, lb, kb * BK, rank * (C / 2), l);
+                            if (ok[s]) {
+                                if (kk == 0) {
+                                    wait_flag3(p.zflags + gt[s], 2 * l + half + 1);
+                                    fence_proxy_async_all();
+                                }
+                                tma_load_4d_cg2_a(st_a + stage * SK_STAGE_BYTES, &p.mapZ, lb, kb * BK, tt0[s], tb[s], l);
+                            }
+                            advance();
+                        }
+            for (int s = 0; s < 2; ++s) {
+                for (int kb = 0; kb < 4; ++kb) {               // skip_projection weights: this CTA's 128 of the 256 rows
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * 16384);
+                    tma_load_2d_cg2_a(st_a + stage * SK_STAGE_BYTES + 16384, &p.mapWsp, mapa_u32(&full[stage], lead), kb * BK, rank * (C / 2));
+                    advance();
+                }
+                for (int kb = 0; kb < 4; ++kb) {               // output_projection weights: this CTA's MF/2 of the MF rows
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * (MF / 2) * 128);
+                    tma_load_2d_cg2_a(st_a + stage * SK_STAGE_BYTES + 16384, &p.mapWfin, mapa_u32(&full[stage], lead), kb * BK, rank * (MF / 2));
+                    advance();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc_h = make_idesc_f16(2 * BM, 256, BF16), idesc_o = make_idesc_f16(2 * BM, MF, BF16);
+            const uint32_t st_lo = desc_lo(st_a), hb_lo = desc_lo(hb_a);
+            int stage = 0;
+            uint32_t phase = 0;
+            auto advance = [&] { if (++stage == SK_STAGES) { stage = 0; phase ^= 1; } };
+            for (int l = 0; l < L; ++l)
+                for (int half = 0; half < 2; ++half)
+                    for (int s = 0; s < 2; ++s) {
+                        for (int kk = 0; kk < 2; ++kk) {
+                            mbar_wait(&full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t a_lo = st_lo + stage * (SK_STAGE_BYTES >> 4), b_lo = a_lo + (16384 >> 4);
+#pragma unroll
+                            for (int k = 0; k < BK / UK; ++k) mma2(tmem_base + s * 256, a_lo + 2 * k, b_lo + 2 * k, idesc_h, (l | half | kk | k) != 0);
+                            umma_commit_cg2_mcast(&empty[stage], pmask);
+                            advance();
+                        }
+                        if (l == L - 1 && half == 1) umma_commit_cg2_mcast(&sfull[s], pmask);
+#ifdef B2S_TLOG
+                        if (p.tlog && blockIdx.x == 0 && half == 1 && s == 1) p.tlog[l * 16 + 9] = globaltimer_ns();
+#endif
+                    }
+            for (int s = 0; s < 2; ++s) {
+                mbar_wait(&hready[0], (uint32_t)s);            // (S + bss) tile of both CTAs is in shared memory
+                tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = hb_lo + kb * (ZSLAB >> 4), b_lo = st_lo + stage * (SK_STAGE_BYTES >> 4) + (16384 >> 4);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) mma2(tmem_base + s * 256, a_lo + 2 * k, b_lo + 2 * k, idesc_h, (kb | k) != 0);
+                    umma_commit_cg2_mcast(&empty[stage], pmask);
+                    advance();
+                }
+                umma_commit_cg2_mcast(hfull0, pmask);
+                mbar_wait(&hready[1], (uint32_t)s);            // hidden tile
+                tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = hb_lo + kb * (ZSLAB >> 4), b_lo = st_lo + stage * (SK_STAGE_BYTES >> 4) + (16384 >> 4);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) mma2(tmem_base + s * 256, a_lo + 2 * k, b_lo + 2 * k, idesc_o, (kb | k) != 0);
+                    umma_commit_cg2_mcast(&empty[stage], pmask);
+                    advance();
+                }
+                umma_commit_cg2_mcast(hfull1, pmask);
+            }
+        }
+    } else if (warp >= 4) {
+        const int e = warp - 4, qd = e & 3, sub = e >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+        const int row = qd * 32 + lane, sw = row & 7;
+        const uint32_t hrow = hb_a + (row >> 3) * 1024 + sw * 128;
+        const uint32_t lr0 = mapa_u32(&hready[0], lead), lr1 = mapa_u32(&hready[1], lead);
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            const bool valid = ok[s] && tt0[s] + row < p.T;
+            // 32 columns of the accumulator -> f(acc, bias) -> 16-bit -> the swizzled operand tile
+            auto to_tile = [&](const float* bias, float alpha, bool relu) {
+#pragma unroll 1
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int J = 4 * sub + jj;
+                    float acc[32];
+                    tmem_ld32(taddr + s * 256 + 32 * J, acc);
+                    tmem_ld_wait();
+                    uint32_t hp[16];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + 32 * J + 4 * i));
+                        float v0 = fmaf(alpha, acc[4 * i], bv.x), v1 = fmaf(alpha, acc[4 * i + 1], bv.y);
+                        float v2 = fmaf(alpha, acc[4 * i + 2], bv.z), v3 = fmaf(alpha, acc[4 * i + 3], bv.w);
+                        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                        hp[2 * i] = valid ? Half16<BF16>::pack2(v0, v1) : 0u;
+                        hp[2 * i + 1] = valid ? Half16<BF16>::pack2(v2, v3) : 0u;
+                    }
+                    const uint32_t slab = hrow + (J >> 1) * ZSLAB;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4)
+                        st_shared_u4(slab + (((4 * (J & 1) + c4) ^ sw) << 4), make_uint4(hp[4 * c4], hp[4 * c4 + 1], hp[4 * c4 + 2], hp[4 * c4 + 3]));
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+            };
+            mbar_wait(&sfull[s], 0);
+            tc_fence_after();
+            to_tile(p.bss, 1.0f, false);                       // the skip sum incl. its summed biases (wavenet.py:96, before the 1/sqrt(L))
+            if (lane == 0) arrive_remote(lr0);
+            mbar_wait(hfull0, (uint32_t)s);
+            tc_fence_after();
+            to_tile(p.b_sp, p.alpha, true);                    // skip_projection + ReLU (wavenet.py:97-98)
+            if (lane == 0) arrive_remote(lr1);
+            mbar_wait(hfull1, (uint32_t)s);
+            tc_fence_after();
+            float* orow = p.out + ((long long)tb[s] * p.T + tt0[s] + row) * MF;
+#pragma unroll 1
+            for (int jj = 0; jj < 4; ++jj) {                   // output_projection (wavenet.py:99): fp32 rows of MF values
+                const int J = 2 * jj + sub;
+                if (32 * J >= MF) break;
+                float acc[32];
+                tmem_ld32(taddr + s * 256 + 32 * J, acc);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int col = 32 * J + 4 * i;
+                        if (col < MF) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.b_fin + col));
+                            *reinterpret_cast<float4*>(orow + col) = make_float4(acc[4 * i] + bv.x, acc[4 * i + 1] + bv.y, acc[4 * i + 2] + bv.z, acc[4 * i + 3] + bv.w);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+#ifdef B2S_TLOG
+    if (p.tlog && blockIdx.x == 0 && threadIdx.x == 0) p.tlog[MAXL * 16 + 5] = globaltimer_ns();
+#endif
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, 512);
     }
 }
 
@@ -266,6 +520,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
     // TMEM columns: [0,256) X (residual stream, lives across all layers), [256,512) accumulator of the stem / of one GEMM1 half
 
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Dependent launch: the skip-sum / head kernel may start NOW.  It is scheduled only once EVERY CTA of this grid has executed this
+    // instruction, i.e. is resident - so it can never take SMs this grid still needs, and this grid never waits for it.
+    if (p.fuse_head) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef B2S_TLOG
     if (p.tlog && blockIdx.x == 2 && threadIdx.x == 0) { p.tlog[MAXL * 16] = globaltimer_ns(); p.tlog[MAXL * 16 + 1] = (unsigned long long)clock64(); }
 #endif
@@ -508,6 +765,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
             for (int h = 0; h < 2; ++h) {
                 if (lane == 0) {
                     mbar_wait(zdone, (uint32_t)h);             // phase 2l + h: both ring buffers hold z slabs 2h, 2h + 1 of layer l
+                    if (p.fuse_head && tile_ok && h == 1) {    // half 0 of this layer has reached global memory: publish it
+                        tma_store_wait_all();
+                        st_release_gpu(p.zflags + blockIdx.x, 2 * l + 1);
+                    }
                     if (tile_ok) {
                         tma_store_4d(&p.mapZ, zs_a, (2 * h) * BK, t0, b, l);
                         tma_store_4d(&p.mapZ, zs_a + ZSLAB, (2 * h + 1) * BK, t0, b, l);
@@ -520,6 +781,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                 __syncwarp();
             }
             if (l + 1 < L) publish(l + 1);
+            if (lane == 0 && p.fuse_head && tile_ok) {         // after the (time-critical) halo hand-off: publish half 1
+                tma_store_wait_all();
+                st_release_gpu(p.zflags + blockIdx.x, 2 * l + 2);
+            }
         }
         if (lane == 0) tma_store_wait_all();
     } else {
@@ -733,7 +998,7 @@ static int launch(const Stack3P& p, int grid, cudaStream_t st) {
     }
     int cs_used = 0, best = 0;
     for (int cs = 8; cs >= 2; cs -= 2) {
-        if (p.tiles_per_b % cs) continue;
+        if (p.tiles_per_b % cs || grid % cs) continue;
         if (forced && cs != forced && cs != 2) continue;
         int& n = max_clusters[dev][cs / 2];
         if (n == 0) {
@@ -751,9 +1016,46 @@ static int launch(const Stack3P& p, int grid, cudaStream_t st) {
                   "%d co-resident clusters for this kernel); split the batch by utterance", grid, best);
         return B2S_ERR_UNSUPPORTED;
     }
+    static const bool verbose = getenv("B2S_STACK3_VERBOSE") != nullptr;
+    if (verbose) {
+        static int last_grid = -1;
+        if (grid != last_grid) {
+            last_grid = grid;
+            fprintf(stderr, "b2s stack3: grid %d (%d layer tiles), cluster size %d; co-resident clusters reported: cs8=%d cs6=%d cs4=%d cs2=%d\n",
+                    grid, p.n_layer_ctas, cs_used, max_clusters[dev][4], max_clusters[dev][3], max_clusters[dev][2], max_clusters[dev][1]);
+        }
+    }
     attr[0].val.clusterDim.x = cs_used;
     cfg.numAttrs = 2;
     B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_stack3_kernel<BF16>, p));
+    return B2S_OK;
+}
+
+// the skip-sum / head kernel: one CTA pair per four layer tiles, launched with programmatic dependent launch behind the layer kernel
+template <int BF16>
+static int launch_skiphead(const Stack3P& p, int grid, cudaStream_t st) {
+    int dev = 0;
+    B2S_CHECK_CUDA(cudaGetDevice(&dev));
+    static bool configured[64] = {};
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_skiphead3_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+        configured[dev] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SK_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_skiphead3_kernel<BF16>, p));
     return B2S_OK;
 }
 
@@ -799,11 +1101,15 @@ extern "C" int b2s_tc_wavenet_stack3_max_tiles(int T, int bf16) {
     return bf16 ? ws3::max_tiles<1>(tpb) : ws3::max_tiles<0>(tpb);
 }
 
-extern "C" int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
-                                     const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum,
-                                     const float* dvec, int d_stride, const int* dilations_host, int L, void* yedge0_h,
-                                     void* yedge1_h, void* z_all_h, int64_t z_layer_stride, int B, int T, int C, int* flags, int bf16,
-                                     void* stream) {
+struct Head3 {            // operands of the fused skip sum + head (all NULL / 0: the plain stack, z_all only)
+    const void* Wskip_h; const float* bss; const void* Wsp_h; const float* b_sp; const void* Wfin_h; const float* b_fin; float* out;
+    int* zflags;
+};
+
+static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
+                       const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum, const float* dvec,
+                       int d_stride, const int* dilations_host, int L, void* yedge0_h, void* yedge1_h, void* z_all_h,
+                       int64_t z_layer_stride, int B, int T, int C, int* flags, int bf16, void* stream, const Head3* hd) {
     B2S_CHECK_ARG(xin_h && Win_h && b_in && Wd_h && cond_h && Wres_h && bsum && dvec && dilations_host && yedge0_h && yedge1_h &&
                       z_all_h && flags, "b2s_tc_wavenet_stack3: null pointer");
     if (C != ws3::C) {
@@ -818,7 +1124,8 @@ extern "C" int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_
     if (B * T == 0) return B2S_OK;
     ws3::Stack3P p{};
     p.tiles_per_b = (ceil_div(T, ws3::BM) + 1) & ~1;
-    const int grid = B * p.tiles_per_b;
+    int grid = B * p.tiles_per_b;
+    p.n_layer_ctas = grid;
     for (int l = 0; l < L; ++l) {
         if (dilations_host[l] < 1 || dilations_host[l] > ws3::HALO) {
             set_error("b2s_tc_wavenet_stack3: dilation %d exceeds the resident halo of %d rows", dilations_host[l], ws3::HALO);
@@ -846,5 +1153,50 @@ extern "C" int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_
     p.cond = cond_h; p.cond_lstride = cond_layer_stride; p.b_in = b_in; p.bsum = bsum; p.dvec = dvec; p.d_stride = d_stride;
     p.flags = flags;
     p.tlog = g_tlog;
-    return bf16 ? ws3::launch<1>(p, grid, (cudaStream_t)stream) : ws3::launch<0>(p, grid, (cudaStream_t)stream);
+    if (hd) {
+        B2S_CHECK_ARG(hd->Wskip_h && hd->bss && hd->Wsp_h && hd->b_sp && hd->Wfin_h && hd->b_fin && hd->out && hd->zflags,
+                      "b2s_tc_wavenet_denoiser3: null pointer");
+        B2S_CHECK_ARG(MF % 16 == 0, "b2s_tc_wavenet_denoiser3: in_dims*n_feats must be a multiple of 16 (got %d)", MF);
+        B2S_CHECK_ARG(al16(hd->Wskip_h) && al16(hd->bss) && al16(hd->Wsp_h) && al16(hd->b_sp) && al16(hd->Wfin_h) && al16(hd->b_fin) &&
+                          al16(hd->out), "b2s_tc_wavenet_denoiser3: misaligned pointer");
+        rc = make_map_w3(&p.mapWskip, hd->Wskip_h, bf16, C, C, L, ws3::BK, C / 2);
+        if (rc) return rc;
+        rc = make_map_w(&p.mapWsp, hd->Wsp_h, bf16, C, C, C, ws3::BK, C / 2);
+        if (rc) return rc;
+        rc = make_map_w(&p.mapWfin, hd->Wfin_h, bf16, C, MF, C, ws3::BK, MF / 2);
+        if (rc) return rc;
+        p.fuse_head = 1;
+        p.bss = hd->bss; p.b_sp = hd->b_sp; p.b_fin = hd->b_fin; p.out = hd->out; p.zflags = hd->zflags;
+        p.alpha = 1.0f / sqrtf((float)L);
+    }
+    rc = bf16 ? ws3::launch<1>(p, grid, (cudaStream_t)stream) : ws3::launch<0>(p, grid, (cudaStream_t)stream);
+    if (rc || !hd) return rc;
+    return bf16 ? ws3::launch_skiphead<1>(p, 2 * ceil_div(grid, 4), (cudaStream_t)stream)
+                : ws3::launch_skiphead<0>(p, 2 * ceil_div(grid, 4), (cudaStream_t)stream);
+}
+
+extern "C" int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
+                                     const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum,
+                                     const float* dvec, int d_stride, const int* dilations_host, int L, void* yedge0_h,
+                                     void* yedge1_h, void* z_all_h, int64_t z_layer_stride, int B, int T, int C, int* flags, int bf16,
+                                     void* stream) {
+    return stack3_impl(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations_host, L,
+                       yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, bf16, stream, nullptr);
+}
+
+/* utterances of T frames ONE b2s_tc_wavenet_denoiser3 launch can hold (layer tiles + the skip / head CTAs behind them); 0 = none */
+extern "C" int b2s_tc_wavenet_denoiser3_max_utterances(int T, int bf16) {
+    const int tpb = (ceil_div(T, ws3::BM) + 1) & ~1;
+    return (bf16 ? ws3::max_tiles<1>(tpb) : ws3::max_tiles<0>(tpb)) / tpb;        // the skip / head kernel has no residency requirement
+}
+
+extern "C" int b2s_tc_wavenet_denoiser3(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
+                                        const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum,
+                                        const float* dvec, int d_stride, const int* dilations_host, int L, void* yedge0_h,
+                                        void* yedge1_h, void* z_all_h, int64_t z_layer_stride, const void* Wskip_h, const float* bss,
+                                        const void* Wsp_h, const float* b_sp, const void* Wfin_h, const float* b_fin, float* out, int B,
+                                        int T, int C, int* flags, int* zflags, int bf16, void* stream) {
+    Head3 hd{Wskip_h, bss, Wsp_h, b_sp, Wfin_h, b_fin, out, zflags};
+    return stack3_impl(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations_host, L,
+                       yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, bf16, stream, &hd);
 }

@@ -111,6 +111,7 @@ class WaveNetEngine:
             self.w_res3_h = h(w_res3.float())
             self.bsum3 = (torch.cumsum(b_res3, 0) - b_res3).float().contiguous()              # [L, C]: sum over k < l
             self.res3_ok = bool(torch.isfinite(self.w_res3_h.float()).all())                  # fp16 range (2^(l/2) <= 2^15.5 at L = 32)
+            self.w_skip3_h = h(self.w_out[:, Cc:, :])                                          # [L, C, C]: skip rows per layer
             self.w_dil_t_h = self.w_cond_t_h = self.b_cond_t = None
             if Cc == C.FUSED_LAYER_CHANNELS:
                 # transposed stack kernel (b2s_tc_wavenet_stack_t): row 256h + 128g + c = (g ? filter : gate) of channel 128h + c,
@@ -266,7 +267,11 @@ class WaveNetSessionTC:
             g3 = C.lib.b2s_tc_wavenet_stack3_max_tiles(T, int(bf)) // tpb
             if g3 > 0:
                 self.stack3, self.stack_group = True, g3
-        self.flags = torch.zeros((B * tpb,), device=dev, dtype=torch.int32) if self.stack_group else None
+        # ... with the skip sum + head (wavenet.py:96-99) in a second kernel that is released (programmatic dependent launch) as soon
+        # as every layer tile is resident: it runs on the SMs the layer tiles leave idle and follows them through the z-tile flags
+        self.head3 = bool(self.stack3 and hparams.get('b2s_stack3_head', True) and eng.MF % 16 == 0
+                          and C.lib.b2s_tc_wavenet_denoiser3_max_utterances(T, int(bf)) >= self.stack_group)
+        self.flags = torch.zeros((2 * B * tpb,), device=dev, dtype=torch.int32) if self.stack_group else None     # tile flags | z flags
         self.tpb = tpb
         self.tgroups = self._plan_transposed(cond_h) if (self.stack_group and hparams.get('b2s_stack_t', False)) else None
         if self.tgroups:
@@ -384,17 +389,27 @@ class WaveNetSessionTC:
             return
         if self.stack3:
             # stem + residual stack in ONE launch per utterance group (z_l of every layer -> z_all), then the deferred skip GEMM
-            # (K = L*C) and the two head GEMMs
+            # (K = L*C) and the two head GEMMs - or, with head3, all of it in that one launch
             LC = L * Cc
             dv = self.dtab.reshape(-1) if self.per_row_t else self.dtab[k]
+            nfl = B * self.tpb
             for gi, b0 in enumerate(range(0, B, self.stack_group)):
                 b1 = min(B, b0 + self.stack_group)
                 r0 = b0 * T
                 tab = self.cond_groups[gi]
+                if self.head3:
+                    C.tc_wavenet_denoiser3(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
+                                           e.w_res3_h, e.bsum3, dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
+                                           e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, e.w_skip3_h,
+                                           e.b_skip_sum, e.w_sp_h, e.b_sp, e.w_fin_h, e.b_fin, out[r0:], b1 - b0, T, Cc,
+                                           self.flags[b0 * self.tpb:], self.flags[nfl + b0 * self.tpb:], bf)
+                    continue
                 C.tc_wavenet_stack3(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
                                     e.w_res3_h, e.bsum3, dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
                                     e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, b1 - b0, T, Cc,
                                     self.flags[b0 * self.tpb:], bf)
+            if self.head3:
+                return
             C.tc_skip_sum(self.z_all, e.w_skipcat_h, e.b_skip_sum, self.skip_h, rows, Cc, L, bf)
             C.tc_linear(self.skip_h, Cc, rows, T, e.w_sp_h, Cc, e.b_sp, Cc, Cc, bf, alpha=1.0 / math.sqrt(L),
                         act=C.ACT_RELU, out_h=self.h_h, ldoh=Cc)
@@ -457,7 +472,8 @@ class WaveNetSessionTC:
         if self.tgroups:
             return 1 + 1 + len(self.tgroups) + 2                   # cast, stem, transposed stack launches, 2 head GEMMs
         if self.stack3:
-            return 1 + -(-self.B // self.stack_group) + 3          # cast (+ flag reset), stack launches, skip GEMM, 2 head GEMMs
+            # cast (+ flag reset), stack launches (+ skip GEMM, 2 head GEMMs unless they run inside the launch)
+            return 1 + -(-self.B // self.stack_group) + (0 if self.head3 else 3)
         if self.stack_group and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256:
             return 1 + -(-self.B // self.stack_group)              # cast (+ flag reset), one denoiser launch per utterance group
         if self.stack_group:
@@ -483,10 +499,16 @@ class WaveNetSessionTC:
                     flops, launch_all, len(self.tgroups))
         if self.stack3:
             # algorithmic FLOPs of this launch: stem + conv (6C^2) + residual half of the output projection (C^2; the last layer's
-            # is not needed) per frame; the skip half runs in the deferred b2s_tc_skip_sum launch
+            # is not needed) per frame; the skip half (C^2 per layer) and the head run in the same launch with head3, else in the
+            # deferred b2s_tc_skip_sum / head GEMM launches
             nb = min(self.stack_group, B)
-            flops = 2.0 * nb * T * (e.MF * Cc + L * 6 * Cc * Cc + (L - 1) * Cc * Cc)
+            per_frame = e.MF * Cc + L * 6 * Cc * Cc + (L - 1) * Cc * Cc
+            if self.head3:
+                per_frame += L * Cc * Cc + Cc * Cc + Cc * e.MF
+            flops = 2.0 * nb * T * per_frame
             dv = self.dtab[0]
+            nfl = B * self.tpb
+            out = torch.empty((self.rows, e.MF), device=self.y_h.device)
 
             def launch_all():
                 self.flags.zero_()
@@ -494,11 +516,19 @@ class WaveNetSessionTC:
                     b1 = min(B, b0 + self.stack_group)
                     r0 = b0 * T
                     tab = self.cond_groups[gi]
-                    C.tc_wavenet_stack3(self.xin_h[r0:], e.MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
-                                        e.w_res3_h, e.bsum3, dv, 0, e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:],
-                                        self.rows * Cc, b1 - b0, T, Cc, self.flags[b0 * self.tpb:], e.bf16)
-            return (f'wavenet_stack3_kernel<{e.precision}> (b2s_tc_wavenet_stack3: stem + {L} layers per launch, skip sum deferred)',
-                    flops, launch_all, -(-B // self.stack_group))
+                    if self.head3:
+                        C.tc_wavenet_denoiser3(self.xin_h[r0:], e.MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab,
+                                               tab.shape[1] * 2 * Cc, e.w_res3_h, e.bsum3, dv, 0, e.dilations, self.y_h[r0:], self.y2_h[r0:],
+                                               self.z_all[:, r0:], self.rows * Cc, e.w_skip3_h, e.b_skip_sum, e.w_sp_h, e.b_sp, e.w_fin_h,
+                                               e.b_fin, out[r0:], b1 - b0, T, Cc, self.flags[b0 * self.tpb:],
+                                               self.flags[nfl + b0 * self.tpb:], e.bf16)
+                    else:
+                        C.tc_wavenet_stack3(self.xin_h[r0:], e.MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
+                                            e.w_res3_h, e.bsum3, dv, 0, e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:],
+                                            self.rows * Cc, b1 - b0, T, Cc, self.flags[b0 * self.tpb:], e.bf16)
+            what = (f'b2s_tc_wavenet_denoiser3: stem + {L} layers + skip sum + head per launch' if self.head3
+                    else f'b2s_tc_wavenet_stack3: stem + {L} layers per launch, skip sum deferred')
+            return (f'wavenet_stack3_kernel<{e.precision}> ({what})', flops, launch_all, -(-B // self.stack_group))
         if self.stack_group:
             flops = 2.0 * min(self.stack_group, B) * T * 8 * Cc * Cc * L      # the whole residual stack of one group per launch
             dv = self.dtab[0]
