@@ -55,6 +55,7 @@ struct __align__(64) Stack3P {
     const float* dvec; int d_stride;                      // step embedding of layer m at dvec + b*d_stride + m*C
     int* flags;                                           // [B * tiles_per_b], zero before the launch
     unsigned long long* tlog;                             // optional phase timestamps (B2S_TLOG builds)
+    int dbg;                                              // B2S_TLOG builds only: 1 = no weight loads, 2 = no gate epilogue math (timing experiments, wrong results)
     // ---- fused skip sum + head (wavenet.py:96-99) on the CTAs behind the layer tiles (fuse_head = 1): blocks [n_layer_ctas, grid)
     //      accumulate S = sum_l z_l Wskip_l^T in TMEM as the z tiles are published (zflags[tile] = completed half-tile stores), then
     //      out = W_fin relu(W_sp (S + bss) / sqrt(L) + b_sp) + b_fin
@@ -579,6 +580,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                     for (int f = 0; f < 12; ++f) {
                         const int tap = (f >> 2) == 0 ? 1 : ((f >> 2) == 1 ? 0 : 2);       // centre tap first: it needs no halo
                         mbar_wait(&empty[stage], phase ^ 1);
+#ifdef B2S_TLOG
+                        if ((p.dbg & 1) && l > 0) { if (rank == 0) mbar_arrive(&full[stage]); advance(); continue; }
+#endif
                         if (rank == 0) mbar_expect_tx(&full[stage], CLUSTER * STAGE_BYTES);
                         tma_load_3d_cg2_a(st_a + stage * STAGE_BYTES, &p.mapWd, mapa_u32(&full[stage], lead), tap * C + (f & 3) * BK,
                                           h * 256 + rank * 128, l);
@@ -897,6 +901,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                         if (lane == 0) arrive_remote(lead_accfree);
                     }
                     uint32_t zp[16];
+#ifdef B2S_TLOG
+                    if (p.dbg & 2) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) zp[i] = __float_as_uint(acc0[i]);
+                    } else
+#endif
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const float* acc = jj ? acc1 : acc0;
@@ -1153,6 +1163,7 @@ static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win,
     p.cond = cond_h; p.cond_lstride = cond_layer_stride; p.b_in = b_in; p.bsum = bsum; p.dvec = dvec; p.d_stride = d_stride;
     p.flags = flags;
     p.tlog = g_tlog;
+    p.dbg = getenv("B2S_STACK3_DBG") ? atoi(getenv("B2S_STACK3_DBG")) : 0;
     if (hd) {
         B2S_CHECK_ARG(hd->Wskip_h && hd->bss && hd->Wsp_h && hd->b_sp && hd->Wfin_h && hd->b_fin && hd->out && hd->zflags,
                       "b2s_tc_wavenet_denoiser3: null pointer");
