@@ -12,11 +12,14 @@ Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
 One "step" = one full sampling call over the batch.  Metric: denoised mel-frames x NFE per second.
     value : inputs resident in HBM, `model(condition_dev, src_spec=src_dev, infer=True)`
     e2e   : the same public call from PINNED HOST buffers, H2D + D2H inside the timed region
-Also reported: roofline of the dominant kernel (CUDA events, isolated launches at the bench shapes),
-the CPU baseline (oracle port on the host cores, bounded sample), SM clocks during the timed region.
+Also reported: roofline of the dominant kernel (CUDA events, the shipped launch at the bench shapes), the CPU baseline
+(bounded sample on the host cores), the reference's eager PyTorch code on the SAME GPU (`gpu_eager_baseline`: the number
+SURVEY.md section 8d calls "the one to beat"), short runs of the other BASELINE configs (`secondary`), SM clocks during
+the timed region.
 
-`--impl reference` times the reference's algorithm on the host CPU (the oracle port; the reference is
-pure Python/PyTorch and is not present on the GPU box) on the same metric, one bounded sample per step.
+`--impl reference` times the reference on the host CPU on the same metric, one bounded sample per step: the UNMODIFIED
+reference from baseline/_ref (baseline/install_reference.sh; `cpu_baseline.kind = "reference"`), or the oracle port when that
+copy is absent (`kind = "port"`).  That arm imports nothing of the product.
 """
 from __future__ import annotations
 
@@ -48,6 +51,9 @@ WORKLOADS = {
     'config4': dict(kind='wavenet_variance', B=64, T=690, k_step=10, layers=10, channels=192, mel=48, out=2, hidden=256, cycle=4,
                     desc='variance multi-predictor (energy + breathiness, 2 x 24 repeat bins), DPM-Solver++ 10 steps, WaveNet 10x192, '
                          'B=64 x T=690 per GPU'),
+    'config4_pitch': dict(kind='wavenet_pitch', B=64, T=690, k_step=10, layers=20, channels=256, mel=64, out=1, hidden=256, cycle=5,
+                          desc='variance pitch predictor (PitchDiffusion, 64 repeat bins), UniPC 10 steps, WaveNet 20x256 (cycle 5), '
+                               'B=64 x T=690 per GPU'),
     'config1': dict(kind='wavenet_ddim', B=1, T=690, k_step=20, layers=20, channels=256, mel=128, hidden=256, cycle=4,
                     desc='DDIM 20 steps (speedup 50), WaveNet 20x256, 128 mel, one 8-s utterance (690 frames)'),
 }
@@ -147,6 +153,17 @@ def make_model(w, precision, device, cuda_graph=True):
                                                             dilation_cycle_length=w['cycle']))
         torch.nn.init.normal_(model.denoise_fn.output_projection.weight, std=SIGMA_W)
         return model.to(device).eval()
+    if kind == 'wavenet_pitch':
+        # configs/variance.yaml:67-77: PitchDiffusion over 64 repeat bins, WaveNet 20 x 256, dilation cycle 5
+        P.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=False,
+                         diff_speedup=1000 // w['k_step'], diff_accelerator='unipc', infer=False, b2s_precision=precision,
+                         b2s_cuda_graph=cuda_graph)
+        torch.manual_seed(0)
+        model = P.PitchDiffusion(vmin=-8., vmax=8., cmin=-12., cmax=12., repeat_bins=w['mel'], backbone_type='wavenet',
+                                 backbone_args=dict(num_layers=w['layers'], num_channels=w['channels'],
+                                                    dilation_cycle_length=w['cycle']))
+        torch.nn.init.normal_(model.denoise_fn.output_projection.weight, std=SIGMA_W)
+        return model.to(device).eval()
     if kind in ('wavenet_unipc', 'wavenet_ddim'):
         P.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=False,
                          diff_speedup=1000 // w['k_step'], diff_accelerator='unipc' if kind == 'wavenet_unipc' else 'ddim',
@@ -179,39 +196,90 @@ def synth_inputs(w, seed):
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's algorithm on the host cores
+# CPU arm: the reference (baseline/_ref) or, when it is absent, the oracle port - on the host cores.  No product imports.
 # ------------------------------------------------------------------------------------------------------
-def cpu_sample_throughput(w, sd, n_utt, n_nfe, repeats, warmup):
-    """frame*NFE/s of the reference algorithm (oracle port, fp32, all host threads) on a bounded sample:
-    ``n_utt`` utterances x T frames, the first ``n_nfe`` ancestral steps of the K_step=400 chain."""
+def oracle_state_dict(w):
+    """Random-init weights of the workload's WaveNet from the oracle's seeded recipe (oracle/weights.py), fp32 CPU."""
     from oracle import denoisers as OD
-    from oracle import samplers as OS
+    from oracle import weights as OW
     cfg = OD.WaveNetCfg(in_dims=w['mel'], n_feats=1, num_layers=w['layers'], num_channels=w['channels'],
                         dilation_cycle_length=w['cycle'], hidden_size=w['hidden'])
-    sd = {k: v.detach().float().cpu() for k, v in sd.items()}
-    denoise = OD.make_denoiser(sd, cfg)
-    sch = OS.DiffusionSchedule(1000, 'linear')
+    return cfg, OW.make_state_dict(cfg, seed=0, sigma_w=SIGMA_W)
+
+
+def reference_model(w, device='cpu'):
+    """The UNMODIFIED reference's GaussianDiffusion (modules/core/ddpm.py:55) with its own WaveNet, or None when the reference
+    is not installed (baseline/_ref absent and no /root/reference)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return None
+    ref = ref_loader.load()
+    ref.hparams.update(hidden_size=w['hidden'], schedule_type='linear', use_shallow_diffusion=True, K_step_infer=w['k_step'],
+                       diff_speedup=1, diff_accelerator='ddim', infer=False)
+    model = ref.ddpm.GaussianDiffusion(
+        w['mel'], timesteps=1000, k_step=w['k_step'], backbone_type='wavenet',
+        backbone_args=dict(num_layers=w['layers'], num_channels=w['channels'], dilation_cycle_length=w['cycle']),
+        spec_min=[-12.], spec_max=[0.])
+    _, sd = oracle_state_dict(w)
+    model.denoise_fn.load_state_dict(sd, strict=True)
+    return model.to(device).eval()
+
+
+def ancestral_sample_throughput(w, n_utt, n_nfe, repeats, warmup, device='cpu', autocast=None):
+    """frame*NFE/s of the reference's ancestral sampler on a bounded sample: ``n_utt`` utterances x T frames, the first ``n_nfe``
+    steps of the K_step = 400 chain (ddpm.py:346-349: x = p_sample(x, t, cond)).  Runs the installed reference when there is
+    one (kind 'reference'), else the oracle port (kind 'port').  Returns (throughput, times, kind)."""
+    from oracle import denoisers as OD
+    from oracle import samplers as OS
     g = torch.Generator().manual_seed(5)
     T = w['T']
-    cond = torch.randn((n_utt, w['hidden'], T), generator=g)
-    x0 = torch.randn((n_utt, 1, w['mel'], T), generator=g)
-    noises = [torch.randn((n_utt, 1, w['mel'], T), generator=g) for _ in range(n_nfe)]
-    times = []
-    with torch.no_grad():
-        for it in range(warmup + repeats):
-            t0 = time.perf_counter()
+    cond = torch.randn((n_utt, w['hidden'], T), generator=g).to(device)
+    x0 = torch.randn((n_utt, 1, w['mel'], T), generator=g).to(device)
+    model = reference_model(w, device)
+    if model is not None:
+        kind = 'reference'
+
+        def one_pass():
             x = x0
             for j in range(n_nfe):
                 i = w['k_step'] - 1 - j
-                eps = denoise(x, torch.full((n_utt,), i, dtype=torch.long), cond)
-                xr = sch.sqrt_recip_alphas_cumprod[i] * x - sch.sqrt_recipm1_alphas_cumprod[i] * eps
-                mean = sch.posterior_mean_coef1[i] * xr + sch.posterior_mean_coef2[i] * x
-                x = mean + (0.5 * sch.posterior_log_variance_clipped[i]).exp() * noises[j]
+                x = model.p_sample(x, torch.full((n_utt,), i, device=device, dtype=torch.long), cond)
+            return x
+    else:
+        kind = 'port'
+        cfg, sd = oracle_state_dict(w)
+        sd = {k: v.to(device) for k, v in sd.items()}
+        sch = OS.DiffusionSchedule(1000, 'linear')
+        noises = [torch.randn((n_utt, 1, w['mel'], T), generator=g).to(device) for _ in range(n_nfe)]
+
+        def one_pass():
+            x = x0
+            for j in range(n_nfe):
+                i = w['k_step'] - 1 - j
+                eps = OD.wavenet_forward(sd, cfg, x, torch.full((n_utt,), i, dtype=torch.long, device=device), cond)
+                xr = float(sch.sqrt_recip_alphas_cumprod[i]) * x - float(sch.sqrt_recipm1_alphas_cumprod[i]) * eps
+                mean = float(sch.posterior_mean_coef1[i]) * xr + float(sch.posterior_mean_coef2[i]) * x
+                x = mean + math.exp(0.5 * float(sch.posterior_log_variance_clipped[i])) * noises[j]
+            return x
+    cuda = str(device).startswith('cuda')
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + repeats):
+            if cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if autocast is not None:
+                with torch.autocast('cuda', dtype=autocast):
+                    one_pass()
+            else:
+                one_pass()
+            if cuda:
+                torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
     per = n_utt * T * n_nfe
-    return per / statistics.median(times), times
+    return per / statistics.median(times), times, kind
 
 
 def run_reference_arm(args, w):
@@ -219,11 +287,9 @@ def run_reference_arm(args, w):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    import xiaoicesing_io_b200 as P   # module construction only (CPU parameters); no kernels are launched
-    model = make_model(w, 'fp32', 'cpu')
     n_utt, n_nfe = 4, 4
     t0 = time.perf_counter()
-    thr, times = cpu_sample_throughput(w, model.denoise_fn.state_dict(), n_utt, n_nfe, args.steps, args.warmup)
+    thr, times, kind = ancestral_sample_throughput(w, n_utt, n_nfe, args.steps, args.warmup)
     sample = f'{n_utt} utterances x {w["T"]} frames x first {n_nfe} of {w["k_step"]} ancestral steps per step'
     line = {
         'impl': 'reference', 'metric': 'denoised mel-frames x NFE per second', 'value': thr, 'unit': 'frame*NFE/s',
@@ -231,7 +297,7 @@ def run_reference_arm(args, w):
         'ms_per_step': 1e3 * statistics.median(times), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': w['desc'], 'sample': sample},
-        'cpu_baseline': {'value': thr, 'unit': 'frame*NFE/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+        'cpu_baseline': {'value': thr, 'unit': 'frame*NFE/s', 'cores': torch.get_num_threads(), 'kind': kind,
                          'sample': sample},
         'e2e': {'value': thr, 'unit': 'frame*NFE/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -288,20 +354,19 @@ def dominant_kernel_roofline(model, w, precision, reps=5):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (reps * n_launch)
-    # DRAM traffic of one launch from the committed `ncu --set full` capture of the SAME kernel at the SAME shapes
+    # DRAM traffic per launch: read from THIS round's `ncu --set full` capture of the same kernel at the same shapes when one is
+    # committed (profiles/r02_ncu_full_<kernel>.csv, `ncu --page raw --csv`), else null - never a constant from an older kernel
     traffic = None
-    prof = os.path.join(ROOT, 'profiles', 'r01_ncu_full_wavenet_stack.csv')
-    if 'wavenet_stack_kernel' in name and os.path.exists(prof) and (B, T, Cc, L) == (16, 690, 256, 20):
+    kern = name.split('<')[0].split(' ')[0]
+    prof = os.path.join(ROOT, 'profiles', f'r02_ncu_full_{kern}.csv')
+    if os.path.exists(prof) and (B, T, Cc, L) == (16, 690, 256, 20):
         try:
             import csv
-            rows = list(csv.reader(open(prof)))
+            rws = list(csv.reader(open(prof)))
             scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-            if rows and 'dram__bytes_read.sum' in rows[0]:      # `ncu --page raw --csv`: header row, unit row, one row per launch
-                cols = [rows[0].index(k) for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum')]
-                traffic = sum(float(rows[2][c].replace(',', '')) * scale[rows[1][c]] for c in cols)
-            else:                                               # one metric per row: name, unit, value
-                vals = {r[0]: (r[1], float(r[2])) for r in rows if len(r) >= 3 and r[0].startswith('dram__bytes')}
-                traffic = sum(v * scale[u] for u, v in vals.values())
+            hdr = next(i for i, r in enumerate(rws) if 'dram__bytes_read.sum' in r)
+            cols = [rws[hdr].index(k) for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum')]
+            traffic = sum(float(rws[hdr + 2][c].replace(',', '')) * scale[rws[hdr + 1][c]] for c in cols)
         except Exception:                                   # noqa: BLE001
             traffic = None
     achieved = flops / (ms * 1e-3) / 1e12
@@ -309,6 +374,57 @@ def dominant_kernel_roofline(model, w, precision, reps=5):
             'frac': achieved / p['bf16_burst'], 'traffic': traffic, 'avg_launch_ms': ms,
             'flops_per_launch': flops, 'peak_source': p['source'], 'launches_per_eval': sess.launches_per_eval,
             'note': 'algorithmic FLOPs of the launch / avg CUDA-event duration of the launches replayed back to back as a CUDA graph'}
+
+
+def time_workload(model, w, dev, steps, warmup):
+    """(frame*NFE/s, ms per sampling call, NFE per call) of one workload, inputs resident, CUDA events."""
+    cond_h, src_h = synth_inputs(w, seed=1000)
+    cond_d, src_d = cond_h.to(dev), src_h.to(dev)
+    kind = w.get('kind', 'wavenet_ddpm_shallow')
+    if kind != 'wavenet_ddpm_shallow':
+        src_d = None
+    variance = kind in ('wavenet_variance', 'wavenet_pitch')
+    run = (lambda: model(cond_d, infer=True)) if variance else (lambda: model(cond_d, src_spec=src_d, infer=True))
+    for _ in range(warmup):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    nfe = model.build_program().n_nfe
+    return w['B'] * w['T'] * nfe / (ms * 1e-3), ms, nfe
+
+
+def run_secondary(args, dev):
+    """Short runs (3 warm-up + 3 timed sampling calls each) of the BASELINE configs the headline is NOT quoted on, so that they are
+    driver-run numbers too; each with the roofline of its own dominant kernel."""
+    import xiaoicesing_io_b200 as P
+    out = {}
+    saved = dict(P.hparams)
+    for name in ('config1', 'config3', 'config4_pitch', 'config4', 'config5'):
+        w = dict(WORKLOADS[name])
+        try:
+            model = make_model(w, args.precision, dev)
+            value, ms, nfe = time_workload(model, w, dev, steps=3, warmup=3)
+            kind = w.get('kind', 'wavenet')
+            F = flops_per_frame_nfe(w['layers'], w['channels'], w['mel'] if kind != 'wavenet_variance' else w['mel'], kind)
+            roof = dominant_kernel_roofline(model, w, args.precision, reps=3)
+            p = peaks()
+            out[name] = {'workload': w['desc'], 'value': value, 'unit': 'frame*NFE/s', 'ms_per_call': ms, 'nfe_per_call': nfe,
+                         'rtf': (ms * 1e-3) / (w['B'] * w['T'] * 512 / 44100.0),
+                         'tflops_algorithmic': value * F / 1e12, 'frac_of_bf16_peak': value * F / 1e12 / p['bf16_burst'],
+                         'roofline': None if roof is None else {k: roof[k] for k in ('kernel', 'achieved', 'peak', 'frac', 'avg_launch_ms')}}
+            del model
+        except Exception as ex:                             # noqa: BLE001
+            out[name] = {'workload': w['desc'], 'error': f'{type(ex).__name__}: {ex}'}
+        torch.cuda.empty_cache()
+    P.hparams.clear()
+    P.hparams.update(saved)
+    return out
 
 
 def run_b200_arm(args, w):
@@ -323,7 +439,7 @@ def run_b200_arm(args, w):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     import xiaoicesing_io_b200 as P
-    from xiaoicesing_io_b200.partition import gather_mels
+    from xiaoicesing_io_b200.partition import MelGather
 
     model = make_model(w, args.precision, dev, cuda_graph=not args.no_graph)
     if args.fuse_io is not None:
@@ -339,30 +455,40 @@ def run_b200_arm(args, w):
     B, T = w['B'], w['T']
     prog = model.build_program()
     nfe = prog.n_nfe
-    index = list(range(rank * B, (rank + 1) * B))
+    parts = [list(range(r * B, (r + 1) * B)) for r in range(world)]     # weak scaling: every rank owns B utterances
 
     shallow = w.get('kind', 'wavenet_ddpm_shallow') == 'wavenet_ddpm_shallow'
     if not shallow:
         src_d = None
 
-    variance = w.get('kind') == 'wavenet_variance'
+    variance = w.get('kind') in ('wavenet_variance', 'wavenet_pitch')
     n_out = w.get('out', w['mel'])
-    run = (lambda c, s: torch.stack(model(c, infer=True), -1)) if variance else (lambda c, s: model(c, src_spec=s, infer=True))
+    def run(c, s):
+        if not variance:
+            return model(c, src_spec=s, infer=True)
+        r = model(c, infer=True)
+        return torch.stack(r, -1) if isinstance(r, (list, tuple)) else r.unsqueeze(-1)
+
+    # the ONLY exchange: one gather of the finished mels to rank 0 into pre-allocated buffers (prepared once: no counts, no
+    # indices, no host synchronisation per step), then ONE device-to-host copy into a pinned buffer
+    out_shape = (T, n_out)
+    gather = MelGather(parts, out_shape, dev, dst=0) if world > 1 else None
+    host_out = torch.empty((world * B,) + out_shape, dtype=torch.float32).pin_memory() if rank == 0 else None
 
     def step_resident():
         mel = run(cond_d, src_d)
-        if world > 1:
-            gather_mels(mel.contiguous(), index, world * B, dst=0)     # the ONLY exchange: final mel gather
+        if gather is not None:
+            gather(mel.contiguous())
         return mel
 
     def step_e2e():
         c = cond_h.to(dev, non_blocking=True)
         s = src_h.to(dev, non_blocking=True) if shallow else None
         mel = run(c, s)
-        if world > 1:
-            full = gather_mels(mel.contiguous(), index, world * B, dst=0)
-            return full.cpu() if full is not None else None
-        return mel.cpu()
+        full = gather(mel.contiguous()) if gather is not None else mel
+        if full is not None and host_out is not None:
+            host_out.copy_(full.reshape(host_out.shape), non_blocking=True)     # completes before the timed region's final sync
+        return full
 
     def barrier():
         if world > 1:
@@ -398,15 +524,25 @@ def run_b200_arm(args, w):
     value = units / (ms_total * 1e-3)
     e2e_value = units / (max(e2e_ms, e2e_wall_ms) * 1e-3)      # host copies: wall clock bounds it from above
 
-    roof = cpu = None
+    roof = cpu = eager = secondary = None
     if rank == 0:
         roof = dominant_kernel_roofline(model, w, args.precision)
         if world == 1 and not args.no_cpu_baseline and shallow:
             torch.set_num_threads(os.cpu_count() or 1)
             n_utt, n_nfe = 4, 4
-            thr, _ = cpu_sample_throughput(w, model.denoise_fn.state_dict(), n_utt, n_nfe, repeats=3, warmup=1)
-            cpu = {'value': thr, 'unit': 'frame*NFE/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            thr, _, kind = ancestral_sample_throughput(w, n_utt, n_nfe, repeats=3, warmup=1)
+            cpu = {'value': thr, 'unit': 'frame*NFE/s', 'cores': torch.get_num_threads(), 'kind': kind,
                    'sample': f'{n_utt} utterances x {T} frames x first {n_nfe} of {w["k_step"]} ancestral steps, median of 3'}
+            # the reference's eager PyTorch code on THIS GPU, full batch: the number SURVEY.md section 8d calls "the one to beat"
+            n_nfe_g = 8
+            e32, _, kind_g = ancestral_sample_throughput(w, B, n_nfe_g, repeats=3, warmup=2, device=dev)
+            e16, _, _ = ancestral_sample_throughput(w, B, n_nfe_g, repeats=3, warmup=2, device=dev, autocast=torch.bfloat16)
+            eager = {'fp32': e32, 'autocast_bf16': e16, 'unit': 'frame*NFE/s', 'kind': kind_g,
+                     'sample': f'{B} utterances x {T} frames x first {n_nfe_g} of {w["k_step"]} ancestral steps, torch eager on cuda '
+                               f'(cudnn/cublas defaults), median of 3',
+                     'speedup_over_fp32': value / e32, 'speedup_over_autocast_bf16': value / e16}
+        if world == 1 and not args.no_secondary and args.workload == 'config2' and not (args.k_step or args.batch or args.frames):
+            secondary = run_secondary(args, dev)
     if rank == 0:
         sess_launches = (roof or {}).get('launches_per_eval', (1 if args.precision == 'fp32' else 2) + 2 * w['layers'] + 2)
         n_lin = sum(1 for op in prog.ops if op.kind == 'lin')
@@ -442,7 +578,7 @@ def run_b200_arm(args, w):
             'rtf': (ms_total / args.steps * 1e-3) / (world * B * T * 512 / 44100.0),
             'tflops_algorithmic': value * F / 1e12,
             'frac_of_bf16_peak': value * F / 1e12 / (world * p['bf16_sustained']),
-            'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks,
+            'roofline': roof, 'cpu_baseline': cpu, 'gpu_eager_baseline': eager, 'secondary': secondary, 'clocks': clocks,
             'wall_ms_per_step': wall_ms / args.steps,
         }
         print(json.dumps(line), flush=True)
@@ -473,12 +609,14 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('B2S_PRECISION', 'bf16'), choices=['fp32', 'bf16', 'fp16'])
+    ap.add_argument('--precision', default=os.environ.get('B2S_PRECISION', 'fp16'), choices=['fp32', 'bf16', 'fp16'],
+                    help='fp16 (default): the 16-bit tensor-core path that meets the 2e-2 parity bound on every config')
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
     ap.add_argument('--k-step', type=int, default=None, help='override K_step (debug only; invalidates the metric)')
     ap.add_argument('--batch', type=int, default=None, help='override utterances per GPU (sweeps only; not the headline config)')
     ap.add_argument('--frames', type=int, default=None, help='override frames per utterance (sweeps only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the short runs of the other BASELINE configs')
     ap.add_argument('--fuse-io', type=int, default=None, help='override hparams b2s_fuse_io (A/B switch)')
     ap.add_argument('--overlap-noise', type=int, default=None, help='override hparams b2s_overlap_noise (A/B switch)')
     ap.add_argument('--hparam', action='append', help='extra hparams entry key=json (A/B switches, e.g. b2s_fuse_cast=false)')

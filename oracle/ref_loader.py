@@ -1,8 +1,9 @@
-"""Oracle (TEST INFRASTRUCTURE): import the UNMODIFIED reference from /root/reference.
+"""Oracle (TEST INFRASTRUCTURE): import the UNMODIFIED reference.
 
-Only usable in the build container (the GPU box has no /root/reference); used by
-``oracle/make_golden.py`` and by the optional live cross-check test.  Nothing in
-the product, ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call this.
+Search order: ``$B2S_REFERENCE_ROOT``, ``/root/reference`` (the build container), ``baseline/_ref`` (the byte-for-byte
+copy ``baseline/install_reference.sh`` makes; git-ignored, it travels to the GPU box with the gpurun snapshot).  Used by
+``oracle/make_golden.py``, by the optional live cross-check test and by ``bench.py``'s CPU legs (``--impl reference`` and
+``cpu_baseline``), which time the reference's own sampling code.  Nothing in the product may import this.
 
 The reference imports ``lightning`` through ``utils/__init__.py:15`` ->
 ``utils/training_utils.py:7``; that one module is stubbed before import
@@ -14,7 +15,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('B2S_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get('B2S_REFERENCE_ROOT'), '/root/reference', os.path.join(_HERE, '..', 'baseline', '_ref')):
+        if cand and os.path.isfile(os.path.join(cand, 'modules', 'core', 'ddpm.py')):
+            return os.path.abspath(cand)
+    return os.environ.get('B2S_REFERENCE_ROOT', '/root/reference')
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from xiaoicesing_io_b200.partition import gather_mels, partition_by_length
+from xiaoicesing_io_b200.partition import MelGather, gather_mels, partition_by_length
 
 
 def test_partition_is_balanced_and_complete():
@@ -38,13 +38,16 @@ def _worker(rank, world, port, lengths, q):
         mine = parts[rank]
         # "sampling result" of utterance i is a tensor filled with i (utterances are independent units)
         local = torch.stack([torch.full((5, 3), float(i)) for i in mine]) if mine else torch.zeros((0, 5, 3))
-        full = gather_mels(local, mine, len(lengths), dst=0)
-        everywhere = gather_mels(local, mine, len(lengths), dst=None)
+        full = gather_mels(local, mine, len(lengths), dst=0)                     # index lists exchanged
+        everywhere = gather_mels(local, mine, len(lengths), dst=None, parts=parts)
+        g = MelGather(parts, (5, 3), 'cpu', dst=0)                                # the prepared gather of the hot path, used twice
+        again = [g(local), g(local * 1.0)][-1]
         ok = everywhere is not None and all(float(everywhere[i, 0, 0]) == i for i in range(len(lengths)))
         if rank == 0:
             ok = ok and full is not None and all(float(full[i, 0, 0]) == i for i in range(len(lengths)))
+            ok = ok and again is not None and torch.equal(again, full)
         else:
-            ok = ok and full is None
+            ok = ok and full is None and again is None
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

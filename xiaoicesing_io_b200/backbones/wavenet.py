@@ -6,6 +6,8 @@ The arithmetic runs in hand-written CUDA kernels through the C ABI; there is no 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -64,12 +66,23 @@ class _B2SBackbone(nn.Module):
     engine_cls = None
 
     def _engine(self):
-        prec = hparams.get('b2s_precision', 'fp32')
+        prec = hparams.get('b2s_precision') or os.environ.get('B2S_PRECISION', 'fp32')
         eng = self.__dict__.get('_b2s_engine')
         if eng is None or eng.precision != prec:
             eng = self.engine_cls(self, prec)
             self.__dict__['_b2s_engine'] = eng
         return eng
+
+    def invalidate(self):
+        """Forces the packed (K-major, 16-bit, interleaved) weight copies and every captured CUDA graph to be rebuilt on the next
+        call.  Weight changes through ``load_state_dict``, optimizer steps, ``.to()``, ``.half()`` or ``p.data = t`` are detected
+        automatically (tensor version counters + storage pointers); call this after writing THROUGH a detached view that shares
+        the parameter's storage (``p.data.copy_(...)`` on an EMA swap-in, custom loaders), which no counter sees."""
+        eng = self.__dict__.get('_b2s_engine')
+        if eng is not None:
+            eng._packed_version = None
+        from ..core._sampling import clear_graph_cache
+        clear_graph_cache()
 
     @torch.no_grad()
     def forward(self, spec, diffusion_step, cond):
@@ -84,6 +97,10 @@ class _B2SBackbone(nn.Module):
         B, F_, M, T = spec.shape
         if B * T == 0:
             return torch.zeros_like(spec, dtype=torch.float32)
+        with torch.cuda.device(spec.device):    # launches and the current stream belong to the tensors' device
+            return self._forward_on_device(spec, diffusion_step, cond, B, F_, M, T)
+
+    def _forward_on_device(self, spec, diffusion_step, cond, B, F_, M, T):
         eng = self._engine()
         cond_bth = _time_major_cond(cond.float())
         t = diffusion_step.reshape(-1).to(device=spec.device, dtype=torch.float32).contiguous()

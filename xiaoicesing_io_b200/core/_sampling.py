@@ -2,6 +2,7 @@
 ``forward(condition, gt_spec, src_spec, infer)`` entry, buffer + noise plumbing and the program run."""
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Callable, Optional
 
 import torch
@@ -101,6 +102,7 @@ class _GraphedLoop:
         self.n_launches = C.N_CALLS - n0        # kernels of libb2s.so in one replay (torch.randn nodes not counted)
 
     def run(self, cond_bth, x_start_bfmt):
+        # (the caller holds torch.cuda.device(device): replay goes to the device the graph was captured on)
         self.cond.copy_(cond_bth)
         if self.x_start is not None:
             self.x_start.copy_(x_start_bfmt.reshape(self.x_start.shape))
@@ -108,8 +110,17 @@ class _GraphedLoop:
         return self.out.clone()
 
 
-_GRAPH_CACHE: 'dict[tuple, object]' = {}
+# Captured graphs, least recently used first.  A graph pins its engine, its session and a private memory pool of hundreds of MB,
+# so only a few are kept; the keys seen ONCE (a graph is captured on the second call with a key) live in their own small LRU so
+# that a stream of new shapes (variable-length batches) never evicts a live graph.
+_GRAPH_CACHE: 'OrderedDict[tuple, object]' = OrderedDict()
 _GRAPH_CACHE_MAX = 4
+_SEEN_KEYS: 'OrderedDict[tuple, None]' = OrderedDict()
+_SEEN_KEYS_MAX = 64
+# hparams that change WHICH kernels a sampling call launches: part of the graph key (toggling one after capture must not replay
+# the old launch structure)
+_STRUCTURE_HPARAMS = ('b2s_stack', 'b2s_stack3', 'b2s_stack3_head', 'b2s_stack_t', 'b2s_stack_t_tile', 'b2s_fuse_io', 'b2s_fuse_update',
+                      'b2s_overlap_noise', 'b2s_fuse_cast', 'b2s_defer_skip', 'b2s_lynx_fold_cond')
 
 
 def _program_key(prog: Program):
@@ -119,6 +130,7 @@ def _program_key(prog: Program):
 
 def clear_graph_cache():
     _GRAPH_CACHE.clear()
+    _SEEN_KEYS.clear()
 
 
 def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: int, out_dims: int,
@@ -146,6 +158,11 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
         raise C.B2SError(f'batch size mismatch: cond has {B} utterances, b={b}')
     F_, M = num_feats, out_dims
     shape = (B, F_, M, T)
+    with torch.cuda.device(device):         # every launch below (and the current stream) belongs to the tensors' device
+        return _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source)
+
+
+def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source):
     eng = backbone._engine()
     eng.pack()
     if prog.needs_x_start:
@@ -163,14 +180,17 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
 
     graph_key = None
     if noise_source is None and hparams.get('b2s_cuda_graph', True):
-        graph_key = (id(backbone), eng._packed_version, eng.precision, _program_key(prog), B, T, F_, M, str(device))
+        structure = tuple(repr(hparams.get(k)) for k in _STRUCTURE_HPARAMS)
+        graph_key = (id(backbone), eng._packed_version, eng.precision, _program_key(prog), B, T, F_, M, str(device), structure)
         entry = _GRAPH_CACHE.get(graph_key)
+        if entry is None and graph_key in _SEEN_KEYS:       # second call with this key: capture
+            del _SEEN_KEYS[graph_key]
+            while len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+                _GRAPH_CACHE.popitem(last=False)            # least recently used graph
+            entry = _GraphedLoop(eng, CompiledProgram(prog, device), B, T, H, F_, M, device)
+            _GRAPH_CACHE[graph_key] = entry
         if entry is not None:
-            if entry == 'seen':                             # second call with this key: capture
-                if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
-                    _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
-                entry = _GraphedLoop(eng, CompiledProgram(prog, device), B, T, H, F_, M, device)
-                _GRAPH_CACHE[graph_key] = entry
+            _GRAPH_CACHE.move_to_end(graph_key)
             xs = None if x_start is None else x_start.to(device=device, dtype=torch.float32)
             return finish(entry.run(cond_bth, xs))
     if noise_source is None:
@@ -191,7 +211,7 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
 
     x = run_program(cp, sess, bufs, lambda j, dst: load(noise_source(shape), dst))   # [B*T, F*M]
     if graph_key is not None:
-        if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
-            _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
-        _GRAPH_CACHE[graph_key] = 'seen'
+        _SEEN_KEYS[graph_key] = None
+        while len(_SEEN_KEYS) > _SEEN_KEYS_MAX:
+            _SEEN_KEYS.popitem(last=False)
     return finish(x)

@@ -392,16 +392,33 @@ inline int make_map_w3(CUtensorMap* m, const void* base, int bf16, int K, int N,
     return B2S_OK;
 }
 
-inline int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+// Attributes such as the SM count or cudaFuncAttributeMaxDynamicSharedMemorySize are PER DEVICE: every cache below is keyed by the
+// current device (a process may drive several GPUs).
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
 }
+inline int num_sms() {
+    static int n[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!n[dev]) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
+    }
+    return n[dev];
+}
+// `static PerDevice configured; if (configured.first()) { cudaFuncSetAttribute(...); }` - true once per device
+struct PerDevice {
+    bool done[MAX_DEVICES] = {};
+    bool first() {
+        const int dev = current_device();
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
 
 inline bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 

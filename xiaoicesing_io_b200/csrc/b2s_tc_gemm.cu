@@ -618,16 +618,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
 // ---- host side (tensor-map builders live in b2s_tc.cuh) ------------------------------------------------
 template <int EPI, int BF16>
 static int launch_one(const TcP& p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (configured.first()) {
         B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
     }
     if (p.cg2) {
-        static bool configured2 = false;
-        if (!configured2) {
+        static PerDevice configured2;
+        if (configured2.first()) {
             B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_cg2_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-            configured2 = true;
         }
         const int num_pt = (p.B * p.tiles_m_per_b / 2) * p.tiles_n;
         const int pairs = num_pt < num_sms() / 2 ? num_pt : num_sms() / 2;

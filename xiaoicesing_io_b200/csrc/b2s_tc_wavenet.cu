@@ -316,10 +316,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_layer_kernel(const __grid
 
 template <int BF16>
 static int launch_layer(const LayerP& p, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (configured.first()) {
         B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_layer_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -628,10 +627,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_layer_cl2_kernel(const __
 
 template <int BF16>
 static int launch_layer(const LayerP& p, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (configured.first()) {
         B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_layer_cl2_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1330,12 +1328,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_kernel(const __grid
     }
 }
 
+// Every CTA of this kernel must be resident at once (tiles spin on their neighbours' flags): the capacity is what the driver
+// reports for THIS launch configuration on THIS device as it is now (2-CTA clusters, 231 KB of shared memory, 384 threads; MPS SM
+// limits, MIG slices and green contexts included), not the SM count.
+template <int BF16>
+static int stack_capacity() {
+    static int cap[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!cap[dev]) {
+        cudaFuncSetAttribute(wavenet_stack_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(CLUSTER);
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int q = 0;
+        if (cudaOccupancyMaxActiveClusters(&q, wavenet_stack_kernel<BF16>, &cfg) != cudaSuccess) { cudaGetLastError(); q = 0; }
+        cap[dev] = q > 0 ? q * CLUSTER : -1;
+    }
+    return cap[dev] > 0 ? cap[dev] : 0;
+}
+
 template <int BF16>
 static int launch_stack(const StackP& p, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (configured.first()) {
         B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_stack_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
+    }
+    if (grid > stack_capacity<BF16>()) {
+        set_error("b2s_tc_wavenet_stack: %d tiles do not fit the device at once (the driver reports room for %d co-resident CTAs of "
+                  "this kernel); split the batch by utterance", grid, stack_capacity<BF16>());
+        return B2S_ERR_UNSUPPORTED;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1711,10 +1740,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_cg2_kernel(const __
 
 template <int BF16>
 static int launch_stack_cg2(const StackP& p, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (configured.first()) {
         B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_stack_cg2_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1779,7 +1807,10 @@ unsigned long long* g_tlog = nullptr;      // shared with b2s_tc_wavenet_t.cu
 /* profiling hook (not part of the product API): device buffer [L][16] of globaltimer ns, or NULL to switch off */
 extern "C" void b2s_debug_set_stack_tlog(void* buf) { g_tlog = (unsigned long long*)buf; }
 
-extern "C" int b2s_tc_wavenet_stack_max_tiles(void) { return num_sms(); }
+extern "C" int b2s_tc_wavenet_stack_max_tiles(void) {
+    const int a = ws::stack_capacity<1>(), b = ws::stack_capacity<0>();      // cudaOccupancyMaxActiveClusters x 2, per device
+    return a < b ? a : b;
+}
 
 struct DenoiserIO {            // stem / head operands of b2s_tc_wavenet_denoiser (all NULL for the plain stack)
     const void* xin_h; int MF; const void* Win_h; int ld_win; const float* b_in;
@@ -1806,9 +1837,9 @@ static int stack_impl(void* y0_h, void* y1_h, const void* Wd_h, const void* cond
     ws::StackP p{};
     p.tiles_per_b = (ceil_div(T, ws::BM) + 1) & ~1;
     const int grid = B * p.tiles_per_b;
-    if (grid > num_sms()) {
-        set_error("b2s_tc_wavenet_stack: %d tiles do not fit the %d SMs at once (every tile must be resident); split the "
-                  "batch by utterance", grid, num_sms());
+    if (grid > b2s_tc_wavenet_stack_max_tiles()) {
+        set_error("b2s_tc_wavenet_stack: %d tiles do not fit the device at once (room for %d co-resident CTAs; every tile must be "
+                  "resident); split the batch by utterance", grid, b2s_tc_wavenet_stack_max_tiles());
         return B2S_ERR_UNSUPPORTED;
     }
     int rc = make_map_act(&p.mapY[0], y0_h, bf16, C, C, T, B, ws::BK, ws::BM);

@@ -393,10 +393,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack_t_kernel(const __gr
 
 template <int NT, int BF16>
 static int launch_t(const StackTP& p, int grid, int smem_bytes, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    if (configured.first()) {
         B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_stack_t_kernel<NT, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

@@ -52,7 +52,10 @@ class WaveNetEngine:
 
     # -- weights ------------------------------------------------------------------------------------
     def _version(self):
-        return tuple(p._version for p in self.net.parameters()) + (str(next(self.net.parameters()).device),)
+        # version counters catch in-place updates (optimizer steps, load_state_dict, p.data.copy_ does NOT bump them but the
+        # storage pointer / dtype part catches p.data = t, .half(), .to()); see _B2SBackbone.invalidate() for the rest
+        ps = list(self.net.parameters())
+        return tuple((p._version, p.data_ptr(), p.dtype) for p in ps) + (str(ps[0].device),)
 
     def pack(self, force=False):
         v = self._version()
@@ -588,7 +591,10 @@ class LYNXNetEngine:
         self.device = None
 
     def _version(self):
-        return tuple(p._version for p in self.net.parameters()) + (str(next(self.net.parameters()).device),)
+        # version counters catch in-place updates (optimizer steps, load_state_dict, p.data.copy_ does NOT bump them but the
+        # storage pointer / dtype part catches p.data = t, .half(), .to()); see _B2SBackbone.invalidate() for the rest
+        ps = list(self.net.parameters())
+        return tuple((p._version, p.data_ptr(), p.dtype) for p in ps) + (str(ps[0].device),)
 
     def pack(self, force=False):
         v = self._version()
@@ -777,6 +783,17 @@ class LYNXNetSessionTC:
     @property
     def launches_per_eval(self) -> int:
         return 2 + 4 * self.eng.L + 2
+
+    def dominant_kernel(self, w=None):
+        """(name, algorithmic FLOPs per launch, callable launching it once per layer, launches) for bench.py's roofline: the
+        SwiGLU up-projection GEMM (lynxnet.py:55-56), 2/3 of the layer's FLOPs."""
+        e = self.eng
+        flops = 2.0 * self.rows * e.C * (2 * e.inner)
+
+        def launch_all():
+            for l in range(e.L):
+                C.tc_lynx_glu(self.h_h, e.w_up_h[l], e.b_up[l], self.g_h, self.rows, e.C, e.inner, e.bf16)
+        return f'tc_gemm_cg2_kernel<EPI_SWIGLU,{e.precision}> (b2s_tc_lynx_glu)', flops, launch_all, e.L
 
 
 # =====================================================================================================

@@ -435,10 +435,10 @@ def build_reflow(algorithm: str, steps: int, t_start: float, use_shallow: bool, 
     else:
         t_start = 0.
         p.lin(X, [(NOISE0, 1.0)])
+    if t_start >= 1:                                          # reflow.py:115-118: x_end is returned before the algorithm is looked up
+        return p
     if algorithm not in ('euler', 'rk2', 'rk4', 'rk5'):
         raise ValueError(f'Unsupported algorithm for Rectified Flow: {algorithm}.')
-    if t_start >= 1:
-        return p
     dt = (1.0 - t_start) / max(1, steps)
     dts = torch.tensor([dt])                                  # fp32 (reflow.py:132)
     tsf = float(time_scale_factor)
