@@ -262,7 +262,10 @@ int b2s_tc_wavenet_denoiser_update(const void* xin_h, int MF, const void* Win_h,
  *   Wres_h [L,C,C]: 2^(l/2) * output_projection.weight[:C];  bsum [L,C] fp32: sum_{k<l} 2^(k/2) * output_projection.bias_k[:C]
  *   dvec: this evaluation's step-embedding row, layer l at dvec + b*d_stride + l*C;  dilations_host: L ints (HOST)
  *   yedge0_h, yedge1_h: 16-bit [B*T, C] scratch (only the first / last 16 rows of every 128-frame tile are touched)
- *   flags: int32 [B * tiles], ZERO at launch.  Every tile must be resident: checked against cudaOccupancyMaxActiveClusters. */
+ *   flags: int32 [B * tiles], ZERO at launch.  Every tile must be resident: checked against cudaOccupancyMaxActiveClusters.
+ *   lens: NULL, or DEVICE int32 [B]: utterance b has lens[b] <= T valid frames (a RAGGED batch padded to T).  Frames at or beyond
+ *         lens[b] are treated exactly like frames beyond T - the conv's zero padding (wavenet.py:22-28) - so every valid frame of
+ *         utterance b gets the bits it would get in a batch of its own with T = lens[b]; outputs of the padded frames are undefined. */
 int b2s_tc_wavenet_stack3_halo(void);
 /* tiles (2*ceil(ceil(T/128)/2) per utterance) ONE launch can hold on the current device for utterances of T frames: cluster size =
  * the largest of 8, 6, 4, 2 dividing the tiles per utterance (halo rows inside a cluster go through distributed shared memory), as
@@ -271,7 +274,7 @@ int b2s_tc_wavenet_stack3_max_tiles(int T, int bf16);
 int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
                           const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum, const float* dvec,
                           int d_stride, const int* dilations_host, int L, void* yedge0_h, void* yedge1_h, void* z_all_h,
-                          int64_t z_layer_stride, int B, int T, int C, int* flags, int bf16, void* stream);
+                          int64_t z_layer_stride, int B, int T, int C, int* flags, const int* lens, int bf16, void* stream);
 
 /* b2s_tc_wavenet_stack3 plus, INSIDE the same launch, the deferred skip sum and the head (wavenet.py:96-99): behind the layer tiles
  * the grid carries one CTA pair per four tiles (on the SMs a 16 x 690-frame batch leaves idle) that accumulates
@@ -287,7 +290,7 @@ int b2s_tc_wavenet_denoiser3(const void* xin_h, int MF, const void* Win_h, int l
                              int d_stride, const int* dilations_host, int L, void* yedge0_h, void* yedge1_h, void* z_all_h,
                              int64_t z_layer_stride, const void* Wskip_h, const float* bss, const void* Wsp_h, const float* b_sp,
                              const void* Wfin_h, const float* b_fin, float* out, int B, int T, int C, int* flags, int* zflags,
-                             int bf16, void* stream);
+                             const int* lens, int bf16, void* stream);
 
 /* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
  * down-projection with the residual add into the fp32 stream. */

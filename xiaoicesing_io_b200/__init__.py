@@ -8,15 +8,18 @@ Public surface (same names and contracts as the reference's ``modules.backbones`
     GaussianDiffusion, RepetitiveDiffusion, PitchDiffusion, MultiVarianceDiffusion
     RectifiedFlow, RepetitiveRectifiedFlow, PitchRectifiedFlow, MultiVarianceRectifiedFlow
     hparams  (the global config dict, utils/hparams.py:13)
+    segments (batched .ds segment driver: ragged batches, per-segment seeds, .mel.pt writer), partition (multi-GPU), B2SError
 
 Importing the package loads ``libb2s.so`` (hand-written CUDA kernels behind the C ABI of
 ``include/b2s.h``); it raises ImportError if the library has not been built.  There is no CPU or
 PyTorch fallback anywhere in this package.
 """
 from . import _cabi  # noqa: F401  (fails loudly when libb2s.so is missing)
+from ._cabi import B2SError
 from .backbones import BACKBONES, LYNXNet, WaveNet, build_backbone, filter_kwargs
 from .core import (GaussianDiffusion, MultiVarianceDiffusion, MultiVarianceRectifiedFlow, PitchDiffusion,
                    PitchRectifiedFlow, RectifiedFlow, RepetitiveDiffusion, RepetitiveRectifiedFlow)
 from .hparams import hparams, set_hparams
+from . import partition, segments  # noqa: E402,F401
 
-__version__ = '0.1.0'
+__version__ = '0.2.0'

@@ -51,9 +51,9 @@ _SIGNATURES = {
     'b2s_tc_wavenet_denoiser_update': [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i,
                                        _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, ctypes.POINTER(_vp), _vp, _vp, _vp, _i, _vp],
     'b2s_tc_wavenet_stack3': [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _i64,
-                              _i, _i, _i, _vp, _i, _vp],
+                              _i, _i, _i, _vp, _vp, _i, _vp],
     'b2s_tc_wavenet_denoiser3': [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _i64,
-                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual_cond': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -306,24 +306,24 @@ def tc_wavenet_denoiser(xin_h, MF, Win_h, ld_win, b_in, y0_h, y1_h, Wd_h, cond_h
 
 
 def tc_wavenet_stack3(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations,
-                      yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, bf16):
+                      yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, bf16, lens=None):
     L = len(dilations)
     dil = (_i * L)(*dilations)
     check(lib.b2s_tc_wavenet_stack3(ptr(xin_h), MF, ptr(Win_h), ld_win, ptr(b_in), ptr(Wd_h), ptr(cond_h), cond_layer_stride,
                                     ptr(Wres_h), ptr(bsum), ptr(dvec), d_stride, dil, L, ptr(yedge0_h), ptr(yedge1_h),
-                                    ptr(z_all_h), z_layer_stride, B, T, C, ptr(flags), int(bf16), stream_ptr()),
+                                    ptr(z_all_h), z_layer_stride, B, T, C, ptr(flags), ptr(lens), int(bf16), stream_ptr()),
           'b2s_tc_wavenet_stack3')
 
 
 def tc_wavenet_denoiser3(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations,
                          yedge0_h, yedge1_h, z_all_h, z_layer_stride, Wskip_h, bss, Wsp_h, b_sp, Wfin_h, b_fin, out, B, T, C, flags,
-                         zflags, bf16):
+                         zflags, bf16, lens=None):
     L = len(dilations)
     dil = (_i * L)(*dilations)
     check(lib.b2s_tc_wavenet_denoiser3(ptr(xin_h), MF, ptr(Win_h), ld_win, ptr(b_in), ptr(Wd_h), ptr(cond_h), cond_layer_stride,
                                        ptr(Wres_h), ptr(bsum), ptr(dvec), d_stride, dil, L, ptr(yedge0_h), ptr(yedge1_h),
                                        ptr(z_all_h), z_layer_stride, ptr(Wskip_h), ptr(bss), ptr(Wsp_h), ptr(b_sp), ptr(Wfin_h),
-                                       ptr(b_fin), ptr(out), B, T, C, ptr(flags), ptr(zflags), int(bf16), stream_ptr()),
+                                       ptr(b_fin), ptr(out), B, T, C, ptr(flags), ptr(zflags), ptr(lens), int(bf16), stream_ptr()),
           'b2s_tc_wavenet_denoiser3')
 
 

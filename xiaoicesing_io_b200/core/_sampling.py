@@ -50,19 +50,29 @@ class SamplerBase(nn.Module):
     def build_program(self) -> Program:                      # pragma: no cover - abstract
         raise NotImplementedError
 
-    def _run(self, cond, b, start, device):
+    def _run(self, cond, b, start, device, lengths=None, initial_noise=None):
         return sample(getattr(self, self.backbone_attr), self.build_program(), cond, b, self.num_feats,
-                      self.out_dims, start, device, noise_source=self._noise_source)
+                      self.out_dims, start, device, noise_source=self._noise_source, lengths=lengths, noise0=initial_noise)
 
     def _training_forward(self, spec, cond, b, device):     # pragma: no cover - abstract
         raise NotImplementedError
 
-    def forward(self, condition, gt_spec=None, src_spec=None, infer=True):
-        """condition [B, T, H] -> de-normalised sample [B, T, M] / [B, F, T, M] (or curves)."""
+    def forward(self, condition, gt_spec=None, src_spec=None, infer=True, lengths=None, initial_noise=None):
+        """condition [B, T, H] -> de-normalised sample [B, T, M] / [B, F, T, M] (or curves).
+
+        Two extensions over the reference's signature (both default to its behaviour), used by the batched segment driver
+        (``xiaoicesing_io_b200.segments``): ``lengths`` [B] - the batch is RAGGED, utterance b has lengths[b] <= T valid frames and
+        every valid frame gets the bits it would get in a batch of its own (frames beyond are undefined); ``initial_noise``
+        [B, F, M, T] - the first noise draw (ddpm.py:227, reflow.py:105), e.g. drawn per segment from the segment's seed."""
         cond = condition.transpose(1, 2)                     # [B, H, T] view, as the reference hands it on
         b, device = condition.shape[0], condition.device
         if infer:
-            x = self.inference(cond, b, self._source_to_state(src_spec), device)
+            kw = {}
+            if lengths is not None:
+                kw['lengths'] = lengths
+            if initial_noise is not None:
+                kw['initial_noise'] = initial_noise
+            x = self.inference(cond, b, self._source_to_state(src_spec), device, **kw)
             return self.denorm_spec(x)
         return self._training_forward(self._source_to_state(gt_spec), cond, b, device)
 
@@ -73,21 +83,23 @@ class _GraphedLoop:
     replayed with a single launch.  Noise comes from ``torch.randn`` inside the graph (graph-safe Philox:
     a replay consumes the default generator exactly like the eager loop, so seeded runs stay reproducible)."""
 
-    def __init__(self, eng, cp: CompiledProgram, B, T, H, F_, M, device):
+    def __init__(self, eng, cp: CompiledProgram, B, T, H, F_, M, device, ragged=False, ext_noise=False):
         prog = cp.prog
         self.cp = cp                     # the coefficient / model-time tables are read by the captured kernels
         self.cond = torch.empty((B, T, H), device=device)
         self.x_start = torch.empty((B, F_ * M, T), device=device) if prog.needs_x_start else None
+        self.lens = torch.full((B,), T, device=device, dtype=torch.int32) if ragged else None      # static inputs of the graph
+        self.noise0 = torch.empty((B, F_ * M, T), device=device) if ext_noise else None
         shape = (B, F_ * M, T)
 
         def body():
-            sess = eng.begin(self.cond, cp.t_values, per_row_t=False)
+            sess = eng.begin(self.cond, cp.t_values, per_row_t=False, lens=self.lens)
             bufs = allocate_buffers(prog, B * T, F_ * M, device)
 
             def load(src, dst):
                 C.transpose(src, dst, B, F_ * M, T)
 
-            noise0 = torch.randn(shape, device=device)
+            noise0 = self.noise0 if ext_noise else torch.randn(shape, device=device)
             if NOISE0 in bufs:
                 load(noise0, bufs[NOISE0])
             if prog.needs_x_start:
@@ -101,9 +113,13 @@ class _GraphedLoop:
             self.out = body()
         self.n_launches = C.N_CALLS - n0        # kernels of libb2s.so in one replay (torch.randn nodes not counted)
 
-    def run(self, cond_bth, x_start_bfmt):
+    def run(self, cond_bth, x_start_bfmt, lens=None, noise0=None):
         # (the caller holds torch.cuda.device(device): replay goes to the device the graph was captured on)
         self.cond.copy_(cond_bth)
+        if self.lens is not None:
+            self.lens.copy_(lens)
+        if self.noise0 is not None:
+            self.noise0.copy_(noise0.reshape(self.noise0.shape))
         if self.x_start is not None:
             self.x_start.copy_(x_start_bfmt.reshape(self.x_start.shape))
         self.graph.replay()
@@ -135,7 +151,7 @@ def clear_graph_cache():
 
 def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: int, out_dims: int,
            x_start: Optional[torch.Tensor], device,
-           noise_source: Optional[Callable[[tuple], torch.Tensor]] = None) -> torch.Tensor:
+           noise_source: Optional[Callable[[tuple], torch.Tensor]] = None, lengths=None, noise0=None) -> torch.Tensor:
     """Runs ``prog`` with ``backbone`` as the denoiser.  Returns [B, T, M] or [B, F, T, M]
     (the transpose of ddpm.py:350 / reflow.py:137 is free: the state is time-major already).
 
@@ -158,11 +174,18 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
         raise C.B2SError(f'batch size mismatch: cond has {B} utterances, b={b}')
     F_, M = num_feats, out_dims
     shape = (B, F_, M, T)
+    lens = None
+    if lengths is not None:
+        lens = torch.as_tensor(lengths).reshape(-1).to(device=device, dtype=torch.int32)
+        if lens.numel() != B:
+            raise C.B2SError(f'lengths must have one entry per utterance (got {lens.numel()} for B={B})')
+    if noise0 is not None and tuple(noise0.shape) != shape:
+        raise C.B2SError(f'initial_noise must have shape {shape} (got {tuple(noise0.shape)})')
     with torch.cuda.device(device):         # every launch below (and the current stream) belongs to the tensors' device
-        return _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source)
+        return _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source, lens, noise0)
 
 
-def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source):
+def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source, lens=None, noise0_in=None):
     eng = backbone._engine()
     eng.pack()
     if prog.needs_x_start:
@@ -181,29 +204,32 @@ def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, 
     graph_key = None
     if noise_source is None and hparams.get('b2s_cuda_graph', True):
         structure = tuple(repr(hparams.get(k)) for k in _STRUCTURE_HPARAMS)
-        graph_key = (id(backbone), eng._packed_version, eng.precision, _program_key(prog), B, T, F_, M, str(device), structure)
+        graph_key = (id(backbone), eng._packed_version, eng.precision, _program_key(prog), B, T, F_, M, str(device), structure,
+                     lens is not None, noise0_in is not None)
         entry = _GRAPH_CACHE.get(graph_key)
         if entry is None and graph_key in _SEEN_KEYS:       # second call with this key: capture
             del _SEEN_KEYS[graph_key]
             while len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
                 _GRAPH_CACHE.popitem(last=False)            # least recently used graph
-            entry = _GraphedLoop(eng, CompiledProgram(prog, device), B, T, H, F_, M, device)
+            entry = _GraphedLoop(eng, CompiledProgram(prog, device), B, T, H, F_, M, device, ragged=lens is not None,
+                                 ext_noise=noise0_in is not None)
             _GRAPH_CACHE[graph_key] = entry
         if entry is not None:
             _GRAPH_CACHE.move_to_end(graph_key)
             xs = None if x_start is None else x_start.to(device=device, dtype=torch.float32)
-            return finish(entry.run(cond_bth, xs))
+            n0 = None if noise0_in is None else noise0_in.to(device=device, dtype=torch.float32)
+            return finish(entry.run(cond_bth, xs, lens, n0))
     if noise_source is None:
         noise_source = lambda s: torch.randn(s, device=device)
     cp = CompiledProgram(prog, device)
-    sess = eng.begin(cond_bth, cp.t_values, per_row_t=False)
+    sess = eng.begin(cond_bth, cp.t_values, per_row_t=False, lens=lens)
     bufs = allocate_buffers(prog, B * T, F_ * M, device)
 
     def load(src_bfmt, dst):
         C.transpose(src_bfmt.to(device=device, dtype=torch.float32).reshape(B, F_ * M, T).contiguous(), dst,
                     B, F_ * M, T)
 
-    noise0 = noise_source(shape)                        # always drawn first (ddpm.py:227, reflow.py:105)
+    noise0 = noise0_in if noise0_in is not None else noise_source(shape)      # always drawn first (ddpm.py:227, reflow.py:105)
     if NOISE0 in bufs:
         load(noise0, bufs[NOISE0])
     if prog.needs_x_start:

@@ -60,9 +60,9 @@ class GaussianDiffusion(SamplerBase):
             speedup=hparams['diff_speedup'], accelerator=hparams.get('diff_accelerator'))
 
     @torch.no_grad()
-    def inference(self, cond, b=1, x_start=None, device=None):
+    def inference(self, cond, b=1, x_start=None, device=None, lengths=None, initial_noise=None):
         """cond [B, H, T]; x_start normalised [B, F, M, T] or None  ->  [B, T, M] / [B, F, T, M]."""
-        return self._run(cond, b, x_start, device)
+        return self._run(cond, b, x_start, device, lengths, initial_noise)
 
     @torch.no_grad()
     def _training_forward(self, spec, cond, b, device):

@@ -40,9 +40,9 @@ class RectifiedFlow(SamplerBase):
                               self.time_scale_factor)
 
     @torch.no_grad()
-    def inference(self, cond, b=1, x_end=None, device=None):
+    def inference(self, cond, b=1, x_end=None, device=None, lengths=None, initial_noise=None):
         """cond [B, H, T]; x_end normalised [B, F, M, T] or None  ->  [B, T, M] / [B, F, T, M]."""
-        return self._run(cond, b, x_end, device)
+        return self._run(cond, b, x_end, device, lengths, initial_noise)
 
     @torch.no_grad()
     def _training_forward(self, spec, cond, b, device):

@@ -54,6 +54,7 @@ struct __align__(64) Stack3P {
     const float* bsum;                                    // [L][C]: sum_{k<m} 2^(k/2) b_res,k[c]
     const float* dvec; int d_stride;                      // step embedding of layer m at dvec + b*d_stride + m*C
     int* flags;                                           // [B * tiles_per_b], zero before the launch
+    const int* lens;                                      // optional [B]: valid frames of utterance b (<= T); rows beyond are the conv's zero padding
     unsigned long long* tlog;                             // optional phase timestamps (B2S_TLOG builds)
     int dbg;                                              // B2S_TLOG builds only: 1 = no weight loads, 2 = no gate epilogue math (timing experiments, wrong results)
     // ---- fused skip sum + head (wavenet.py:96-99) on the CTAs behind the layer tiles (fuse_head = 1): blocks [n_layer_ctas, grid)
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
         const uint32_t lr0 = mapa_u32(&hready[0], lead), lr1 = mapa_u32(&hready[1], lead);
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
-            const bool valid = ok[s] && tt0[s] + row < p.T;
+            const bool valid = ok[s] && tt0[s] + row < (p.lens ? __ldg(p.lens + tb[s]) : p.T);
             // 32 columns of the accumulator -> f(acc, bias) -> 16-bit -> the swizzled operand tile
             auto to_tile = [&](const float* bias, float alpha, bool relu) {
 #pragma unroll 1
@@ -796,7 +797,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
         const int e = warp - 4, qd = e & 3, sub = e >> 2;
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
         const int row = qd * 32 + lane;
-        const bool valid = t0 + row < p.T;
+        // rows at or beyond the utterance's length are the conv's zero padding: y and z are forced to 0 there (ragged batches: lens)
+        const bool valid = t0 + row < (p.lens ? __ldg(p.lens + b) : p.T);
         const int sw = row & 7;
         const uint32_t zrow = smem_u32(zs) + (row >> 3) * 1024 + sw * 128;
         const uint32_t yrow = smem_u32(ys) + ((row + HALO) >> 3) * 1024 + sw * 128;       // HALO % 8 == 0: same swizzle phase
@@ -1119,7 +1121,8 @@ struct Head3 {            // operands of the fused skip sum + head (all NULL / 0
 static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
                        const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum, const float* dvec,
                        int d_stride, const int* dilations_host, int L, void* yedge0_h, void* yedge1_h, void* z_all_h,
-                       int64_t z_layer_stride, int B, int T, int C, int* flags, int bf16, void* stream, const Head3* hd) {
+                       int64_t z_layer_stride, int B, int T, int C, int* flags, const int* lens, int bf16, void* stream,
+                       const Head3* hd) {
     B2S_CHECK_ARG(xin_h && Win_h && b_in && Wd_h && cond_h && Wres_h && bsum && dvec && dilations_host && yedge0_h && yedge1_h &&
                       z_all_h && flags, "b2s_tc_wavenet_stack3: null pointer");
     if (C != ws3::C) {
@@ -1162,6 +1165,7 @@ static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win,
     p.wd = Wd_h; p.wres = Wres_h;
     p.cond = cond_h; p.cond_lstride = cond_layer_stride; p.b_in = b_in; p.bsum = bsum; p.dvec = dvec; p.d_stride = d_stride;
     p.flags = flags;
+    p.lens = lens;
     p.tlog = g_tlog;
     p.dbg = getenv("B2S_STACK3_DBG") ? atoi(getenv("B2S_STACK3_DBG")) : 0;
     if (hd) {
@@ -1189,10 +1193,10 @@ static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win,
 extern "C" int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
                                      const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum,
                                      const float* dvec, int d_stride, const int* dilations_host, int L, void* yedge0_h,
-                                     void* yedge1_h, void* z_all_h, int64_t z_layer_stride, int B, int T, int C, int* flags, int bf16,
-                                     void* stream) {
+                                     void* yedge1_h, void* z_all_h, int64_t z_layer_stride, int B, int T, int C, int* flags,
+                                     const int* lens, int bf16, void* stream) {
     return stack3_impl(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations_host, L,
-                       yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, bf16, stream, nullptr);
+                       yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, lens, bf16, stream, nullptr);
 }
 
 /* utterances of T frames ONE b2s_tc_wavenet_denoiser3 launch can hold (layer tiles + the skip / head CTAs behind them); 0 = none */
@@ -1206,8 +1210,8 @@ extern "C" int b2s_tc_wavenet_denoiser3(const void* xin_h, int MF, const void* W
                                         const float* dvec, int d_stride, const int* dilations_host, int L, void* yedge0_h,
                                         void* yedge1_h, void* z_all_h, int64_t z_layer_stride, const void* Wskip_h, const float* bss,
                                         const void* Wsp_h, const float* b_sp, const void* Wfin_h, const float* b_fin, float* out, int B,
-                                        int T, int C, int* flags, int* zflags, int bf16, void* stream) {
+                                        int T, int C, int* flags, int* zflags, const int* lens, int bf16, void* stream) {
     Head3 hd{Wskip_h, bss, Wsp_h, b_sp, Wfin_h, b_fin, out, zflags};
     return stack3_impl(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations_host, L,
-                       yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, bf16, stream, &hd);
+                       yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, lens, bf16, stream, &hd);
 }

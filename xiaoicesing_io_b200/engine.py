@@ -155,12 +155,17 @@ class WaveNetEngine:
         C.linear(cond_bth, H, self.w_cond, H, self.b_cond, tab, N, B * T, N, H)
         return tab
 
-    def begin(self, cond_bth: torch.Tensor, t_values: torch.Tensor, per_row_t: bool = False) -> 'WaveNetSession':
+    def begin(self, cond_bth: torch.Tensor, t_values: torch.Tensor, per_row_t: bool = False, lens=None) -> 'WaveNetSession':
+        """``lens``: optional int32 device tensor [B] - a RAGGED batch padded to T; frames at or beyond lens[b] are treated as the
+        conv's zero padding (only the whole-stack tensor-core path implements this)."""
         self.pack()
         C.require_cuda(cond_bth, 'cond')
         C.require_cuda(t_values, 't_values')
         if self.precision != 'fp32':
-            return WaveNetSessionTC(self, cond_bth, t_values, per_row_t)
+            return WaveNetSessionTC(self, cond_bth, t_values, per_row_t, lens)
+        if lens is not None:
+            raise C.B2SError("ragged batches (lengths=...) need the 16-bit whole-stack path (b2s_precision 'fp16' / 'bf16', 256 channels, "
+                             "dilations <= 16); batch equal-length segments instead")
         return WaveNetSession(self, cond_bth, t_values, per_row_t)
 
 
@@ -231,9 +236,12 @@ class WaveNetSessionTC:
     bf16 / fp16 MMA operands (y, z, hoisted cond table, weights) and fp32 residual stream, skip sum,
     biases, step embeddings and sampler state."""
 
-    def __init__(self, eng: WaveNetEngine, cond_bth, t_values, per_row_t):
+    def __init__(self, eng: WaveNetEngine, cond_bth, t_values, per_row_t, lens=None):
         self.eng = eng
         B, T, H = cond_bth.shape
+        self.lens = lens
+        if lens is not None and (lens.dtype != torch.int32 or not lens.is_cuda or lens.numel() != B):
+            raise C.B2SError('lens must be an int32 CUDA tensor with one entry per utterance')
         if H != eng.H:
             raise C.B2SError(f'condition has {H} channels, backbone expects hidden_size={eng.H}')
         if per_row_t and t_values.numel() != B:
@@ -274,6 +282,9 @@ class WaveNetSessionTC:
         # as every layer tile is resident: it runs on the SMs the layer tiles leave idle and follows them through the z-tile flags
         self.head3 = bool(self.stack3 and hparams.get('b2s_stack3_head', True) and eng.MF % 16 == 0
                           and C.lib.b2s_tc_wavenet_denoiser3_max_utterances(T, int(bf)) >= self.stack_group)
+        if lens is not None and not self.stack3:
+            raise C.B2SError('ragged batches (lengths=...) need the whole-stack kernel (256 channels, dilations <= 16, b2s_stack3 on); '
+                             'batch equal-length segments instead')
         self.flags = torch.zeros((2 * B * tpb,), device=dev, dtype=torch.int32) if self.stack_group else None     # tile flags | z flags
         self.tpb = tpb
         self.tgroups = self._plan_transposed(cond_h) if (self.stack_group and hparams.get('b2s_stack_t', False)) else None
@@ -405,12 +416,13 @@ class WaveNetSessionTC:
                                            e.w_res3_h, e.bsum3, dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
                                            e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, e.w_skip3_h,
                                            e.b_skip_sum, e.w_sp_h, e.b_sp, e.w_fin_h, e.b_fin, out[r0:], b1 - b0, T, Cc,
-                                           self.flags[b0 * self.tpb:], self.flags[nfl + b0 * self.tpb:], bf)
+                                           self.flags[b0 * self.tpb:], self.flags[nfl + b0 * self.tpb:], bf,
+                                           lens=None if self.lens is None else self.lens[b0:])
                     continue
                 C.tc_wavenet_stack3(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
                                     e.w_res3_h, e.bsum3, dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
                                     e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, b1 - b0, T, Cc,
-                                    self.flags[b0 * self.tpb:], bf)
+                                    self.flags[b0 * self.tpb:], bf, lens=None if self.lens is None else self.lens[b0:])
             if self.head3:
                 return
             C.tc_skip_sum(self.z_all, e.w_skipcat_h, e.b_skip_sum, self.skip_h, rows, Cc, L, bf)
@@ -663,7 +675,9 @@ class LYNXNetEngine:
         C.linear(cond_bth, H, self.w_cond, H, self.b_cond, tab, N, B * T, N, H)
         return tab
 
-    def begin(self, cond_bth, t_values, per_row_t=False):
+    def begin(self, cond_bth, t_values, per_row_t=False, lens=None):
+        if lens is not None:
+            raise C.B2SError('ragged batches (lengths=...) are implemented for the WaveNet whole-stack path only; batch equal-length segments')
         self.pack()
         C.require_cuda(cond_bth, 'cond')
         C.require_cuda(t_values, 't_values')

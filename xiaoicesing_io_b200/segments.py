@@ -1,0 +1,179 @@
+"""Batched segment driver: what feeds the fast sampling path in real use.
+
+The reference synthesises a ``.ds`` project ONE SEGMENT AT A TIME (inference/ds_acoustic.py:189-246: B = 1 per segment, reseeded
+per segment at :212-217, results collected as ``{'offset', 'mel', 'f0'}`` and saved with ``torch.save`` as ``<title>.mel.pt``
+at :220-225, :243).  One 8-second segment occupies 6 of the 148 SMs; this module
+
+  1. reads the ``.ds`` JSON (scripts/infer.py:129-133: a list of segment dicts, or one dict) and derives every segment's frame
+     count exactly as ``preprocess_input`` does (ds_acoustic.py:79-83: ``round(cumsum(ph_dur) / timestep + 0.5)``);
+  2. buckets the segments by length into RAGGED batches - padded to a multiple of 128 frames (one tile of the whole-stack kernel,
+     so captured CUDA graphs are re-used across calls) under a frame budget;
+  3. runs each batch through the sampler with ``lengths=`` (frames beyond a segment's length are the conv's zero padding, exactly
+     as in a batch of its own) and ``initial_noise=`` drawn PER SEGMENT from the segment's seed with the reference's own reseeding
+     rule - so every segment receives the bits of its own B = 1 run (deterministic samplers: DDIM / PNDM / DPM-Solver++ / UniPC /
+     rectified flow; the ancestral sampler draws fresh noise per step from the global stream);
+  4. on several GPUs partitions the segments by length (``partition_by_length``), every rank sampling its share with no collective,
+     and gathers the results once;
+  5. writes the reference's ``.mel.pt`` layout.
+
+The linguistic encoder that turns a segment into ``condition [T, H]`` (modules/fastspeech) is outside the
+hot path: the caller passes ``cond_fn(segment, frames) -> (condition [T, H], src_spec [T, M] or None, f0 [T] or None)``.
+"""
+from __future__ import annotations
+
+import json
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .partition import partition_by_length
+
+TILE = 128     # frames per tile of the whole-stack kernel: ragged batches are padded to a multiple of it
+
+
+def load_ds(path) -> List[dict]:
+    """A ``.ds`` file: a JSON list of segment dicts or a single dict (scripts/infer.py:129-133)."""
+    with open(path, 'r', encoding='utf-8') as f:
+        params = json.load(f)
+    if not isinstance(params, list):
+        params = [params]
+    if not params:
+        raise ValueError(f'{path}: the project has no segments')
+    return params
+
+
+def segment_frames(param: dict, timestep: float) -> int:
+    """Frames of one segment, as ``preprocess_input`` derives them (ds_acoustic.py:79-83): the last entry of
+    ``round(cumsum(ph_dur) / timestep + 0.5)``, computed in fp32 like the reference."""
+    ph_dur = torch.tensor([float(v) for v in str(param['ph_dur']).split()], dtype=torch.float32)
+    if ph_dur.numel() == 0:
+        return 0
+    ph_acc = torch.round(torch.cumsum(ph_dur, dim=0) / timestep + 0.5).long()
+    return int(ph_acc[-1])
+
+
+def segment_seed(param: dict, seed: int = -1) -> Optional[int]:
+    """The seed the reference would set before this segment (ds_acoustic.py:212-217), or None (no reseeding)."""
+    if 'seed' in param:
+        return int(param['seed']) & 0xffff_ffff
+    if seed >= 0:
+        return seed & 0xffff_ffff
+    return None
+
+
+def plan_batches(lengths: Sequence[int], max_batch_frames: int = 16 * 704, max_batch_size: int = 64,
+                 tile: int = TILE) -> List[List[int]]:
+    """Groups segment indices into ragged batches: longest first, a batch is padded to ``ceil(longest / tile) * tile`` frames and
+    grows while ``size * padded_T <= max_batch_frames`` and ``size <= max_batch_size``.  Zero-length segments are dropped.
+    Deterministic; every non-empty segment appears in exactly one batch."""
+    order = sorted((i for i in range(len(lengths)) if int(lengths[i]) > 0), key=lambda i: (-int(lengths[i]), i))
+    batches: List[List[int]] = []
+    cur: List[int] = []
+    cur_T = 0
+    for i in order:
+        if not cur:
+            cur, cur_T = [i], -(-int(lengths[i]) // tile) * tile
+            continue
+        if len(cur) < max_batch_size and (len(cur) + 1) * cur_T <= max_batch_frames:
+            cur.append(i)
+        else:
+            batches.append(cur)
+            cur, cur_T = [i], -(-int(lengths[i]) // tile) * tile
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+def seeded_noise(shape: Tuple[int, ...], seed: Optional[int], device) -> torch.Tensor:
+    """The first noise draw of a B = 1 run of the reference on ``device`` after its per-segment reseeding:
+    ``torch.manual_seed(seed); torch.cuda.manual_seed_all(seed); randn(1, F, M, T, device=device)`` (ds_acoustic.py:212-217,
+    ddpm.py:227).  ``seed`` None: drawn from the current global stream."""
+    if seed is not None:
+        torch.manual_seed(seed)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed_all(seed)
+    return torch.randn(shape, device=device)
+
+
+CondFn = Callable[[dict, int], Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]]
+
+
+@torch.no_grad()
+def sample_segments(model, params: Sequence[dict], cond_fn: CondFn, timestep: float, device, seed: int = -1,
+                    max_batch_frames: int = 16 * 704, max_batch_size: int = 64, indices: Optional[Sequence[int]] = None
+                    ) -> Dict[int, dict]:
+    """Runs the acoustic sampler over the segments ``indices`` (default: all) in ragged batches.  Returns
+    ``{segment index: {'offset', 'mel' [1, T, M] (CPU), 'f0' [1, T] or None}}`` - the entries the reference appends to its
+    ``.mel.pt`` list (ds_acoustic.py:220-225)."""
+    device = torch.device(device)
+    idx = list(range(len(params))) if indices is None else list(indices)
+    frames = {i: segment_frames(params[i], timestep) for i in idx}
+    out: Dict[int, dict] = {}
+    F_, M = model.num_feats, model.out_dims
+    for batch in plan_batches([frames[i] for i in idx], max_batch_frames, max_batch_size):
+        seg = [idx[j] for j in batch]
+        lens = [frames[i] for i in seg]
+        T = -(-max(lens) // TILE) * TILE
+        conds, srcs, f0s = [], [], []
+        for i in seg:
+            c, s, f0 = cond_fn(params[i], frames[i])
+            if c.shape[0] != frames[i]:
+                raise ValueError(f'segment {i}: cond_fn returned {c.shape[0]} frames, the segment has {frames[i]}')
+            conds.append(c)
+            srcs.append(s)
+            f0s.append(f0)
+        H = conds[0].shape[1]
+        condition = torch.zeros((len(seg), T, H), device=device)
+        noise = torch.zeros((len(seg), F_, M, T), device=device)
+        src = None
+        if any(s is not None for s in srcs):
+            src = torch.zeros((len(seg), T, M), device=device)
+        for k, i in enumerate(seg):
+            condition[k, :lens[k]] = conds[k].to(device)
+            noise[k, ..., :lens[k]] = seeded_noise((1, F_, M, lens[k]), segment_seed(params[i], seed), device)[0]
+            if src is not None and srcs[k] is not None:
+                src[k, :lens[k]] = srcs[k].to(device)
+        mel = model(condition, src_spec=src, infer=True, lengths=torch.tensor(lens, dtype=torch.int32), initial_noise=noise)
+        for k, i in enumerate(seg):
+            out[i] = {'offset': float(params[i].get('offset', 0.)), 'mel': mel[k:k + 1, :lens[k]].float().cpu(),
+                      'f0': None if f0s[k] is None else f0s[k].reshape(1, -1).float().cpu()}
+    for i in idx:
+        if i not in out:                                        # zero-length segment
+            out[i] = {'offset': float(params[i].get('offset', 0.)), 'mel': torch.zeros((1, 0, M)), 'f0': torch.zeros((1, 0))}
+    return out
+
+
+@torch.no_grad()
+def sample_segments_distributed(model, params: Sequence[dict], cond_fn: CondFn, timestep: float, device, seed: int = -1,
+                                group=None, dst: int = 0, **kw) -> Optional[List[dict]]:
+    """``sample_segments`` over the ranks of ``torch.distributed``: segments are partitioned by length (no collective inside the
+    loop), the finished entries are gathered ONCE on rank ``dst`` (``gather_object``: variable-length results, off the hot loop)
+    and returned there in segment order; None elsewhere.  Single process: the same list."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        res = sample_segments(model, params, cond_fn, timestep, device, seed, **kw)
+        return [res[i] for i in range(len(params))]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = partition_by_length([segment_frames(p, timestep) for p in params], world)
+    mine = sample_segments(model, params, cond_fn, timestep, device, seed, indices=parts[rank], **kw)
+    gathered = [None] * world if rank == dst else None
+    dist.gather_object(mine, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    merged: Dict[int, dict] = {}
+    for g in gathered:
+        merged.update(g)
+    return [merged[i] for i in range(len(params))]
+
+
+def save_mel_pt(path, entries: Sequence[dict]) -> None:
+    """The reference's ``.mel.pt`` layout (ds_acoustic.py:220-225, :243): ``torch.save`` of the list of
+    ``{'offset': float, 'mel': [1, T, M], 'f0': [1, T]}`` in segment order (read back by scripts/vocode.py)."""
+    torch.save([{'offset': e['offset'], 'mel': e['mel'], 'f0': e['f0']} for e in entries], path)
+
+
+def real_time_factor(entries: Sequence[dict], seconds: float, timestep: float) -> float:
+    """Wall seconds per second of synthesised audio."""
+    audio = sum(e['mel'].shape[1] for e in entries) * timestep
+    return math.inf if audio == 0 else seconds / audio
