@@ -200,13 +200,17 @@ int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const void* cond_h, 
  *   y0_h      layer 0's input y = x + d_0 (written by the stem); y1_h the ping-pong partner
  *   Wd_h [L,2C,3C], Wo_h [L,2C,C], bo [L,2C]; cond_h: the table of b2s_tc_cond_table_tiled for THIS call's B and T,
  *   cond_layer_stride = B*tpb*128*2C elements (ld_cond is ignored)
- *   dvec: this evaluation's step-embedding row, layer l at dvec + b*d_stride + l*C;  dilations_host: L ints (HOST) */
+ *   dvec: this evaluation's step-embedding row, layer l at dvec + b*d_stride + l*C;  dilations_host: L ints (HOST)
+ * b2s_tc_wavenet_stack_max_tiles(): CTAs of this kernel the CURRENT device can hold at once = 2 x cudaOccupancyMaxActiveClusters for
+ * its launch configuration (MPS / MIG / green-context limits included), not the SM count. */
 int b2s_tc_wavenet_stack_max_tiles(void);
+int b2s_has_experiments(void);   /* 1: built with B2S_BUILD_EXPERIMENTS=1 */
 int b2s_tc_wavenet_stack(void* y0_h, void* y1_h, const void* Wd_h, const void* cond_h, int ld_cond,
                          int64_t cond_layer_stride, const void* Wo_h, const float* bo, float* x, float* skip, void* skip_h,
                          const float* dvec, int d_stride, const int* dilations_host, int L, int B, int T, int C, int* flags,
                          int bf16, void* stream);
 
+#ifdef B2S_EXPERIMENTS   /* measured-and-rejected variants; exported only by B2S_BUILD_EXPERIMENTS=1 builds */
 /* The residual stack with the GEMMs TRANSPOSED (channels on the tensor-core M axis, frames on N), C = 256: the frame tile
  * NT is 32, 48, 64 or 80 instead of 128, so a small batch still fills the SMs (16 x 690 frames = 144 tiles of 80); the fp32
  * residual stream lives in registers and the skip sum in TMEM for all L layers (wavenet.py:33-48, 92-96).
@@ -223,6 +227,8 @@ int b2s_tc_wavenet_stack_t(void* y0_h, void* y1_h, const void* Wd_h, const void*
                            const float* x, void* skip_h, const float* dvec, int d_stride, const int* dilations_host, int L,
                            int B, int T, int C, int NT, int* flags, int bf16, void* stream);
 
+#endif /* B2S_EXPERIMENTS */
+
 /* ONE launch per denoiser evaluation (wavenet.py:75-107 without the step-embedding MLP, which is hoisted into the step
  * table): b2s_tc_wavenet_stack plus, inside the same persistent kernel, the stem x = relu(W_in x_in + b_in), y_0 = x + d_0
  * (wavenet.py:86-88, :36) before the first layer and the head out = W_fin relu(W_sp skip/sqrt(L) + b_sp) + b_fin
@@ -235,6 +241,7 @@ int b2s_tc_wavenet_denoiser(const void* xin_h, int MF, const void* Win_h, int ld
                             const void* Wsp_h, const float* b_sp, const void* Wfin_h, const float* b_fin, float* out, int B, int T,
                             int C, int* flags, int bf16, void* stream);
 
+#ifdef B2S_EXPERIMENTS
 /* b2s_tc_wavenet_denoiser + the sampler update that consumes its output, in the same launch (ancestral / DDIM-type steps,
  * ddpm.py:149-167): x' = sum_i coef[i] * src_i for n_terms <= 3 terms in the order given, where srcs_host[i] == NULL stands
  * for THIS evaluation's output (eps_hat) and the other sources are fp32 [B*T, MF] buffers (the state x, the step's noise);
@@ -250,6 +257,8 @@ int b2s_tc_wavenet_denoiser_update(const void* xin_h, int MF, const void* Win_h,
                                    const float* b_fin, int B, int T, int C, int* flags, int* flags_next, int n_terms,
                                    const float* const* srcs_host, const float* coef, float* x_out, void* x_out_h, int bf16,
                                    void* stream);
+
+#endif /* B2S_EXPERIMENTS */
 
 /* Third design of the whole-stack kernel (round 2; csrc/b2s_tc_wavenet3.cu), C = 256, dilations <= b2s_tc_wavenet_stack3_halo():
  * stem + all L residual layers in ONE persistent launch of cta_group::2 pairs (two neighbouring 128-frame tiles form one 256-row

@@ -9,9 +9,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
+def _declared(experiments=False):
     text = open(os.path.join(ROOT, 'include', 'b2s.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    if not experiments:                      # declarations of B2S_BUILD_EXPERIMENTS=1 builds only
+        text = re.sub(r'#ifdef B2S_EXPERIMENTS.*?#endif', '', text, flags=re.S)
     return sorted(set(re.findall(r'\b(b2s_[a-z0-9_]+)\s*\(', text)))
 
 
@@ -24,12 +26,14 @@ def lib():
 
 
 def test_every_declared_symbol_is_exported(lib):
-    names = _declared()
+    names = _declared(experiments=lib.HAS_EXPERIMENTS)
     assert len(names) >= 10
     raw = ctypes.CDLL(lib.LIB_PATH)
     for n in names:
         assert hasattr(raw, n), f'{n} declared in include/b2s.h but not exported by libb2s.so'
-    assert set(names) == set(lib.EXPORTED_SYMBOLS), 'ctypes table and header disagree'
+    table = set(lib.EXPORTED_SYMBOLS) | (set(lib.EXPERIMENTAL) if lib.HAS_EXPERIMENTS else set())
+    assert set(names) == table, ('ctypes table and header disagree', set(names) ^ table)
+    assert set(_declared(True)) - set(_declared(False)) == set(lib.EXPERIMENTAL)
 
 
 def test_abi_version(lib):

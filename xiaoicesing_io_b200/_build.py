@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, os.environ.get('B2S_LIB_OUT', 'libb2s.so'))      # B2S_LIB_OUT: side builds (profiling variants)
-OBJ_DIR = os.path.join(HERE, 'csrc', '_obj' + ('_tlog' if os.environ.get('B2S_BUILD_TLOG') else ''))
+OBJ_DIR = os.path.join(HERE, 'csrc', '_obj' + ('_tlog' if os.environ.get('B2S_BUILD_TLOG') else '') + ('_exp' if os.environ.get('B2S_BUILD_EXPERIMENTS') else ''))
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
@@ -24,6 +24,8 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get('B2S_BUILD_EXPERIMENTS'):   # measured-and-rejected kernel variants: transposed stack kernel, single-CTA
+    NVCC_FLAGS.append('-DB2S_EXPERIMENTS')    # fused layer / GEMM, cta_group::2 variant of the round-1 stack kernel, update inside the denoiser launch
 if os.environ.get('B2S_BUILD_TLOG'):          # profiling build: in-kernel phase timestamps (scripts/stack_timeline.py)
     NVCC_FLAGS.append('-DB2S_TLOG')
 

@@ -62,7 +62,10 @@ _SIGNATURES = {
     'b2s_lynx_dwconv_h': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
 }
 
-EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', 'b2s_tc_wavenet_stack_max_tiles', 'b2s_tc_wavenet_stack3_halo', 'b2s_tc_wavenet_stack3_max_tiles', 'b2s_tc_wavenet_denoiser3_max_utterances', *_SIGNATURES]
+# entry points of B2S_BUILD_EXPERIMENTS=1 builds only (measured-and-rejected variants)
+EXPERIMENTAL = ('b2s_tc_wavenet_stack_t_tiles', 'b2s_tc_cond_retile', 'b2s_tc_wavenet_stack_t', 'b2s_tc_wavenet_denoiser_update')
+
+EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', 'b2s_has_experiments', 'b2s_tc_wavenet_stack_max_tiles', 'b2s_tc_wavenet_stack3_halo', 'b2s_tc_wavenet_stack3_max_tiles', 'b2s_tc_wavenet_denoiser3_max_utterances', *[n for n in _SIGNATURES if n not in EXPERIMENTAL]]
 
 ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU, ACT_SILU = 0, 1, 2, 3, 4
 
@@ -91,7 +94,11 @@ def _load():
     lib.b2s_tc_wavenet_stack3_max_tiles.argtypes = [c_int, c_int]
     lib.b2s_tc_wavenet_denoiser3_max_utterances.restype = c_int
     lib.b2s_tc_wavenet_denoiser3_max_utterances.argtypes = [c_int, c_int]
+    lib.b2s_has_experiments.restype = c_int
+    lib.b2s_has_experiments.argtypes = []
     for name, args in _SIGNATURES.items():
+        if name in EXPERIMENTAL and not lib.b2s_has_experiments():
+            continue
         fn = getattr(lib, name)
         fn.restype = c_int
         fn.argtypes = args
@@ -100,6 +107,13 @@ def _load():
 
 lib = _load()
 LIB_PATH = _build.LIB_PATH
+HAS_EXPERIMENTS = bool(lib.b2s_has_experiments())
+
+
+def require_experiments(what: str):
+    if not HAS_EXPERIMENTS:
+        raise B2SError(f'{what} is a measured-and-rejected experiment (DESIGN.md section 3.3): rebuild libb2s.so with '
+                       f'B2S_BUILD_EXPERIMENTS=1 to use it')
 
 
 N_CALLS = 0     # successful kernel-launching C-ABI calls so far (every entry point launches exactly one kernel)
@@ -259,6 +273,7 @@ def tc_wavenet_denoiser_update(xin_h, MF, Win_h, ld_win, b_in, y0_h, y1_h, Wd_h,
                                d_stride, dilations, Wsp_h, b_sp, Wfin_h, b_fin, B, T, C, flags, flags_next, srcs, coef, x_out,
                                x_out_h, bf16):
     """srcs: fp32 tensors or None (None = this evaluation's output), in term order; coef: device fp32 view of len(srcs)."""
+    require_experiments('b2s_tc_wavenet_denoiser_update')
     L = len(dilations)
     dil = (_i * L)(*dilations)
     arr = (_vp * len(srcs))(*[None if t is None else t.data_ptr() for t in srcs])
@@ -284,10 +299,12 @@ def tc_skip_sum(z_all_h, Wcat_h, bias, out_h, rows, C, L, bf16):
 
 
 def tc_cond_retile(table_h, L, B, T, n2, NT, out_h):
+    require_experiments('b2s_tc_cond_retile')
     check(lib.b2s_tc_cond_retile(ptr(table_h), L, B, T, n2, NT, ptr(out_h), stream_ptr()), 'b2s_tc_cond_retile')
 
 
 def tc_wavenet_stack_t(y0_h, y1_h, Wd_h, cond_t, Wo_h, bo, x, skip_h, dvec, d_stride, dilations, B, T, C, NT, flags, bf16):
+    require_experiments('b2s_tc_wavenet_stack_t')
     L = len(dilations)
     dil = (_i * L)(*dilations)
     check(lib.b2s_tc_wavenet_stack_t(ptr(y0_h), ptr(y1_h), ptr(Wd_h), ptr(cond_t), ptr(Wo_h), ptr(bo), ptr(x), ptr(skip_h),

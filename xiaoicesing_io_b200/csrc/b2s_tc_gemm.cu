@@ -208,6 +208,7 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
     }
 }
 
+#ifdef B2S_EXPERIMENTS     // the single-CTA kernel (B2S_GEMM_CG1=1): superseded by the cta_group::2 kernel below
 // ---- the kernel ------------------------------------------------------------------------------------
 template <int EPI, int BF16>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ TcP p) {
@@ -393,6 +394,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
+
+#endif  // B2S_EXPERIMENTS
 
 // ---- the same kernel with cta_group::2 MMAs (the default) ----------------------------------------------------
 // Two CTAs of a cluster take two neighbouring M tiles of the same N tile and form ONE 256-row MMA: each CTA keeps its own
@@ -618,10 +621,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
 // ---- host side (tensor-map builders live in b2s_tc.cuh) ------------------------------------------------
 template <int EPI, int BF16>
 static int launch_one(const TcP& p, cudaStream_t st) {
+#ifdef B2S_EXPERIMENTS
     static PerDevice configured;
     if (configured.first()) {
         B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     }
+#endif
     if (p.cg2) {
         static PerDevice configured2;
         if (configured2.first()) {
@@ -646,6 +651,10 @@ static int launch_one(const TcP& p, cudaStream_t st) {
         B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg2, tc_gemm_cg2_kernel<EPI, BF16>, p));
         return B2S_OK;
     }
+#ifndef B2S_EXPERIMENTS
+    set_error("the single-CTA GEMM kernel is an experiment: build with B2S_BUILD_EXPERIMENTS=1");
+    return B2S_ERR_UNSUPPORTED;
+#else
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -659,6 +668,7 @@ static int launch_one(const TcP& p, cudaStream_t st) {
     cfg.numAttrs = 1;
     B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BF16>, p));
     return B2S_OK;
+#endif
 }
 template <int EPI>
 static int launch(const TcP& p, int bf16, cudaStream_t st) {
@@ -672,7 +682,11 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     const int Bm = per_utt ? B : 1, Tm = per_utt ? T : B * T;
     int rc = make_map_act(&p.mapA, A, bf16, a_cols, lda, Tm, Bm, BLOCK_K, BLOCK_M);
     if (rc) return rc;
+#ifdef B2S_EXPERIMENTS
     static const bool cg1 = getenv("B2S_GEMM_CG1") != nullptr;      // A/B switch: the single-CTA kernel
+#else
+    const bool cg1 = false;
+#endif
     p.cg2 = cg1 ? 0 : 1;
     p.bn = (p.cg2 && N % 192 == 0 && N % 256 != 0) ? 192 : BLOCK_N;      // no half-empty second tile for the C = 192 models
     rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, p.cg2 ? p.bn / 2 : BLOCK_N);

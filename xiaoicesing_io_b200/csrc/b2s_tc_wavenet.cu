@@ -69,6 +69,7 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+#ifdef B2S_EXPERIMENTS     // version 1 (single CTA per tile): superseded by the 2-CTA cluster version below
 template <int BF16>
 __global__ void __launch_bounds__(NTHREADS, 1) wavenet_layer_kernel(const __grid_constant__ LayerP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -333,6 +334,8 @@ static int launch_layer(const LayerP& p, int grid, cudaStream_t st) {
     B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_layer_kernel<BF16>, p));
     return B2S_OK;
 }
+
+#endif  // B2S_EXPERIMENTS
 
 }  // namespace wl
 
@@ -1386,6 +1389,7 @@ static int launch_stack(const StackP& p, int grid, cudaStream_t st) {
 
 }  // namespace ws
 
+#ifdef B2S_EXPERIMENTS
 // =====================================================================================================================
 // Version 4: the whole-stack kernel with cta_group::2 MMAs.  The two CTAs of a cluster (neighbouring time tiles) form ONE
 // 256-row MMA: each keeps its own A tile and HALF of every weight tile in shared memory (32 KB per K slab instead of
@@ -1763,6 +1767,7 @@ static int launch_stack_cg2(const StackP& p, int grid, cudaStream_t st) {
 }
 
 }  // namespace ws2
+#endif  // B2S_EXPERIMENTS
 }  // namespace tc
 }  // namespace b2s
 
@@ -1785,8 +1790,12 @@ extern "C" int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const voi
                       al16(x) && al16(skip) && (!y_next_h || al16(y_next_h)) && (!skip_h || al16(skip_h)),
                   "b2s_tc_wavenet_layer: bad dilation / alignment");
     if (B * T == 0) return B2S_OK;
-    // variant 2 (2-CTA cluster, multicast weights) unless B2S_LAYER_V1 is set in the environment (A/B comparison)
+    // variant 2 (2-CTA cluster, multicast weights); experiment builds: variant 1 when B2S_LAYER_V1 is set (A/B comparison)
+#ifdef B2S_EXPERIMENTS
     static const bool v1 = getenv("B2S_LAYER_V1") != nullptr;
+#else
+    const bool v1 = false;
+#endif
     wl::LayerP p{};
     int rc = make_map_act(&p.mapY, y_h, bf16, C, C, T, B, wl::BK, wl::BM);
     if (rc) return rc;
@@ -1799,13 +1808,24 @@ extern "C" int b2s_tc_wavenet_layer(const void* y_h, const void* Wd_h, const voi
     p.cond = cond_h; p.ldc = ld_cond; p.bo = bo; p.x = x; p.y_next = y_next_h; p.skip = skip; p.skip_h = skip_h;
     p.dvec = dvec_next; p.d_stride = d_stride; p.first = first_layer;
     const int grid = B * p.tiles_per_b;
-    if (!v1) return bf16 ? wl2::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl2::launch_layer<0>(p, grid, (cudaStream_t)stream);
-    return bf16 ? wl::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl::launch_layer<0>(p, grid, (cudaStream_t)stream);
+#ifdef B2S_EXPERIMENTS
+    if (v1) return bf16 ? wl::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl::launch_layer<0>(p, grid, (cudaStream_t)stream);
+#endif
+    return bf16 ? wl2::launch_layer<1>(p, grid, (cudaStream_t)stream) : wl2::launch_layer<0>(p, grid, (cudaStream_t)stream);
 }
 
 unsigned long long* g_tlog = nullptr;      // shared with b2s_tc_wavenet_t.cu
 /* profiling hook (not part of the product API): device buffer [L][16] of globaltimer ns, or NULL to switch off */
 extern "C" void b2s_debug_set_stack_tlog(void* buf) { g_tlog = (unsigned long long*)buf; }
+
+/* 1 when the library was built with B2S_BUILD_EXPERIMENTS=1 (the measured-and-rejected variants of DESIGN.md section 3.3) */
+extern "C" int b2s_has_experiments(void) {
+#ifdef B2S_EXPERIMENTS
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 extern "C" int b2s_tc_wavenet_stack_max_tiles(void) {
     const int a = ws::stack_capacity<1>(), b = ws::stack_capacity<0>();      // cudaOccupancyMaxActiveClusters x 2, per device
@@ -1846,7 +1866,6 @@ static int stack_impl(void* y0_h, void* y1_h, const void* Wd_h, const void* cond
     if (rc) return rc;
     rc = make_map_act(&p.mapY[1], y1_h, bf16, C, C, T, B, ws::BK, ws::BM);
     if (rc) return rc;
-    static const bool cg2 = getenv("B2S_STACK_CG2") != nullptr && atoi(getenv("B2S_STACK_CG2")) != 0;
     rc = make_map_w3(&p.mapWd, Wd_h, bf16, 3 * C, 2 * C, L, ws::BK, ws::BN / 2);
     if (rc) return rc;
     rc = make_map_w3(&p.mapWo, Wo_h, bf16, C, 2 * C, L, ws::BK, ws::BN / 2);
@@ -1890,7 +1909,10 @@ static int stack_impl(void* y0_h, void* y1_h, const void* Wd_h, const void* cond
     static const int dbg = getenv("B2S_STACK_DBG") ? atoi(getenv("B2S_STACK_DBG")) : 0;
     p.dbg = dbg;
     p.tlog = g_tlog;
+#ifdef B2S_EXPERIMENTS
+    static const bool cg2 = getenv("B2S_STACK_CG2") != nullptr && atoi(getenv("B2S_STACK_CG2")) != 0;
     if (cg2 && !io) return bf16 ? ws2::launch_stack_cg2<1>(p, grid, (cudaStream_t)stream) : ws2::launch_stack_cg2<0>(p, grid, (cudaStream_t)stream);
+#endif
     return bf16 ? ws::launch_stack<1>(p, grid, (cudaStream_t)stream) : ws::launch_stack<0>(p, grid, (cudaStream_t)stream);
 }
 
@@ -1912,6 +1934,7 @@ extern "C" int b2s_tc_wavenet_denoiser(const void* xin_h, int MF, const void* Wi
                       L, B, T, C, flags, bf16, stream, &io);
 }
 
+#ifdef B2S_EXPERIMENTS
 extern "C" int b2s_tc_wavenet_denoiser_update(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, void* y0_h,
                                               void* y1_h, const void* Wd_h, const void* cond_h, int64_t cond_layer_stride,
                                               const void* Wo_h, const float* bo, float* x, float* skip, const float* dvec, int d_stride,
@@ -1926,3 +1949,4 @@ extern "C" int b2s_tc_wavenet_denoiser_update(const void* xin_h, int MF, const v
     return stack_impl(y0_h, y1_h, Wd_h, cond_h, 2 * C, cond_layer_stride, Wo_h, bo, x, skip, nullptr, dvec, d_stride, dilations_host,
                       L, B, T, C, flags, bf16, stream, &io);
 }
+#endif  // B2S_EXPERIMENTS

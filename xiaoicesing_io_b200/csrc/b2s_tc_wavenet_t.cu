@@ -20,6 +20,9 @@
 #include <stdlib.h>
 
 #include "b2s_common.cuh"
+// EXPERIMENT (measured slower than the 128-row kernels, DESIGN.md section 3.3 'instruction floor'): compiled only with
+// B2S_BUILD_EXPERIMENTS=1 (-DB2S_EXPERIMENTS).
+#ifdef B2S_EXPERIMENTS
 #include "b2s_tc.cuh"
 
 namespace b2s {
@@ -536,3 +539,5 @@ extern "C" int b2s_tc_wavenet_stack_t(void* y0_h, void* y1_h, const void* Wd_h, 
 #undef B2S_LAUNCH_T
     return B2S_ERR_UNSUPPORTED;
 }
+
+#endif  // B2S_EXPERIMENTS

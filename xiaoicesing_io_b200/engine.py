@@ -287,6 +287,8 @@ class WaveNetSessionTC:
                              'batch equal-length segments instead')
         self.flags = torch.zeros((2 * B * tpb,), device=dev, dtype=torch.int32) if self.stack_group else None     # tile flags | z flags
         self.tpb = tpb
+        if hparams.get('b2s_stack_t', False):
+            C.require_experiments("hparams['b2s_stack_t'] (the transposed stack kernel)")
         self.tgroups = self._plan_transposed(cond_h) if (self.stack_group and hparams.get('b2s_stack_t', False)) else None
         if self.tgroups:
             self.flags = torch.zeros((max(B * tpb, sum(g[4] for g in self.tgroups)),), device=dev, dtype=torch.int32)
@@ -358,7 +360,8 @@ class WaveNetSessionTC:
 
     @property
     def can_fuse_update(self) -> bool:
-        return bool(self.stack_group) and not self.tgroups and not self.stack3 and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256
+        return (C.HAS_EXPERIMENTS and bool(self.stack_group) and not self.tgroups and not self.stack3
+                and hparams.get('b2s_fuse_io', True) and self.eng.MF <= 256)
 
     def eval_update(self, x_in, k, srcs, coef, x_dst, precast=False):
         """One launch: denoiser evaluation + ``x_dst <- sum coef[i] * srcs[i]`` (``None`` in srcs = the evaluation's output),
