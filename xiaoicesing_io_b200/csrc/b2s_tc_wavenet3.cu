@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
     uint64_t* empty = full + STAGES;
     uint64_t* accfull = empty + STAGES;        //     GEMM1 half accumulator complete               (commit, both CTAs)
     uint64_t* accfree = accfull + 2;           //     ... drained by both CTAs' epilogues           (leader, 16 arrivals)
-    uint64_t* zready = accfree + 2;            // [4] z K slab written in both CTAs                 (leader, 8: the 4 warps of one column half x 2)
+    uint64_t* zready = accfree + 2;            // [4] z K slab written in both CTAs                 (leader, 16)
     uint64_t* yready = zready + 4;             //     own rows of y_m in shared memory, both CTAs   (leader, 16)
     uint64_t* halofull = yready + 1;           //     halo rows of y_m landed in both CTAs          (leader, tx)
     uint64_t* g1done = halofull + 1;           //     every GEMM1 MMA of the layer retired          (commit, both CTAs)
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
             mbar_init(&efree[i], EPI_WARPS);
             mbar_init(&zfree[i], 2);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(&zready[i], (EPI_WARPS / 2) * CLUSTER);
+        for (int i = 0; i < 4; ++i) mbar_init(&zready[i], EPI_WARPS * CLUSTER);
         mbar_init(yready, EPI_WARPS * CLUSTER);
         mbar_init(halofull, 1);
         mbar_init(g1done, 1 + ((rank == 0 ? dsm_left : dsm_right) ? 1 : 0));       // own pair + the pair whose halo this CTA writes
@@ -804,6 +804,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
         const uint32_t yrow = smem_u32(ys) + ((row + HALO) >> 3) * 1024 + sw * 128;       // HALO % 8 == 0: same swizzle phase
         const uint32_t et = smem_u32(etab);
         const uint32_t lead_yready = mapa_u32(yready, lead);
+        const bool all_valid = __all_sync(0xffffffffu, valid);
         // y_m (own rows) = valid ? s * X + e_m[c] : 0 for this warp's four 32-column chunks -> swizzled shared-memory tile.
         // STEM: X = relu(acc + b_in) is first written to the X columns of TMEM.
         auto produce_y = [&](int m, bool stem) {
@@ -874,12 +875,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
             // tile/chunk-major cond table: (chunk J of 32 packed columns, 16-byte piece i) of this tile = 128 rows x 16 B contiguous
             const uint16_t* ctile = reinterpret_cast<const uint16_t*>(p.cond) + l * p.cond_lstride + (long long)blockIdx.x * (BM * 2 * C) + row * 8;
             uint4 c[2][4];
-            auto load_cond = [&](int h, int pr) {              // chunks 2*pr, 2*pr + 1 of this warp's four in half h
+            // Half h of GEMM1 = z K slabs 2h and 2h + 1.  ALL eight warps gate slab 2h first (pr = 0), then slab 2h + 1 (pr = 1): the
+            // residual GEMM's K slab 2h is issued while the second slab is still being gated, so that after the layer's last gate
+            // epilogue only ONE K slab (4 MMAs) remains before the y epilogue.  Warp (qd, sub) takes chunks 4 pr + 2 sub + {0, 1}.
+            auto load_cond = [&](int h, int pr) {
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        c[jj][i] = valid ? ldg_nc_u4(ctile + ((8 * h + 4 * sub + 2 * pr + jj) * 4 + i) * (BM * 8)) : make_uint4(0, 0, 0, 0);
+                        c[jj][i] = valid ? ldg_nc_u4(ctile + ((8 * h + 4 * pr + 2 * sub + jj) * 4 + i) * (BM * 8)) : make_uint4(0, 0, 0, 0);
             };
             const uint32_t lead_accfree = mapa_u32(accfree, lead);
             load_cond(0, 0);
@@ -888,14 +892,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                 mbar_wait(accfull, (uint32_t)h);               // phase 2l + h
                 tc_fence_after();
                 if (e == 0 && lane == 0) TLOG3(l, 2 + 2 * h);
-                // this warp's four 32-column chunks of the half = z channels [128h + 64 sub, +64) = K slab 2h + sub of z, which
-                // lives in ring buffer `sub`
-                const uint32_t slab = zrow + sub * ZSLAB;
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
                     float acc0[32], acc1[32];
-                    tmem_ld32(taddr + 256 + 32 * (4 * sub + 2 * pr), acc0);
-                    tmem_ld32(taddr + 256 + 32 * (4 * sub + 2 * pr + 1), acc1);
+                    tmem_ld32(taddr + 256 + 32 * (4 * pr + 2 * sub), acc0);
+                    tmem_ld32(taddr + 256 + 32 * (4 * pr + 2 * sub + 1), acc1);
                     tmem_ld_wait();
                     if (pr == 1) {                             // the accumulator is in registers: hand it back to the MMA issuer
                         tc_fence_before();
@@ -918,26 +919,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                             const float2 ca = Half16<BF16>::unpack2(cw[2 * i]), cb = Half16<BF16>::unpack2(cw[2 * i + 1]);
                             const float z0 = sigmoid_fast(acc[4 * i] + ca.x) * tanh_fast(acc[4 * i + 1] + ca.y);
                             const float z1 = sigmoid_fast(acc[4 * i + 2] + cb.x) * tanh_fast(acc[4 * i + 3] + cb.y);
-                            zp[8 * jj + i] = valid ? Half16<BF16>::pack2(z0, z1) : 0u;
+                            zp[8 * jj + i] = Half16<BF16>::pack2(z0, z1);
                         }
                     }
-                    if (pr == 0) {
-                        load_cond(h, 1);
-                        // write n = 2l + h of ring buffer `sub`: the previous occupant's GEMM2 slab and TMA store are through
-                        if (l + h > 0) mbar_wait(&zfree[sub], (uint32_t)(2 * l + h - 1) & 1u);
+                    if (!all_valid) {                          // only the last tile of an utterance has padding rows
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) zp[i] = valid ? zp[i] : 0u;
                     }
+                    // cond rows of the next step: the other slab of this half, the next half, or (h = 1, pr = 1) nothing: the next
+                    // layer's first rows are requested at the top of the layer loop, after the y epilogue
+                    if (pr == 0) load_cond(h, 1);
+                    else if (h == 0) load_cond(1, 0);
+                    // write 2l + h of ring buffer pr: the previous occupant's GEMM2 slab has retired and its TMA store has read it
+                    if (l + h > 0) mbar_wait(&zfree[pr], (uint32_t)(2 * l + h - 1) & 1u);
+                    // z channels [64 (2h + pr) + 32 sub, +32) of this row: K slab 2h + pr (ring buffer pr), 16-byte pieces 4 sub .. 4 sub + 3
+                    const uint32_t slab = zrow + pr * ZSLAB;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4)
-                        st_shared_u4(slab + (((4 * pr + c4) ^ sw) << 4), make_uint4(zp[4 * c4], zp[4 * c4 + 1], zp[4 * c4 + 2], zp[4 * c4 + 3]));
+                        st_shared_u4(slab + (((4 * sub + c4) ^ sw) << 4), make_uint4(zp[4 * c4], zp[4 * c4 + 1], zp[4 * c4 + 2], zp[4 * c4 + 3]));
+                    fence_proxy_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_remote(mapa_u32(&zready[2 * h + pr], lead));
                 }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    arrive_remote(mapa_u32(&zready[2 * h + sub], lead));
-                    mbar_arrive(zdone);
-                }
-                if (h == 0) load_cond(1, 0);
+                if (lane == 0) mbar_arrive(zdone);
                 if (e == 0 && lane == 0) TLOG3(l, 3 + 2 * h);
             }
             if (l + 1 < L) {
