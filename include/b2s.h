@@ -51,6 +51,16 @@ const char* b2s_last_error(void);
  * and the time-major internal layout. */
 int b2s_transpose_f32(const float* in, float* out, int batch, int rows, int cols, void* stream);
 
+/* norm_spec / denorm_spec (ddpm.py:379-383, reflow.py:140-144) fused with the layout change between the caller's spec tensor
+ * [B, T, M] (F = 1) or [B, F, T, M] and the sampler's time-major state [B*T, F*M] (the reference transposes to [B, F, M, T] at
+ * ddpm.py:370-373 and back at :350).  spec_min / spec_max: [F*M] fp32 (the registered buffers, flattened).
+ *   norm:   state[(b*T + t), f*M + m] = (spec[b, f, t, m] - min) / (max - min) * 2 - 1
+ *   denorm: spec[b, f, t, m] = (state[(b*T + t), f*M + m] + 1) / 2 * (max - min) + min */
+int b2s_spec_norm_f32(const float* spec, const float* spec_min, const float* spec_max, float* state, int B, int F, int T, int M,
+                      void* stream);
+int b2s_spec_denorm_f32(const float* state, const float* spec_min, const float* spec_max, float* spec, int B, int F, int T, int M,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Sampler update: dst = sum_i coef[i] * src[i]   (one vectorised elementwise kernel)
  *

@@ -425,3 +425,25 @@ def test_tc_stack3_against_fp64(C, kind, hd, eps):
             print('stack3', tag, ['%.1e' % v for v in errs])
             # z in (-1, 1); one 16-bit rounding of y moves a pre-activation by ~eps * |y| * sqrt(3C) * |w| ~ a few eps
             assert max(errs) < 24 * eps, (tag, errs)
+
+
+@pytest.mark.parametrize('F_', [1, 2])
+def test_spec_norm_denorm_fused_with_layout(C, F_):
+    """b2s_spec_norm_f32 / b2s_spec_denorm_f32: norm_spec / denorm_spec (ddpm.py:379-383) fused with the layout
+    change between [B, T, M] / [B, F, T, M] and the time-major sampler state [B*T, F*M]."""
+    B, T, M = 3, 77, 24
+    torch.manual_seed(F_)
+    lo = (torch.rand(F_, M, device='cuda') * -10 - 2)
+    hi = lo + torch.rand(F_, M, device='cuda') * 8 + 1
+    spec = torch.randn((B, T, M) if F_ == 1 else (B, F_, T, M), device='cuda') * 5
+    state = torch.full((B * T, F_ * M), float('nan'), device='cuda')
+    C.spec_norm(spec, lo.reshape(-1).contiguous(), hi.reshape(-1).contiguous(), state, B, F_, T, M)
+    l4, h4 = (lo.reshape(1, 1, M), hi.reshape(1, 1, M)) if F_ == 1 else (lo.reshape(1, F_, 1, M), hi.reshape(1, F_, 1, M))
+    want = (spec - l4) / (h4 - l4) * 2 - 1                                          # the reference's expression
+    want_tm = want.reshape(B * T, M) if F_ == 1 else want.permute(0, 2, 1, 3).reshape(B * T, F_ * M)
+    assert torch.equal(state, want_tm)
+    back = torch.full_like(spec, float('nan'))
+    C.spec_denorm(state, lo.reshape(-1).contiguous(), hi.reshape(-1).contiguous(), back, B, F_, T, M)
+    want_back = (want + 1) / 2 * (h4 - l4) + l4
+    assert torch.equal(back, want_back)
+    C.spec_norm(spec[:0], lo.reshape(-1), hi.reshape(-1), state[:0], 0, F_, T, M)   # empty batch: no launch, no error

@@ -18,6 +18,8 @@ _vp, _i, _f, _i64 = c_void_p, c_int, c_float, c_int64
 # name -> argtypes (all return int except where noted); mirrors include/b2s.h line by line
 _SIGNATURES = {
     'b2s_transpose_f32': [_vp, _vp, _i, _i, _i, _vp],
+    'b2s_spec_norm_f32': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    'b2s_spec_denorm_f32': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_sampler_lincomb_f32': [_vp, ctypes.POINTER(_vp), _vp, _i, _i64, _vp],
     'b2s_sampler_lincomb_f32_h': [_vp, ctypes.POINTER(_vp), _vp, _i, _i64, _vp, _i, _vp, _i, _vp],
     'b2s_sinusoid_f32': [_vp, _vp, _i, _i, _vp],
@@ -150,6 +152,14 @@ def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
 # ---- thin typed wrappers (argument order = include/b2s.h) ------------------------------------------
 def transpose(inp, out, batch, rows, cols):
     check(lib.b2s_transpose_f32(ptr(inp), ptr(out), batch, rows, cols, stream_ptr()), 'b2s_transpose_f32')
+
+
+def spec_norm(spec, lo, hi, state, B, F, T, M):
+    check(lib.b2s_spec_norm_f32(ptr(spec), ptr(lo), ptr(hi), ptr(state), B, F, T, M, stream_ptr()), 'b2s_spec_norm_f32')
+
+
+def spec_denorm(state, lo, hi, spec, B, F, T, M):
+    check(lib.b2s_spec_denorm_f32(ptr(state), ptr(lo), ptr(hi), ptr(spec), B, F, T, M, stream_ptr()), 'b2s_spec_denorm_f32')
 
 
 def lincomb(dst, srcs, coef_dev):

@@ -50,9 +50,15 @@ class SamplerBase(nn.Module):
     def build_program(self) -> Program:                      # pragma: no cover - abstract
         raise NotImplementedError
 
-    def _run(self, cond, b, start, device, lengths=None, initial_noise=None):
+    def _run(self, cond, b, start, device, lengths=None, initial_noise=None, denorm=None):
         return sample(getattr(self, self.backbone_attr), self.build_program(), cond, b, self.num_feats,
-                      self.out_dims, start, device, noise_source=self._noise_source, lengths=lengths, noise0=initial_noise)
+                      self.out_dims, start, device, noise_source=self._noise_source, lengths=lengths, noise0=initial_noise,
+                      denorm=denorm)
+
+    def _fused_norm(self) -> bool:
+        """True when (de)normalisation is exactly the base expression (no repeat-bin / clip / multi-curve mixin): then norm_spec,
+        denorm_spec and the layout changes around the sampler run as ONE kernel each (b2s_spec_norm_f32 / b2s_spec_denorm_f32)."""
+        return type(self).norm_spec is SamplerBase.norm_spec and type(self).denorm_spec is SamplerBase.denorm_spec
 
     def _training_forward(self, spec, cond, b, device):     # pragma: no cover - abstract
         raise NotImplementedError
@@ -72,9 +78,31 @@ class SamplerBase(nn.Module):
                 kw['lengths'] = lengths
             if initial_noise is not None:
                 kw['initial_noise'] = initial_noise
+            if self._fused_norm() and condition.is_cuda and type(self).inference in _BASE_INFERENCE:
+                # acoustic models: norm_spec + transpose and transpose + denorm_spec fused into one kernel each
+                # the registered bounds are [1, 1, K] / [1, F, 1, K] with K = 1 (one value for all bins) or M: flat [F*M] for the kernel
+                flat = lambda v: v.reshape(self.num_feats, v.shape[-1]).expand(self.num_feats, self.out_dims).contiguous().reshape(-1)
+                lo, hi = flat(self.spec_min), flat(self.spec_max)
+                start = None
+                if src_spec is not None:
+                    T, M, F_ = condition.shape[1], self.out_dims, self.num_feats
+                    start = TimeMajorState(torch.empty((b * T, F_ * M), device=device))
+                    with torch.cuda.device(device):
+                        C.spec_norm(src_spec.to(device=device, dtype=torch.float32).contiguous(), lo, hi, start.t, b, F_, T, M)
+                return self._run(cond, b, start, device, denorm=(lo, hi), **kw)
             x = self.inference(cond, b, self._source_to_state(src_spec), device, **kw)
             return self.denorm_spec(x)
         return self._training_forward(self._source_to_state(gt_spec), cond, b, device)
+
+
+class TimeMajorState:
+    """A normalised start state that is ALREADY in the sampler's time-major layout [B*T, F*M] (b2s_spec_norm_f32 wrote it): the
+    reference's [B, F, M, T] round trip (ddpm.py:370-373) is skipped."""
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+
+
+_BASE_INFERENCE: set = set()     # the stock ``inference`` methods of GaussianDiffusion / RectifiedFlow (filled by core/__init__)
 
 
 class _GraphedLoop:
@@ -83,11 +111,12 @@ class _GraphedLoop:
     replayed with a single launch.  Noise comes from ``torch.randn`` inside the graph (graph-safe Philox:
     a replay consumes the default generator exactly like the eager loop, so seeded runs stay reproducible)."""
 
-    def __init__(self, eng, cp: CompiledProgram, B, T, H, F_, M, device, ragged=False, ext_noise=False):
+    def __init__(self, eng, cp: CompiledProgram, B, T, H, F_, M, device, ragged=False, ext_noise=False, start_tm=False):
         prog = cp.prog
         self.cp = cp                     # the coefficient / model-time tables are read by the captured kernels
         self.cond = torch.empty((B, T, H), device=device)
-        self.x_start = torch.empty((B, F_ * M, T), device=device) if prog.needs_x_start else None
+        self.start_tm = start_tm         # x_start arrives time-major [B*T, F*M] (fused norm_spec): a copy instead of a transpose
+        self.x_start = (torch.empty((B * T, F_ * M) if start_tm else (B, F_ * M, T), device=device)) if prog.needs_x_start else None
         self.lens = torch.full((B,), T, device=device, dtype=torch.int32) if ragged else None      # static inputs of the graph
         self.noise0 = torch.empty((B, F_ * M, T), device=device) if ext_noise else None
         shape = (B, F_ * M, T)
@@ -103,7 +132,10 @@ class _GraphedLoop:
             if NOISE0 in bufs:
                 load(noise0, bufs[NOISE0])
             if prog.needs_x_start:
-                load(self.x_start, bufs[XSTART])
+                if start_tm:
+                    bufs[XSTART].copy_(self.x_start)
+                else:
+                    load(self.x_start, bufs[XSTART])
             self.keep = (sess, bufs)     # every buffer a captured kernel touches stays owned by this object
             return run_program(cp, sess, bufs, lambda j, dst: load(torch.randn(shape, device=device), dst))
 
@@ -123,7 +155,7 @@ class _GraphedLoop:
         if self.x_start is not None:
             self.x_start.copy_(x_start_bfmt.reshape(self.x_start.shape))
         self.graph.replay()
-        return self.out.clone()
+        return self.out              # static buffer: the caller copies / de-normalises it before the next replay
 
 
 # Captured graphs, least recently used first.  A graph pins its engine, its session and a private memory pool of hundreds of MB,
@@ -151,7 +183,8 @@ def clear_graph_cache():
 
 def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: int, out_dims: int,
            x_start: Optional[torch.Tensor], device,
-           noise_source: Optional[Callable[[tuple], torch.Tensor]] = None, lengths=None, noise0=None) -> torch.Tensor:
+           noise_source: Optional[Callable[[tuple], torch.Tensor]] = None, lengths=None, noise0=None,
+           denorm=None) -> torch.Tensor:
     """Runs ``prog`` with ``backbone`` as the denoiser.  Returns [B, T, M] or [B, F, T, M]
     (the transpose of ddpm.py:350 / reflow.py:137 is free: the state is time-major already).
 
@@ -182,17 +215,30 @@ def sample(backbone, prog: Program, cond_bht: torch.Tensor, b: int, num_feats: i
     if noise0 is not None and tuple(noise0.shape) != shape:
         raise C.B2SError(f'initial_noise must have shape {shape} (got {tuple(noise0.shape)})')
     with torch.cuda.device(device):         # every launch below (and the current stream) belongs to the tensors' device
-        return _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source, lens, noise0)
+        return _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source, lens, noise0,
+                                 denorm)
 
 
-def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source, lens=None, noise0_in=None):
+def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, device, noise_source, lens=None, noise0_in=None,
+                      denorm=None):
     eng = backbone._engine()
     eng.pack()
     if prog.needs_x_start:
         assert x_start is not None, 'Missing shallow diffusion source.'
     cond_bth = _time_major_cond(cond_bht.float())
 
-    def finish(x):
+    start_tm = isinstance(x_start, TimeMajorState)
+    if start_tm:
+        x_start = x_start.t
+
+    def finish(x, static=False):
+        if denorm is not None:                              # denorm_spec + layout change in one kernel (also un-aliases a static buffer)
+            out = torch.empty((B, T, M) if F_ == 1 else (B, F_, T, M), device=device)
+            if B * T:
+                C.spec_denorm(x, denorm[0], denorm[1], out, B, F_, T, M)
+            return out
+        if static:
+            x = x.clone()
         x = x.reshape(B, T, F_, M)
         if F_ == 1:
             return x[:, :, 0, :]                            # [B, T, M]
@@ -205,20 +251,20 @@ def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, 
     if noise_source is None and hparams.get('b2s_cuda_graph', True):
         structure = tuple(repr(hparams.get(k)) for k in _STRUCTURE_HPARAMS)
         graph_key = (id(backbone), eng._packed_version, eng.precision, _program_key(prog), B, T, F_, M, str(device), structure,
-                     lens is not None, noise0_in is not None)
+                     lens is not None, noise0_in is not None, start_tm)
         entry = _GRAPH_CACHE.get(graph_key)
         if entry is None and graph_key in _SEEN_KEYS:       # second call with this key: capture
             del _SEEN_KEYS[graph_key]
             while len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
                 _GRAPH_CACHE.popitem(last=False)            # least recently used graph
             entry = _GraphedLoop(eng, CompiledProgram(prog, device), B, T, H, F_, M, device, ragged=lens is not None,
-                                 ext_noise=noise0_in is not None)
+                                 ext_noise=noise0_in is not None, start_tm=start_tm)
             _GRAPH_CACHE[graph_key] = entry
         if entry is not None:
             _GRAPH_CACHE.move_to_end(graph_key)
             xs = None if x_start is None else x_start.to(device=device, dtype=torch.float32)
             n0 = None if noise0_in is None else noise0_in.to(device=device, dtype=torch.float32)
-            return finish(entry.run(cond_bth, xs, lens, n0))
+            return finish(entry.run(cond_bth, xs, lens, n0), static=True)
     if noise_source is None:
         noise_source = lambda s: torch.randn(s, device=device)
     cp = CompiledProgram(prog, device)
@@ -233,7 +279,10 @@ def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, 
     if NOISE0 in bufs:
         load(noise0, bufs[NOISE0])
     if prog.needs_x_start:
-        load(x_start, bufs[XSTART])
+        if start_tm:
+            bufs[XSTART].copy_(x_start)
+        else:
+            load(x_start, bufs[XSTART])
 
     x = run_program(cp, sess, bufs, lambda j, dst: load(noise_source(shape), dst))   # [B*T, F*M]
     if graph_key is not None:

@@ -265,6 +265,53 @@ static int lincomb_impl(const char* who, float* dst, const float* const* srcs_ho
     return B2S_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// norm_spec / denorm_spec (ddpm.py:379-383, reflow.py:140-144) fused with the layout change between the caller's
+// [B, T, M] / [B, F, T, M] and the sampler's time-major state [B*T, F*M] (the reference transposes to [B, F, M, T] at
+// ddpm.py:370-373 and back at :350): one pass each, once per sampling call
+// ------------------------------------------------------------------------------------------------
+template <int INVERSE>
+__global__ void spec_norm_kernel(const float* __restrict__ in, const float* __restrict__ lo, const float* __restrict__ hi,
+                                 float* __restrict__ out, int B, int F, int T, int M) {
+    const long long n = (long long)B * F * T * M;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        // i indexes the time-major state [b, t, f, m]; the spec tensor is [b, f, t, m]
+        const int m = (int)(i % M);
+        long long r = i / M;
+        const int f = (int)(r % F);
+        r /= F;
+        const int t = (int)(r % T);
+        const long long b = r / T;
+        const long long j = ((b * F + f) * T + t) * M + m;
+        const float l = __ldg(lo + f * M + m), h = __ldg(hi + f * M + m);
+        if (INVERSE) out[j] = (in[i] + 1.0f) / 2.0f * (h - l) + l;         // denorm_spec: state -> spec, the reference's expression
+        else out[i] = (in[j] - l) / (h - l) * 2.0f - 1.0f;                 // norm_spec: spec -> state
+    }
+}
+
+static int spec_norm_impl(const char* who, int inverse, const float* in, const float* lo, const float* hi, float* out, int B, int F,
+                          int T, int M, void* stream) {
+    B2S_CHECK_ARG(B >= 0 && F >= 1 && T >= 0 && M >= 1, "%s: bad dims B=%d F=%d T=%d M=%d", who, B, F, T, M);
+    const long long n = (long long)B * F * T * M;
+    if (n == 0) return B2S_OK;
+    B2S_CHECK_ARG(in && lo && hi && out, "%s: null pointer", who);
+    long long want = (n + 255) / 256;
+    const int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    if (inverse) spec_norm_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, lo, hi, out, B, F, T, M);
+    else spec_norm_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, lo, hi, out, B, F, T, M);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_spec_norm_f32(const float* spec, const float* spec_min, const float* spec_max, float* state, int B, int F, int T,
+                                 int M, void* stream) {
+    return spec_norm_impl("b2s_spec_norm_f32", 0, spec, spec_min, spec_max, state, B, F, T, M, stream);
+}
+extern "C" int b2s_spec_denorm_f32(const float* state, const float* spec_min, const float* spec_max, float* spec, int B, int F, int T,
+                                   int M, void* stream) {
+    return spec_norm_impl("b2s_spec_denorm_f32", 1, state, spec_min, spec_max, spec, B, F, T, M, stream);
+}
+
 extern "C" int b2s_sampler_lincomb_f32(float* dst, const float* const* srcs_host, const float* coef, int n_src,
                                        int64_t n, void* stream) {
     return lincomb_impl("b2s_sampler_lincomb_f32", dst, srcs_host, coef, n_src, n, nullptr, 0, nullptr, 0, stream);
