@@ -284,8 +284,10 @@ __global__ void spec_norm_kernel(const float* __restrict__ in, const float* __re
         const long long b = r / T;
         const long long j = ((b * F + f) * T + t) * M + m;
         const float l = __ldg(lo + f * M + m), h = __ldg(hi + f * M + m);
-        if (INVERSE) out[j] = (in[i] + 1.0f) / 2.0f * (h - l) + l;         // denorm_spec: state -> spec, the reference's expression
-        else out[i] = (in[j] - l) / (h - l) * 2.0f - 1.0f;                 // norm_spec: spec -> state
+        // the reference's expressions op by op (round-to-nearest intrinsics: no FMA contraction), so the result is bit-identical to
+        // torch's (x + 1) / 2 * (max - min) + min  and  (x - min) / (max - min) * 2 - 1
+        if (INVERSE) out[j] = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(in[i], 1.0f), 2.0f), __fsub_rn(h, l)), l);
+        else out[i] = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(in[j], l), __fsub_rn(h, l)), 2.0f), 1.0f);
     }
 }
 
