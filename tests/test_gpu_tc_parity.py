@@ -209,6 +209,47 @@ def _bf16_backbone(dev, stack, L=4, fuse_io=False, in_dims=128, n_feats=1, stack
     return net.to(dev).eval()
 
 
+@pytest.mark.parametrize('precision', ['fp16', 'bf16'])
+@pytest.mark.parametrize('channels,L,cycle,in_dims,n_feats,B,T', [(192, 10, 4, 24, 2, 7, 690), (192, 4, 5, 128, 1, 3, 257),
+                                                                  (136, 3, 2, 64, 1, 2, 130)])
+def test_narrow_wavenet_on_the_padded_whole_stack_kernel(channels, L, cycle, in_dims, n_feats, B, T, precision, dev):
+    """Narrow WaveNets (config 4's 192-channel variance predictor) run on the 256-channel whole-stack kernel with zero-padded
+    channels (engine.py: a padded channel is exactly 0 everywhere).  Checked against the CPU oracle at the model's own width, and -
+    where the unpadded two-kernel path exists (C % 64 == 0) - against that path to 16-bit rounding; padded output bins do not
+    exist (the head's rows are not padded), and the session must really have taken the whole-stack path."""
+    import xiaoicesing_io_b200 as P
+    from oracle import weights as OW
+    cfg = OD.WaveNetCfg(in_dims=in_dims, n_feats=n_feats, num_layers=L, num_channels=channels, dilation_cycle_length=cycle)
+    sd = OW.make_state_dict(cfg, seed=2, sigma_w=0.01)
+    g = torch.Generator().manual_seed(channels + T)
+    spec = torch.randn((B, n_feats, in_dims, T), generator=g)
+    cond = torch.randn((B, cfg.hidden_size, T), generator=g)
+    t = torch.arange(B, dtype=torch.float32) * 29 + 3
+    outs = {}
+    for pad in (True, False):
+        if not pad and channels % 64:
+            continue
+        P.hparams.clear()
+        P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision=precision, b2s_pad_channels=pad)
+        net = P.build_backbone(in_dims, n_feats, 'wavenet', dict(num_layers=L, num_channels=channels, dilation_cycle_length=cycle))
+        net.load_state_dict(sd, strict=True)
+        net = net.to(dev).eval()
+        outs[pad] = net(spec.to(dev), t.to(dev), cond.to(dev)).cpu()
+        eng = net._engine()
+        assert eng.C == (256 if pad else channels) and eng.C0 == channels
+        sess = eng.begin(cond.to(dev).transpose(1, 2).contiguous(), t.to(dev), per_row_t=True)
+        assert sess.stack3 == pad and sess.head3 == pad
+    ref = OD.make_denoiser(sd, cfg)(spec, t.long(), cond)
+    eps = 2 ** -8 if precision == 'bf16' else 2 ** -11
+    scale = float(ref.abs().max())
+    err = _maxabs(outs[True], ref)
+    _report(test='narrow_wavenet_padded', channels=channels, L=L, precision=precision, max_abs_err=err, ref_scale=scale)
+    assert err <= 2e-2 * max(1.0, scale), (err, scale)
+    if False in outs:
+        d = _maxabs(outs[True], outs[False])
+        assert d <= 6 * eps * scale, (d, scale)
+
+
 @pytest.mark.parametrize('B,T', [(30, 690), (5, 129), (1, 19500)])
 def test_stack_kernel_grouping_and_fallback_match_per_layer_path(B, T, dev):
     """The whole-stack kernel needs every tile resident: batches with more tiles than SMs are split by utterance into

@@ -68,8 +68,10 @@ class _B2SBackbone(nn.Module):
     def _engine(self):
         prec = hparams.get('b2s_precision') or os.environ.get('B2S_PRECISION', 'fp32')
         eng = self.__dict__.get('_b2s_engine')
-        if eng is None or eng.precision != prec:
+        pad = bool(hparams.get('b2s_pad_channels', True))
+        if eng is None or eng.precision != prec or getattr(eng, 'pad_channels', pad) != pad:
             eng = self.engine_cls(self, prec)
+            eng.pad_channels = pad
             self.__dict__['_b2s_engine'] = eng
         return eng
 

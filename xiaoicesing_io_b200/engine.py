@@ -42,11 +42,20 @@ class WaveNetEngine:
             raise ValueError(f'unknown precision {precision!r}; available: {PRECISIONS}')
         self.net = net
         self.precision = precision
-        self.C = net.num_channels
+        self.C0 = net.num_channels                            # the model's channel count (step-embedding MLP, algorithmic FLOPs)
         self.L = net.num_layers
         self.MF = net.in_dims * net.n_feats
         self.H = net.hidden_size
         self.dilations = [layer.dilation for layer in net.residual_layers]
+        # Narrow WaveNets (the 192-channel variance predictor) run on the 256-channel whole-stack kernel with
+        # ZERO-PADDED channels: a padded channel has zero stem / conv / conditioner / residual / skip rows and zero step embedding,
+        # so it stays exactly 0 through every layer (gate: sigmoid(0) * tanh(0) = 0) and contributes exactly 0 to every real
+        # channel - the same result, (256 / C)^2 more tensor-core work, but one persistent kernel instead of 2 launches per layer.
+        self.C = self.C0
+        if (precision != 'fp32' and hparams.get('b2s_pad_channels', True) and self.C0 < C.FUSED_LAYER_CHANNELS
+                and self.C0 % 8 == 0 and (self.C0 > 128 or self.C0 % 64) and max(self.dilations) <= 16 and self.L <= 32
+                and self.MF <= 256):
+            self.C = C.FUSED_LAYER_CHANNELS
         self._packed_version = None
         self.device = None
 
@@ -65,32 +74,50 @@ class WaveNetEngine:
         dev = next(net.parameters()).device
         if dev.type != 'cuda':
             raise C.B2SError('the denoiser lives on the CPU; this path has no CPU fallback - move the module to a CUDA device')
-        Cc, L = self.C, self.L
+        Cc, C0, L = self.C, self.C0, self.L
         f = lambda t: _dev_f32(t, dev)
+
+        def P(t, modes):
+            # channel padding C0 -> C (no-op when equal): per dim 'c' = a channel axis, 'g' = a [gate | filter] or
+            # [residual | skip] axis of 2*C0 rows (each half padded on its own), '-' = left alone
+            t = t.detach()
+            if Cc == C0:
+                return t
+            for d, m in enumerate(modes):
+                if m == 'c':
+                    shp = list(t.shape); shp[d] = Cc - C0
+                    t = torch.cat([t, t.new_zeros(shp)], d)
+                elif m == 'g':
+                    a, b = t.split(C0, d)
+                    shp = list(a.shape); shp[d] = Cc - C0
+                    z = t.new_zeros(shp)
+                    t = torch.cat([a, z, b, z], d)
+            return t
+
         self.device = dev
-        self.w_in = f(net.input_projection.weight[:, :, 0])                  # [C, MF]
-        self.b_in = f(net.input_projection.bias)
-        self.w_mlp0, self.b_mlp0 = f(net.mlp[0].weight), f(net.mlp[0].bias)  # [4C, C]
-        self.w_mlp2, self.b_mlp2 = f(net.mlp[2].weight), f(net.mlp[2].bias)  # [C, 4C]
+        self.w_in = f(P(net.input_projection.weight[:, :, 0], 'c-'))         # [C, MF]
+        self.b_in = f(P(net.input_projection.bias, 'c'))
+        self.w_mlp0, self.b_mlp0 = f(net.mlp[0].weight), f(net.mlp[0].bias)  # [4C0, C0]
+        self.w_mlp2, self.b_mlp2 = f(net.mlp[2].weight), f(net.mlp[2].bias)  # [C0, 4C0]
         layers = net.residual_layers
-        # all L diffusion projections as one [L*C, C] matrix -> one GEMM for the whole step table
-        self.w_dp = f(torch.cat([l.diffusion_projection.weight for l in layers], 0))
-        self.b_dp = f(torch.cat([l.diffusion_projection.bias for l in layers], 0))
+        # all L diffusion projections as one [L*C, C0] matrix -> one GEMM for the whole step table
+        self.w_dp = f(torch.cat([P(l.diffusion_projection.weight, 'c-') for l in layers], 0))
+        self.b_dp = f(torch.cat([P(l.diffusion_projection.bias, 'c') for l in layers], 0))
         # gate/filter interleave: packed row 2j = gate j (reference row j), 2j+1 = filter j (row C+j)
         perm = torch.stack([torch.arange(Cc), torch.arange(Cc) + Cc], 1).reshape(-1).to(dev)
         wc, bc, wd = [], [], []
         for l in layers:
-            wc.append(l.conditioner_projection.weight[:, :, 0][perm])         # [2C, H]
-            bc.append((l.conditioner_projection.bias + l.dilated_conv.bias)[perm])   # both biases folded
-            w = l.dilated_conv.weight[perm]                                   # [2C, C, 3]
+            wc.append(P(l.conditioner_projection.weight[:, :, 0], 'g-')[perm])          # [2C, H]
+            bc.append(P(l.conditioner_projection.bias + l.dilated_conv.bias, 'g')[perm])   # both biases folded
+            w = P(l.dilated_conv.weight, 'gc-')[perm]                         # [2C, C, 3]
             wd.append(w.permute(0, 2, 1).reshape(2 * Cc, 3 * Cc))             # column = tap*C + c
         self.w_cond = f(torch.cat(wc, 0))                                     # [L*2C, H]
         self.b_cond = f(torch.cat(bc, 0))
         self.w_dil = f(torch.stack(wd, 0))                                    # [L, 2C, 3C]
-        self.w_out = f(torch.stack([l.output_projection.weight[:, :, 0] for l in layers], 0))   # [L, 2C, C]
-        self.b_out = f(torch.stack([l.output_projection.bias for l in layers], 0))             # [L, 2C]
-        self.w_sp, self.b_sp = f(net.skip_projection.weight[:, :, 0]), f(net.skip_projection.bias)
-        self.w_fin, self.b_fin = f(net.output_projection.weight[:, :, 0]), f(net.output_projection.bias)
+        self.w_out = f(torch.stack([P(l.output_projection.weight[:, :, 0], 'gc') for l in layers], 0))   # [L, 2C, C]
+        self.b_out = f(torch.stack([P(l.output_projection.bias, 'g') for l in layers], 0))               # [L, 2C]
+        self.w_sp, self.b_sp = f(P(net.skip_projection.weight[:, :, 0], 'cc')), f(P(net.skip_projection.bias, 'c'))
+        self.w_fin, self.b_fin = f(P(net.output_projection.weight[:, :, 0], '-c')), f(net.output_projection.bias)
         if self.precision != 'fp32':
             if Cc % 64:
                 raise C.B2SError(f'the {self.precision} tensor-core path needs num_channels % 64 == 0 (got {Cc}); '
@@ -116,7 +143,7 @@ class WaveNetEngine:
             self.res3_ok = bool(torch.isfinite(self.w_res3_h.float()).all())                  # fp16 range (2^(l/2) <= 2^15.5 at L = 32)
             self.w_skip3_h = h(self.w_out[:, Cc:, :])                                          # [L, C, C]: skip rows per layer
             self.w_dil_t_h = self.w_cond_t_h = self.b_cond_t = None
-            if Cc == C.FUSED_LAYER_CHANNELS:
+            if C0 == C.FUSED_LAYER_CHANNELS and C.HAS_EXPERIMENTS:
                 # transposed stack kernel (b2s_tc_wavenet_stack_t): row 256h + 128g + c = (g ? filter : gate) of channel 128h + c,
                 # i.e. gate and filter of a channel land on the same TMEM lane of two neighbouring accumulator blocks
                 n = torch.arange(2 * Cc, device=dev)
@@ -135,7 +162,7 @@ class WaveNetEngine:
     def step_table(self, t_values: torch.Tensor) -> torch.Tensor:
         """t_values [K] fp32 (device) -> [K, L*C]: diffusion_projection_l(mlp(sinusoid(t))) for all l."""
         K = t_values.numel()
-        Cc = self.C
+        Cc, LC = self.C0, self.L * self.C                    # the MLP has the model's width; the table the (padded) kernels' width
         dev = self.device
         sin = torch.empty((K, Cc), device=dev)
         C.sinusoid(t_values, sin, K, Cc)
@@ -143,8 +170,8 @@ class WaveNetEngine:
         C.linear(sin, Cc, self.w_mlp0, Cc, self.b_mlp0, h, 4 * Cc, K, 4 * Cc, Cc, act=C.ACT_MISH)
         e = torch.empty((K, Cc), device=dev)
         C.linear(h, 4 * Cc, self.w_mlp2, 4 * Cc, self.b_mlp2, e, Cc, K, Cc, 4 * Cc)
-        tab = torch.empty((K, self.L * Cc), device=dev)
-        C.linear(e, Cc, self.w_dp, Cc, self.b_dp, tab, self.L * Cc, K, self.L * Cc, Cc)
+        tab = torch.empty((K, LC), device=dev)
+        C.linear(e, Cc, self.w_dp, Cc, self.b_dp, tab, LC, K, LC, Cc)
         return tab
 
     def cond_table(self, cond_bth: torch.Tensor) -> torch.Tensor:
@@ -520,9 +547,10 @@ class WaveNetSessionTC:
             # is not needed) per frame; the skip half (C^2 per layer) and the head run in the same launch with head3, else in the
             # deferred b2s_tc_skip_sum / head GEMM launches
             nb = min(self.stack_group, B)
-            per_frame = e.MF * Cc + L * 6 * Cc * Cc + (L - 1) * Cc * Cc
+            Ca = e.C0                                          # ALGORITHMIC: the model's width, not the zero-padded one
+            per_frame = e.MF * Ca + L * 6 * Ca * Ca + (L - 1) * Ca * Ca
             if self.head3:
-                per_frame += L * Cc * Cc + Cc * Cc + Cc * e.MF
+                per_frame += L * Ca * Ca + Ca * Ca + Ca * e.MF
             flops = 2.0 * nb * T * per_frame
             dv = self.dtab[0]
             nfl = B * self.tpb
