@@ -447,3 +447,28 @@ def test_spec_norm_denorm_fused_with_layout(C, F_):
     want_back = (want + 1) / 2 * (h4 - l4) + l4
     assert torch.equal(back, want_back)
     C.spec_norm(spec[:0], lo.reshape(-1), hi.reshape(-1), state[:0], 0, F_, T, M)   # empty batch: no launch, no error
+
+
+@pytest.mark.parametrize('kind,hd,eps', HALF)
+@pytest.mark.parametrize('B,T,inner,K', [(3, 130, 192, 31), (2, 19, 64, 31), (1, 704, 2048, 31), (2, 257, 128, 7), (2, 128, 70, 31),
+                                         (1, 1, 64, 31), (2, 300, 256, 1)])
+def test_lynx_dwconv_h_against_fp64(C, kind, hd, eps, B, T, inner, K):
+    """Depthwise conv along time + bias + PReLU on 16-bit activations (lynxnet.py:57-58): the tensor-core Toeplitz kernel
+    (inner % 64 == 0; taps rounded to 16 bits like every weight of that path) and the register-window fallback (inner = 70,
+    fp32 taps), tiles that end inside an utterance, utterances shorter than the kernel (zero padding on both sides), kernel
+    sizes below 31, frames of the NEXT utterance never leaking in."""
+    import torch.nn.functional as F
+    bf = kind == 'bf16'
+    torch.manual_seed(T + inner + K)
+    g = torch.randn(B, T, inner, device='cuda').to(hd)
+    w = torch.randn(inner, K, device='cuda') / K ** 0.5
+    bias = torch.randn(inner, device='cuda')
+    slope = torch.rand(inner, device='cuda')
+    out = torch.full((B, T, inner), float('nan'), device='cuda').to(hd)
+    C.lynx_dwconv_h(g, w.t().contiguous(), bias, slope, out, B, T, inner, K, 0, bf)
+    conv = F.conv1d(g.double().transpose(1, 2), w.double()[:, None, :], bias.double(), padding=K // 2, groups=inner)
+    want = torch.where(conv >= 0, conv, slope.double()[None, :, None] * conv).transpose(1, 2)
+    assert bool(torch.isfinite(out.float()).all())
+    err = (out.double() - want).abs()
+    mass = F.conv1d(g.double().abs().transpose(1, 2), w.double().abs()[:, None, :], None, padding=K // 2, groups=inner).transpose(1, 2)
+    assert float((err - eps * (want.abs() + mass)).max()) < 1e-5, float(err.max())

@@ -221,6 +221,208 @@ __global__ void __launch_bounds__(128, 2) dwconv_h_kernel(const uint16_t* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Depthwise conv on the tensor cores.  The register-window kernel above is issue-bound (1.46 instructions per output: 198 us for
+// the 2048-channel, 45 056-frame conv of config 3, 40 % of the fp32 pipe).  Per channel the conv is a product with a Toeplitz
+// matrix: with t = 16 a + b,
+//     out[16 a + b] = sum_{j = 0}^{47} in[16 a + j - 15] * Wt[j][b],      Wt[j][b] = w31[j - b]   (0 outside the 31 taps)
+// i.e. a [T/16 x 48] x [48 x 16] GEMM whose A operand is the input read with overlapping rows (a Hankel view of the same shared
+// memory) - 1.55 x the MACs, on mma.sync.m16n8k16 (fp32 accumulate) instead of FFMA: 0.22 instructions per output.
+//   * block = 256 threads = one utterance x 64 channels, looping over 256-frame tiles with double-buffered cp.async staging
+//     (frames outside the utterance zero-filled = the conv's padding); warp w owns channels 8 w .. 8 w + 7 (one 16-byte chunk)
+//   * A fragments: a thread needs frame pairs (r, r + 1) of its channels: two LDS.128 (8 channels of one frame each) + 8 PRMT
+//     give 8 channels' registers at once; the chunk index is XOR-swizzled with frame bits 1, 2, 4 -> conflict-free quarter-warps
+//   * B fragments: Toeplitz, so all six (k-block, n-block) fragments of a channel are windows of SEVEN packed tap pairs
+//     P[m] = (w31[d + 8 m], w31[d + 8 m + 1]), d = 2 (lane % 4) - lane / 4, m = -1 .. 5, kept in registers for the whole block
+//   * taps are rounded to the activations' 16-bit type (like every other weight of the 16-bit path); kernel sizes below 31 are
+//     centred in the 31-tap window
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool ok) {
+    const int n = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int BF16>
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if (BF16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int DWM_TILE = 256;                 // output frames per tile
+constexpr int DWM_ROWS = DWM_TILE + 32;       // staged frames: row i = frame f0 - 15 + i, rows 0 .. 287 are read
+constexpr int DWM_BUF = DWM_ROWS * 128;       // 64 channels x 2 B per row
+constexpr int DWM_SMEM = 3 * DWM_BUF;            // + 31 x 65 fp32 taps behind it
+constexpr int DWM_SMEM_ALL = DWM_SMEM + 31 * 65 * 4;
+
+__device__ __forceinline__ int dwm_swz(int row) { return ((row >> 1) & 3) | (((row >> 4) & 1) << 2); }
+
+template <int BF16, bool PRELU>
+__global__ void __launch_bounds__(256, 1) dwconv_mma_kernel(const uint16_t* __restrict__ g, const float* __restrict__ WdwT,
+                                                            const float* __restrict__ bias, const float* __restrict__ slope,
+                                                            uint16_t* __restrict__ p, int B, int T, int inner, int ksize,
+                                                            int act) {
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane & 3, gq = lane >> 2;
+    const int ch0 = blockIdx.x * 64;                       // inner % 64 == 0 (host-checked)
+    const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(dw_smem);
+    const int n_tiles = (T + DWM_TILE - 1) / DWM_TILE;
+    // work items of this block: utterances blockIdx.y, blockIdx.y + gridDim.y, ... x their tiles, in order; item j is staged in
+    // buffer j % 3, two items ahead of the one being computed (a group is committed per item even when it is empty, so that
+    // wait_group counts stay uniform)
+    const int n_items = ((B - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y) * n_tiles;
+    auto load_item = [&](int j) {
+        if (j < n_items) {
+            const int b = blockIdx.y + (j / n_tiles) * gridDim.y, it = j % n_tiles;
+            const uint16_t* gb = g + (long long)b * T * inner + ch0 + (lane & 7) * 8;
+            const int f0 = it * DWM_TILE - 15;
+            const uint32_t dst = smem_s + (j % 3) * DWM_BUF;
+            // 288 rows, 8 chunks of 16 B each: a warp instruction covers 4 rows, the block 32 rows
+#pragma unroll
+            for (int r0 = 0; r0 < DWM_ROWS; r0 += 32) {
+                const int r = r0 + warp * 4 + (lane >> 3);
+                const int s = f0 + r;
+                const bool ok = s >= 0 && s < T;
+                cp_async16_zfill(dst + r * 128 + (((lane & 7) ^ dwm_swz(r)) << 4), gb + (long long)(ok ? s : 0) * inner, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    load_item(0);
+    load_item(1);
+
+    // the block's 31 x 64 taps (fp32, centred in the 31-tap window) staged once, coalesced; pitch 65 keeps the per-lane reads of
+    // different taps on different banks
+    float* wsm = reinterpret_cast<float*>(dw_smem + DWM_SMEM);
+    const int koff = 15 - ksize / 2;                       // w31[k] = w[k - koff]
+    for (int i = threadIdx.x; i < 31 * 64; i += 256) {
+        const int k = i >> 6, c = i & 63, kk = k - koff;
+        wsm[k * 65 + c] = (kk >= 0 && kk < ksize) ? __ldg(WdwT + (long long)kk * inner + ch0 + c) : 0.f;
+    }
+    __syncthreads();
+    // this warp's 8 channels: Toeplitz tap pairs, bias, PReLU slope
+    const int chw = ch0 + warp * 8;
+    const int d = 2 * q - gq;
+    uint32_t P[8][7];
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        const int i0 = d + 8 * (m - 1), i1 = i0 + 1;
+        const bool ok0 = i0 >= 0 && i0 < 31, ok1 = i1 >= 0 && i1 < 31;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float w0 = ok0 ? wsm[i0 * 65 + warp * 8 + c] : 0.f;
+            const float w1 = ok1 ? wsm[i1 * 65 + warp * 8 + c] : 0.f;
+            P[c][m] = tc::Half16<BF16>::pack2(w0, w1);
+        }
+    }
+    float bs[8], sl[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { bs[c] = __ldg(bias + chw + c); sl[c] = (PRELU ? __ldg(slope + chw + c) : 1.f) - 1.f; }
+    for (int j = 0; j < n_items; ++j) {
+        const int buf = j % 3;
+        const int b = blockIdx.y + (j / n_tiles) * gridDim.y, it = j % n_tiles;
+        load_item(j + 2);             // into the buffer item j - 1 used (released by the barrier that ended its iteration)
+        cp_async_wait<2>();
+        __syncthreads();
+        const uint8_t* tile = dw_smem + buf * DWM_BUF;
+        float acc[8][2][4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[c][nb][i] = bs[c];
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) {
+            uint32_t A[8][4];
+            // a0 = rows (g + kb) pair e = 0, a1 = rows (g + 8 + kb) e = 0, a2 = (g + kb) e = 1, a3 = (g + 8 + kb) e = 1
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const int r = 16 * (gq + kb + ((f & 1) ? 8 : 0)) + ((f & 2) ? 8 : 0) + 2 * q;
+                const uint4 x0 = *reinterpret_cast<const uint4*>(tile + r * 128 + ((warp ^ dwm_swz(r)) << 4));
+                const uint4 x1 = *reinterpret_cast<const uint4*>(tile + (r + 1) * 128 + ((warp ^ dwm_swz(r + 1)) << 4));
+                A[0][f] = __byte_perm(x0.x, x1.x, 0x5410); A[1][f] = __byte_perm(x0.x, x1.x, 0x7632);
+                A[2][f] = __byte_perm(x0.y, x1.y, 0x5410); A[3][f] = __byte_perm(x0.y, x1.y, 0x7632);
+                A[4][f] = __byte_perm(x0.z, x1.z, 0x5410); A[5][f] = __byte_perm(x0.z, x1.z, 0x7632);
+                A[6][f] = __byte_perm(x0.w, x1.w, 0x5410); A[7][f] = __byte_perm(x0.w, x1.w, 0x7632);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) mma_16816<BF16>(acc[c][nb], A[c], P[c][2 * kb - nb + 1], P[c][2 * kb - nb + 2]);
+            }
+        }
+        // epilogue: activation, 16-bit; the tile is transposed through the (consumed) input buffer so that the global stores are
+        // whole 128-byte rows (a direct store from the accumulator layout touches 32 rows per instruction)
+        __syncthreads();
+        uint8_t* otile = dw_smem + buf * DWM_BUF;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 16 * (gq + ((i & 2) ? 8 : 0)) + 8 * nb + 2 * q + (i & 1);
+                float o[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float v = acc[c][nb][i];
+                    // PReLU as v + (slope - 1) * min(v, 0): one FMNMX + one FFMA
+                    o[c] = PRELU ? fmaf(sl[c], fminf(v, 0.f), v) : apply_act(v, act);
+                }
+                uint4 w;
+                w.x = tc::Half16<BF16>::pack2(o[0], o[1]);
+                w.y = tc::Half16<BF16>::pack2(o[2], o[3]);
+                w.z = tc::Half16<BF16>::pack2(o[4], o[5]);
+                w.w = tc::Half16<BF16>::pack2(o[6], o[7]);
+                *reinterpret_cast<uint4*>(otile + r * 128 + ((warp ^ dwm_swz(r)) << 4)) = w;
+            }
+        }
+        __syncthreads();
+        {
+            uint16_t* po = p + ((long long)b * T + (long long)it * DWM_TILE) * inner + ch0 + (lane & 7) * 8;
+            const int rows = min(DWM_TILE, T - it * DWM_TILE);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = j * 32 + warp * 4 + (lane >> 3);
+                if (r < rows)
+                    *reinterpret_cast<uint4*>(po + (long long)r * inner) =
+                        *reinterpret_cast<const uint4*>(otile + r * 128 + (((lane & 7) ^ dwm_swz(r)) << 4));
+            }
+        }
+        __syncthreads();          // this buffer is refilled by the next iteration's load_item
+    }
+}
+
+template <int BF16>
+static int launch_dwconv_mma(const void* g_h, const float* WdwT, const float* bias, const float* slope, void* p_h, int B, int T,
+                             int inner, int ksize, int act, cudaStream_t st) {
+    static tc::PerDevice configured;
+    if (configured.first()) {
+        B2S_CHECK_CUDA(cudaFuncSetAttribute(dwconv_mma_kernel<BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWM_SMEM_ALL));
+        B2S_CHECK_CUDA(cudaFuncSetAttribute(dwconv_mma_kernel<BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWM_SMEM_ALL));
+    }
+    // persistent over utterances: one block per SM (255 registers), channel tile fastest so that concurrently running blocks
+    // read neighbouring 128-byte columns of the same frames
+    const int n_ct = inner / 64;
+    dim3 grid(n_ct, std::max(1, std::min(B, tc::num_sms() / n_ct)));
+    if (act == 0)
+        dwconv_mma_kernel<BF16, true><<<grid, 256, DWM_SMEM_ALL, st>>>((const uint16_t*)g_h, WdwT, bias, slope, (uint16_t*)p_h, B, T, inner, ksize, act);
+    else
+        dwconv_mma_kernel<BF16, false><<<grid, 256, DWM_SMEM_ALL, st>>>((const uint16_t*)g_h, WdwT, bias, slope, (uint16_t*)p_h, B, T, inner, ksize, act);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+static bool dwconv_use_mma() {
+    static const bool on = [] { const char* e = getenv("B2S_DWCONV_MMA"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
 template <int K>
 static int launch_dwconv_h(const void* g_h, const float* WdwT, const float* bias, const float* slope, void* p_h, int B, int T,
                            int inner, int act, int bf16, cudaStream_t st) {
@@ -270,6 +472,10 @@ extern "C" int b2s_lynx_dwconv_h(const void* g_h, const float* WdwT, const float
     B2S_CHECK_ARG(B < 65536, "b2s_lynx_dwconv_h: B too large");
     if (B <= 0 || T <= 0) return B2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    // tensor-core formulation (Toeplitz GEMM on mma.sync): 64-channel tiles, 16-byte rows
+    if (inner % 64 == 0 && tc::al16(g_h) && tc::al16(p_h) && dwconv_use_mma())
+        return bf16 ? launch_dwconv_mma<1>(g_h, WdwT, bias, slope, p_h, B, T, inner, ksize, act, st)
+                    : launch_dwconv_mma<0>(g_h, WdwT, bias, slope, p_h, B, T, inner, ksize, act, st);
     switch (ksize) {          // the window ring is a compile-time structure: one instantiation per (odd) kernel size
 #define B2S_DW_CASE(KK) case KK: return launch_dwconv_h<KK>(g_h, WdwT, bias, slope, p_h, B, T, inner, act, bf16, st);
         B2S_DW_CASE(1) B2S_DW_CASE(3) B2S_DW_CASE(5) B2S_DW_CASE(7) B2S_DW_CASE(9) B2S_DW_CASE(11) B2S_DW_CASE(13) B2S_DW_CASE(15)
