@@ -359,8 +359,9 @@ __global__ void __launch_bounds__(256, 1) dwconv_mma_kernel(const uint16_t* __re
             }
         }
         // epilogue: activation, 16-bit; the tile is transposed through the (consumed) input buffer so that the global stores are
-        // whole 128-byte rows (a direct store from the accumulator layout touches 32 rows per instruction)
-        __syncthreads();
+        // whole 128-byte rows (a direct store from the accumulator layout touches 32 rows per instruction).  A warp reads and
+        // writes only ITS chunk column of the buffer, so a warp-level barrier orders its reads before its writes
+        __syncwarp();
         uint8_t* otile = dw_smem + buf * DWM_BUF;
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
