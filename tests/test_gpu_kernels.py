@@ -242,8 +242,10 @@ def test_tc_fused_layer_matches_gate_plus_out(C, kind, hd, eps):
                            None if last else dvec, 0, first, B, T, Cc, d, bf)
         torch.cuda.synchronize()
         tag = (kind, B, T, d)
-        assert float((xa - xb).abs().max()) < 1e-5, tag
-        assert float((sa - sb).abs().max()) < 1e-5, tag
+        # the two paths add the 3 x C conv terms in different orders (the gate GEMM walks channel slabs x taps, the fused kernel
+        # taps x channel slabs), so a z value may round to the neighbouring 16-bit number: a few eps in x and skip
+        assert float((xa - xb).abs().max()) < 4 * eps, tag
+        assert float((sa - sb).abs().max()) < 4 * eps, tag
         assert float((ya.float() - yb.float()).abs().max()) <= eps * 8, tag
         assert float((sha.float() - shb.float()).abs().max()) <= eps * 8, tag
         # fp64 reference on the same 16-bit operands (z rounded to 16 bits in between)

@@ -58,6 +58,10 @@ struct __align__(64) TcP {
     int cg2;                   // 1: cta_group::2 kernel (tiles_m_per_b even, weight map box = 128 rows)
     int bn;                    // N tile of the cta_group::2 kernel: 256, or 192 when N is a multiple of 192 but not of 256 (C = 192 models)
     int k_layered;             // 1: K block group g = kb / kb_per_tap selects the THIRD coordinate of the A map (A = [L][rows][C], K = L*C)
+    // EPI_GATE with dilation <= CONV3_HALO: a pipeline stage holds ONE 64-channel slab of the tile WITH its halo (mapA3: box of
+    // BLOCK_M + 2 * CONV3_HALO rows) and the weight slabs of all three taps; the taps read it through row-shifted descriptors
+    CUtensorMap mapA3;
+    int conv3;
 };
 
 // ---- 16-bit helpers --------------------------------------------------------------------------------
@@ -407,13 +411,25 @@ constexpr int STAGES2 = 6;
 constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;       // 16 KB
 constexpr int STAGE2_BYTES = A_BYTES + BH_BYTES;            // 32 KB
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + STG_BYTES + 1024 + 256;
+// Dilated conv (EPI_GATE) with the A slab resident across the three taps: the mainloop above sits on the L2 -> SM cap (32 KB per
+// four MMAs and CTA = 11.7 TB/s chip-wide when MMA-bound, the measured cap); loading the slab once with its halo instead of once
+// per tap moves 68 KB instead of 96 KB per three K blocks.  K order becomes (channel slab, tap) instead of (tap, channel slab).
+constexpr int CONV3_HALO = 16;
+constexpr int A3_ROWS = BLOCK_M + 2 * CONV3_HALO;            // 160
+constexpr int A3_BYTES = A3_ROWS * BLOCK_K * 2;              // 20 KB
+constexpr int STAGE3_BYTES = A3_BYTES + 3 * BH_BYTES;        // 68 KB
+constexpr int STAGES3 = 3;
+constexpr int SMEM3_BYTES = STAGES3 * STAGE3_BYTES + STG_BYTES + 1024 + 256;
+static_assert(SMEM3_BYTES <= 232448, "conv3 ring does not fit");
 
 template <int EPI, int BF16>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_constant__ TcP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* stg_all = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES + STG_BYTES);
+    const bool conv3 = EPI == EPI_GATE && p.conv3 != 0;
+    const int ring_bytes = conv3 ? STAGES3 * STAGE3_BYTES : STAGES2 * STAGE2_BYTES;
+    float* stg_all = reinterpret_cast<float*>(smem + ring_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + ring_bytes + STG_BYTES);
     uint64_t* empty = full + STAGES2;
     uint64_t* tfull = empty + STAGES2;
     uint64_t* tempty = tfull + 2;
@@ -425,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
     const int num_pt = (p.B * p.tiles_m_per_b / 2) * p.tiles_n;      // tiles_m_per_b is even (host)
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&p.mapA);
+        prefetch_tmap(conv3 ? &p.mapA3 : &p.mapA);
         prefetch_tmap(&p.mapW);
     }
     if (warp == 1 && lane == 0) {
@@ -477,6 +493,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
             const int b = m_tile / p.tiles_m_per_b, t0 = (m_tile - b * p.tiles_m_per_b) * BLOCK_M;
             const int n0 = n_tile * p.bn;
             prefetch_cond(pt + npairs);
+            if (conv3) {
+                for (int cs = 0; cs < p.kb_per_tap; ++cs) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (lane == 0) {
+                        uint8_t* sa = smem + stage * STAGE3_BYTES;
+                        const uint32_t lbar = mapa_u32(&full[stage], 0);
+                        if (rank == 0) mbar_expect_tx(&full[stage], 2 * (A3_BYTES + 3 * (p.bn / 2) * BLOCK_K * 2));
+                        tma_load_3d_cg2(sa, &p.mapA3, lbar, cs * BLOCK_K, t0 - CONV3_HALO, b);
+#pragma unroll
+                        for (int tap = 0; tap < 3; ++tap)
+                            tma_load_2d_cg2(sa + A3_BYTES + tap * BH_BYTES, &p.mapW, lbar, (tap * p.kb_per_tap + cs) * BLOCK_K,
+                                            n0 + rank * (p.bn / 2));
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+                }
+                continue;
+            }
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 if (lane == 0) {
@@ -501,6 +535,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
             mbar_wait(&tempty[as], aphase ^ 1);          // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+            if (conv3) {
+                for (int cs = 0; cs < p.kb_per_tap; ++cs) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t s_addr = smem_u32(smem + stage * STAGE3_BYTES);
+#pragma unroll
+                        for (int tap = 0; tap < 3; ++tap) {
+                            // rows t0 + (tap - 1) * dil + i of the utterance = rows HALO + (tap - 1) * dil + i of the slab: the swizzle
+                            // is a function of the absolute shared-memory address, so a row-shifted start address reads them in place
+                            const uint32_t a_addr = s_addr + (CONV3_HALO + (tap - 1) * p.dil) * (BLOCK_K * 2);
+                            const uint32_t b_addr = s_addr + A3_BYTES + tap * BH_BYTES;
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                umma_ss_cg2(d_tmem, make_sw128_kmajor_desc(a_addr + k * (UMMA_K * 2)),
+                                            make_sw128_kmajor_desc(b_addr + k * (UMMA_K * 2)), idesc, (cs | tap | k) != 0);
+                            }
+                        }
+                        umma_commit_cg2_mcast(&empty[stage], 3);
+                        if (cs == p.kb_per_tap - 1) umma_commit_cg2_mcast(&tfull[as], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+                }
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+                continue;
+            }
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
@@ -629,15 +691,16 @@ static int launch_one(const TcP& p, cudaStream_t st) {
 #endif
     if (p.cg2) {
         static PerDevice configured2;
+        constexpr int smem_max = EPI == EPI_GATE ? (SMEM3_BYTES > SMEM2_BYTES ? SMEM3_BYTES : SMEM2_BYTES) : SMEM2_BYTES;
         if (configured2.first()) {
-            B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_cg2_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+            B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_cg2_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         }
         const int num_pt = (p.B * p.tiles_m_per_b / 2) * p.tiles_n;
         const int pairs = num_pt < num_sms() / 2 ? num_pt : num_sms() / 2;
         cudaLaunchConfig_t cfg2{};
         cfg2.gridDim = dim3(2 * pairs);
         cfg2.blockDim = dim3(NTHREADS);
-        cfg2.dynamicSmemBytes = SMEM2_BYTES;
+        cfg2.dynamicSmemBytes = (EPI == EPI_GATE && p.conv3) ? SMEM3_BYTES : SMEM2_BYTES;
         cfg2.stream = st;
         cudaLaunchAttribute attr2[2];
         attr2[0].id = cudaLaunchAttributeClusterDimension;
@@ -770,6 +833,12 @@ extern "C" int b2s_tc_wavenet_gate_ld(const void* y_h, const void* Wd_h, const v
     int rc = setup(p, y_h, C, C, B, T, true, Wd_h, 3 * C, 2 * C, 3 * C, C / BLOCK_K, dilation, bf16);
     if (rc) return rc;
     p.cond = cond_h; p.ldc = ld_cond; p.out_h = z_h; p.ldoh = ld_z;
+    static const bool conv3_on = [] { const char* e = getenv("B2S_GATE_CONV3"); return !e || atoi(e) != 0; }();
+    if (p.cg2 && conv3_on && dilation <= CONV3_HALO) {
+        rc = make_map_act(&p.mapA3, y_h, bf16, C, C, T, B, BLOCK_K, A3_ROWS);
+        if (rc) return rc;
+        p.conv3 = 1;
+    }
     return launch<EPI_GATE>(p, bf16, (cudaStream_t)stream);
 }
 
