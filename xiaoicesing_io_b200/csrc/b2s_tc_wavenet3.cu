@@ -194,12 +194,14 @@ __device__ __forceinline__ void wait_flag3(const int* f, int want) {
 // tile 4*pair + 2s + r; one cta_group::2 MMA covers the two tiles of a slot.  S_s = sum_l z_l Wskip_l^T accumulates in TMEM columns
 // [256 s, +256) over all layers (z tiles arrive through zflags), then per slot: (S + bss) -> 16-bit tile in shared memory ->
 // skip_projection -> relu(alpha acc + b_sp) -> 16-bit tile -> output_projection -> + b_fin -> out (fp32).
-// Shared memory: [0, 64K) head operand tile (4 swizzled K slabs), then 5 stages of {A 16 KB, B 16 KB}.
+// Shared memory: [0, 128K) one head operand tile (4 swizzled K slabs) per slot, then 3 stages of {A 16 KB, B 16 KB}.  The head of
+// the two slots is software-pipelined: while the tensor core runs slot 0's skip_projection the epilogue warps convert slot 1's
+// skip sum, and so on (the head is the tail of every denoiser evaluation: nothing else runs beside it).
 // A kernel of its own (clusters of 2, any number of pairs, no co-residency requirement) launched behind the layer kernel with
 // programmatic dependent launch: it starts on the SMs the layer tiles leave idle (52 of 148 at 16 x 690 frames) once every layer
 // CTA is resident, and follows the layer kernel through the z-tile flags.
 // =====================================================================================================================
-constexpr int SK_STAGES = 5, SK_STAGE_BYTES = 32768, SK_HBUF = 65536;
+constexpr int SK_STAGES = 3, SK_STAGE_BYTES = 32768, SK_HTILE = 65536, SK_HBUF = 2 * SK_HTILE;      // one head operand tile per slot
 
 constexpr int SK_SMEM_BYTES = SK_HBUF + SK_STAGES * SK_STAGE_BYTES + 256;
 
@@ -209,10 +211,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + SK_HBUF + SK_STAGES * SK_STAGE_BYTES);
     uint64_t* empty = full + SK_STAGES;
     uint64_t* sfull = empty + SK_STAGES;       // [2] skip sum of slot s complete          (commit, both CTAs)
-    uint64_t* hready = sfull + 2;              // [2] head operand tile written, both CTAs (leader, 16)
-    uint64_t* hfull0 = hready + 2;             //     skip_projection accumulator complete (commit, both CTAs)
-    uint64_t* hfull1 = hfull0 + 1;             //     output_projection accumulator complete
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hfull1 + 1);
+    uint64_t* hready = sfull + 2;              // [2 s + i] head operand tile i (0: skip sum, 1: hidden) of slot s written, both CTAs (leader, 16)
+    uint64_t* hfull0 = hready + 4;             // [2] skip_projection accumulator of slot s complete (commit, both CTAs)
+    uint64_t* hfull1 = hfull0 + 2;             // [2] output_projection accumulator of slot s complete
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hfull1 + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank() & 1u, lead = 0;
     const uint16_t pmask = 3;
@@ -229,10 +231,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sfull[i], 1);
-            mbar_init(&hready[i], EPI_WARPS * CLUSTER);
+            mbar_init(&hfull0[i], 1);
+            mbar_init(&hfull1[i], 1);
         }
-        mbar_init(hfull0, 1);
-        mbar_init(hfull1, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&hready[i], EPI_WARPS * CLUSTER);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_cg2(tmem_ptr, 512);
@@ -283,20 +285,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
                             }
                             advance();
                         }
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < 2; ++s)
                 for (int kb = 0; kb < 4; ++kb) {               // skip_projection weights: this CTA's 128 of the 256 rows
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * 16384);
                     tma_load_2d_cg2_a(st_a + stage * SK_STAGE_BYTES + 16384, &p.mapWsp, mapa_u32(&full[stage], lead), kb * BK, rank * (C / 2));
                     advance();
                 }
+            for (int s = 0; s < 2; ++s)
                 for (int kb = 0; kb < 4; ++kb) {               // output_projection weights: this CTA's MF/2 of the MF rows
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * (MF / 2) * 128);
                     tma_load_2d_cg2_a(st_a + stage * SK_STAGE_BYTES + 16384, &p.mapWfin, mapa_u32(&full[stage], lead), kb * BK, rank * (MF / 2));
                     advance();
                 }
-            }
         }
     } else if (warp == 1) {
         if (rank == 0 && lane == 0) {
@@ -323,30 +325,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
 #endif
                     }
             for (int s = 0; s < 2; ++s) {
-                mbar_wait(&hready[0], (uint32_t)s);            // (S + bss) tile of both CTAs is in shared memory
+                mbar_wait(&hready[2 * s], 0);                  // (S + bss) tile of slot s, both CTAs, is in shared memory
                 tc_fence_after();
                 for (int kb = 0; kb < 4; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_lo = hb_lo + kb * (ZSLAB >> 4), b_lo = st_lo + stage * (SK_STAGE_BYTES >> 4) + (16384 >> 4);
+                    const uint32_t a_lo = hb_lo + s * (SK_HTILE >> 4) + kb * (ZSLAB >> 4), b_lo = st_lo + stage * (SK_STAGE_BYTES >> 4) + (16384 >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) mma2(tmem_base + s * 256, a_lo + 2 * k, b_lo + 2 * k, idesc_h, (kb | k) != 0);
                     umma_commit_cg2_mcast(&empty[stage], pmask);
                     advance();
                 }
-                umma_commit_cg2_mcast(hfull0, pmask);
-                mbar_wait(&hready[1], (uint32_t)s);            // hidden tile
+                umma_commit_cg2_mcast(&hfull0[s], pmask);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_wait(&hready[2 * s + 1], 0);              // hidden tile of slot s
                 tc_fence_after();
                 for (int kb = 0; kb < 4; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_lo = hb_lo + kb * (ZSLAB >> 4), b_lo = st_lo + stage * (SK_STAGE_BYTES >> 4) + (16384 >> 4);
+                    const uint32_t a_lo = hb_lo + s * (SK_HTILE >> 4) + kb * (ZSLAB >> 4), b_lo = st_lo + stage * (SK_STAGE_BYTES >> 4) + (16384 >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) mma2(tmem_base + s * 256, a_lo + 2 * k, b_lo + 2 * k, idesc_o, (kb | k) != 0);
                     umma_commit_cg2_mcast(&empty[stage], pmask);
                     advance();
                 }
-                umma_commit_cg2_mcast(hfull1, pmask);
+                umma_commit_cg2_mcast(&hfull1[s], pmask);
             }
         }
     } else if (warp >= 4) {
@@ -354,46 +358,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
         const int row = qd * 32 + lane, sw = row & 7;
         const uint32_t hrow = hb_a + (row >> 3) * 1024 + sw * 128;
-        const uint32_t lr0 = mapa_u32(&hready[0], lead), lr1 = mapa_u32(&hready[1], lead);
+        const uint32_t lr = mapa_u32(hready, lead);
+        bool valid[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) valid[s] = ok[s] && tt0[s] + row < (p.lens ? __ldg(p.lens + tb[s]) : p.T);
+        // 32 columns of slot s's accumulator -> f(acc, bias) -> 16-bit -> the slot's swizzled operand tile
+        auto to_tile = [&](int s, const float* bias, float alpha, bool relu) {
+#pragma unroll 1
+            for (int jj = 0; jj < 4; ++jj) {
+                const int J = 4 * sub + jj;
+                float acc[32];
+                tmem_ld32(taddr + s * 256 + 32 * J, acc);
+                tmem_ld_wait();
+                uint32_t hp[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + 32 * J + 4 * i));
+                    float v0 = fmaf(alpha, acc[4 * i], bv.x), v1 = fmaf(alpha, acc[4 * i + 1], bv.y);
+                    float v2 = fmaf(alpha, acc[4 * i + 2], bv.z), v3 = fmaf(alpha, acc[4 * i + 3], bv.w);
+                    if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                    hp[2 * i] = valid[s] ? Half16<BF16>::pack2(v0, v1) : 0u;
+                    hp[2 * i + 1] = valid[s] ? Half16<BF16>::pack2(v2, v3) : 0u;
+                }
+                const uint32_t slab = hrow + s * SK_HTILE + (J >> 1) * ZSLAB;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                    st_shared_u4(slab + (((4 * (J & 1) + c4) ^ sw) << 4), make_uint4(hp[4 * c4], hp[4 * c4 + 1], hp[4 * c4 + 2], hp[4 * c4 + 3]));
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+        };
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
-            const bool valid = ok[s] && tt0[s] + row < (p.lens ? __ldg(p.lens + tb[s]) : p.T);
-            // 32 columns of the accumulator -> f(acc, bias) -> 16-bit -> the swizzled operand tile
-            auto to_tile = [&](const float* bias, float alpha, bool relu) {
-#pragma unroll 1
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int J = 4 * sub + jj;
-                    float acc[32];
-                    tmem_ld32(taddr + s * 256 + 32 * J, acc);
-                    tmem_ld_wait();
-                    uint32_t hp[16];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + 32 * J + 4 * i));
-                        float v0 = fmaf(alpha, acc[4 * i], bv.x), v1 = fmaf(alpha, acc[4 * i + 1], bv.y);
-                        float v2 = fmaf(alpha, acc[4 * i + 2], bv.z), v3 = fmaf(alpha, acc[4 * i + 3], bv.w);
-                        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-                        hp[2 * i] = valid ? Half16<BF16>::pack2(v0, v1) : 0u;
-                        hp[2 * i + 1] = valid ? Half16<BF16>::pack2(v2, v3) : 0u;
-                    }
-                    const uint32_t slab = hrow + (J >> 1) * ZSLAB;
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4)
-                        st_shared_u4(slab + (((4 * (J & 1) + c4) ^ sw) << 4), make_uint4(hp[4 * c4], hp[4 * c4 + 1], hp[4 * c4 + 2], hp[4 * c4 + 3]));
-                }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                __syncwarp();
-            };
             mbar_wait(&sfull[s], 0);
             tc_fence_after();
-            to_tile(p.bss, 1.0f, false);                       // the skip sum incl. its summed biases (wavenet.py:96, before the 1/sqrt(L))
-            if (lane == 0) arrive_remote(lr0);
-            mbar_wait(hfull0, (uint32_t)s);
+            to_tile(s, p.bss, 1.0f, false);                    // the skip sum incl. its summed biases (wavenet.py:96, before the 1/sqrt(L))
+            if (lane == 0) arrive_remote(lr + 16 * s);
+        }
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            mbar_wait(&hfull0[s], 0);
             tc_fence_after();
-            to_tile(p.b_sp, p.alpha, true);                    // skip_projection + ReLU (wavenet.py:97-98)
-            if (lane == 0) arrive_remote(lr1);
-            mbar_wait(hfull1, (uint32_t)s);
+            to_tile(s, p.b_sp, p.alpha, true);                 // skip_projection + ReLU (wavenet.py:97-98)
+            if (lane == 0) arrive_remote(lr + 16 * s + 8);
+        }
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            mbar_wait(&hfull1[s], 0);
             tc_fence_after();
             float* orow = p.out + ((long long)tb[s] * p.T + tt0[s] + row) * MF;
 #pragma unroll 1
@@ -403,7 +415,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
                 float acc[32];
                 tmem_ld32(taddr + s * 256 + 32 * J, acc);
                 tmem_ld_wait();
-                if (valid) {
+                if (valid[s]) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int col = 32 * J + 4 * i;
