@@ -334,7 +334,22 @@ int b2s_lynx_prenorm_h(float* x, const void* cond_h /* may be NULL: cond already
 int b2s_layernorm_h(const float* x, const float* gamma, const float* beta, void* h_h, int rows, int C, int bf16,
                     void* stream);
 int b2s_lynx_dwconv_h(const void* g_h, const float* WdwT, const float* bias, const float* slope, void* p_h, int B, int T,
-                      int inner, int ksize, int act, int bf16, void* stream);
+                      int inner, int ksize, int act /* 0: PReLU(slope), B2S_ACT_*: that activation, < 0: none */, int bf16,
+                      void* stream);
+
+/* ---- ConvNeXt aux decoder (the producer of x_start for shallow diffusion; reference modules/aux_decoder/convnext.py:58-87) ----
+ * b2s_tc_conv1d: dense Conv1d along time, stride 1, 'same' zero padding per utterance, as ONE tcgen05 GEMM over ksize taps
+ *   (inconv / outconv, convnext.py:64-67, :73-76).  a_h [B, T, Cin] 16-bit (Cin % 64 == 0), W_h [N, ksize * Cin] with column
+ *   tap * Cin + c, out = act(conv + bias) as fp32 rows (out_f32, ldo) and / or 16-bit rows (out_h, ldoh).
+ * b2s_layernorm_hh: LayerNorm over the channels of 16-bit rows -> 16-bit rows, fp32 statistics, eps given (convnext.py:27, :44).
+ * b2s_tc_linear_residual_scaled: x <- x + gamma * (p W^T + bias) on the fp32 residual stream (pwconv2 + layer scale + residual,
+ *   convnext.py:49-57), gamma may be NULL; x_h (may be NULL) receives the new x as 16-bit rows for the next block's depthwise conv. */
+int b2s_tc_conv1d(const void* a_h, const void* W_h, const float* bias, float* out_f32, int ldo, void* out_h, int ldoh, int B, int T,
+                  int Cin, int N, int ksize, int act, int bf16, void* stream);
+int b2s_layernorm_hh(const void* in_h, const float* gamma, const float* beta, void* out_h, int rows, int C, float eps, int bf16,
+                     void* stream);
+int b2s_tc_linear_residual_scaled(const void* p_h, const void* W_h, const float* bias, const float* gamma, float* x, void* x_h,
+                                  int rows, int C, int inner, int bf16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -129,7 +129,39 @@ def diffusion_case(name, cls_name, ctor, hp, B, T, seed, src=None, n_draws=1, va
     _save(name, meta, arrays, bb.state_dict())
 
 
+def aux_case(name, args, out_dims, n_feats, spec_min, spec_max, B, T, seed, infer=True):
+    """Runs ``AuxDecoderAdaptor(condition, infer)`` of modules/aux_decoder/__init__.py (ConvNeXt decoder, the producer of x_start)."""
+    ref_loader.load()
+    from modules.aux_decoder import AuxDecoderAdaptor
+    torch.manual_seed(seed)
+    model = AuxDecoderAdaptor(in_dims=HIDDEN, out_dims=out_dims, num_feats=n_feats, spec_min=spec_min, spec_max=spec_max,
+                              aux_decoder_arch='convnext', aux_decoder_args=args).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for pname, p in model.named_parameters():
+            if pname.endswith('gamma'):                    # layer scale is initialised to 1e-6: make the blocks matter
+                p.copy_(0.5 + 0.5 * torch.rand(p.shape, generator=g))
+            elif pname.endswith('norm.weight') or pname.endswith('norm.bias'):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    condition = torch.randn((B, T, HIDDEN), generator=g)
+    with torch.no_grad():
+        out = model(condition, infer=infer)
+    meta = dict(kind='aux_decoder', args=args, in_dims=HIDDEN, out_dims=out_dims, num_feats=n_feats, spec_min=spec_min,
+                spec_max=spec_max, infer=infer)
+    _save(name, meta, dict(condition=condition, out=out), model.decoder.state_dict())
+
+
+def aux_main():
+    aux_case('aux_convnext_mel', dict(num_channels=32, num_layers=2, kernel_size=7, dropout_rate=0.1), 16, 1,
+             [-12.] * 16, [0.] * 16, 2, 37, 300)
+    aux_case('aux_convnext_feats2_k5', dict(num_channels=48, num_layers=3, kernel_size=5, dropout_rate=0.0), 8, 2,
+             [[-10.] * 8, [-4.] * 8], [[2.] * 8, [6.] * 8], 3, 23, 301)
+    aux_case('aux_convnext_train_mode_output', dict(num_channels=32, num_layers=1, kernel_size=7), 16, 1,
+             [-12.] * 16, [0.] * 16, 1, 9, 302, infer=False)
+
+
 def main():
+    aux_main()
     # ---- backbone forward ------------------------------------------------------------------
     backbone_case('bb_wavenet_int_t', 'wavenet', WN_SMALL, 16, 1, 2, 37, torch.tensor([950, 3]), 10)
     backbone_case('bb_wavenet_float_t1', 'wavenet', WN_CYC, 16, 1, 3, 41, torch.tensor([437.25]), 11)
@@ -199,4 +231,7 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'aux':
+        aux_main()                                          # only the aux-decoder fixtures
+    else:
+        main()

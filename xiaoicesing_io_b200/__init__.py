@@ -7,6 +7,7 @@ Public surface (same names and contracts as the reference's ``modules.backbones`
     BACKBONES, build_backbone, WaveNet, LYNXNet
     GaussianDiffusion, RepetitiveDiffusion, PitchDiffusion, MultiVarianceDiffusion
     RectifiedFlow, RepetitiveRectifiedFlow, PitchRectifiedFlow, MultiVarianceRectifiedFlow
+    AUX_DECODERS, build_aux_decoder, ConvNeXtDecoder, AuxDecoderAdaptor   (modules.aux_decoder: the producer of x_start)
     hparams  (the global config dict, utils/hparams.py:13)
     segments (batched .ds segment driver: ragged batches, per-segment seeds, .mel.pt writer), partition (multi-GPU), B2SError
 
@@ -20,6 +21,7 @@ from .backbones import BACKBONES, LYNXNet, WaveNet, build_backbone, filter_kwarg
 from .core import (GaussianDiffusion, MultiVarianceDiffusion, MultiVarianceRectifiedFlow, PitchDiffusion,
                    PitchRectifiedFlow, RectifiedFlow, RepetitiveDiffusion, RepetitiveRectifiedFlow)
 from .hparams import hparams, set_hparams
+from .aux_decoder import AUX_DECODERS, AuxDecoderAdaptor, ConvNeXtDecoder, build_aux_decoder
 from . import partition, segments  # noqa: E402,F401
 
 __version__ = '0.2.0'

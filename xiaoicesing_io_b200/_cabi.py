@@ -62,6 +62,9 @@ _SIGNATURES = {
     'b2s_lynx_prenorm_h': [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_layernorm_h': [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     'b2s_lynx_dwconv_h': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_tc_conv1d': [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_layernorm_hh': [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp],
+    'b2s_tc_linear_residual_scaled': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
 }
 
 # entry points of B2S_BUILD_EXPERIMENTS=1 builds only (measured-and-rejected variants)
@@ -376,6 +379,21 @@ def lynx_prenorm_h(x, cond_h, ld_cond, dvec, d_stride, gamma, beta, h_h, B, T, C
 
 def layernorm_h(x, gamma, beta, h_h, rows, C, bf16):
     check(lib.b2s_layernorm_h(ptr(x), ptr(gamma), ptr(beta), ptr(h_h), rows, C, int(bf16), stream_ptr()), 'b2s_layernorm_h')
+
+
+def tc_conv1d(a_h, W_h, bias, out_f32, ldo, out_h, ldoh, B, T, Cin, N, ksize, act, bf16):
+    check(lib.b2s_tc_conv1d(ptr(a_h), ptr(W_h), ptr(bias), ptr(out_f32), ldo, ptr(out_h), ldoh, B, T, Cin, N, ksize, act, int(bf16),
+                            stream_ptr()), 'b2s_tc_conv1d')
+
+
+def layernorm_hh(in_h, gamma, beta, out_h, rows, C, eps, bf16):
+    check(lib.b2s_layernorm_hh(ptr(in_h), ptr(gamma), ptr(beta), ptr(out_h), rows, C, float(eps), int(bf16), stream_ptr()),
+          'b2s_layernorm_hh')
+
+
+def tc_linear_residual_scaled(p_h, W_h, bias, gamma, x, x_h, rows, C, inner, bf16):
+    check(lib.b2s_tc_linear_residual_scaled(ptr(p_h), ptr(W_h), ptr(bias), ptr(gamma), ptr(x), ptr(x_h), rows, C, inner, int(bf16),
+                                            stream_ptr()), 'b2s_tc_linear_residual_scaled')
 
 
 def lynx_dwconv_h(g_h, Wdw, bias, slope, p_h, B, T, inner, ksize, act, bf16):

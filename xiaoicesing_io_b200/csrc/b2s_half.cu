@@ -143,6 +143,51 @@ __global__ void __launch_bounds__(256) layernorm_h_kernel(float* __restrict__ x,
     }
 }
 
+// LayerNorm over the channels of 16-bit rows -> 16-bit rows, fp32 statistics, eps as an argument (ConvNeXt block, convnext.py:44:
+// eps 1e-6, input = the depthwise conv's output).  One warp per row, the row kept in registers (C <= 2048).
+__global__ void __launch_bounds__(256) layernorm_hh_kernel(const uint16_t* __restrict__ in, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, uint16_t* __restrict__ out, int rows,
+                                                           int C, float eps, int bf16) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= rows) return;
+    float4 v[16];                                   // C / 128 quads per lane
+    const int nq = C >> 7;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (i < nq) {
+            v[i] = ld_h4(in + (long long)r * C + i * 128 + lane * 4, bf16);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (i < nq) {
+            const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+            var += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (i < nq) {
+            const int c = i * 128 + lane * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+            st_h4(out + (long long)r * C + c,
+                  make_float4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                              (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w), bf16);
+        }
+    }
+}
+
 // Depthwise conv along time + bias + activation, 16-bit in / out, fp32 math (lynxnet.py:57-58).
 // Thread = 2 adjacent channels (4-byte accesses, a warp reads 128 contiguous bytes per frame), one block = 256 channels x
 // a strip of DWH_STRIP frames of one utterance.  Per iteration a thread produces G = 8 consecutive output frames from a
@@ -460,6 +505,18 @@ extern "C" int b2s_layernorm_h(const float* x, const float* gamma, const float* 
     size_t smem = (size_t)warps * C * sizeof(float);
     layernorm_h_kernel<false><<<ceil_div(rows, warps), warps * 32, smem, (cudaStream_t)stream>>>(
         const_cast<float*>(x), nullptr, 0, nullptr, 0, gamma, beta, (uint16_t*)h_h, rows, 1, C, 0, bf16);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+extern "C" int b2s_layernorm_hh(const void* in_h, const float* gamma, const float* beta, void* out_h, int rows, int C, float eps,
+                                int bf16, void* stream) {
+    B2S_CHECK_ARG(in_h && gamma && beta && out_h, "b2s_layernorm_hh: null pointer");
+    B2S_CHECK_ARG(C > 0 && C <= 2048 && C % 128 == 0, "b2s_layernorm_hh: C must be a multiple of 128, at most 2048 (C=%d)", C);
+    B2S_CHECK_ARG(tc::al16(in_h) && tc::al16(out_h) && tc::al16(gamma) && tc::al16(beta), "b2s_layernorm_hh: misaligned pointer");
+    if (rows <= 0) return B2S_OK;
+    layernorm_hh_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in_h, gamma, beta, (uint16_t*)out_h,
+                                                                             rows, C, eps, bf16);
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }

@@ -62,6 +62,7 @@ struct __align__(64) TcP {
     // BLOCK_M + 2 * CONV3_HALO rows) and the weight slabs of all three taps; the taps read it through row-shifted descriptors
     CUtensorMap mapA3;
     int conv3;
+    int tap_c;                 // conv GEMMs: tap k reads rows t + (k - tap_c) * dil (1 for the 3-tap dilated conv, ksize / 2 in general)
 };
 
 // ---- 16-bit helpers --------------------------------------------------------------------------------
@@ -115,6 +116,7 @@ __device__ __forceinline__ EpiConst epilogue_consts(const TcP& p, int col) {
     }
     if ((EPI == EPI_LINEAR || EPI == EPI_RESSKIP) && p.y_h && p.d_stride == 0 && col + 4 <= p.N && (EPI != EPI_RESSKIP || col < p.C))
         c.d = __ldg(reinterpret_cast<const float4*>(p.dvec + col));
+    if (EPI == EPI_RESIDUAL && p.dvec) c.d = __ldg(reinterpret_cast<const float4*>(p.dvec + col));     // layer scale (ConvNeXt gamma)
     return c;
 }
 
@@ -184,7 +186,9 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
         store_h2<BF16>(p.out_h, r * p.ldoh + (col >> 1), (acc.x + k.bias.x) * (g0 * sigmoid_fast(g0)),
                        (acc.z + k.bias.z) * (g1 * sigmoid_fast(g1)));
     } else if (EPI == EPI_RESIDUAL) {
-        float4 xn = add4(in, add4(acc, k.bias));
+        float4 o = add4(acc, k.bias);
+        if (p.dvec) o = make_float4(o.x * k.d.x, o.y * k.d.y, o.z * k.d.z, o.w * k.d.w);      // x + gamma * (acc + b), convnext.py:51-56
+        float4 xn = add4(in, o);
         if (p.cond) {
             // strong_cond LYNXNet: the NEXT layer's front_cond_inject (x += cond_proj(cond), lynxnet.py:77-82) folded into this
             // layer's residual epilogue, so the next LayerNorm kernel neither reads the cond table nor writes x back
@@ -193,6 +197,7 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
             xn = add4(xn, make_float4(c0.x, c0.y, c1.x, c1.y));
         }
         *reinterpret_cast<float4*>(p.x + r * p.C + col) = xn;
+        if (p.y_h) store_h4<BF16>(p.y_h, r * p.ldy + col, xn);                                 // 16-bit copy for the next depthwise conv
     } else {   // EPI_RESSKIP: reference column order, [0, C) residual, [C, 2C) skip
         const float inv_sqrt2 = 0.70710678118654752440f;
         const float4 o = add4(acc, k.bias);
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
-                    tma_load_3d(sa, &p.mapA, &full[stage], c0, t0 + (tap - 1) * p.dil, p.k_layered ? tap : b);
+                    tma_load_3d(sa, &p.mapA, &full[stage], c0, t0 + (tap - p.tap_c) * p.dil, p.k_layered ? tap : b);
                     tma_load_2d(sa + A_BYTES, &p.mapW, &full[stage], kb * BLOCK_K, n0);
                 }
                 __syncwarp();
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + (p.bn / 2) * BLOCK_K * 2));
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
-                    tma_load_3d_cg2(sa, &p.mapA, lbar, c0, t0 + (tap - 1) * p.dil, p.k_layered ? tap : b);
+                    tma_load_3d_cg2(sa, &p.mapA, lbar, c0, t0 + (tap - p.tap_c) * p.dil, p.k_layered ? tap : b);
                     tma_load_2d_cg2(sa + A_BYTES, &p.mapW, lbar, kb * BLOCK_K, n0 + rank * (p.bn / 2));
                 }
                 __syncwarp();
@@ -759,6 +764,7 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     p.num_kb = ceil_div(K, BLOCK_K);
     p.kb_per_tap = kb_per_tap > 0 ? kb_per_tap : p.num_kb;
     p.dil = dil;
+    p.tap_c = 1;
     p.tiles_m_per_b = ceil_div(Tm, BLOCK_M);
     if (p.cg2) p.tiles_m_per_b = (p.tiles_m_per_b + 1) & ~1;       // whole CTA pairs; a padding tile has no valid row
     p.tiles_n = ceil_div(N, p.bn);
@@ -921,6 +927,40 @@ static int linear_residual_impl(const void* p_h, const void* W_h, const float* b
     int rc = setup(p, p_h, inner, inner, 1, rows, false, W_h, inner, C, inner, 0, 0, bf16);
     if (rc) return rc;
     p.bias = bias; p.x = x; p.C = C; p.cond = cond_next_h; p.ldc = ld_cond;
+    return launch<EPI_RESIDUAL>(p, bf16, (cudaStream_t)stream);
+}
+
+// Dense Conv1d along time (stride 1, 'same' zero padding per utterance) as ONE GEMM over ksize taps: A = [B, T, Cin] 16-bit,
+// W = [N, ksize * Cin] (column = tap * Cin + c), out = act(A * W + bias) as fp32 and / or 16-bit rows (aux_decoder/convnext.py:64-67, :73-76)
+extern "C" int b2s_tc_conv1d(const void* a_h, const void* W_h, const float* bias, float* out_f32, int ldo, void* out_h, int ldoh,
+                             int B, int T, int Cin, int N, int ksize, int act, int bf16, void* stream) {
+    B2S_CHECK_ARG(a_h && W_h && (out_f32 || out_h), "b2s_tc_conv1d: null pointer");
+    B2S_CHECK_ARG(Cin % 64 == 0 && N > 0 && ksize >= 1 && (ksize & 1) && ksize <= 63, "b2s_tc_conv1d: needs Cin %% 64 == 0 (Cin=%d) and an odd kernel size (%d)", Cin, ksize);
+    B2S_CHECK_ARG(al16(a_h) && al16(W_h) && (!out_f32 || (ldo % 4 == 0 && al16(out_f32))) && (!out_h || (ldoh % 8 == 0 && al16(out_h))),
+                  "b2s_tc_conv1d: misaligned pointer / leading dimension");
+    if (B * T == 0) return B2S_OK;
+    TcP p{};
+    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, 1, bf16);
+    if (rc) return rc;
+    p.tap_c = ksize / 2;
+    p.bias = bias; p.alpha = 1.0f; p.act = act;
+    p.out_f = out_f32; p.ldo = ldo; p.out_h = out_h; p.ldoh = ldoh;
+    return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
+}
+
+// x <- x + gamma * (p * W^T + bias) (fp32 residual stream, per-channel layer scale), optionally also x as 16-bit rows
+// (aux_decoder/convnext.py:49-57)
+extern "C" int b2s_tc_linear_residual_scaled(const void* p_h, const void* W_h, const float* bias, const float* gamma, float* x,
+                                             void* x_h, int rows, int C, int inner, int bf16, void* stream) {
+    B2S_CHECK_ARG(p_h && W_h && bias && x, "b2s_tc_linear_residual_scaled: null pointer");
+    B2S_CHECK_ARG(C % 32 == 0 && inner % 8 == 0, "b2s_tc_linear_residual_scaled: bad dims C=%d inner=%d", C, inner);
+    B2S_CHECK_ARG(al16(p_h) && al16(W_h) && al16(bias) && al16(x) && (!gamma || al16(gamma)) && (!x_h || al16(x_h)),
+                  "b2s_tc_linear_residual_scaled: misaligned pointer");
+    if (rows == 0) return B2S_OK;
+    TcP p{};
+    int rc = setup(p, p_h, inner, inner, 1, rows, false, W_h, inner, C, inner, 0, 0, bf16);
+    if (rc) return rc;
+    p.bias = bias; p.x = x; p.C = C; p.dvec = gamma; p.y_h = x_h; p.ldy = C;
     return launch<EPI_RESIDUAL>(p, bf16, (cudaStream_t)stream);
 }
 
