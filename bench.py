@@ -422,9 +422,46 @@ def run_secondary(args, dev):
         except Exception as ex:                             # noqa: BLE001
             out[name] = {'workload': w['desc'], 'error': f'{type(ex).__name__}: {ex}'}
         torch.cuda.empty_cache()
+    try:
+        out['aux_decoder'] = time_aux_decoder(args.precision, dev)
+    except Exception as ex:                                 # noqa: BLE001
+        out['aux_decoder'] = {'error': f'{type(ex).__name__}: {ex}'}
+    torch.cuda.empty_cache()
     P.hparams.clear()
     P.hparams.update(saved)
     return out
+
+
+def time_aux_decoder(precision, dev, B=16, T=690, reps=5):
+    """The step BEFORE the path: the ConvNeXt aux decoder that produces x_start for shallow diffusion
+    (configs/acoustic.yaml:101-105: 512 channels, 6 blocks, k = 7), once per utterance batch - config 2's batch.  Random-init
+    weights with layer scale 0.5; device-timed with CUDA events."""
+    import xiaoicesing_io_b200 as P
+    P.hparams.clear()
+    P.hparams.update(b2s_precision=precision if precision != 'fp32' else 'fp16')
+    torch.manual_seed(0)
+    m = P.AuxDecoderAdaptor(in_dims=256, out_dims=128, num_feats=1, spec_min=[-12.0] * 128, spec_max=[0.0] * 128,
+                            aux_decoder_arch='convnext', aux_decoder_args=dict(num_channels=512, num_layers=6, kernel_size=7))
+    with torch.no_grad():
+        for blk in m.decoder.conv:
+            blk.gamma.fill_(0.5)
+    m = m.to(dev).eval()
+    cond = torch.randn((B, T, 256), device=dev)
+    for _ in range(3):
+        m(cond, infer=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        m(cond, infer=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    macs = 7 * 256 * 512 + 6 * (2 * 512 * 2048 + 7 * 512) + 7 * 512 * 128        # per frame: inconv, blocks (pointwise + depthwise), outconv
+    tf = 2.0 * macs * B * T / (ms * 1e-3) / 1e12
+    return {'workload': f'ConvNeXt aux decoder 6x512 (k=7), 256 -> 128 mel, B={B} x T={T}: x_start for shallow diffusion, once per batch',
+            'ms_per_call': ms, 'frames_per_s': B * T / (ms * 1e-3), 'tflops_algorithmic': tf,
+            'frac_of_bf16_peak': tf / peaks()['bf16_burst'], 'launches_per_call': 2 + 4 * 6 + 1}
 
 
 def run_b200_arm(args, w):
