@@ -143,6 +143,74 @@ __global__ void __launch_bounds__(256) layernorm_h_kernel(float* __restrict__ x,
     }
 }
 
+// The same with the row held in REGISTERS (C a multiple of 128, at most 2048): no shared-memory round trip, every load of the row
+// issued before the first reduction.  The staged variant above took 72 us at config 3's shape (276 MB: 36 us at the HBM roofline).
+template <bool PRE, int NQ>
+__global__ void __launch_bounds__(256) layernorm_h_reg_kernel(float* __restrict__ x, const uint16_t* __restrict__ cond, int ld_cond,
+                                                              const float* __restrict__ dvec, int d_stride,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              uint16_t* __restrict__ h, int rows, int T, int strong, int bf16) {
+    constexpr int C = NQ * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= rows) return;
+    const int b = PRE ? r / T : 0;
+    float4 v[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) v[i] = *reinterpret_cast<const float4*>(x + (long long)r * C + i * 128 + lane * 4);
+    if (PRE) {
+        if (cond) {
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                const float4 cc = ld_h4(cond + (long long)r * ld_cond + i * 128 + lane * 4, bf16);
+                v[i] = make_float4(v[i].x + cc.x, v[i].y + cc.y, v[i].z + cc.z, v[i].w + cc.w);
+                if (strong) *reinterpret_cast<float4*>(x + (long long)r * C + i * 128 + lane * 4) = v[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dvec + (long long)b * d_stride + i * 128 + lane * 4));
+            v[i] = make_float4(v[i].x + d.x, v[i].y + d.y, v[i].z + d.z, v[i].w + d.w);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        var += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / (float)C + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const int c = i * 128 + lane * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+        st_h4(h + (long long)r * C + c,
+              make_float4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y, (v[i].z - mean) * rstd * g.z + bb.z,
+                          (v[i].w - mean) * rstd * g.w + bb.w), bf16);
+    }
+}
+
+template <bool PRE>
+static bool launch_layernorm_reg(float* x, const uint16_t* cond, int ld_cond, const float* dvec, int d_stride, const float* gamma,
+                                 const float* beta, uint16_t* h, int rows, int T, int C, int strong, int bf16, cudaStream_t st) {
+    const int grid = ceil_div(rows, 8);
+    switch (C) {
+#define B2S_LN_CASE(NQ) case NQ * 128: layernorm_h_reg_kernel<PRE, NQ><<<grid, 256, 0, st>>>(x, cond, ld_cond, dvec, d_stride, gamma, beta, h, rows, T, strong, bf16); return true;
+        B2S_LN_CASE(1) B2S_LN_CASE(2) B2S_LN_CASE(3) B2S_LN_CASE(4) B2S_LN_CASE(6) B2S_LN_CASE(8) B2S_LN_CASE(12) B2S_LN_CASE(16)
+#undef B2S_LN_CASE
+    }
+    return false;
+}
+
 // LayerNorm over the channels of 16-bit rows -> 16-bit rows, fp32 statistics, eps as an argument (ConvNeXt block, convnext.py:44:
 // eps 1e-6, input = the depthwise conv's output).  One warp per row, the row kept in registers (C <= 2048).
 __global__ void __launch_bounds__(256) layernorm_hh_kernel(const uint16_t* __restrict__ in, const float* __restrict__ gamma,
@@ -488,6 +556,11 @@ extern "C" int b2s_lynx_prenorm_h(float* x, const void* cond_h, int ld_cond, con
     B2S_CHECK_ARG(C > 0 && C <= 8192 && C % 4 == 0 && ld_cond % 4 == 0 && d_stride % 4 == 0, "b2s_lynx_prenorm_h: C, ld_cond, d_stride must be multiples of 4");
     const int rows = B * T;
     if (rows <= 0) return B2S_OK;
+    if (launch_layernorm_reg<true>(x, (const uint16_t*)cond_h, ld_cond, dvec, d_stride, gamma, beta, (uint16_t*)h_h, rows, T, C,
+                                   strong_cond, bf16, (cudaStream_t)stream)) {
+        B2S_CHECK_LAUNCH();
+        return B2S_OK;
+    }
     const int warps = C <= 1024 ? 8 : (C <= 2048 ? 4 : 1);
     size_t smem = (size_t)warps * C * sizeof(float);
     layernorm_h_kernel<true><<<ceil_div(rows, warps), warps * 32, smem, (cudaStream_t)stream>>>(
@@ -501,6 +574,11 @@ extern "C" int b2s_layernorm_h(const float* x, const float* gamma, const float* 
     B2S_CHECK_ARG(x && gamma && beta && h_h, "b2s_layernorm_h: null pointer");
     B2S_CHECK_ARG(C > 0 && C <= 8192 && C % 4 == 0, "b2s_layernorm_h: C must be a multiple of 4");
     if (rows <= 0) return B2S_OK;
+    if (launch_layernorm_reg<false>(const_cast<float*>(x), nullptr, 0, nullptr, 0, gamma, beta, (uint16_t*)h_h, rows, 1, C, 0, bf16,
+                                    (cudaStream_t)stream)) {
+        B2S_CHECK_LAUNCH();
+        return B2S_OK;
+    }
     const int warps = C <= 1024 ? 8 : (C <= 2048 ? 4 : 1);
     size_t smem = (size_t)warps * C * sizeof(float);
     layernorm_h_kernel<false><<<ceil_div(rows, warps), warps * 32, smem, (cudaStream_t)stream>>>(
