@@ -122,7 +122,7 @@ class _GraphedLoop:
         shape = (B, F_ * M, T)
 
         def body():
-            sess = eng.begin(self.cond, cp.t_values, per_row_t=False, lens=self.lens)
+            sess = eng.begin(self.cond, cp.t_values, per_row_t=False, lens=self.lens, table_owner=cp)
             bufs = allocate_buffers(prog, B * T, F_ * M, device)
 
             def load(src, dst):
@@ -268,7 +268,7 @@ def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, 
     if noise_source is None:
         noise_source = lambda s: torch.randn(s, device=device)
     cp = CompiledProgram(prog, device)
-    sess = eng.begin(cond_bth, cp.t_values, per_row_t=False, lens=lens)
+    sess = eng.begin(cond_bth, cp.t_values, per_row_t=False, lens=lens, table_owner=cp)
     bufs = allocate_buffers(prog, B * T, F_ * M, device)
 
     def load(src_bfmt, dst):

@@ -161,6 +161,9 @@ class WaveNetEngine:
     # -- per-call tables ---------------------------------------------------------------------------
     def step_table(self, t_values: torch.Tensor) -> torch.Tensor:
         """t_values [K] fp32 (device) -> [K, L*C]: diffusion_projection_l(mlp(sinusoid(t))) for all l."""
+        return _cached_step_table(self, t_values, self._step_table)
+
+    def _step_table(self, t_values: torch.Tensor) -> torch.Tensor:
         K = t_values.numel()
         Cc, LC = self.C0, self.L * self.C                    # the MLP has the model's width; the table the (padded) kernels' width
         dev = self.device
@@ -182,18 +185,44 @@ class WaveNetEngine:
         C.linear(cond_bth, H, self.w_cond, H, self.b_cond, tab, N, B * T, N, H)
         return tab
 
-    def begin(self, cond_bth: torch.Tensor, t_values: torch.Tensor, per_row_t: bool = False, lens=None) -> 'WaveNetSession':
+    def begin(self, cond_bth: torch.Tensor, t_values: torch.Tensor, per_row_t: bool = False, lens=None, table_owner=None) -> 'WaveNetSession':
         """``lens``: optional int32 device tensor [B] - a RAGGED batch padded to T; frames at or beyond lens[b] are treated as the
-        conv's zero padding (only the whole-stack tensor-core path implements this)."""
+        conv's zero padding (only the whole-stack tensor-core path implements this).  ``table_owner``: the compiled sampler program
+        ``t_values`` belongs to - the step table (a function of the weights and of the program's model times only) is then computed
+        once and kept on it instead of once per sampling call."""
         self.pack()
         C.require_cuda(cond_bth, 'cond')
         C.require_cuda(t_values, 't_values')
-        if self.precision != 'fp32':
-            return WaveNetSessionTC(self, cond_bth, t_values, per_row_t, lens)
-        if lens is not None:
-            raise C.B2SError("ragged batches (lengths=...) need the 16-bit whole-stack path (b2s_precision 'fp16' / 'bf16', 256 channels, "
-                             "dilations <= 16); batch equal-length segments instead")
-        return WaveNetSession(self, cond_bth, t_values, per_row_t)
+        self._table_owner = table_owner
+        try:
+            if self.precision != 'fp32':
+                return WaveNetSessionTC(self, cond_bth, t_values, per_row_t, lens)
+            if lens is not None:
+                raise C.B2SError("ragged batches (lengths=...) need the 16-bit whole-stack path (b2s_precision 'fp16' / 'bf16', 256 channels, "
+                                 "dilations <= 16); batch equal-length segments instead")
+            return WaveNetSession(self, cond_bth, t_values, per_row_t)
+        finally:
+            self._table_owner = None
+
+
+def _cached_step_table(eng, t_values, compute):
+    """The step table of (engine weights, sampler program): three tiny fp32 GEMMs that cost ~0.3 ms per sampling call - 5 % of a
+    one-utterance DDIM-20 call - although nothing in them changes between calls.  Kept on the compiled program (``table_owner``),
+    keyed by the engine and its packed-weight version; never created while a CUDA graph is being captured (a captured fill would
+    only be valid after that graph's replay), so the first, eager call of a shape fills it and the captured graphs read it."""
+    owner = getattr(eng, '_table_owner', None)
+    if owner is None:
+        return compute(t_values)
+    cache = owner.__dict__.setdefault('_b2s_step_tables', {})
+    key = (id(eng), eng._packed_version)
+    tab = cache.get(key)
+    if tab is None:
+        tab = compute(t_values)
+        if not torch.cuda.is_current_stream_capturing():
+            if len(cache) >= 4:
+                cache.clear()
+            cache[key] = tab
+    return tab
 
 
 def _pad_cols(w: torch.Tensor, mult: int) -> torch.Tensor:
@@ -687,6 +716,9 @@ class LYNXNetEngine:
         self._packed_version = v
 
     def step_table(self, t_values):
+        return _cached_step_table(self, t_values, self._step_table)
+
+    def _step_table(self, t_values):
         K = t_values.numel()
         Cc, dev = self.C, self.device
         sin = torch.empty((K, Cc), device=dev)
@@ -706,15 +738,19 @@ class LYNXNetEngine:
         C.linear(cond_bth, H, self.w_cond, H, self.b_cond, tab, N, B * T, N, H)
         return tab
 
-    def begin(self, cond_bth, t_values, per_row_t=False, lens=None):
+    def begin(self, cond_bth, t_values, per_row_t=False, lens=None, table_owner=None):
         if lens is not None:
             raise C.B2SError('ragged batches (lengths=...) are implemented for the WaveNet whole-stack path only; batch equal-length segments')
         self.pack()
         C.require_cuda(cond_bth, 'cond')
         C.require_cuda(t_values, 't_values')
-        if self.precision != 'fp32':
-            return LYNXNetSessionTC(self, cond_bth, t_values, per_row_t)
-        return LYNXNetSession(self, cond_bth, t_values, per_row_t)
+        self._table_owner = table_owner
+        try:
+            if self.precision != 'fp32':
+                return LYNXNetSessionTC(self, cond_bth, t_values, per_row_t)
+            return LYNXNetSession(self, cond_bth, t_values, per_row_t)
+        finally:
+            self._table_owner = None
 
 
 class LYNXNetSession:
