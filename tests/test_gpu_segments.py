@@ -86,3 +86,19 @@ def test_mel_pt_written_in_segment_order(tmp_path):
     assert [b['mel'].shape[1] for b in back] == frames and [b['offset'] for b in back] == [0.0, 2.0, 4.0]
     assert all(b['f0'].shape == (1, n) for b, n in zip(back, frames))
     assert all(bool(torch.isfinite(b['mel']).all()) for b in back)
+
+
+def test_seeded_noise_equals_the_reference_reseeding_rule():
+    """ds_acoustic.py:212-217 reseeds the process-wide generators before every segment; seeded_noise draws the same bits from a
+    private generator (and leaves the global stream alone)."""
+    from xiaoicesing_io_b200 import segments as SG
+    dev = torch.device('cuda:0')
+    for seed, shape in ((0, (1, 1, 128, 690)), (123456789, (1, 2, 24, 37)), (0xffffffff, (1, 1, 128, 1))):
+        torch.manual_seed(seed)
+        torch.cuda.manual_seed_all(seed)
+        want = torch.randn(shape, device=dev)
+        torch.manual_seed(99)
+        before = torch.cuda.get_rng_state(dev).clone()
+        got = SG.seeded_noise(shape, seed, dev)
+        assert torch.equal(got, want), seed
+        assert torch.equal(torch.cuda.get_rng_state(dev), before)

@@ -162,7 +162,7 @@ class _GraphedLoop:
 # so only a few are kept; the keys seen ONCE (a graph is captured on the second call with a key) live in their own small LRU so
 # that a stream of new shapes (variable-length batches) never evicts a live graph.
 _GRAPH_CACHE: 'OrderedDict[tuple, object]' = OrderedDict()
-_GRAPH_CACHE_MAX = 4
+_GRAPH_CACHE_MAX = 4          # default; hparams['b2s_graph_cache'] overrides (the segment driver asks for one graph per length bucket)
 _SEEN_KEYS: 'OrderedDict[tuple, None]' = OrderedDict()
 _SEEN_KEYS_MAX = 64
 # hparams that change WHICH kernels a sampling call launches: part of the graph key (toggling one after capture must not replay
@@ -255,7 +255,7 @@ def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, 
         entry = _GRAPH_CACHE.get(graph_key)
         if entry is None and graph_key in _SEEN_KEYS:       # second call with this key: capture
             del _SEEN_KEYS[graph_key]
-            while len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+            while len(_GRAPH_CACHE) >= max(1, int(hparams.get('b2s_graph_cache', _GRAPH_CACHE_MAX))):
                 _GRAPH_CACHE.popitem(last=False)            # least recently used graph
             entry = _GraphedLoop(eng, CompiledProgram(prog, device), B, T, H, F_, M, device, ragged=lens is not None,
                                  ext_noise=noise0_in is not None, start_tm=start_tm)

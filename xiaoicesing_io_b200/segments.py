@@ -30,6 +30,7 @@ import torch
 from .partition import partition_by_length
 
 TILE = 128     # frames per tile of the whole-stack kernel: ragged batches are padded to a multiple of it
+GRAPH_BUCKETS = 24   # CUDA graphs kept while a project is sampled: one per padded length (30 s = 21 tiles), see sample_segments
 
 
 def load_ds(path) -> List[dict]:
@@ -85,15 +86,23 @@ def plan_batches(lengths: Sequence[int], max_batch_frames: int = 16 * 704, max_b
     return batches
 
 
+_GENERATORS: Dict[str, torch.Generator] = {}
+
+
 def seeded_noise(shape: Tuple[int, ...], seed: Optional[int], device) -> torch.Tensor:
     """The first noise draw of a B = 1 run of the reference on ``device`` after its per-segment reseeding:
     ``torch.manual_seed(seed); torch.cuda.manual_seed_all(seed); randn(1, F, M, T, device=device)`` (ds_acoustic.py:212-217,
-    ddpm.py:227).  ``seed`` None: drawn from the current global stream."""
-    if seed is not None:
-        torch.manual_seed(seed)
-        if torch.cuda.is_available():
-            torch.cuda.manual_seed_all(seed)
-    return torch.randn(shape, device=device)
+    ddpm.py:227).  Drawn from a private generator seeded the same way (same Philox seed, offset 0 -> the same bits; checked by
+    tests/test_gpu_segments.py) so that a batch of segments does not reseed the process-wide generators once per segment (two
+    global reseeds cost more host time than the draw).  ``seed`` None: drawn from the current global stream."""
+    if seed is None:
+        return torch.randn(shape, device=device)
+    device = torch.device(device)
+    g = _GENERATORS.get(str(device))
+    if g is None:
+        g = _GENERATORS[str(device)] = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return torch.randn(shape, device=device, generator=g)
 
 
 CondFn = Callable[[dict, int], Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]]
@@ -111,32 +120,51 @@ def sample_segments(model, params: Sequence[dict], cond_fn: CondFn, timestep: fl
     frames = {i: segment_frames(params[i], timestep) for i in idx}
     out: Dict[int, dict] = {}
     F_, M = model.num_feats, model.out_dims
-    for batch in plan_batches([frames[i] for i in idx], max_batch_frames, max_batch_size):
-        seg = [idx[j] for j in batch]
-        lens = [frames[i] for i in seg]
-        T = -(-max(lens) // TILE) * TILE
-        conds, srcs, f0s = [], [], []
-        for i in seg:
-            c, s, f0 = cond_fn(params[i], frames[i])
-            if c.shape[0] != frames[i]:
-                raise ValueError(f'segment {i}: cond_fn returned {c.shape[0]} frames, the segment has {frames[i]}')
-            conds.append(c)
-            srcs.append(s)
-            f0s.append(f0)
-        H = conds[0].shape[1]
-        condition = torch.zeros((len(seg), T, H), device=device)
-        noise = torch.zeros((len(seg), F_, M, T), device=device)
-        src = None
-        if any(s is not None for s in srcs):
-            src = torch.zeros((len(seg), T, M), device=device)
+    pending = []          # (segments, lengths, mel on the device, f0s): results stay on the device until every batch is enqueued,
+    #                       so the host prepares batch i + 1 (conditions, seeded noise) while the GPU samples batch i
+    from .hparams import hparams
+    saved_cap = hparams.get('b2s_graph_cache')
+    hparams['b2s_graph_cache'] = max(GRAPH_BUCKETS, int(saved_cap or 0))
+    try:
+        for batch in plan_batches([frames[i] for i in idx], max_batch_frames, max_batch_size):
+            seg = [idx[j] for j in batch]
+            lens = [frames[i] for i in seg]
+            T = -(-max(lens) // TILE) * TILE
+            # ONE batch shape per padded length: the batch always has the capacity of its bucket, unused slots are utterances of
+            # length 0 (lengths= makes them the conv's zero padding; a launch holds every tile of the batch anyway, so they cost no
+            # time) - a project of any size replays at most one captured graph per bucket instead of capturing one per (B, T)
+            cap = max(len(seg), min(max_batch_size, max(1, max_batch_frames // T)))
+            conds, srcs, f0s = [], [], []
+            for i in seg:
+                c, s, f0 = cond_fn(params[i], frames[i])
+                if c.shape[0] != frames[i]:
+                    raise ValueError(f'segment {i}: cond_fn returned {c.shape[0]} frames, the segment has {frames[i]}')
+                conds.append(c)
+                srcs.append(s)
+                f0s.append(f0)
+            H = conds[0].shape[1]
+            condition = torch.zeros((cap, T, H), device=device)
+            noise = torch.zeros((cap, F_, M, T), device=device)
+            src = None
+            if any(s is not None for s in srcs):
+                src = torch.zeros((cap, T, M), device=device)
+            for k, i in enumerate(seg):
+                condition[k, :lens[k]] = conds[k].to(device, non_blocking=True)
+                noise[k, ..., :lens[k]] = seeded_noise((1, F_, M, lens[k]), segment_seed(params[i], seed), device)[0]
+                if src is not None and srcs[k] is not None:
+                    src[k, :lens[k]] = srcs[k].to(device, non_blocking=True)
+            lengths = torch.tensor(lens + [0] * (cap - len(seg)), dtype=torch.int32)
+            mel = model(condition, src_spec=src, infer=True, lengths=lengths, initial_noise=noise)
+            pending.append((seg, lens, mel, f0s))
+    finally:
+        if saved_cap is None:
+            hparams.pop('b2s_graph_cache', None)
+        else:
+            hparams['b2s_graph_cache'] = saved_cap
+    for seg, lens, mel, f0s in pending:
+        mel_h = mel.float().cpu()                              # the first copy waits for the stream; the rest are plain copies
         for k, i in enumerate(seg):
-            condition[k, :lens[k]] = conds[k].to(device)
-            noise[k, ..., :lens[k]] = seeded_noise((1, F_, M, lens[k]), segment_seed(params[i], seed), device)[0]
-            if src is not None and srcs[k] is not None:
-                src[k, :lens[k]] = srcs[k].to(device)
-        mel = model(condition, src_spec=src, infer=True, lengths=torch.tensor(lens, dtype=torch.int32), initial_noise=noise)
-        for k, i in enumerate(seg):
-            out[i] = {'offset': float(params[i].get('offset', 0.)), 'mel': mel[k:k + 1, :lens[k]].float().cpu(),
+            out[i] = {'offset': float(params[i].get('offset', 0.)), 'mel': mel_h[k:k + 1, :lens[k]].clone(),
                       'f0': None if f0s[k] is None else f0s[k].reshape(1, -1).float().cpu()}
     for i in idx:
         if i not in out:                                        # zero-length segment
