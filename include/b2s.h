@@ -310,6 +310,16 @@ int b2s_tc_wavenet_denoiser3(const void* xin_h, int MF, const void* Win_h, int l
                              int64_t z_layer_stride, const void* Wskip_h, const float* bss, const void* Wsp_h, const float* b_sp,
                              const void* Wfin_h, const float* b_fin, float* out, int B, int T, int C, int* flags, int* zflags,
                              const int* lens, int bf16, void* stream);
+/* The same launch as one of SEVERAL utterance groups of ONE evaluation issued back to back on the stream (batches larger than
+ * b2s_tc_wavenet_denoiser3_max_utterances).  chain bit 0: this launch follows another group of the evaluation, bit 1: another group
+ * follows.  Same results; a following group's layer kernel does not wait for this group's skip / head tail (it waits at its end
+ * instead, so stream-order completion still holds for the kernel after the last group). */
+int b2s_tc_wavenet_denoiser3_chained(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
+                             const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum, const float* dvec,
+                             int d_stride, const int* dilations_host, int L, void* yedge0_h, void* yedge1_h, void* z_all_h,
+                             int64_t z_layer_stride, const void* Wskip_h, const float* bss, const void* Wsp_h, const float* b_sp,
+                             const void* Wfin_h, const float* b_fin, float* out, int B, int T, int C, int* flags, int* zflags,
+                             const int* lens, int bf16, int chain, void* stream);
 
 /* LYNXNet pointwise convs on the tensor cores (lynxnet.py:55-56, 60): SwiGLU up-projection and the
  * down-projection with the residual add into the fp32 stream. */

@@ -250,6 +250,46 @@ def test_narrow_wavenet_on_the_padded_whole_stack_kernel(channels, L, cycle, in_
         assert d <= 6 * eps * scale, (d, scale)
 
 
+@pytest.mark.parametrize('B,T', [(40, 690), (70, 345), (150, 129)])
+def test_chained_utterance_groups_do_not_change_a_bit(B, T, dev):
+    """Batches larger than one launch run as several utterance groups per evaluation; by default a group's layer kernel does not
+    wait for the previous group's skip / head tail (b2s_tc_wavenet_denoiser3_chained: late griddepcontrol.wait).  Same bits as the
+    plain back-to-back launches, single call and a whole sampling loop (eager and CUDA-graph replay)."""
+    import xiaoicesing_io_b200 as P
+    g = torch.Generator().manual_seed(B + T)
+    spec = torch.randn((B, 1, 128, T), generator=g).to(dev)
+    cond = torch.randn((B, 256, T), generator=g).to(dev)
+    t = (torch.arange(B, dtype=torch.float32) * 7 + 3).to(dev)
+    outs = []
+    for chain in (True, False):
+        net = _bf16_backbone(dev, stack=True, L=6, precision='fp16', stack3=True)
+        P.hparams['b2s_chain_groups'] = chain
+        sess = net._engine().begin(cond.transpose(1, 2).contiguous(), t, per_row_t=True)
+        assert sess.stack3 and sess.head3 and B > sess.stack_group, 'the shape must need several groups'
+        outs.append(net(spec, t, cond))
+    assert bool(torch.isfinite(outs[0]).all())
+    assert torch.equal(outs[0], outs[1])
+    from oracle import weights as OW
+    res = []
+    for chain in (True, False):
+        cfg = OD.WaveNetCfg(num_layers=4)
+        P.hparams.clear()
+        P.hparams.update(hidden_size=cfg.hidden_size, schedule_type='linear', use_shallow_diffusion=False, diff_speedup=100,
+                         diff_accelerator='ddim', b2s_precision='fp16', b2s_chain_groups=chain)
+        m = P.GaussianDiffusion(out_dims=128, num_feats=1, timesteps=1000, k_step=1000, backbone_type='wavenet',
+                                backbone_args=dict(num_layers=4, num_channels=256, dilation_cycle_length=4),
+                                spec_min=[-12.0], spec_max=[0.0])
+        m.denoise_fn.load_state_dict(OW.make_state_dict(cfg, seed=0, sigma_w=0.01), strict=True)
+        m = m.to(dev).eval()
+        runs = []
+        for _ in range(3):                                  # eager, capture, replay
+            torch.manual_seed(5)
+            runs.append(m(cond.transpose(1, 2).contiguous(), infer=True))
+        assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+        res.append(runs[0])
+    assert torch.equal(res[0], res[1])
+
+
 @pytest.mark.parametrize('B,T', [(30, 690), (5, 129), (1, 19500)])
 def test_stack_kernel_grouping_and_fallback_match_per_layer_path(B, T, dev):
     """The whole-stack kernel needs every tile resident: batches with more tiles than SMs are split by utterance into

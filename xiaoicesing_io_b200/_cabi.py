@@ -56,6 +56,8 @@ _SIGNATURES = {
                               _i, _i, _i, _vp, _vp, _i, _vp],
     'b2s_tc_wavenet_denoiser3': [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    'b2s_tc_wavenet_denoiser3_chained': [_vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _i64,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     'b2s_tc_lynx_glu': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual_cond': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_tc_linear_residual': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -347,13 +349,15 @@ def tc_wavenet_stack3(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_s
 
 def tc_wavenet_denoiser3(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations,
                          yedge0_h, yedge1_h, z_all_h, z_layer_stride, Wskip_h, bss, Wsp_h, b_sp, Wfin_h, b_fin, out, B, T, C, flags,
-                         zflags, bf16, lens=None):
+                         zflags, bf16, lens=None, chain=0):
+    """``chain``: bit 0 - this launch follows another utterance group of the same evaluation, bit 1 - another group follows."""
     L = len(dilations)
     dil = (_i * L)(*dilations)
-    check(lib.b2s_tc_wavenet_denoiser3(ptr(xin_h), MF, ptr(Win_h), ld_win, ptr(b_in), ptr(Wd_h), ptr(cond_h), cond_layer_stride,
-                                       ptr(Wres_h), ptr(bsum), ptr(dvec), d_stride, dil, L, ptr(yedge0_h), ptr(yedge1_h),
-                                       ptr(z_all_h), z_layer_stride, ptr(Wskip_h), ptr(bss), ptr(Wsp_h), ptr(b_sp), ptr(Wfin_h),
-                                       ptr(b_fin), ptr(out), B, T, C, ptr(flags), ptr(zflags), ptr(lens), int(bf16), stream_ptr()),
+    check(lib.b2s_tc_wavenet_denoiser3_chained(ptr(xin_h), MF, ptr(Win_h), ld_win, ptr(b_in), ptr(Wd_h), ptr(cond_h), cond_layer_stride,
+                                               ptr(Wres_h), ptr(bsum), ptr(dvec), d_stride, dil, L, ptr(yedge0_h), ptr(yedge1_h),
+                                               ptr(z_all_h), z_layer_stride, ptr(Wskip_h), ptr(bss), ptr(Wsp_h), ptr(b_sp), ptr(Wfin_h),
+                                               ptr(b_fin), ptr(out), B, T, C, ptr(flags), ptr(zflags), ptr(lens), int(bf16), int(chain),
+                                               stream_ptr()),
           'b2s_tc_wavenet_denoiser3')
 
 

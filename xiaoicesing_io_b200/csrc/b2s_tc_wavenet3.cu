@@ -61,6 +61,9 @@ struct __align__(64) Stack3P {
     //      accumulate S = sum_l z_l Wskip_l^T in TMEM as the z tiles are published (zflags[tile] = completed half-tile stores), then
     //      out = W_fin relu(W_sp (S + bss) / sqrt(L) + b_sp) + b_fin
     int n_layer_ctas, fuse_head;
+    // several utterance groups of ONE evaluation launched back to back (bit 0: this launch follows another group, bit 1: another
+    // group follows): the next group's layer kernel must not wait for this group's skip / head tail - see wavenet_stack3_kernel
+    int chain;
     CUtensorMap mapWskip, mapWsp, mapWfin;
     const float* bss; const float* b_sp; const float* b_fin; float alpha; float* out;
     int* zflags;                                          // [B * tiles_per_b], zero before the launch
@@ -246,8 +249,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
 #ifdef B2S_TLOG
     if (p.tlog && blockIdx.x == 0 && threadIdx.x == 0) p.tlog[MAXL * 16 + 4] = globaltimer_ns();
 #endif
-    // NO griddepcontrol.wait: this kernel is released while the layer kernel runs and follows its z tiles through zflags
+    // NO griddepcontrol.wait here: this kernel is released while the layer kernel runs and follows its z tiles through zflags
     // (release / acquire); everything else it reads (weights, biases) was written before the layer kernel was launched.
+    // Chained groups (bit 1): the next group's layer kernel is released now, to be scheduled as this group's layer CTAs exit.
+    if (p.chain & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int L = p.L, MF = p.MF;
     const int pairidx = (int)blockIdx.x >> 1;
     int gt[2], tb[2], tt0[2];
@@ -434,6 +439,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
 #ifdef B2S_TLOG
     if (p.tlog && blockIdx.x == 0 && threadIdx.x == 0) p.tlog[MAXL * 16 + 5] = globaltimer_ns();
 #endif
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // completion of this kernel implies completion of its layer kernel (chained groups)
     cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
@@ -533,7 +539,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
     const uint32_t tmem_base = *tmem_ptr;
     // TMEM columns: [0,256) X (residual stream, lives across all layers), [256,512) accumulator of the stem / of one GEMM1 half
 
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Programmatic dependent launch.  Normally: wait for the predecessor (the sampler update that wrote x_in) here.  A launch that
+    // follows another utterance group of the SAME evaluation (chain bit 0) depends on nothing its predecessor - that group's skip /
+    // head kernel - writes (its inputs were complete before the first group started, which did wait): it starts as soon as the
+    // previous group's layer CTAs leave their SMs, i.e. under the previous group's 12-23 us head tail, and waits at its END instead,
+    // so that "this kernel completed" still implies "everything before it completed" for whoever waits on the last one.
+    if (!(p.chain & 1)) asm volatile("griddepcontrol.wait;" ::: "memory");
     // Dependent launch: the skip-sum / head kernel may start NOW.  It is scheduled only once EVERY CTA of this grid has executed this
     // instruction, i.e. is resident - so it can never take SMs this grid still needs, and this grid never waits for it.
     if (p.fuse_head) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -972,6 +983,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
 #ifdef B2S_TLOG
     if (p.tlog && blockIdx.x == 2 && threadIdx.x == 0) { p.tlog[MAXL * 16 + 2] = globaltimer_ns(); p.tlog[MAXL * 16 + 3] = (unsigned long long)clock64(); }
 #endif
+    if (p.chain & 1) asm volatile("griddepcontrol.wait;" ::: "memory");
     cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
@@ -1133,6 +1145,7 @@ extern "C" int b2s_tc_wavenet_stack3_max_tiles(int T, int bf16) {
 struct Head3 {            // operands of the fused skip sum + head (all NULL / 0: the plain stack, z_all only)
     const void* Wskip_h; const float* bss; const void* Wsp_h; const float* b_sp; const void* Wfin_h; const float* b_fin; float* out;
     int* zflags;
+    int chain;
 };
 
 static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
@@ -1198,6 +1211,7 @@ static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win,
         rc = make_map_w(&p.mapWfin, hd->Wfin_h, bf16, C, MF, C, ws3::BK, MF / 2);
         if (rc) return rc;
         p.fuse_head = 1;
+        p.chain = hd->chain & 3;
         p.bss = hd->bss; p.b_sp = hd->b_sp; p.b_fin = hd->b_fin; p.out = hd->out; p.zflags = hd->zflags;
         p.alpha = 1.0f / sqrtf((float)L);
     }
@@ -1228,7 +1242,22 @@ extern "C" int b2s_tc_wavenet_denoiser3(const void* xin_h, int MF, const void* W
                                         void* yedge1_h, void* z_all_h, int64_t z_layer_stride, const void* Wskip_h, const float* bss,
                                         const void* Wsp_h, const float* b_sp, const void* Wfin_h, const float* b_fin, float* out, int B,
                                         int T, int C, int* flags, int* zflags, const int* lens, int bf16, void* stream) {
-    Head3 hd{Wskip_h, bss, Wsp_h, b_sp, Wfin_h, b_fin, out, zflags};
+    Head3 hd{Wskip_h, bss, Wsp_h, b_sp, Wfin_h, b_fin, out, zflags, 0};
+    return stack3_impl(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations_host, L,
+                       yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, lens, bf16, stream, &hd);
+}
+
+/* The same launch as one of SEVERAL utterance groups of one evaluation, issued back to back on the stream.  chain bit 0: this launch
+ * follows another group of the evaluation, bit 1: another group follows.  Results are those of b2s_tc_wavenet_denoiser3; the groups'
+ * skip / head tails overlap the next group's layers. */
+extern "C" int b2s_tc_wavenet_denoiser3_chained(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,
+                                                const void* cond_h, int64_t cond_layer_stride, const void* Wres_h, const float* bsum,
+                                                const float* dvec, int d_stride, const int* dilations_host, int L, void* yedge0_h,
+                                                void* yedge1_h, void* z_all_h, int64_t z_layer_stride, const void* Wskip_h,
+                                                const float* bss, const void* Wsp_h, const float* b_sp, const void* Wfin_h,
+                                                const float* b_fin, float* out, int B, int T, int C, int* flags, int* zflags,
+                                                const int* lens, int bf16, int chain, void* stream) {
+    Head3 hd{Wskip_h, bss, Wsp_h, b_sp, Wfin_h, b_fin, out, zflags, chain};
     return stack3_impl(xin_h, MF, Win_h, ld_win, b_in, Wd_h, cond_h, cond_layer_stride, Wres_h, bsum, dvec, d_stride, dilations_host, L,
                        yedge0_h, yedge1_h, z_all_h, z_layer_stride, B, T, C, flags, lens, bf16, stream, &hd);
 }

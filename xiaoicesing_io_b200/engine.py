@@ -414,6 +414,13 @@ class WaveNetSessionTC:
         input can write its 16-bit copy (and re-arm the flags) itself - ``eval(..., precast=True)`` then skips the cast."""
         return self.xin_h, self.flags, self.eng.bf16
 
+    def _chain_bits(self, b0: int, b1: int) -> int:
+        """Several utterance groups per evaluation: a group's layer kernel does not wait for the previous group's skip / head tail
+        (b2s_tc_wavenet_denoiser3_chained); hparams['b2s_chain_groups'] = False restores the plain back-to-back launches."""
+        if not hparams.get('b2s_chain_groups', True):
+            return 0
+        return (1 if b0 > 0 else 0) | (2 if b1 < self.B else 0)
+
     @property
     def can_fuse_update(self) -> bool:
         return (C.HAS_EXPERIMENTS and bool(self.stack_group) and not self.tgroups and not self.stack3
@@ -476,7 +483,8 @@ class WaveNetSessionTC:
                                            e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, e.w_skip3_h,
                                            e.b_skip_sum, e.w_sp_h, e.b_sp, e.w_fin_h, e.b_fin, out[r0:], b1 - b0, T, Cc,
                                            self.flags[b0 * self.tpb:], self.flags[nfl + b0 * self.tpb:], bf,
-                                           lens=None if self.lens is None else self.lens[b0:])
+                                           lens=None if self.lens is None else self.lens[b0:],
+                                           chain=self._chain_bits(b0, b1))
                     continue
                 C.tc_wavenet_stack3(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
                                     e.w_res3_h, e.bsum3, dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
@@ -596,7 +604,7 @@ class WaveNetSessionTC:
                                                tab.shape[1] * 2 * Cc, e.w_res3_h, e.bsum3, dv, 0, e.dilations, self.y_h[r0:], self.y2_h[r0:],
                                                self.z_all[:, r0:], self.rows * Cc, e.w_skip3_h, e.b_skip_sum, e.w_sp_h, e.b_sp, e.w_fin_h,
                                                e.b_fin, out[r0:], b1 - b0, T, Cc, self.flags[b0 * self.tpb:],
-                                               self.flags[nfl + b0 * self.tpb:], e.bf16)
+                                               self.flags[nfl + b0 * self.tpb:], e.bf16, chain=self._chain_bits(b0, b1))
                     else:
                         C.tc_wavenet_stack3(self.xin_h[r0:], e.MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
                                             e.w_res3_h, e.bsum3, dv, 0, e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:],
