@@ -76,3 +76,48 @@ def test_empty_batch():
     dec = P.build_aux_decoder(64, 16, 'convnext', dict(num_channels=128, num_layers=1)).cuda()
     assert dec(torch.zeros(0, 10, 64, device='cuda')).shape == (0, 10, 16)
     assert dec(torch.zeros(2, 0, 64, device='cuda')).shape == (2, 0, 16)
+
+
+def test_aux_decoder_feeds_shallow_diffusion_like_the_reference_toplevel():
+    """The reference's acoustic inference (modules/toplevel.py:94-102): ``aux_mel = aux_decoder(condition, infer=True)`` then
+    ``mel = diffusion(condition, src_spec=aux_mel, infer=True)`` (shallow diffusion from x_start = aux_mel noised to K_step).
+    Both stages on the B200 kernels (fp16 operands) against the chain of their oracles, same injected noise."""
+    import xiaoicesing_io_b200 as P
+    from oracle import denoisers as OD, samplers as OS, weights as OW
+    dev = torch.device('cuda:0')
+    B, T = 2, 300
+    acfg = OA.ConvNeXtCfg(num_channels=256, num_layers=3)
+    asd = _random_sd(acfg, 21)
+    wcfg = OD.WaveNetCfg()
+    wsd = OW.make_state_dict(wcfg, seed=0, sigma_w=0.01)
+    smin, smax = [-12.] * 128, [0.] * 128
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, schedule_type='linear', infer=False, use_shallow_diffusion=True, K_step_infer=100,
+                     diff_speedup=10, diff_accelerator='ddim', b2s_precision='fp16')
+    aux = P.AuxDecoderAdaptor(in_dims=256, out_dims=128, num_feats=1, spec_min=smin, spec_max=smax, aux_decoder_arch='convnext',
+                              aux_decoder_args=dict(num_channels=256, num_layers=3, kernel_size=7))
+    aux.decoder.load_state_dict(asd, strict=True)
+    aux = aux.to(dev).eval()
+    diff = P.GaussianDiffusion(128, k_step=100, backbone_type='wavenet',
+                               backbone_args=dict(num_layers=20, num_channels=256, dilation_cycle_length=4), spec_min=smin, spec_max=smax)
+    diff.denoise_fn.load_state_dict(wsd, strict=True)
+    diff = diff.to(dev).eval()
+    g = torch.Generator().manual_seed(77)
+    cond = torch.randn((B, T, 256), generator=g)
+    noise0 = torch.randn((B, 1, 128, T), generator=g)
+    diff._noise_source = lambda shape: noise0.to(dev)
+    aux_mel = aux(cond.to(dev), infer=True)
+    mel = diff(cond.to(dev), src_spec=aux_mel, infer=True).cpu()
+    # oracle chain
+    ref_aux = OA.aux_adaptor_forward(asd, acfg, cond, smin, smax, infer=True)
+    sch = OS.DiffusionSchedule(1000, 'linear')
+    x_start = OS.norm_spec(ref_aux, torch.tensor(-12.), torch.tensor(0.)).transpose(-2, -1)[:, None]
+    with torch.no_grad():
+        x = OS.gaussian_diffusion_inference(OD.make_denoiser(wsd, wcfg), sch, cond.transpose(1, 2), k_step=100, timesteps=1000,
+                                            use_shallow=True, K_step_infer=100, speedup=10, accelerator='ddim', noise0=noise0,
+                                            x_start=x_start, step_noise=[])
+    ref = OS.denorm_spec(x, torch.tensor(-12.), torch.tensor(0.))
+    e_aux = float((aux_mel.cpu().double() - ref_aux.double()).abs().max())
+    e_mel = float((mel.double() - ref.double()).abs().max())
+    print(dict(test='aux_then_shallow_diffusion', aux_max_abs=e_aux, mel_max_abs=e_mel, ref_absmax=float(ref.abs().max())))
+    assert e_aux <= 2e-2 and e_mel <= 2e-2, (e_aux, e_mel)
