@@ -108,6 +108,17 @@ def seeded_noise(shape: Tuple[int, ...], seed: Optional[int], device) -> torch.T
 CondFn = Callable[[dict, int], Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]]
 
 
+MAX_PENDING = 16     # finished batches whose mels may wait on the device for their copy to the host
+
+
+def _drain(pending, params, out) -> None:
+    for seg, lens, mel, f0s in pending:
+        mel_h = mel.float().cpu()                              # the first copy waits for the stream; the rest are plain copies
+        for k, i in enumerate(seg):
+            out[i] = {'offset': float(params[i].get('offset', 0.)), 'mel': mel_h[k:k + 1, :lens[k]].clone(),
+                      'f0': None if f0s[k] is None else f0s[k].reshape(1, -1).float().cpu()}
+
+
 @torch.no_grad()
 def sample_segments(model, params: Sequence[dict], cond_fn: CondFn, timestep: float, device, seed: int = -1,
                     max_batch_frames: int = 16 * 704, max_batch_size: int = 64, indices: Optional[Sequence[int]] = None
@@ -156,16 +167,15 @@ def sample_segments(model, params: Sequence[dict], cond_fn: CondFn, timestep: fl
             lengths = torch.tensor(lens + [0] * (cap - len(seg)), dtype=torch.int32)
             mel = model(condition, src_spec=src, infer=True, lengths=lengths, initial_noise=noise)
             pending.append((seg, lens, mel, f0s))
+            if len(pending) >= 2 * MAX_PENDING:                # bound the device memory held by finished batches
+                _drain(pending[:MAX_PENDING], params, out)
+                del pending[:MAX_PENDING]
     finally:
         if saved_cap is None:
             hparams.pop('b2s_graph_cache', None)
         else:
             hparams['b2s_graph_cache'] = saved_cap
-    for seg, lens, mel, f0s in pending:
-        mel_h = mel.float().cpu()                              # the first copy waits for the stream; the rest are plain copies
-        for k, i in enumerate(seg):
-            out[i] = {'offset': float(params[i].get('offset', 0.)), 'mel': mel_h[k:k + 1, :lens[k]].clone(),
-                      'f0': None if f0s[k] is None else f0s[k].reshape(1, -1).float().cpu()}
+    _drain(pending, params, out)
     for i in idx:
         if i not in out:                                        # zero-length segment
             out[i] = {'offset': float(params[i].get('offset', 0.)), 'mel': torch.zeros((1, 0, M)), 'f0': torch.zeros((1, 0))}
