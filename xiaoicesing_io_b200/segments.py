@@ -108,12 +108,12 @@ def seeded_noise(shape: Tuple[int, ...], seed: Optional[int], device) -> torch.T
 CondFn = Callable[[dict, int], Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]]
 
 
-MAX_PENDING = 16     # finished batches whose mels may wait on the device for their copy to the host
+MAX_PENDING = 16     # batches in flight (enqueued or finished) whose pinned host copies have not been handed out yet
 
 
 def _drain(pending, params, out) -> None:
-    for seg, lens, mel, f0s in pending:
-        mel_h = mel.float().cpu()                              # the first copy waits for the stream; the rest are plain copies
+    for seg, lens, mel_h, f0s, done in pending:
+        done.synchronize()                                     # this batch's device-to-host copy has landed
         for k, i in enumerate(seg):
             out[i] = {'offset': float(params[i].get('offset', 0.)), 'mel': mel_h[k:k + 1, :lens[k]].clone(),
                       'f0': None if f0s[k] is None else f0s[k].reshape(1, -1).float().cpu()}
@@ -165,8 +165,11 @@ def sample_segments(model, params: Sequence[dict], cond_fn: CondFn, timestep: fl
                 if src is not None and srcs[k] is not None:
                     src[k, :lens[k]] = srcs[k].to(device, non_blocking=True)
             lengths = torch.tensor(lens + [0] * (cap - len(seg)), dtype=torch.int32)
-            mel = model(condition, src_spec=src, infer=True, lengths=lengths, initial_noise=noise)
-            pending.append((seg, lens, mel, f0s))
+            mel = model(condition, src_spec=src, infer=True, lengths=lengths, initial_noise=noise).float()
+            # asynchronous copy into pinned host memory, stream-ordered behind this batch: the host never waits for a batch here
+            host = torch.empty(mel.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(mel, non_blocking=True)
+            pending.append((seg, lens, host, f0s, torch.cuda.current_stream(device).record_event()))
             if len(pending) >= 2 * MAX_PENDING:                # bound the device memory held by finished batches
                 _drain(pending[:MAX_PENDING], params, out)
                 del pending[:MAX_PENDING]
