@@ -151,6 +151,60 @@ def aux_case(name, args, out_dims, n_feats, spec_min, spec_max, B, T, seed, infe
     _save(name, meta, dict(condition=condition, out=out), model.decoder.state_dict())
 
 
+def enc_case(name, hp, vocab, B, L, T, seed, extras=()):
+    """Runs ``FastSpeech2Acoustic(txt_tokens, mel2ph, f0, ...)`` of modules/fastspeech/acoustic_encoder.py (the producer of the
+    condition tensor), rotary-position configuration."""
+    ref = ref_loader.load()
+    ref.hparams.clear()
+    ref.hparams.update(hidden_size=32, enc_layers=2, enc_ffn_kernel_size=3, ffn_act='gelu', dropout=0.1, num_heads=2,
+                       use_pos_embed=True, rel_pos=True, use_rope=True, use_spk_id=False, num_spk=1)
+    ref.hparams.update(hp)
+    from modules.fastspeech.acoustic_encoder import FastSpeech2Acoustic
+    torch.manual_seed(seed)
+    model = FastSpeech2Acoustic(vocab).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for pname, p in model.named_parameters():
+            if pname.endswith('bias') or 'layer_norm' in pname:       # biases are initialised to 0, LayerNorm to (1, 0): exercise them
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    lens = torch.randint(max(2, L // 2), L + 1, (B,), generator=g)
+    lens[0] = L
+    tokens = torch.zeros((B, L), dtype=torch.long)
+    mel2ph = torch.zeros((B, T), dtype=torch.long)
+    for b in range(B):
+        n = int(lens[b])
+        tokens[b, :n] = torch.randint(1, vocab, (n,), generator=g)
+        frames = int(T if b == 0 else torch.randint(T // 2, T + 1, (1,), generator=g))
+        cuts = torch.sort(torch.randint(0, frames + 1, (n - 1,), generator=g)).values
+        bounds = torch.cat([torch.tensor([0]), cuts, torch.tensor([frames])])
+        for j in range(n):
+            mel2ph[b, int(bounds[j]):int(bounds[j + 1])] = j + 1          # 1-based token index per frame, 0 = padding frame
+    f0 = 100 + 300 * torch.rand((B, T), generator=g)
+    kw, arrays = {}, dict(txt_tokens=tokens, mel2ph=mel2ph, f0=f0)
+    for e in extras:
+        if e == 'spk':
+            kw['spk_embed_id'] = torch.randint(0, hp['num_spk'], (B,), generator=g)
+            arrays['spk_embed_id'] = kw['spk_embed_id']
+        else:
+            kw[e] = torch.randn((B, T), generator=g)
+            arrays[e] = kw[e]
+    with torch.no_grad():
+        out = model(tokens, mel2ph, f0, **kw)
+    arrays['out'] = out
+    meta = dict(kind='acoustic_encoder', hparams={k: ref.hparams[k] for k in ('hidden_size', 'enc_layers', 'enc_ffn_kernel_size',
+                'ffn_act', 'num_heads', 'use_spk_id', 'num_spk')}, vocab=vocab, extras=list(extras),
+                flags={k: bool(ref.hparams.get(k, False)) for k in ('use_energy_embed', 'use_breathiness_embed', 'use_voicing_embed',
+                                                                   'use_tension_embed', 'use_key_shift_embed', 'use_speed_embed')})
+    _save(name, meta, arrays, model.state_dict())
+
+
+def enc_main():
+    enc_case('enc_fs2_plain', {}, 12, 2, 7, 23, 400)
+    enc_case('enc_fs2_all_embeds_k9', dict(enc_layers=3, enc_ffn_kernel_size=9, use_spk_id=True, num_spk=3, use_energy_embed=True,
+                                           use_breathiness_embed=True, use_key_shift_embed=True, use_speed_embed=True),
+             20, 3, 11, 41, 401, extras=('spk', 'energy', 'breathiness', 'key_shift', 'speed'))
+
+
 def aux_main():
     aux_case('aux_convnext_mel', dict(num_channels=32, num_layers=2, kernel_size=7, dropout_rate=0.1), 16, 1,
              [-12.] * 16, [0.] * 16, 2, 37, 300)
@@ -162,6 +216,7 @@ def aux_main():
 
 def main():
     aux_main()
+    enc_main()
     # ---- backbone forward ------------------------------------------------------------------
     backbone_case('bb_wavenet_int_t', 'wavenet', WN_SMALL, 16, 1, 2, 37, torch.tensor([950, 3]), 10)
     backbone_case('bb_wavenet_float_t1', 'wavenet', WN_CYC, 16, 1, 3, 41, torch.tensor([437.25]), 11)
@@ -233,5 +288,7 @@ def main():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'aux':
         aux_main()                                          # only the aux-decoder fixtures
+    elif len(sys.argv) > 1 and sys.argv[1] == 'enc':
+        enc_main()                                          # only the acoustic-encoder fixtures
     else:
         main()
