@@ -426,10 +426,43 @@ def run_secondary(args, dev):
         out['aux_decoder'] = time_aux_decoder(args.precision, dev)
     except Exception as ex:                                 # noqa: BLE001
         out['aux_decoder'] = {'error': f'{type(ex).__name__}: {ex}'}
+    try:
+        out['acoustic_encoder'] = time_acoustic_encoder(args.precision, dev)
+    except Exception as ex:                                 # noqa: BLE001
+        out['acoustic_encoder'] = {'error': f'{type(ex).__name__}: {ex}'}
     torch.cuda.empty_cache()
     P.hparams.clear()
     P.hparams.update(saved)
     return out
+
+
+def time_acoustic_encoder(precision, dev, B=16, L=64, T=690, reps=5):
+    """The other step BEFORE the path: the FastSpeech2 acoustic encoder that produces the condition
+    tensor (configs/acoustic.yaml + base.yaml: H 256, 4 layers, 2 heads, 3-tap conv FFN, rotary positions), once per utterance
+    batch - config 2's batch with 64 phoneme tokens per utterance.  Random-init weights; device-timed with CUDA events."""
+    import xiaoicesing_io_b200 as P
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, enc_layers=4, enc_ffn_kernel_size=3, ffn_act='gelu', num_heads=2, use_pos_embed=True, rel_pos=True,
+                     use_rope=True, dropout=0.1, use_spk_id=False, num_spk=1, b2s_precision=precision if precision != 'fp32' else 'fp16')
+    torch.manual_seed(0)
+    m = P.FastSpeech2Acoustic(60).to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    tokens = torch.randint(1, 60, (B, L), generator=g).to(dev)
+    mel2ph = (torch.arange(T)[None, :] * L // T + 1).expand(B, T).contiguous().to(dev)
+    f0 = (100 + 300 * torch.rand((B, T), generator=g)).to(dev)
+    for _ in range(3):
+        m(tokens, mel2ph, f0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        m(tokens, mel2ph, f0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {'workload': f'FastSpeech2 acoustic encoder 4x256 (2 heads, rotary, conv-3 FFN), B={B} x {L} tokens -> {T} frames: the '
+                        f'condition tensor, once per batch', 'ms_per_call': ms, 'frames_per_s': B * T / (ms * 1e-3),
+            'launches_per_call': 2 + 10 * 4 + 2}
 
 
 def time_aux_decoder(precision, dev, B=16, T=690, reps=5):

@@ -361,6 +361,30 @@ int b2s_layernorm_hh(const void* in_h, const float* gamma, const float* beta, vo
 int b2s_tc_linear_residual_scaled(const void* p_h, const void* W_h, const float* bias, const float* gamma, float* x, void* x_h,
                                   int rows, int C, int inner, int bf16, void* stream);
 
+/* ---- FastSpeech2 acoustic encoder (the producer of the condition tensor; reference modules/fastspeech/acoustic_encoder.py:79-109,
+ * modules/fastspeech/tts_modules.py:353-428, modules/commons/common_layers.py:152-263; rotary-position configuration) ----
+ * Token-rate tensors are rows r = b * L + l (L = padded tokens per utterance), frame-rate tensors rows b * T + t.  The GEMMs of the
+ * transformer layers use b2s_tc_linear / b2s_tc_conv1d / b2s_tc_linear_residual; these are the remaining pieces:
+ * b2s_enc_mel2ph_to_dur  dur[b, l] = number of frames with mel2ph == l + 1                              (tts_modules.py:345-351)
+ * b2s_enc_embed          x = (sqrt(H) E[token] + dur w_dur + b_dur) * keep, keep = (token != 0)         (tts_modules.py:385-389, :415)
+ * b2s_enc_rope           rotary embedding of the q and k thirds of qkv [rows, 3H] fp32, in place; freqs [H / heads / 2]
+ * b2s_enc_attention      softmax(q k^T / sqrt(d), padded keys masked) v per (utterance, head) -> 16-bit rows [rows, H]
+ * b2s_enc_mask_rows      x[r, :] = 0 where keep[r] == 0
+ * b2s_enc_layernorm_mask enc[b, 1 + l, :] = LayerNorm(x[b, l, :]) * keep, enc[b, 0, :] = 0   (table [B, L + 1, H], acoustic_encoder.py:89)
+ * b2s_enc_assemble       cond[b, t, :] = enc[b, mel2ph[b, t], :] + spk[b, :] + sum_i (val_i[b, t] w_i + bias_i); val_0 is f0 and enters
+ *                        as log(1 + f0 / 700); embeddings [n_var_first, n_var_first + n_var) are summed among themselves first (:61-107). */
+int b2s_enc_mel2ph_to_dur(const int64_t* mel2ph, float* dur, int B, int T, int L, void* stream);
+int b2s_enc_embed(const int64_t* tokens, const float* dur, const float* E, const float* w_dur, const float* b_dur, float* x, float* keep,
+                  int rows, int H, int vocab, void* stream);
+int b2s_enc_rope(float* qkv, const float* freqs, int B, int L, int H, int num_heads, void* stream);
+int b2s_enc_attention(const float* qkv, const float* keep, void* out_h, int B, int L, int H, int num_heads, int bf16, void* stream);
+int b2s_enc_mask_rows(float* x, const float* keep, int rows, int H, void* stream);
+int b2s_enc_layernorm_mask(const float* x, const float* gamma, const float* beta, const float* keep, float* enc, int B, int L, int H,
+                           float eps, void* stream);
+int b2s_enc_assemble(const float* enc, const int64_t* mel2ph, const float* spk /* may be NULL */, const float* const* vals_host,
+                     const float* const* w_host, const float* const* bias_host, int n, int n_var_first, int n_var, float* cond, int B,
+                     int T, int L, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

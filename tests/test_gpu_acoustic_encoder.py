@@ -1,0 +1,75 @@
+"""GPU parity of the FastSpeech2 acoustic encoder (producer of the condition tensor) against the CPU oracle
+(oracle/acoustic_encoder.py, pinned by tests/golden/enc_*.npz) through the product's public API.  GEMM operands are 16 bits, the
+rest fp32: the condition must agree within 2e-2 absolute (it is cast to 16 bits by the sampling path anyway)."""
+import pytest
+import torch
+
+from oracle import acoustic_encoder as OE
+from tol16 import check16
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(cfg, B, L, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(max(2, L // 2), L + 1, (B,), generator=g)
+    lens[0] = L
+    tokens = torch.zeros((B, L), dtype=torch.long)
+    mel2ph = torch.zeros((B, T), dtype=torch.long)
+    for b in range(B):
+        n = int(lens[b])
+        tokens[b, :n] = torch.randint(1, cfg.vocab_size, (n,), generator=g)
+        frames = T if b == 0 else int(torch.randint(T // 2, T + 1, (1,), generator=g))
+        cuts = torch.sort(torch.randint(0, frames + 1, (n - 1,), generator=g)).values
+        bounds = torch.cat([torch.tensor([0]), cuts, torch.tensor([frames])])
+        for j in range(n):
+            mel2ph[b, int(bounds[j]):int(bounds[j + 1])] = j + 1
+    f0 = 100 + 300 * torch.rand((B, T), generator=g)
+    extra = {n: torch.randn((B, T), generator=g) for n in cfg.variance_embeds}
+    ks = torch.randn((B, T), generator=g) if cfg.use_key_shift_embed else None
+    sp = torch.randn((B, T), generator=g) if cfg.use_speed_embed else None
+    spk = torch.randint(0, cfg.num_spk, (B,), generator=g) if cfg.use_spk_id else None
+    return tokens, mel2ph, f0, extra, ks, sp, spk
+
+
+@pytest.mark.parametrize('precision', ['fp16', 'bf16'])
+@pytest.mark.parametrize('case', ['acoustic_default', 'all_embeds_k9', 'tiny'])
+def test_acoustic_encoder_against_oracle(case, precision):
+    import xiaoicesing_io_b200 as P
+    dev = torch.device('cuda:0')
+    if case == 'acoustic_default':       # configs/acoustic.yaml + base.yaml: H 256, 4 layers, 2 heads, 3-tap FFN conv
+        cfg, B, L, T = OE.AcousticEncoderCfg(), 3, 61, 690
+    elif case == 'all_embeds_k9':
+        cfg = OE.AcousticEncoderCfg(vocab_size=40, hidden_size=128, enc_layers=2, num_heads=2, ffn_kernel_size=9,
+                                    variance_embeds=['energy', 'breathiness', 'tension'], use_key_shift_embed=True,
+                                    use_speed_embed=True, use_spk_id=True, num_spk=5)
+        B, L, T = 4, 23, 257
+    else:                                # one token, one frame / a handful
+        cfg, B, L, T = OE.AcousticEncoderCfg(hidden_size=64, enc_layers=1, num_heads=4), 2, 2, 3
+    P.hparams.clear()
+    P.hparams.update(hidden_size=cfg.hidden_size, enc_layers=cfg.enc_layers, enc_ffn_kernel_size=cfg.ffn_kernel_size, ffn_act='gelu',
+                     num_heads=cfg.num_heads, use_pos_embed=True, rel_pos=True, use_rope=True, dropout=0.1, use_spk_id=cfg.use_spk_id,
+                     num_spk=cfg.num_spk, use_key_shift_embed=cfg.use_key_shift_embed, use_speed_embed=cfg.use_speed_embed,
+                     b2s_precision=precision, **{f'use_{n}_embed': True for n in cfg.variance_embeds})
+    torch.manual_seed(3)
+    model = P.FastSpeech2Acoustic(cfg.vocab_size)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('bias') or 'layer_norm' in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(dev).eval()
+    tokens, mel2ph, f0, extra, ks, sp, spk = _inputs(cfg, B, L, T, 11)
+    kw = {n: v.to(dev) for n, v in extra.items()}
+    out = model(tokens.to(dev), mel2ph.to(dev), f0.to(dev), key_shift=None if ks is None else ks.to(dev),
+                speed=None if sp is None else sp.to(dev), spk_embed_id=None if spk is None else spk.to(dev), **kw)
+    ref = OE.acoustic_encoder_forward(sd, cfg, tokens, mel2ph, f0, key_shift=ks, speed=sp, spk_embed_id=spk, variances=extra,
+                                      dtype=torch.float64)
+    assert out.shape == ref.shape and bool(torch.isfinite(out).all())
+    err, scale = float((out.double().cpu() - ref).abs().max()), float(ref.abs().max())
+    print(dict(test='acoustic_encoder', case=case, precision=precision, max_abs=err, ref_absmax=scale))
+    check16(precision, err, scale)
+    # padding frames (mel2ph == 0) carry only the frame-rate embeddings; a second call reproduces the bits
+    assert torch.equal(out, model(tokens.to(dev), mel2ph.to(dev), f0.to(dev), key_shift=None if ks is None else ks.to(dev),
+                                  speed=None if sp is None else sp.to(dev), spk_embed_id=None if spk is None else spk.to(dev), **kw))

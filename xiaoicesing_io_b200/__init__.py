@@ -8,6 +8,7 @@ Public surface (same names and contracts as the reference's ``modules.backbones`
     GaussianDiffusion, RepetitiveDiffusion, PitchDiffusion, MultiVarianceDiffusion
     RectifiedFlow, RepetitiveRectifiedFlow, PitchRectifiedFlow, MultiVarianceRectifiedFlow
     AUX_DECODERS, build_aux_decoder, ConvNeXtDecoder, AuxDecoderAdaptor   (modules.aux_decoder: the producer of x_start)
+    FastSpeech2Acoustic, FastSpeech2Encoder   (modules.fastspeech: the producer of the condition tensor, rotary configuration)
     hparams  (the global config dict, utils/hparams.py:13)
     segments (batched .ds segment driver: ragged batches, per-segment seeds, .mel.pt writer), partition (multi-GPU), B2SError
 
@@ -22,6 +23,7 @@ from .core import (GaussianDiffusion, MultiVarianceDiffusion, MultiVarianceRecti
                    PitchRectifiedFlow, RectifiedFlow, RepetitiveDiffusion, RepetitiveRectifiedFlow)
 from .hparams import hparams, set_hparams
 from .aux_decoder import AUX_DECODERS, AuxDecoderAdaptor, ConvNeXtDecoder, build_aux_decoder
+from .acoustic_encoder import FastSpeech2Acoustic, FastSpeech2Encoder
 from . import partition, segments  # noqa: E402,F401
 
 __version__ = '0.2.0'

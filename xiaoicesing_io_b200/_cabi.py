@@ -67,6 +67,13 @@ _SIGNATURES = {
     'b2s_tc_conv1d': [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'b2s_layernorm_hh': [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp],
     'b2s_tc_linear_residual_scaled': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    'b2s_enc_mel2ph_to_dur': [_vp, _vp, _i, _i, _i, _vp],
+    'b2s_enc_embed': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    'b2s_enc_rope': [_vp, _vp, _i, _i, _i, _i, _vp],
+    'b2s_enc_attention': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    'b2s_enc_mask_rows': [_vp, _vp, _i, _i, _vp],
+    'b2s_enc_layernorm_mask': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
+    'b2s_enc_assemble': [_vp, _vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
 }
 
 # entry points of B2S_BUILD_EXPERIMENTS=1 builds only (measured-and-rejected variants)
@@ -398,6 +405,39 @@ def layernorm_hh(in_h, gamma, beta, out_h, rows, C, eps, bf16):
 def tc_linear_residual_scaled(p_h, W_h, bias, gamma, x, x_h, rows, C, inner, bf16):
     check(lib.b2s_tc_linear_residual_scaled(ptr(p_h), ptr(W_h), ptr(bias), ptr(gamma), ptr(x), ptr(x_h), rows, C, inner, int(bf16),
                                             stream_ptr()), 'b2s_tc_linear_residual_scaled')
+
+
+def enc_mel2ph_to_dur(mel2ph, dur, B, T, L):
+    check(lib.b2s_enc_mel2ph_to_dur(ptr(mel2ph), ptr(dur), B, T, L, stream_ptr()), 'b2s_enc_mel2ph_to_dur')
+
+
+def enc_embed(tokens, dur, E, w_dur, b_dur, x, keep, rows, H, vocab):
+    check(lib.b2s_enc_embed(ptr(tokens), ptr(dur), ptr(E), ptr(w_dur), ptr(b_dur), ptr(x), ptr(keep), rows, H, vocab, stream_ptr()),
+          'b2s_enc_embed')
+
+
+def enc_rope(qkv, freqs, B, L, H, heads):
+    check(lib.b2s_enc_rope(ptr(qkv), ptr(freqs), B, L, H, heads, stream_ptr()), 'b2s_enc_rope')
+
+
+def enc_attention(qkv, keep, out_h, B, L, H, heads, bf16):
+    check(lib.b2s_enc_attention(ptr(qkv), ptr(keep), ptr(out_h), B, L, H, heads, int(bf16), stream_ptr()), 'b2s_enc_attention')
+
+
+def enc_mask_rows(x, keep, rows, H):
+    check(lib.b2s_enc_mask_rows(ptr(x), ptr(keep), rows, H, stream_ptr()), 'b2s_enc_mask_rows')
+
+
+def enc_layernorm_mask(x, gamma, beta, keep, enc, B, L, H, eps):
+    check(lib.b2s_enc_layernorm_mask(ptr(x), ptr(gamma), ptr(beta), ptr(keep), ptr(enc), B, L, H, float(eps), stream_ptr()),
+          'b2s_enc_layernorm_mask')
+
+
+def enc_assemble(enc, mel2ph, spk, vals, ws, biases, n_var_first, n_var, cond, B, T, L, H):
+    n = len(vals)
+    mk = lambda ts: (_vp * n)(*[t.data_ptr() for t in ts])
+    check(lib.b2s_enc_assemble(ptr(enc), ptr(mel2ph), ptr(spk), mk(vals), mk(ws), mk(biases), n, n_var_first, n_var, ptr(cond), B, T, L, H,
+                               stream_ptr()), 'b2s_enc_assemble')
 
 
 def lynx_dwconv_h(g_h, Wdw, bias, slope, p_h, B, T, inner, ksize, act, bf16):
