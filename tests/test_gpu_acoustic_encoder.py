@@ -73,3 +73,62 @@ def test_acoustic_encoder_against_oracle(case, precision):
     # padding frames (mel2ph == 0) carry only the frame-rate embeddings; a second call reproduces the bits
     assert torch.equal(out, model(tokens.to(dev), mel2ph.to(dev), f0.to(dev), key_shift=None if ks is None else ks.to(dev),
                                   speed=None if sp is None else sp.to(dev), spk_embed_id=None if spk is None else spk.to(dev), **kw))
+
+
+def test_whole_acoustic_model_tokens_to_mel():
+    """``DiffSingerAcoustic`` (modules/toplevel.py:32-102): tokens -> FastSpeech2 encoder -> ConvNeXt aux decoder -> shallow DDIM sampling,
+    every stage on the B200 kernels, against the chain of the three oracles with the same injected noise; frames with mel2ph == 0
+    come out as zeros like the reference's."""
+    import xiaoicesing_io_b200 as P
+    from oracle import aux_decoder as OA, denoisers as OD, samplers as OS
+    dev = torch.device('cuda:0')
+    B, L, T = 2, 31, 300
+    ecfg = OE.AcousticEncoderCfg(vocab_size=30, enc_layers=2)
+    acfg = OA.ConvNeXtCfg(num_channels=256, num_layers=2)
+    wcfg = OD.WaveNetCfg(num_layers=6)
+    smin, smax = [-12.] * 128, [0.] * 128
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, enc_layers=2, enc_ffn_kernel_size=3, ffn_act='gelu', num_heads=2, use_pos_embed=True, rel_pos=True,
+                     use_rope=True, dropout=0.1, use_spk_id=False, num_spk=1, schedule_type='linear', infer=False,
+                     use_shallow_diffusion=True, K_step_infer=100, diff_speedup=10, diff_accelerator='ddim', timesteps=1000, K_step=100,
+                     spec_min=smin, spec_max=smax, diffusion_type='ddpm', backbone_type='wavenet',
+                     backbone_args=dict(num_layers=6, num_channels=256, dilation_cycle_length=4),
+                     shallow_diffusion_args=dict(train_aux_decoder=True, train_diffusion=True, val_gt_start=False, aux_decoder_grad=0.1,
+                                                 aux_decoder_arch='convnext',
+                                                 aux_decoder_args=dict(num_channels=256, num_layers=2, kernel_size=7)),
+                     b2s_precision='fp16')
+    torch.manual_seed(8)
+    model = P.DiffSingerAcoustic(30, 128)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('gamma'):
+                p.copy_(0.2 + 0.3 * torch.rand(p.shape, generator=g))
+            elif n.startswith('diffusion') and n.endswith('output_projection.weight') and p.dim() == 3 and p.shape[0] == 128:
+                p.copy_(0.01 * torch.randn(p.shape, generator=g))
+            elif n.startswith('fs2') and (n.endswith('bias') or 'layer_norm' in n):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(dev).eval()
+    tokens, mel2ph, f0, _, _, _, _ = _inputs(ecfg, B, L, T, 13)
+    noise0 = torch.randn((B, 1, 128, T), generator=g)
+    model.diffusion._noise_source = lambda shape: noise0.to(dev)
+    out = model(tokens.to(dev), mel2ph.to(dev), f0.to(dev), infer=True)
+    # oracle chain
+    sub = lambda pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    cond = OE.acoustic_encoder_forward(sub('fs2.'), ecfg, tokens, mel2ph, f0)
+    keep = (mel2ph > 0).float()[:, :, None]
+    aux = OA.aux_adaptor_forward(sub('aux_decoder.decoder.'), acfg, cond, smin, smax, infer=True) * keep
+    sch = OS.DiffusionSchedule(1000, 'linear')
+    x_start = OS.norm_spec(aux, torch.tensor(-12.), torch.tensor(0.)).transpose(-2, -1)[:, None]
+    with torch.no_grad():
+        x = OS.gaussian_diffusion_inference(OD.make_denoiser(sub('diffusion.denoise_fn.'), wcfg), sch, cond.transpose(1, 2), k_step=100,
+                                            timesteps=1000, use_shallow=True, K_step_infer=100, speedup=10, accelerator='ddim',
+                                            noise0=noise0, x_start=x_start, step_noise=[])
+    ref = OS.denorm_spec(x, torch.tensor(-12.), torch.tensor(0.)) * keep
+    e_aux = float((out.aux_out.cpu().double() - aux.double()).abs().max())
+    e_mel = float((out.diff_out.cpu().double() - ref.double()).abs().max())
+    print(dict(test='tokens_to_mel', aux_max_abs=e_aux, mel_max_abs=e_mel, ref_absmax=float(ref.abs().max())))
+    assert e_aux <= 2e-2 and e_mel <= 2e-2, (e_aux, e_mel)
+    pad = (mel2ph == 0)
+    assert pad.any() and float(out.diff_out.cpu()[pad].abs().max()) == 0.0

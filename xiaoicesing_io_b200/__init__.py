@@ -9,6 +9,7 @@ Public surface (same names and contracts as the reference's ``modules.backbones`
     RectifiedFlow, RepetitiveRectifiedFlow, PitchRectifiedFlow, MultiVarianceRectifiedFlow
     AUX_DECODERS, build_aux_decoder, ConvNeXtDecoder, AuxDecoderAdaptor   (modules.aux_decoder: the producer of x_start)
     FastSpeech2Acoustic, FastSpeech2Encoder   (modules.fastspeech: the producer of the condition tensor, rotary configuration)
+    DiffSingerAcoustic, ShallowDiffusionOutput   (modules.toplevel: tokens -> condition -> x_start -> mel, inference)
     hparams  (the global config dict, utils/hparams.py:13)
     segments (batched .ds segment driver: ragged batches, per-segment seeds, .mel.pt writer), partition (multi-GPU), B2SError
 
@@ -24,6 +25,7 @@ from .core import (GaussianDiffusion, MultiVarianceDiffusion, MultiVarianceRecti
 from .hparams import hparams, set_hparams
 from .aux_decoder import AUX_DECODERS, AuxDecoderAdaptor, ConvNeXtDecoder, build_aux_decoder
 from .acoustic_encoder import FastSpeech2Acoustic, FastSpeech2Encoder
+from .toplevel import DiffSingerAcoustic, ShallowDiffusionOutput
 from . import partition, segments  # noqa: E402,F401
 
 __version__ = '0.2.0'
