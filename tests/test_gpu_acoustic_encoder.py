@@ -132,3 +132,30 @@ def test_whole_acoustic_model_tokens_to_mel():
     assert e_aux <= 2e-2 and e_mel <= 2e-2, (e_aux, e_mel)
     pad = (mel2ph == 0)
     assert pad.any() and float(out.diff_out.cpu()[pad].abs().max()) == 0.0
+
+
+def test_whole_acoustic_model_training_branch_forward_values():
+    """``infer=False`` (modules/toplevel.py:103-120): the aux decoder's normalised prediction and (x_recon, noise) of the denoiser on
+    q_sample(gt_mel) - forward values for validation losses."""
+    import xiaoicesing_io_b200 as P
+    dev = torch.device('cuda:0')
+    smin, smax = [-12.] * 128, [0.] * 128
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, enc_layers=1, enc_ffn_kernel_size=3, ffn_act='gelu', num_heads=2, use_pos_embed=True, rel_pos=True,
+                     use_rope=True, use_spk_id=False, num_spk=1, schedule_type='linear', infer=False, use_shallow_diffusion=True,
+                     timesteps=1000, K_step=100, spec_min=smin, spec_max=smax, diffusion_type='ddpm', backbone_type='wavenet',
+                     backbone_args=dict(num_layers=4, num_channels=256, dilation_cycle_length=4),
+                     shallow_diffusion_args=dict(train_aux_decoder=True, train_diffusion=True, val_gt_start=False, aux_decoder_grad=0.1,
+                                                 aux_decoder_arch='convnext',
+                                                 aux_decoder_args=dict(num_channels=128, num_layers=1, kernel_size=7)),
+                     b2s_precision='fp16')
+    torch.manual_seed(8)
+    model = P.DiffSingerAcoustic(30, 128).to(dev).eval()
+    tokens, mel2ph, f0, _, _, _, _ = _inputs(OE.AcousticEncoderCfg(vocab_size=30), 2, 17, 150, 5)
+    gt = (torch.rand(2, 150, 128) * 12 - 12).to(dev)
+    out = model(tokens.to(dev), mel2ph.to(dev), f0.to(dev), gt_mel=gt, infer=False)
+    x_recon, noise = out.diff_out
+    assert tuple(out.aux_out.shape) == (2, 150, 128) and x_recon.shape == noise.shape == (2, 1, 128, 150)
+    assert bool(torch.isfinite(out.aux_out).all()) and bool(torch.isfinite(x_recon).all())
+    with pytest.raises(P.B2SError):
+        model(tokens.to(dev), mel2ph.to(dev), f0.to(dev), infer=False)

@@ -3,8 +3,9 @@ x_start (ConvNeXt aux decoder, shallow diffusion) -> mel (diffusion / rectified-
 modules/toplevel.py:32-102 (``DiffSingerAcoustic``), same constructor, same ``hparams`` keys, same sub-module names (``fs2``,
 ``aux_decoder``, ``diffusion``), so a reference acoustic checkpoint loads with ``load_state_dict(strict=True)``.
 
-Inference only (``infer=True``): the training branch of the reference (``modules/toplevel.py:103-120``) needs autograd through the
-denoiser, which this package does not provide.
+``infer=False`` returns the FORWARD values of the reference's training branch (``modules/toplevel.py:103-120``: the aux decoder's
+normalised prediction and the denoiser's output on q_sample(gt_mel) with the drawn noise) - enough for validation losses; there is
+no autograd through the kernels.
 """
 from __future__ import annotations
 
@@ -71,10 +72,20 @@ class DiffSingerAcoustic(nn.Module):
     @torch.no_grad()
     def forward(self, txt_tokens, mel2ph, f0, key_shift=None, speed=None, spk_embed_id=None, gt_mel=None, infer=True, **kwargs
                 ) -> ShallowDiffusionOutput:
-        if not infer:
-            raise C.B2SError('DiffSingerAcoustic on the B200 path is inference only (the training branch needs autograd through the '
-                             'denoiser: SURVEY section 8 row f-4)')
         condition = self.fs2(txt_tokens, mel2ph, f0, key_shift=key_shift, speed=speed, spk_embed_id=spk_embed_id, **kwargs)
+        if not infer:                                                      # forward values only: validation losses
+            if gt_mel is None:
+                raise C.B2SError('infer=False needs gt_mel (modules/toplevel.py:103-120)')
+            aux_out = diff_out = None
+            if self.use_shallow_diffusion:
+                if self.shallow_args.get('train_aux_decoder', True):
+                    g = float(self.shallow_args.get('aux_decoder_grad', 1.0))
+                    aux_out = self.aux_decoder(condition * g + condition * (1 - g), infer=False)          # :108 (values; no autograd)
+                if self.shallow_args.get('train_diffusion', True):
+                    diff_out = self.diffusion(condition, gt_spec=gt_mel, infer=False)
+            else:
+                diff_out = self.diffusion(condition, gt_spec=gt_mel, infer=False)
+            return ShallowDiffusionOutput(aux_out=aux_out, diff_out=diff_out)
         keep = (mel2ph > 0).float()[:, :, None]                            # modules/toplevel.py:95, :101
         if self.use_shallow_diffusion:
             aux_mel_pred = self.aux_decoder(condition, infer=True)
