@@ -427,6 +427,11 @@ def run_secondary(args, dev):
     except Exception as ex:                                 # noqa: BLE001
         out['aux_decoder'] = {'error': f'{type(ex).__name__}: {ex}'}
     try:
+        out['tokens_to_mel_one_utterance'] = time_tokens_to_mel(args.precision, dev)
+    except Exception as ex:                                 # noqa: BLE001
+        out['tokens_to_mel_one_utterance'] = {'error': f'{type(ex).__name__}: {ex}'}
+    torch.cuda.empty_cache()
+    try:
         out['acoustic_encoder'] = time_acoustic_encoder(args.precision, dev)
     except Exception as ex:                                 # noqa: BLE001
         out['acoustic_encoder'] = {'error': f'{type(ex).__name__}: {ex}'}
@@ -436,7 +441,48 @@ def run_secondary(args, dev):
     return out
 
 
-def time_acoustic_encoder(precision, dev, B=16, L=64, T=690, reps=5):
+def time_tokens_to_mel(precision, dev, L=64, T=690, reps=10, extra_hparams=None):
+    """The reference's real inference shape end to end (modules/toplevel.py:79-102, inference/ds_acoustic.py:189-246): ONE 8-second
+    utterance, phoneme tokens -> FastSpeech2 encoder -> ConvNeXt aux decoder -> shallow DDIM sampling (K_step 400, speedup 20 = 20
+    evaluations of WaveNet 20x256) -> mel, every stage on the B200 kernels (xiaoicesing_io_b200.DiffSingerAcoustic).  Wall clock per
+    call with a host synchronisation, CUDA graphs replayed."""
+    import xiaoicesing_io_b200 as P
+    P.hparams.clear()
+    P.hparams.update(hidden_size=256, enc_layers=4, enc_ffn_kernel_size=3, ffn_act='gelu', num_heads=2, use_pos_embed=True, rel_pos=True,
+                     use_rope=True, dropout=0.1, use_spk_id=False, num_spk=1, schedule_type='linear', infer=False,
+                     use_shallow_diffusion=True, K_step_infer=400, diff_speedup=20, diff_accelerator='ddim', timesteps=1000, K_step=400,
+                     spec_min=[-12.0] * 128, spec_max=[0.0] * 128, diffusion_type='ddpm', backbone_type='wavenet',
+                     backbone_args=dict(num_layers=20, num_channels=256, dilation_cycle_length=4),
+                     shallow_diffusion_args=dict(train_aux_decoder=True, train_diffusion=True, val_gt_start=False, aux_decoder_grad=0.1,
+                                                 aux_decoder_arch='convnext',
+                                                 aux_decoder_args=dict(num_channels=512, num_layers=6, kernel_size=7)),
+                     b2s_precision=precision if precision != 'fp32' else 'fp16')
+    P.hparams.update(extra_hparams or {})
+    torch.manual_seed(0)
+    m = P.DiffSingerAcoustic(60, 128)
+    with torch.no_grad():
+        torch.nn.init.normal_(m.diffusion.denoise_fn.output_projection.weight, std=0.01)
+        for blk in m.aux_decoder.decoder.conv:
+            blk.gamma.fill_(0.5)
+    m = m.to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    tokens = torch.randint(1, 60, (1, L), generator=g).to(dev)
+    mel2ph = (torch.arange(T)[None, :] * L // T + 1).contiguous().to(dev)
+    f0 = (100 + 300 * torch.rand((1, T), generator=g)).to(dev)
+    for _ in range(4):
+        m(tokens, mel2ph, f0, infer=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        mel = m(tokens, mel2ph, f0, infer=True).diff_out
+        torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    return {'workload': f'one utterance ({L} tokens, {T} frames = 8 s): encoder 4x256 -> aux decoder 6x512 -> shallow DDIM 20 evaluations of '
+                        f'WaveNet 20x256 -> mel', 'ms_per_call': ms, 'rtf': ms * 1e-3 / (T * 512 / 44100.0),
+            'finite': bool(torch.isfinite(mel).all())}
+
+
+def time_acoustic_encoder(precision, dev, B=16, L=64, T=690, reps=5, extra_hparams=None):
     """The other step BEFORE the path: the FastSpeech2 acoustic encoder that produces the condition
     tensor (configs/acoustic.yaml + base.yaml: H 256, 4 layers, 2 heads, 3-tap conv FFN, rotary positions), once per utterance
     batch - config 2's batch with 64 phoneme tokens per utterance.  Random-init weights; device-timed with CUDA events."""
@@ -444,6 +490,7 @@ def time_acoustic_encoder(precision, dev, B=16, L=64, T=690, reps=5):
     P.hparams.clear()
     P.hparams.update(hidden_size=256, enc_layers=4, enc_ffn_kernel_size=3, ffn_act='gelu', num_heads=2, use_pos_embed=True, rel_pos=True,
                      use_rope=True, dropout=0.1, use_spk_id=False, num_spk=1, b2s_precision=precision if precision != 'fp32' else 'fp16')
+    P.hparams.update(extra_hparams or {})
     torch.manual_seed(0)
     m = P.FastSpeech2Acoustic(60).to(dev).eval()
     g = torch.Generator().manual_seed(1)
@@ -465,13 +512,14 @@ def time_acoustic_encoder(precision, dev, B=16, L=64, T=690, reps=5):
             'launches_per_call': 2 + 10 * 4 + 2}
 
 
-def time_aux_decoder(precision, dev, B=16, T=690, reps=5):
+def time_aux_decoder(precision, dev, B=16, T=690, reps=5, extra_hparams=None):
     """The step BEFORE the path: the ConvNeXt aux decoder that produces x_start for shallow diffusion
     (configs/acoustic.yaml:101-105: 512 channels, 6 blocks, k = 7), once per utterance batch - config 2's batch.  Random-init
     weights with layer scale 0.5; device-timed with CUDA events."""
     import xiaoicesing_io_b200 as P
     P.hparams.clear()
     P.hparams.update(b2s_precision=precision if precision != 'fp32' else 'fp16')
+    P.hparams.update(extra_hparams or {})
     torch.manual_seed(0)
     m = P.AuxDecoderAdaptor(in_dims=256, out_dims=128, num_feats=1, spec_min=[-12.0] * 128, spec_max=[0.0] * 128,
                             aux_decoder_arch='convnext', aux_decoder_args=dict(num_channels=512, num_layers=6, kernel_size=7))

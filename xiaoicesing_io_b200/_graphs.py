@@ -1,0 +1,58 @@
+"""CUDA-graph replay of a fixed launch sequence (the condition producers: 27 / 44 launches of a few microseconds each are bound by
+the host's launch rate - one utterance costs 0.4-0.6 ms of launches for ~0.1 ms of GPU work).
+
+Same policy as the sampler's graph cache (core/_sampling.py): the first call with a key runs eagerly (it also performs the kernels'
+one-time ``cudaFuncSetAttribute`` set-up, which must not happen during capture), the second call captures, later calls copy their
+inputs into the graph's static buffers and replay.  A small LRU bounds the private memory pools that captured graphs pin.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from .hparams import hparams
+
+
+class GraphedLaunches:
+    def __init__(self, max_graphs: int = 8, max_seen: int = 64):
+        self._graphs: 'OrderedDict[tuple, tuple]' = OrderedDict()
+        self._seen: 'OrderedDict[tuple, None]' = OrderedDict()
+        self.max_graphs, self.max_seen = max_graphs, max_seen
+
+    def clear(self):
+        self._graphs.clear()
+        self._seen.clear()
+
+    def __call__(self, key: tuple, inputs: Sequence[Optional[torch.Tensor]], fn: Callable[[List[Optional[torch.Tensor]]], torch.Tensor]
+                 ) -> torch.Tensor:
+        """``fn(inputs) -> output`` launches kernels on the current stream and allocates what it needs; ``inputs`` are device tensors
+        (or None) whose shapes / dtypes are part of ``key``.  Returns a tensor the caller owns."""
+        if not hparams.get('b2s_cuda_graph', True) or torch.cuda.is_current_stream_capturing():
+            return fn(list(inputs))
+        entry = self._graphs.get(key)
+        if entry is None:
+            if key not in self._seen:
+                self._seen[key] = None
+                while len(self._seen) > self.max_seen:
+                    self._seen.popitem(last=False)
+                return fn(list(inputs))
+            del self._seen[key]
+            static_in = [None if t is None else t.clone() for t in inputs]
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = fn(static_in)
+            entry = (graph, static_in, static_out)
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.popitem(last=False)
+            self._graphs[key] = entry
+        else:
+            self._graphs.move_to_end(key)
+        graph, static_in, static_out = entry
+        for s, t in zip(static_in, inputs):
+            if s is not None:
+                s.copy_(t)
+        graph.replay()
+        return static_out.clone()

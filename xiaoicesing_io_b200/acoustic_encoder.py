@@ -26,6 +26,7 @@ import torch
 from torch import nn
 
 from . import _cabi as C
+from ._graphs import GraphedLaunches
 from .hparams import hparams
 
 VARIANCE_NAMES = ('energy', 'breathiness', 'voicing', 'tension')     # the reference's order (acoustic_encoder.py:34-41)
@@ -125,6 +126,7 @@ class FastSpeech2Acoustic(nn.Module):
         if self.use_spk_id:
             self.spk_embed = nn.Embedding(hparams['num_spk'], H)
             nn.init.normal_(self.spk_embed.weight, mean=0, std=H ** -0.5)
+        self.__dict__['_graphs'] = GraphedLaunches()           # not a sub-module: CUDA graphs of the launch sequence per input shape
 
     # ------------------------------------------------------------------------------------------------------------------
     def _pack(self):
@@ -180,9 +182,66 @@ class FastSpeech2Acoustic(nn.Module):
         H, enc = self.hidden_size, self.encoder
         nh, k = enc.num_heads, enc.ffn_kernel_size
         rows = B * L
-        cond = torch.empty((B, T, H), device=dev)
         if B * T == 0:
+            return torch.empty((B, T, H), device=dev)
+        vals = []
+        for w, b_, name in st['scal']:
+            if name is None:
+                v = f0
+            elif name == 'key_shift':
+                v = key_shift
+            elif name == 'speed':
+                v = speed
+            else:
+                v = kwargs.get(name)
+            if v is None:
+                raise C.B2SError(f'the acoustic encoder was built with the {name} embedding: pass {name}=[B, T]')
+            vals.append(v.to(device=dev, dtype=torch.float32).expand(B, T).contiguous())
+        spk = None
+        if self.use_spk_id:
+            mix = kwargs.get('spk_mix_embed')
+            if mix is not None:
+                if mix.shape[1] != 1:
+                    raise C.B2SError('per-frame speaker mixes (spk_mix_embed [B, T, H]) are not implemented; pass [B, 1, H]')
+                spk = mix.to(device=dev, dtype=torch.float32).reshape(B, H).contiguous()
+            else:
+                spk = st['spk'][spk_embed_id.to(dev).reshape(-1)].contiguous()                # [B, H] rows of the embedding table
+
+        def launches(inp):
+            tok, m2p, spk_, *vals_ = inp
+            cond = torch.empty((B, T, H), device=dev)
+            dur = torch.empty((B, L), device=dev)
+            C.enc_mel2ph_to_dur(m2p, dur, B, T, L)
+            table = torch.empty((B, L + 1, H), device=dev)
+            x = torch.empty((rows, H), device=dev)
+            keep = torch.empty((rows,), device=dev)
+            if rows:
+                C.enc_embed(tok, dur, st['E'], st['w_dur'], st['b_dur'], x, keep, rows, H, self.vocab_size)
+                n_h = torch.empty((rows, H), device=dev, dtype=hd)
+                a_h = torch.empty((rows, H), device=dev, dtype=hd)
+                qkv = torch.empty((rows, 3 * H), device=dev)
+                f_h = torch.empty((rows, 4 * H), device=dev, dtype=hd)
+                for lay in st['layers']:
+                    C.layernorm_h(x, lay['ln1'][0], lay['ln1'][1], n_h, rows, H, bf)
+                    C.tc_linear(n_h, H, rows, 0, lay['w_in'], H, None, 3 * H, H, bf, out_f32=qkv, ldo=3 * H)
+                    C.enc_rope(qkv, lay['freqs'], B, L, H, nh)
+                    C.enc_attention(qkv, keep, a_h, B, L, H, nh, bf)
+                    C.tc_linear_residual(a_h, lay['w_out'], st['zero_bias'], x, rows, H, H, bf)
+                    C.enc_mask_rows(x, keep, rows, H)
+                    C.layernorm_h(x, lay['ln2'][0], lay['ln2'][1], n_h, rows, H, bf)
+                    C.tc_conv1d(n_h, lay['w1'], lay['b1'], None, 0, f_h, 4 * H, B, L, H, 4 * H, k, C.ACT_GELU, bf)
+                    C.tc_linear_residual(f_h, lay['w2'], lay['b2'], x, rows, H, 4 * H, bf)
+                    C.enc_mask_rows(x, keep, rows, H)
+            C.enc_layernorm_mask(x, st['ln'][0], st['ln'][1], keep, table, B, L, H, st['ln'][2])
+            C.enc_assemble(table, m2p, spk_, list(vals_), [w for w, _, _ in st['scal']], [b2 for _, b2, _ in st['scal']],
+                           st['n_var_first'], st['n_var'], cond, B, T, L, H)
             return cond
+
+        with torch.cuda.device(dev):
+            tok = txt_tokens.to(torch.int64).contiguous()
+            m2p = mel2ph.to(torch.int64).contiguous()
+            key = (st['ver'], B, L, T, spk is not None)
+            return self._graphs(key, [tok, m2p, spk, *vals], launches)
         with torch.cuda.device(dev):
             tok = txt_tokens.to(torch.int64).contiguous()
             m2p = mel2ph.to(torch.int64).contiguous()

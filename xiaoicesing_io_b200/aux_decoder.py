@@ -22,6 +22,7 @@ import torch
 from torch import nn
 
 from . import _cabi as C
+from ._graphs import GraphedLaunches
 from .hparams import hparams
 
 
@@ -44,6 +45,7 @@ class _ConvNeXtEngine:
     def __init__(self, net: 'ConvNeXtDecoder'):
         self.net = net
         self._version = None
+        self._graphs = GraphedLaunches()                        # CUDA graphs of the 27-launch sequence, per (weights, B, T)
 
     def _ver(self):
         ps = list(self.net.parameters())
@@ -107,12 +109,15 @@ class _ConvNeXtEngine:
             raise C.B2SError(f'condition has {H} channels, the aux decoder expects in_dims={net.in_dims}')
         Cc, k, N = net.num_channels, net.kernel_size, net.out_dims
         rows = B * T
-        out = torch.empty((B, T, N), device=dev)
         if rows == 0:
-            return out
-        with torch.cuda.device(dev):
+            return torch.empty((B, T, N), device=dev)
+        w_out, b_out = self.out_weights(scale, shift)
+
+        def launches(inp):
+            cond_, = inp
+            out = torch.empty((B, T, N), device=dev)
             c_h = torch.empty((rows, H), device=dev, dtype=hd)
-            C.cast_h(cond.float().contiguous(), c_h, bf)
+            C.cast_h(cond_, c_h, bf)
             x = torch.empty((rows, Cc), device=dev)
             x_h = torch.empty((rows, Cc), device=dev, dtype=hd)
             d_h = torch.empty((rows, Cc), device=dev, dtype=hd)
@@ -127,9 +132,12 @@ class _ConvNeXtEngine:
                 C.layernorm_hh(d_h, blk['ln_g'], blk['ln_b'], n_h, rows, Cc, blk['eps'], bf)
                 C.tc_linear(n_h, Cc, rows, 0, blk['w1'], Cc, blk['b1'], inner, Cc, bf, act=C.ACT_GELU, out_h=g_h, ldoh=inner)
                 C.tc_linear_residual_scaled(g_h, blk['w2'], blk['b2'], blk['gamma'], x, x_h, rows, Cc, inner, bf)
-            w_out, b_out = self.out_weights(scale, shift)
             C.tc_conv1d(x_h, w_out, b_out, out, N, None, 0, B, T, Cc, N, k, C.ACT_NONE, bf)
-        return out
+            return out
+
+        with torch.cuda.device(dev):
+            key = (self._version, B, T, w_out.data_ptr(), b_out.data_ptr())
+            return self._graphs(key, [cond.float().contiguous()], launches)
 
 
 class ConvNeXtDecoder(nn.Module):
