@@ -371,7 +371,8 @@ def dominant_kernel_roofline(model, w, precision, reps=5):
             traffic = None
     achieved = flops / (ms * 1e-3) / 1e12
     return {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': p['bf16_burst'], 'unit': 'TFLOP/s',
-            'frac': achieved / p['bf16_burst'], 'traffic': traffic, 'avg_launch_ms': ms,
+            'frac': achieved / p['bf16_burst'], 'frac_of_sustained_peak': achieved / p['bf16_sustained'], 'traffic': traffic,
+            'avg_launch_ms': ms,
             'flops_per_launch': flops, 'peak_source': p['source'], 'launches_per_eval': sess.launches_per_eval,
             'note': 'algorithmic FLOPs of the launch / avg CUDA-event duration of the launches replayed back to back as a CUDA graph'}
 
