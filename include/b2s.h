@@ -381,7 +381,8 @@ int b2s_enc_attention(const float* qkv, const float* keep, void* out_h, int B, i
 int b2s_enc_mask_rows(float* x, const float* keep, int rows, int H, void* stream);
 int b2s_enc_layernorm_mask(const float* x, const float* gamma, const float* beta, const float* keep, float* enc, int B, int L, int H,
                            float eps, void* stream);
-int b2s_enc_assemble(const float* enc, const int64_t* mel2ph, const float* spk /* may be NULL */, const float* const* vals_host,
+int b2s_enc_assemble(const float* enc, const int64_t* mel2ph, const float* spk /* may be NULL; [B, H], or [B, T, H] with spk_per_frame */,
+                     int spk_per_frame, const float* const* vals_host,
                      const float* const* w_host, const float* const* bias_host, int n, int n_var_first, int n_var, float* cond, int B,
                      int T, int L, int H, void* stream);
 

@@ -104,7 +104,7 @@ def encoder_forward(sd, cfg: AcousticEncoderCfg, txt_embed, dur_embed, padding_m
 
 
 def acoustic_encoder_forward(sd, cfg: AcousticEncoderCfg, txt_tokens, mel2ph, f0, key_shift=None, speed=None, spk_embed_id=None,
-                             variances=None, dtype=torch.float32):
+                             variances=None, dtype=torch.float32, spk_mix_embed=None):
     """FastSpeech2Acoustic.forward (acoustic_encoder.py:79-109): tokens [B, L] int64, mel2ph [B, T] int64, f0 [B, T] ->
     condition [B, T, H]."""
     H = cfg.hidden_size
@@ -115,7 +115,10 @@ def acoustic_encoder_forward(sd, cfg: AcousticEncoderCfg, txt_tokens, mel2ph, f0
     enc = F.pad(enc, [0, 0, 1, 0])                                                                    # :89
     cond = torch.gather(enc, 1, mel2ph[..., None].repeat([1, 1, H]))                                  # :90-91
     if cfg.use_spk_id:
-        cond = cond + F.embedding(spk_embed_id, _c(sd, 'spk_embed.weight', dtype))[:, None, :]        # :98-99
+        if spk_mix_embed is not None:                                                                 # :93-96 ([B, 1 or T, H])
+            cond = cond + spk_mix_embed.to(dtype)
+        else:
+            cond = cond + F.embedding(spk_embed_id, _c(sd, 'spk_embed.weight', dtype))[:, None, :]    # :98-99
     f0_mel = (1 + f0.to(dtype) / 700).log()                                                           # :101
     cond = cond + F.linear(f0_mel[:, :, None], _c(sd, 'pitch_embed.weight', dtype), _c(sd, 'pitch_embed.bias', dtype))
     if cfg.variance_embeds:                                                                           # :62-67: stacked, summed, then added

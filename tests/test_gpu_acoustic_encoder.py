@@ -70,6 +70,15 @@ def test_acoustic_encoder_against_oracle(case, precision):
     err, scale = float((out.double().cpu() - ref).abs().max()), float(ref.abs().max())
     print(dict(test='acoustic_encoder', case=case, precision=precision, max_abs=err, ref_absmax=scale))
     check16(precision, err, scale)
+    if cfg.use_spk_id:       # speaker mixes (spk_mix_embed, acoustic_encoder.py:93-96): one row per utterance and one row per frame
+        E = sd['spk_embed.weight']
+        wgt = torch.rand((B, T, 1), generator=torch.Generator().manual_seed(2))
+        for mix in (E[spk][:, None, :] * 0.3 + E[(spk + 1) % cfg.num_spk][:, None, :] * 0.7,
+                    E[spk][:, None, :] * wgt + E[(spk + 1) % cfg.num_spk][:, None, :] * (1 - wgt)):
+            o2 = model(tokens.to(dev), mel2ph.to(dev), f0.to(dev), key_shift=ks.to(dev), speed=sp.to(dev), spk_mix_embed=mix.to(dev), **kw)
+            r2 = OE.acoustic_encoder_forward(sd, cfg, tokens, mel2ph, f0, key_shift=ks, speed=sp, variances=extra, dtype=torch.float64,
+                                             spk_mix_embed=mix)
+            check16(precision, float((o2.double().cpu() - r2).abs().max()), float(r2.abs().max()))
     # padding frames (mel2ph == 0) carry only the frame-rate embeddings; a second call reproduces the bits
     assert torch.equal(out, model(tokens.to(dev), mel2ph.to(dev), f0.to(dev), key_shift=None if ks is None else ks.to(dev),
                                   speed=None if sp is None else sp.to(dev), spk_embed_id=None if spk is None else spk.to(dev), **kw))

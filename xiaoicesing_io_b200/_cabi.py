@@ -73,7 +73,7 @@ _SIGNATURES = {
     'b2s_enc_attention': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_enc_mask_rows': [_vp, _vp, _i, _i, _vp],
     'b2s_enc_layernorm_mask': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
-    'b2s_enc_assemble': [_vp, _vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
+    'b2s_enc_assemble': [_vp, _vp, _vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
 }
 
 # entry points of B2S_BUILD_EXPERIMENTS=1 builds only (measured-and-rejected variants)
@@ -436,7 +436,8 @@ def enc_layernorm_mask(x, gamma, beta, keep, enc, B, L, H, eps):
 def enc_assemble(enc, mel2ph, spk, vals, ws, biases, n_var_first, n_var, cond, B, T, L, H):
     n = len(vals)
     mk = lambda ts: (_vp * n)(*[t.data_ptr() for t in ts])
-    check(lib.b2s_enc_assemble(ptr(enc), ptr(mel2ph), ptr(spk), mk(vals), mk(ws), mk(biases), n, n_var_first, n_var, ptr(cond), B, T, L, H,
+    per_frame = int(spk is not None and spk.dim() == 3)
+    check(lib.b2s_enc_assemble(ptr(enc), ptr(mel2ph), ptr(spk), per_frame, mk(vals), mk(ws), mk(biases), n, n_var_first, n_var, ptr(cond), B, T, L, H,
                                stream_ptr()), 'b2s_enc_assemble')
 
 

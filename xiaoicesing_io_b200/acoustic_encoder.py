@@ -200,10 +200,9 @@ class FastSpeech2Acoustic(nn.Module):
         spk = None
         if self.use_spk_id:
             mix = kwargs.get('spk_mix_embed')
-            if mix is not None:
-                if mix.shape[1] != 1:
-                    raise C.B2SError('per-frame speaker mixes (spk_mix_embed [B, T, H]) are not implemented; pass [B, 1, H]')
-                spk = mix.to(device=dev, dtype=torch.float32).reshape(B, H).contiguous()
+            if mix is not None:                                  # [B, 1, H] or per frame [B, T, H] (acoustic_encoder.py:93-97)
+                mix = mix.to(device=dev, dtype=torch.float32)
+                spk = mix.reshape(B, H).contiguous() if mix.shape[1] == 1 else mix.expand(B, T, H).contiguous()
             else:
                 spk = st['spk'][spk_embed_id.to(dev).reshape(-1)].contiguous()                # [B, H] rows of the embedding table
 
@@ -240,7 +239,7 @@ class FastSpeech2Acoustic(nn.Module):
         with torch.cuda.device(dev):
             tok = txt_tokens.to(torch.int64).contiguous()
             m2p = mel2ph.to(torch.int64).contiguous()
-            key = (st['ver'], B, L, T, spk is not None)
+            key = (st['ver'], B, L, T, None if spk is None else spk.dim())
             return self._graphs(key, [tok, m2p, spk, *vals], launches)
         with torch.cuda.device(dev):
             tok = txt_tokens.to(torch.int64).contiguous()

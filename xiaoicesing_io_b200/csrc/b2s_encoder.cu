@@ -164,8 +164,8 @@ struct AssembleArgs {
 
 // cond[b, t, :] = enc[b, mel2ph[b, t], :] (+ spk[b, :]) + sum of scalar embeddings; one warp per frame
 __global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__ enc, const long long* __restrict__ mel2ph,
-                                                       const float* __restrict__ spk, const AssembleArgs a, float* __restrict__ cond,
-                                                       int B, int T, int L, int H) {
+                                                       const float* __restrict__ spk, int spk_per_frame, const AssembleArgs a,
+                                                       float* __restrict__ cond, int B, int T, int L, int H) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (r >= (long long)B * T) return;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__
     s[0] = logf(__fadd_rn(1.f, __fdiv_rn(s[0], 700.f)));                    // f0_mel = (1 + f0 / 700).log()   :101
     for (int c = lane; c < H; c += 32) {
         float v = e[c];
-        if (spk) v = __fadd_rn(v, __ldg(spk + (long long)b * H + c));        // :98-99
+        if (spk) v = __fadd_rn(v, __ldg(spk + (spk_per_frame ? r : (long long)b) * H + c));   // :93-99 (spk_mix_embed [B, T, H] or one row per utterance)
         float var = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -279,7 +279,7 @@ extern "C" int b2s_enc_layernorm_mask(const float* x, const float* gamma, const 
     return B2S_OK;
 }
 
-extern "C" int b2s_enc_assemble(const float* enc, const int64_t* mel2ph, const float* spk, const float* const* vals_host,
+extern "C" int b2s_enc_assemble(const float* enc, const int64_t* mel2ph, const float* spk, int spk_per_frame, const float* const* vals_host,
                                 const float* const* w_host, const float* const* bias_host, int n, int n_var_first, int n_var,
                                 float* cond, int B, int T, int L, int H, void* stream) {
     B2S_CHECK_ARG(B >= 0 && T >= 0 && L >= 0 && H > 0, "b2s_enc_assemble: bad dims");
@@ -293,7 +293,7 @@ extern "C" int b2s_enc_assemble(const float* enc, const int64_t* mel2ph, const f
         a.val[i] = vals_host[i]; a.w[i] = w_host[i]; a.bias[i] = bias_host[i];
     }
     a.n = n; a.n_var_first = n_var_first; a.n_var = n_var;
-    assemble_kernel<<<ceil_div((long long)B * T, 8), 256, 0, (cudaStream_t)stream>>>(enc, (const long long*)mel2ph, spk, a, cond, B, T, L, H);
+    assemble_kernel<<<ceil_div((long long)B * T, 8), 256, 0, (cudaStream_t)stream>>>(enc, (const long long*)mel2ph, spk, spk_per_frame, a, cond, B, T, L, H);
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }
