@@ -121,3 +121,34 @@ def test_aux_decoder_feeds_shallow_diffusion_like_the_reference_toplevel():
     e_mel = float((mel.double() - ref.double()).abs().max())
     print(dict(test='aux_then_shallow_diffusion', aux_max_abs=e_aux, mel_max_abs=e_mel, ref_absmax=float(ref.abs().max())))
     assert e_aux <= 2e-2 and e_mel <= 2e-2, (e_aux, e_mel)
+
+
+def test_graphed_launches_policy():
+    """_graphs.GraphedLaunches: first call with a key eager, second captures, later calls replay with fresh inputs; a new key does not
+    disturb an existing graph; the LRU bound holds; b2s_cuda_graph = False bypasses it."""
+    import xiaoicesing_io_b200 as P
+    from xiaoicesing_io_b200._graphs import GraphedLaunches
+    P.hparams.clear()
+    dev = torch.device('cuda:0')
+    calls = []
+
+    def fn(inp):
+        calls.append(torch.cuda.is_current_stream_capturing())
+        return inp[0] * 2 + 1
+
+    gl = GraphedLaunches(max_graphs=2)
+    xs = [torch.full((4,), float(i), device=dev) for i in range(5)]
+    outs = [gl(('k', 4), [x], fn) for x in xs]
+    assert calls == [False, True]                       # eager once, captured once, then replays only
+    for i, o in enumerate(outs):
+        assert torch.equal(o, xs[i] * 2 + 1)
+    outs[2].add_(100)                                   # the caller owns what it gets
+    assert torch.equal(gl(('k', 4), [xs[1]], fn), xs[1] * 2 + 1)
+    for key in ('a', 'b', 'c'):
+        gl((key,), [xs[0]], fn), gl((key,), [xs[0]], fn)
+    assert len(gl._graphs) == 2 and ('k', 4) not in gl._graphs
+    P.hparams['b2s_cuda_graph'] = False
+    n = len(calls)
+    gl(('c',), [xs[0]], fn)
+    assert len(calls) == n + 1 and calls[-1] is False
+    P.hparams.clear()
