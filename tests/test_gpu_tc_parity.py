@@ -250,6 +250,62 @@ def test_narrow_wavenet_on_the_padded_whole_stack_kernel(channels, L, cycle, in_
         assert d <= 6 * eps * scale, (d, scale)
 
 
+def test_whole_stack_path_randomised_shapes(dev):
+    """Randomised shapes through the whole-stack kernels (fixed seed): batch sizes that need one / several chained groups, utterance
+    lengths from 1 frame to 9 tiles (clusters of 2 / 4 / 6 / 8 and utterances spanning clusters), ragged lengths, 2-20 layers,
+    dilation cycles 1-5, 24-128 packed bins.  Each case: finite, equal to itself on a second run (no race), and equal to the
+    per-layer kernels within 16-bit rounding of the layer inputs."""
+    import random
+    import xiaoicesing_io_b200 as P
+    rnd = random.Random(1234)
+    for case in range(14):
+        L = rnd.choice([2, 3, 5, 8, 20])
+        cycle = rnd.choice([1, 2, 4, 5])
+        in_dims = rnd.choice([24, 64, 128])
+        T = rnd.choice([1, 37, 128, 129, 300, 511, 690, 1023, 1100])
+        B = rnd.choice([1, 2, 5, 17, 33])
+        if B * T > 24000:
+            B = max(1, 24000 // T)
+        g = torch.Generator().manual_seed(case)
+        spec = torch.randn((B, 1, in_dims, T), generator=g).to(dev)
+        cond = torch.randn((B, 256, T), generator=g).to(dev)
+        t = (torch.arange(B, dtype=torch.float32) * 3 + 1).to(dev)
+        net = _bf16_backbone(dev, stack=True, L=L, cycle=cycle, in_dims=in_dims, precision='fp16', stack3=True)
+        a = net(spec, t, cond)
+        a2 = net(spec, t, cond)
+        b = _bf16_backbone(dev, stack=False, L=L, cycle=cycle, in_dims=in_dims, precision='fp16')(spec, t, cond)
+        tag = (case, B, T, L, cycle, in_dims)
+        assert bool(torch.isfinite(a).all()), tag
+        assert torch.equal(a, a2), tag
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 4 * 2 ** -11 * max(scale, 1e-3), (tag, float((a - b).abs().max()), scale)
+        # ragged: every utterance's valid frames equal the run of that utterance alone at its own length
+        if T >= 130 and B >= 2:
+            P.hparams.update(b2s_stack=True, b2s_stack3=True)          # (the per-layer reference above switched them off)
+            lens = [T] + [rnd.randrange(1, T + 1) for _ in range(B - 1)]
+            sess_out = _ragged_eval(net, spec, t, cond, lens)
+            for bi in (1, B - 1):
+                n = lens[bi]
+                solo = net(spec[bi:bi + 1, ..., :n].contiguous(), t[bi:bi + 1], cond[bi:bi + 1, :, :n].contiguous())
+                assert torch.equal(sess_out[bi, ..., :n], solo[0]), (tag, bi, n)
+
+
+def _ragged_eval(net, spec, t, cond, lens):
+    """One backbone evaluation of a ragged batch through the engine session (the public ragged entry is the sampler's lengths=)."""
+    from xiaoicesing_io_b200 import _cabi as C
+    B, F_, M, T = spec.shape
+    dev = spec.device
+    eng = net._engine()
+    sess = eng.begin(cond.transpose(1, 2).contiguous(), t, per_row_t=True, lens=torch.tensor(lens, dtype=torch.int32, device=dev))
+    x_tm = torch.empty((B * T, F_ * M), device=dev)
+    C.transpose(spec.reshape(B, F_ * M, T).contiguous(), x_tm, B, F_ * M, T)
+    out_tm = torch.empty_like(x_tm)
+    sess.eval(x_tm, 0, out_tm)
+    out = torch.empty((B, F_ * M, T), device=dev)
+    C.transpose(out_tm, out, B, T, F_ * M)
+    return out.reshape(B, F_, M, T)
+
+
 @pytest.mark.parametrize('B,T', [(40, 690), (70, 345), (150, 129)])
 def test_chained_utterance_groups_do_not_change_a_bit(B, T, dev):
     """Batches larger than one launch run as several utterance groups per evaluation; by default a group's layer kernel does not
