@@ -239,6 +239,22 @@ def test_narrow_wavenet_on_the_padded_whole_stack_kernel(channels, L, cycle, in_
         assert eng.C == (256 if pad else channels) and eng.C0 == channels
         sess = eng.begin(cond.to(dev).transpose(1, 2).contiguous(), t.to(dev), per_row_t=True)
         assert sess.stack3 == pad and sess.head3 == pad
+    # the narrow-model mode of the whole-stack kernels (the all-zero fourth K slab skipped, GEMM1's second half with N = 128) adds
+    # and multiplies exact zeros less: bit-identical to the plain padded run, with and without the skip / head kernel
+    for head3 in (True, False):
+        res = []
+        for narrow in (True, False):
+            P.hparams.clear()
+            P.hparams.update(hidden_size=cfg.hidden_size, b2s_precision=precision, b2s_pad_channels=True, b2s_narrow_slabs=narrow,
+                             b2s_stack3_head=head3)
+            net = P.build_backbone(in_dims, n_feats, 'wavenet', dict(num_layers=L, num_channels=channels, dilation_cycle_length=cycle))
+            net.load_state_dict(sd, strict=True)
+            net = net.to(dev).eval()
+            assert net._engine().C_used == (192 if narrow else 256)
+            res.append(net(spec.to(dev), t.to(dev), cond.to(dev)))
+        assert torch.equal(res[0], res[1]), (head3, float((res[0] - res[1]).abs().max()))
+        if head3:
+            assert torch.equal(res[0].cpu(), outs[True])
     ref = OD.make_denoiser(sd, cfg)(spec, t.long(), cond)
     eps = 2 ** -8 if precision == 'bf16' else 2 ** -11
     scale = float(ref.abs().max())

@@ -68,7 +68,7 @@ class _B2SBackbone(nn.Module):
     def _engine(self):
         prec = hparams.get('b2s_precision') or os.environ.get('B2S_PRECISION', 'fp32')
         eng = self.__dict__.get('_b2s_engine')
-        pad = bool(hparams.get('b2s_pad_channels', True))
+        pad = (bool(hparams.get('b2s_pad_channels', True)), bool(hparams.get('b2s_narrow_slabs', True)))
         if eng is None or eng.precision != prec or getattr(eng, 'pad_channels', pad) != pad:
             eng = self.engine_cls(self, prec)
             eng.pad_channels = pad

@@ -168,7 +168,7 @@ _SEEN_KEYS_MAX = 64
 # hparams that change WHICH kernels a sampling call launches: part of the graph key (toggling one after capture must not replay
 # the old launch structure)
 _STRUCTURE_HPARAMS = ('b2s_stack', 'b2s_stack3', 'b2s_stack3_head', 'b2s_stack_t', 'b2s_stack_t_tile', 'b2s_fuse_io', 'b2s_fuse_update',
-                      'b2s_overlap_noise', 'b2s_fuse_cast', 'b2s_defer_skip', 'b2s_lynx_fold_cond', 'b2s_pad_channels', 'b2s_chain_groups')
+                      'b2s_overlap_noise', 'b2s_fuse_cast', 'b2s_defer_skip', 'b2s_lynx_fold_cond', 'b2s_pad_channels', 'b2s_chain_groups', 'b2s_narrow_slabs')
 
 
 def _program_key(prog: Program):

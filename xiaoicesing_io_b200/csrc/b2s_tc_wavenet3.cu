@@ -64,6 +64,11 @@ struct __align__(64) Stack3P {
     // several utterance groups of ONE evaluation launched back to back (bit 0: this launch follows another group, bit 1: another
     // group follows): the next group's layer kernel must not wait for this group's skip / head tail - see wavenet_stack3_kernel
     int chain;
+    // NARROW MODELS (zero-padded to 256 channels, engine.py): only the first ks = 3 of the 4 64-channel K slabs are non-zero, so the
+    // K slabs >= ks of every GEMM are skipped and GEMM1's second half (channels 128 .. 191) is issued with N = 128; the barrier
+    // choreography of the dead slab is kept (arrivals without work), so every phase count is the one of the full kernel.
+    // Skipped terms are exact zeros: the results are bit-identical to the padded run.
+    int ks;
     CUtensorMap mapWskip, mapWsp, mapWfin;
     const float* bss; const float* b_sp; const float* b_fin; float alpha; float* out;
     int* zflags;                                          // [B * tiles_per_b], zero before the launch
@@ -208,7 +213,7 @@ constexpr int SK_STAGES = 3, SK_STAGE_BYTES = 32768, SK_HTILE = 65536, SK_HBUF =
 
 constexpr int SK_SMEM_BYTES = SK_HBUF + SK_STAGES * SK_STAGE_BYTES + 256;
 
-template <int BF16>
+template <int BF16, int KS>
 __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __grid_constant__ Stack3P p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + SK_HBUF + SK_STAGES * SK_STAGE_BYTES);
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
                     for (int s = 0; s < 2; ++s)
                         for (int kk = 0; kk < 2; ++kk) {
                             const int kb = 2 * half + kk;
+                            if (KS < 4 && kb >= KS) continue;        // narrow model: this K slab is all zeros
                             mbar_wait(&empty[stage], phase ^ 1);
                             const uint32_t lb = mapa_u32(&full[stage], lead);
                             if (rank == 0) mbar_expect_tx(&full[stage], 2 * 16384 + (ok[s] ? 16384 : 0) + (okp[s] ? 16384 : 0));
@@ -291,14 +297,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
                             advance();
                         }
             for (int s = 0; s < 2; ++s)
-                for (int kb = 0; kb < 4; ++kb) {               // skip_projection weights: this CTA's 128 of the 256 rows
+                for (int kb = 0; kb < KS; ++kb) {            // skip_projection weights: this CTA's 128 of the 256 rows
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * 16384);
                     tma_load_2d_cg2_a(st_a + stage * SK_STAGE_BYTES + 16384, &p.mapWsp, mapa_u32(&full[stage], lead), kb * BK, rank * (C / 2));
                     advance();
                 }
             for (int s = 0; s < 2; ++s)
-                for (int kb = 0; kb < 4; ++kb) {               // output_projection weights: this CTA's MF/2 of the MF rows
+                for (int kb = 0; kb < KS; ++kb) {            // output_projection weights: this CTA's MF/2 of the MF rows
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * (MF / 2) * 128);
                     tma_load_2d_cg2_a(st_a + stage * SK_STAGE_BYTES + 16384, &p.mapWfin, mapa_u32(&full[stage], lead), kb * BK, rank * (MF / 2));
@@ -316,6 +322,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
                 for (int half = 0; half < 2; ++half)
                     for (int s = 0; s < 2; ++s) {
                         for (int kk = 0; kk < 2; ++kk) {
+                            if (KS < 4 && 2 * half + kk >= KS) continue;
                             mbar_wait(&full[stage], phase);
                             tc_fence_after();
                             const uint32_t a_lo = st_lo + stage * (SK_STAGE_BYTES >> 4), b_lo = a_lo + (16384 >> 4);
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
             for (int s = 0; s < 2; ++s) {
                 mbar_wait(&hready[2 * s], 0);                  // (S + bss) tile of slot s, both CTAs, is in shared memory
                 tc_fence_after();
-                for (int kb = 0; kb < 4; ++kb) {
+                for (int kb = 0; kb < KS; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_lo = hb_lo + s * (SK_HTILE >> 4) + kb * (ZSLAB >> 4), b_lo = st_lo + stage * (SK_STAGE_BYTES >> 4) + (16384 >> 4);
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
             for (int s = 0; s < 2; ++s) {
                 mbar_wait(&hready[2 * s + 1], 0);              // hidden tile of slot s
                 tc_fence_after();
-                for (int kb = 0; kb < 4; ++kb) {
+                for (int kb = 0; kb < KS; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_lo = hb_lo + s * (SK_HTILE >> 4) + kb * (ZSLAB >> 4), b_lo = st_lo + stage * (SK_STAGE_BYTES >> 4) + (16384 >> 4);
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_skiphead3_kernel(const __
     }
 }
 
-template <int BF16>
+template <int BF16, int KS>
 __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __grid_constant__ Stack3P p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* ys = smem;
@@ -601,7 +608,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                     advance();
                 };
                 for (int h = 0; h < 2; ++h) {
+                    const int nrow = (h == 1 && KS == 3) ? 64 : 128;      // narrow model: half 1 is issued with N = 128
                     for (int f = 0; f < 12; ++f) {
+                        if (KS < 4 && (f & 3) >= KS) continue;                      // ... and K slab 3 of every tap is all zeros
                         const int tap = (f >> 2) == 0 ? 1 : ((f >> 2) == 1 ? 0 : 2);       // centre tap first: it needs no halo
                         mbar_wait(&empty[stage], phase ^ 1);
 #ifdef B2S_TLOG
@@ -609,12 +618,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
 #endif
                         if (rank == 0) mbar_expect_tx(&full[stage], CLUSTER * STAGE_BYTES);
                         tma_load_3d_cg2_a(st_a + stage * STAGE_BYTES, &p.mapWd, mapa_u32(&full[stage], lead), tap * C + (f & 3) * BK,
-                                          h * 256 + rank * 128, l);
+                                          h * 256 + rank * nrow, l);
                         advance();
                     }
                 }
                 if (l + 1 < L)
-                    for (int kb = 0; kb < 4; ++kb) fill_g2(kb);
+                    for (int kb = 0; kb < KS; ++kb) fill_g2(kb);
             }
         }
     } else if (warp == 1) {
@@ -629,6 +638,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
         // ===================== MMA issuer (leader CTA, one lane): every MMA spans both CTAs (M = 256) =====================
         if (rank == 0 && lane == 0) {
             const uint32_t idesc_h = make_idesc_f16(2 * BM, 256, BF16);
+            const uint32_t idesc_h1 = KS == 3 ? make_idesc_f16(2 * BM, 128, BF16) : idesc_h;     // narrow model: half 1 has 128 columns
             // GEMM1-retired signal: this pair's CTAs and the neighbouring CTAs that write this pair's halo rows
             const uint16_t gmask = (uint16_t)(pmask | (lead > 0 ? (1u << (lead - 1)) : 0u) | (lead + 2 < CS ? (1u << (lead + 2)) : 0u));
             const uint32_t ys_lo = desc_lo(smem_u32(ys)), zs_lo = desc_lo(smem_u32(zs)), st_lo = desc_lo(smem_u32(stages));
@@ -657,6 +667,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                 auto g2 = [&](int kb) {                        // residual GEMM K slab kb: X += z[:, 64kb..] . (2^(l/2) Wres)^T
                     mbar_wait(&zready[kb], par);
                     tc_fence_after();
+                    if (KS < 4 && kb >= KS) {                    // narrow model: nothing to multiply, keep the ring's phase count
+                        umma_commit_cg2_mcast(&zfree[kb & 1], pmask);
+                        return;
+                    }
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_lo = zs_lo + (kb & 1) * (ZSLAB >> 4), b_lo = st_lo + stage * (STAGE_BYTES >> 4);
@@ -681,12 +695,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                             tc_fence_after();
                             TLOG3(l, 1);
                         }
+                        if (KS < 4 && (f & 3) >= KS) continue;
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_lo = ys_lo + (f & 3) * (YSLAB >> 4) + (uint32_t)(HALO + (tap - 1) * dil) * (128 >> 4);
                         const uint32_t b_lo = st_lo + stage * (STAGE_BYTES >> 4);
+                        const uint32_t idh = h ? idesc_h1 : idesc_h;
 #pragma unroll
-                        for (int k = 0; k < BK / UK; ++k) mma2(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_h, (f | k) != 0);
+                        for (int k = 0; k < BK / UK; ++k) mma2(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idh, (f | k) != 0);
                         umma_commit_cg2_mcast(&empty[stage], pmask);
                         advance();
                     }
@@ -735,7 +751,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                 // Only the d = dilation(m) rows next to the boundary are read by layer m's side taps: d x 512 B per side
                 const int d = p.dil[m];
                 // arm this CTA's own halo barrier for layer m (phase m-1 is complete: GEMM1 of layer m-1 needed it)
-                if (lane == 0) mbar_expect_tx(haloin, (uint32_t)((dsm_left ? 1 : 0) + (dsm_right ? 1 : 0)) * d * 512);
+                if (lane == 0) mbar_expect_tx(haloin, (uint32_t)((dsm_left ? 1 : 0) + (dsm_right ? 1 : 0)) * d * 128 * KS);
                 if (m >= 1) mbar_wait(g1done, (uint32_t)(m - 1) & 1u);      // the neighbours no longer read the halo rows of y_{m-1}
                 auto copy_side = [&](uint32_t src, uint32_t dst, uint32_t bar) {     // d rows of each of the 4 slabs: 32 d pieces of 16 B
                     for (int i0 = 0; i0 < d; i0 += 4) {
@@ -743,14 +759,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int idx = (i0 + i) * 32 + lane, s4 = idx / (8 * d), off = (idx - s4 * 8 * d) * 16;
-                            if (i0 + i < d)
+                            if (i0 + i < d && (KS == 4 || s4 < KS))
                                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
                                              : "r"(src + s4 * YSLAB + off));
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int idx = (i0 + i) * 32 + lane, s4 = idx / (8 * d), off = (idx - s4 * 8 * d) * 16;
-                            if (i0 + i < d) st_async_u4(dst + s4 * YSLAB + off, v[i], bar);
+                            if (i0 + i < d && (KS == 4 || s4 < KS)) st_async_u4(dst + s4 * YSLAB + off, v[i], bar);
                         }
                     }
                 };
@@ -764,6 +780,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                 if (pub_left || pub_right) {
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
+                        if (KS < 4 && s >= KS) break;
                         if (pub_left) tma_store_3d_a(&p.mapYe[m & 1], ys_a + s * YSLAB + HALO * 128, s * BK, t0, b);
                         if (pub_right) tma_store_3d_a(&p.mapYe[m & 1], ys_a + s * YSLAB + BM * 128, s * BK, t0 + BM - HALO, b);
                     }
@@ -780,11 +797,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                     const uint32_t lb = mapa_u32(halofull, lead);
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
+                        if (KS < 4 && s >= KS) break;
                         if (g_left) tma_load_3d_cg2_a(ys_a + s * YSLAB, &p.mapYe[m & 1], lb, s * BK, t0 - HALO, b);
                         if (g_right) tma_load_3d_cg2_a(ys_a + s * YSLAB + (HALO + BM) * 128, &p.mapYe[m & 1], lb, s * BK, t0 + BM, b);
                     }
                 }
-                if (rank == 0 && pair_glob) mbar_expect_tx(halofull, pair_glob * 4 * HALO * 128);
+                if (rank == 0 && pair_glob) mbar_expect_tx(halofull, pair_glob * KS * HALO * 128);
             }
             __syncwarp();
         };
@@ -799,7 +817,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                     }
                     if (tile_ok) {
                         tma_store_4d(&p.mapZ, zs_a, (2 * h) * BK, t0, b, l);
-                        tma_store_4d(&p.mapZ, zs_a + ZSLAB, (2 * h + 1) * BK, t0, b, l);
+                        if (KS == 4 || 2 * h + 1 < KS) tma_store_4d(&p.mapZ, zs_a + ZSLAB, (2 * h + 1) * BK, t0, b, l);
                         tma_store_commit();
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stores have READ the ring
                     }
@@ -838,6 +856,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
 #pragma unroll 1
             for (int jj = 0; jj < 4; ++jj) {
                 const int J = 4 * sub + jj;                    // columns (= channels) [32J, 32J + 32)
+                if (KS < 4 && J >= 2 * KS) break;                      // narrow model: channels >= 64 ks are zero padding, never read
                 float acc[32];
                 tmem_ld32(taddr + (stem ? 256 : 0) + 32 * J, acc);
                 tmem_ld_wait();
@@ -917,10 +936,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                 if (e == 0 && lane == 0) TLOG3(l, 2 + 2 * h);
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
+                    // narrow model: K slab 3 (half 1, pr 1) does not exist - its barrier arrivals are kept, its work is skipped
+                    const bool dead = KS < 4 && 2 * h + pr >= KS;
                     float acc0[32], acc1[32];
-                    tmem_ld32(taddr + 256 + 32 * (4 * pr + 2 * sub), acc0);
-                    tmem_ld32(taddr + 256 + 32 * (4 * pr + 2 * sub + 1), acc1);
-                    tmem_ld_wait();
+                    if (!dead) {
+                        tmem_ld32(taddr + 256 + 32 * (4 * pr + 2 * sub), acc0);
+                        tmem_ld32(taddr + 256 + 32 * (4 * pr + 2 * sub + 1), acc1);
+                        tmem_ld_wait();
+                    }
                     if (pr == 1) {                             // the accumulator is in registers: hand it back to the MMA issuer
                         tc_fence_before();
                         __syncwarp();
@@ -933,6 +956,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                         for (int i = 0; i < 16; ++i) zp[i] = __float_as_uint(acc0[i]);
                     } else
 #endif
+                    if (!dead)
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const float* acc = jj ? acc1 : acc0;
@@ -951,15 +975,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
                     }
                     // cond rows of the next step: the other slab of this half, the next half, or (h = 1, pr = 1) nothing: the next
                     // layer's first rows are requested at the top of the layer loop, after the y epilogue
-                    if (pr == 0) load_cond(h, 1);
+                    if (pr == 0) { if (KS == 4 || 2 * h + 1 < KS) load_cond(h, 1); }
                     else if (h == 0) load_cond(1, 0);
                     // write 2l + h of ring buffer pr: the previous occupant's GEMM2 slab has retired and its TMA store has read it
                     if (l + h > 0) mbar_wait(&zfree[pr], (uint32_t)(2 * l + h - 1) & 1u);
                     // z channels [64 (2h + pr) + 32 sub, +32) of this row: K slab 2h + pr (ring buffer pr), 16-byte pieces 4 sub .. 4 sub + 3
                     const uint32_t slab = zrow + pr * ZSLAB;
+                    if (!dead) {
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4)
-                        st_shared_u4(slab + (((4 * sub + c4) ^ sw) << 4), make_uint4(zp[4 * c4], zp[4 * c4 + 1], zp[4 * c4 + 2], zp[4 * c4 + 3]));
+                        for (int c4 = 0; c4 < 4; ++c4)
+                            st_shared_u4(slab + (((4 * sub + c4) ^ sw) << 4), make_uint4(zp[4 * c4], zp[4 * c4 + 1], zp[4 * c4 + 2], zp[4 * c4 + 3]));
+                    }
                     fence_proxy_async_smem();
                     tc_fence_before();
                     __syncwarp();
@@ -1013,7 +1039,7 @@ static int make_map_z4(CUtensorMap* m, const void* base, int bf16, int T, int B,
 // configuration fit the device as it is now (MPS / MIG / green-context limits included).  Cluster size: the largest of 8, 6, 4, 2
 // that divides the tiles per utterance (halo rows inside a cluster travel through distributed shared memory); smaller if the
 // device cannot co-schedule enough clusters of that size.
-template <int BF16>
+template <int BF16, int KS>
 static int launch(const Stack3P& p, int grid, cudaStream_t st) {
     int dev = 0;
     B2S_CHECK_CUDA(cudaGetDevice(&dev));
@@ -1034,7 +1060,7 @@ static int launch(const Stack3P& p, int grid, cudaStream_t st) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     if (!configured[dev]) {
-        B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_stack3_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_stack3_kernel<BF16, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured[dev] = true;
     }
     int cs_used = 0, best = 0;
@@ -1046,7 +1072,7 @@ static int launch(const Stack3P& p, int grid, cudaStream_t st) {
             attr[0].val.clusterDim.x = cs;
             cfg.numAttrs = 1;
             int q = 0;
-            if (cudaOccupancyMaxActiveClusters(&q, wavenet_stack3_kernel<BF16>, &cfg) != cudaSuccess) { cudaGetLastError(); q = 0; }
+            if (cudaOccupancyMaxActiveClusters(&q, wavenet_stack3_kernel<BF16, 4>, &cfg) != cudaSuccess) { cudaGetLastError(); q = 0; }
             n = q > 0 ? q : -1;
         }
         if (n > best * 1) best = n > best ? n : best;
@@ -1068,18 +1094,18 @@ static int launch(const Stack3P& p, int grid, cudaStream_t st) {
     }
     attr[0].val.clusterDim.x = cs_used;
     cfg.numAttrs = 2;
-    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_stack3_kernel<BF16>, p));
+    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_stack3_kernel<BF16, KS>, p));
     return B2S_OK;
 }
 
 // the skip-sum / head kernel: one CTA pair per four layer tiles, launched with programmatic dependent launch behind the layer kernel
-template <int BF16>
+template <int BF16, int KS>
 static int launch_skiphead(const Stack3P& p, int grid, cudaStream_t st) {
     int dev = 0;
     B2S_CHECK_CUDA(cudaGetDevice(&dev));
     static bool configured[64] = {};
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_skiphead3_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+        B2S_CHECK_CUDA(cudaFuncSetAttribute(wavenet_skiphead3_kernel<BF16, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
         configured[dev] = true;
     }
     cudaLaunchConfig_t cfg{};
@@ -1096,7 +1122,7 @@ static int launch_skiphead(const Stack3P& p, int grid, cudaStream_t st) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_skiphead3_kernel<BF16>, p));
+    B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wavenet_skiphead3_kernel<BF16, KS>, p));
     return B2S_OK;
 }
 
@@ -1105,7 +1131,7 @@ template <int BF16>
 static int max_tiles(int tiles_per_b) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
-    cudaFuncSetAttribute(wavenet_stack3_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(wavenet_stack3_kernel<BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(tiles_per_b);
     cfg.blockDim = dim3(NTHREADS);
@@ -1121,7 +1147,7 @@ static int max_tiles(int tiles_per_b) {
         if (tiles_per_b % cs) continue;
         attr[0].val.clusterDim.x = cs;
         int q = 0;
-        if (cudaOccupancyMaxActiveClusters(&q, wavenet_stack3_kernel<BF16>, &cfg) != cudaSuccess) { cudaGetLastError(); q = 0; }
+        if (cudaOccupancyMaxActiveClusters(&q, wavenet_stack3_kernel<BF16, 4>, &cfg) != cudaSuccess) { cudaGetLastError(); q = 0; }
         if (q * cs > best) best = q * cs;
     }
     return best;
@@ -1155,10 +1181,14 @@ static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win,
                        const Head3* hd) {
     B2S_CHECK_ARG(xin_h && Win_h && b_in && Wd_h && cond_h && Wres_h && bsum && dvec && dilations_host && yedge0_h && yedge1_h &&
                       z_all_h && flags, "b2s_tc_wavenet_stack3: null pointer");
-    if (C != ws3::C) {
-        set_error("b2s_tc_wavenet_stack3: specialised for %d residual channels (got %d)", ws3::C, C);
+    // C = 256, or 192 for a narrower model whose operands are zero-padded to the 256-channel layout (channels >= 192 all zero in the
+    // weights, biases, cond table and step embeddings): the all-zero fourth K slab of every GEMM is then skipped (Stack3P::ks)
+    if (C != ws3::C && C != 192) {
+        set_error("b2s_tc_wavenet_stack3: specialised for %d residual channels, or 192 used channels in the 256-channel layout (got %d)", ws3::C, C);
         return B2S_ERR_UNSUPPORTED;
     }
+    const int ks = C == 192 ? 3 : 4;
+    C = ws3::C;                                   // every operand is laid out for 256 channels
     B2S_CHECK_ARG(L >= 1 && L <= ws3::MAXL, "b2s_tc_wavenet_stack3: 1 <= L <= %d (got %d)", ws3::MAXL, L);
     B2S_CHECK_ARG(MF > 0 && MF <= 256 && MF % 8 == 0 && ld_win % 8 == 0, "b2s_tc_wavenet_stack3: in_dims*n_feats must be a multiple of 8 and <= 256 (got %d)", MF);
     B2S_CHECK_ARG(yedge0_h != yedge1_h && d_stride % 4 == 0 && cond_layer_stride % 8 == 0, "b2s_tc_wavenet_stack3: bad strides / aliasing");
@@ -1192,6 +1222,7 @@ static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win,
     rc = ws3::make_map_z4(&p.mapZ, z_all_h, bf16, T, B, L, z_layer_stride);
     if (rc) return rc;
     p.B = B; p.T = T; p.L = L; p.MF = MF; p.kb_in = ceil_div(MF, ws3::BK);
+    p.ks = ks;
     p.wd = Wd_h; p.wres = Wres_h;
     p.cond = cond_h; p.cond_lstride = cond_layer_stride; p.b_in = b_in; p.bsum = bsum; p.dvec = dvec; p.d_stride = d_stride;
     p.flags = flags;
@@ -1215,10 +1246,13 @@ static int stack3_impl(const void* xin_h, int MF, const void* Win_h, int ld_win,
         p.bss = hd->bss; p.b_sp = hd->b_sp; p.b_fin = hd->b_fin; p.out = hd->out; p.zflags = hd->zflags;
         p.alpha = 1.0f / sqrtf((float)L);
     }
-    rc = bf16 ? ws3::launch<1>(p, grid, (cudaStream_t)stream) : ws3::launch<0>(p, grid, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ks == 3) rc = bf16 ? ws3::launch<1, 3>(p, grid, st) : ws3::launch<0, 3>(p, grid, st);
+    else rc = bf16 ? ws3::launch<1, 4>(p, grid, st) : ws3::launch<0, 4>(p, grid, st);
     if (rc || !hd) return rc;
-    return bf16 ? ws3::launch_skiphead<1>(p, 2 * ceil_div(grid, 4), (cudaStream_t)stream)
-                : ws3::launch_skiphead<0>(p, 2 * ceil_div(grid, 4), (cudaStream_t)stream);
+    const int sgrid = 2 * ceil_div(grid, 4);
+    if (ks == 3) return bf16 ? ws3::launch_skiphead<1, 3>(p, sgrid, st) : ws3::launch_skiphead<0, 3>(p, sgrid, st);
+    return bf16 ? ws3::launch_skiphead<1, 4>(p, sgrid, st) : ws3::launch_skiphead<0, 4>(p, sgrid, st);
 }
 
 extern "C" int b2s_tc_wavenet_stack3(const void* xin_h, int MF, const void* Win_h, int ld_win, const float* b_in, const void* Wd_h,

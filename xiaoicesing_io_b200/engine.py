@@ -56,6 +56,9 @@ class WaveNetEngine:
                 and self.C0 % 8 == 0 and (self.C0 > 128 or self.C0 % 64) and max(self.dilations) <= 16 and self.L <= 32
                 and self.MF <= 256):
             self.C = C.FUSED_LAYER_CHANNELS
+        # channels the whole-stack kernels are told about: 192 when the model fits three of the four 64-channel K slabs (the zero
+        # fourth slab of every GEMM is skipped, bit-identical results), else the layout's 256
+        self.C_used = 192 if (self.C != self.C0 and self.C0 <= 192 and hparams.get('b2s_narrow_slabs', True)) else self.C
         self._packed_version = None
         self.device = None
 
@@ -363,7 +366,10 @@ class WaveNetSessionTC:
         del self._cond_h
         # two-kernel path: the L skip outputs are summed by ONE K = L*C GEMM after the last layer (no per-layer fp32 skip RMW)
         self.defer_skip = (not self.fused) and hparams.get('b2s_defer_skip', True) and rows * L * Cc * 2 <= 8e9
-        self.z_all = torch.empty((L, rows, Cc), device=dev, dtype=hd) if (self.defer_skip or self.stack3) else None     # layer-major: contiguous rows per layer
+        # layer-major: contiguous rows per layer (zero-initialised for narrow models: their fourth K slab is never written, and the
+        # deferred skip GEMM of the non-head3 path multiplies it with zero weights)
+        alloc = torch.zeros if eng.C_used != Cc else torch.empty
+        self.z_all = alloc((L, rows, Cc), device=dev, dtype=hd) if (self.defer_skip or self.stack3) else None
         self.skip_h = torch.empty((rows, Cc), device=dev, dtype=hd)
         self.h_h = torch.empty((rows, Cc), device=dev, dtype=hd)
 
@@ -481,14 +487,14 @@ class WaveNetSessionTC:
                     C.tc_wavenet_denoiser3(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
                                            e.w_res3_h, e.bsum3, dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
                                            e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, e.w_skip3_h,
-                                           e.b_skip_sum, e.w_sp_h, e.b_sp, e.w_fin_h, e.b_fin, out[r0:], b1 - b0, T, Cc,
+                                           e.b_skip_sum, e.w_sp_h, e.b_sp, e.w_fin_h, e.b_fin, out[r0:], b1 - b0, T, e.C_used,
                                            self.flags[b0 * self.tpb:], self.flags[nfl + b0 * self.tpb:], bf,
                                            lens=None if self.lens is None else self.lens[b0:],
                                            chain=self._chain_bits(b0, b1))
                     continue
                 C.tc_wavenet_stack3(self.xin_h[r0:], MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
                                     e.w_res3_h, e.bsum3, dv[b0 * LC:] if self.per_row_t else dv, LC if self.per_row_t else 0,
-                                    e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, b1 - b0, T, Cc,
+                                    e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:], rows * Cc, b1 - b0, T, e.C_used,
                                     self.flags[b0 * self.tpb:], bf, lens=None if self.lens is None else self.lens[b0:])
             if self.head3:
                 return
@@ -603,12 +609,12 @@ class WaveNetSessionTC:
                         C.tc_wavenet_denoiser3(self.xin_h[r0:], e.MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab,
                                                tab.shape[1] * 2 * Cc, e.w_res3_h, e.bsum3, dv, 0, e.dilations, self.y_h[r0:], self.y2_h[r0:],
                                                self.z_all[:, r0:], self.rows * Cc, e.w_skip3_h, e.b_skip_sum, e.w_sp_h, e.b_sp, e.w_fin_h,
-                                               e.b_fin, out[r0:], b1 - b0, T, Cc, self.flags[b0 * self.tpb:],
+                                               e.b_fin, out[r0:], b1 - b0, T, e.C_used, self.flags[b0 * self.tpb:],
                                                self.flags[nfl + b0 * self.tpb:], e.bf16, chain=self._chain_bits(b0, b1))
                     else:
                         C.tc_wavenet_stack3(self.xin_h[r0:], e.MF, e.w_in_h, e.w_in_h.shape[1], e.b_in, e.w_dil_h, tab, tab.shape[1] * 2 * Cc,
                                             e.w_res3_h, e.bsum3, dv, 0, e.dilations, self.y_h[r0:], self.y2_h[r0:], self.z_all[:, r0:],
-                                            self.rows * Cc, b1 - b0, T, Cc, self.flags[b0 * self.tpb:], e.bf16)
+                                            self.rows * Cc, b1 - b0, T, e.C_used, self.flags[b0 * self.tpb:], e.bf16)
             what = (f'b2s_tc_wavenet_denoiser3: stem + {L} layers + skip sum + head per launch' if self.head3
                     else f'b2s_tc_wavenet_stack3: stem + {L} layers per launch, skip sum deferred')
             return (f'wavenet_stack3_kernel<{e.precision}> ({what})', flops, launch_all, -(-B // self.stack_group))
