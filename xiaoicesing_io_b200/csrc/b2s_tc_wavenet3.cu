@@ -721,8 +721,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
         }
     } else if (warp == 2) {
         // ===================== step-embedding rows: e_m[c] = 2^(-m/2) Bsum_m[c] + d_m[c], double-buffered in shared memory ====
+        // ... and the halo hand-off INSIDE the cluster: the d = dilation(m) edge rows of y_m go to the neighbour tiles through
+        // distributed shared memory as soon as y_m is written.  This warp has nothing else to wait for, so it always stands at the
+        // ydone barrier in time (the IO warp, which did this copy first, arrived 1 - 1.5 us late: its TMA stores of the z tiles take
+        // ~3 us to read the ring behind the queued weight loads - in-kernel timeline - and the MMA stream stalls on the halo rows).
         const float* dv = p.dvec + (long long)b * p.d_stride;
-        for (int m = 0; m < L; ++m) {
+        const uint32_t ys_a = smem_u32(ys);
+        const uint32_t nl_ys = dsm_left ? mapa_u32(ys, crank - 1) : 0u, nr_ys = dsm_right ? mapa_u32(ys, crank + 1) : 0u;
+        const uint32_t nl_bar = dsm_left ? mapa_u32(haloin, crank - 1) : 0u, nr_bar = dsm_right ? mapa_u32(haloin, crank + 1) : 0u;
+        auto e_rows = [&](int m) {
             if (m >= 2) mbar_wait(&efree[m & 1], (uint32_t)((m - 2) >> 1) & 1u);
             const float s = exp2f(-0.5f * (float)m);
             float* dst = etab + (m & 1) * C;
@@ -733,6 +740,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&eready[m & 1]);
+        };
+        auto halo_dsm = [&](int m) {
+            mbar_wait(ydone, (uint32_t)m & 1u);                // own rows of y_m are in shared memory
+            TLOG3(m, 12);
+            // Only the d = dilation(m) rows next to the boundary are read by layer m's side taps: d x 128 B per slab and side
+            const int d = p.dil[m];
+            // arm this CTA's own halo barrier for layer m (phase m-1 is complete: GEMM1 of layer m-1 needed it)
+            if (lane == 0) mbar_expect_tx(haloin, (uint32_t)((dsm_left ? 1 : 0) + (dsm_right ? 1 : 0)) * d * 128 * KS);
+            if (m >= 1) mbar_wait(g1done, (uint32_t)(m - 1) & 1u);      // the neighbours no longer read the halo rows of y_{m-1}
+            auto copy_side = [&](uint32_t src, uint32_t dst, uint32_t bar) {     // d rows of each slab: 8 d pieces of 16 B per slab
+                for (int i0 = 0; i0 < d; i0 += 4) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = (i0 + i) * 32 + lane, s4 = idx / (8 * d), off = (idx - s4 * 8 * d) * 16;
+                        if (i0 + i < d && (KS == 4 || s4 < KS))
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                                         : "r"(src + s4 * YSLAB + off));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = (i0 + i) * 32 + lane, s4 = idx / (8 * d), off = (idx - s4 * 8 * d) * 16;
+                        if (i0 + i < d && (KS == 4 || s4 < KS)) st_async_u4(dst + s4 * YSLAB + off, v[i], bar);
+                    }
+                }
+            };
+            // my first d rows -> rows 144.. of the left neighbour (its +d tap); my last d rows -> rows [16 - d, 16) of the right
+            // neighbour (its -d tap); both row offsets differ by 128: the swizzle phase is preserved
+            if (dsm_left) copy_side(ys_a + HALO * 128, nl_ys + (HALO + BM) * 128, nl_bar);
+            if (dsm_right) copy_side(ys_a + (HALO + BM - d) * 128, nr_ys + (HALO - d) * 128, nr_bar);
+            TLOG3(m, 13);
+        };
+        e_rows(0);
+        for (int m = 0; m < L; ++m) {
+            if (m + 1 < L) e_rows(m + 1);                      // (efree of m - 1 was released before ydone(m - 1), which halo_dsm(m - 1) saw)
+            halo_dsm(m);
         }
     } else if (warp == 3) {
         // ===================== IO warp: z ring -> z_all (TMA store), edge rows of y_m -> the neighbours' halo rows =====================
@@ -742,40 +785,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wavenet_stack3_kernel(const __gri
         const uint32_t ys_a = smem_u32(ys), zs_a = smem_u32(zs);
         const int* fl = p.flags + b * p.tiles_per_b;
         const bool pub_left = g_left && tile_ok, pub_right = g_right;
-        const uint32_t nl_ys = dsm_left ? mapa_u32(ys, crank - 1) : 0u, nr_ys = dsm_right ? mapa_u32(ys, crank + 1) : 0u;
-        const uint32_t nl_bar = dsm_left ? mapa_u32(haloin, crank - 1) : 0u, nr_bar = dsm_right ? mapa_u32(haloin, crank + 1) : 0u;
+        // the edge rows that cross a CLUSTER boundary (utterances longer than a cluster) go through global memory; the hand-off
+        // inside the cluster is warp 2's
         auto publish = [&](int m) {
+            if (!(pub_left || pub_right || g_left || g_right || (rank == 0 && pair_glob))) return;
             mbar_wait(ydone, (uint32_t)m & 1u);                // own rows of y_m are in shared memory
-            TLOG3(m, 12);
-            {
-                // Only the d = dilation(m) rows next to the boundary are read by layer m's side taps: d x 512 B per side
-                const int d = p.dil[m];
-                // arm this CTA's own halo barrier for layer m (phase m-1 is complete: GEMM1 of layer m-1 needed it)
-                if (lane == 0) mbar_expect_tx(haloin, (uint32_t)((dsm_left ? 1 : 0) + (dsm_right ? 1 : 0)) * d * 128 * KS);
-                if (m >= 1) mbar_wait(g1done, (uint32_t)(m - 1) & 1u);      // the neighbours no longer read the halo rows of y_{m-1}
-                auto copy_side = [&](uint32_t src, uint32_t dst, uint32_t bar) {     // d rows of each of the 4 slabs: 32 d pieces of 16 B
-                    for (int i0 = 0; i0 < d; i0 += 4) {
-                        uint4 v[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int idx = (i0 + i) * 32 + lane, s4 = idx / (8 * d), off = (idx - s4 * 8 * d) * 16;
-                            if (i0 + i < d && (KS == 4 || s4 < KS))
-                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
-                                             : "r"(src + s4 * YSLAB + off));
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int idx = (i0 + i) * 32 + lane, s4 = idx / (8 * d), off = (idx - s4 * 8 * d) * 16;
-                            if (i0 + i < d && (KS == 4 || s4 < KS)) st_async_u4(dst + s4 * YSLAB + off, v[i], bar);
-                        }
-                    }
-                };
-                // my first d rows -> rows 144.. of the left neighbour (its +d tap); my last d rows -> rows [16 - d, 16) of the right
-                // neighbour (its -d tap); both row offsets differ by 128: the swizzle phase is preserved
-                if (dsm_left) copy_side(ys_a + HALO * 128, nl_ys + (HALO + BM) * 128, nl_bar);
-                if (dsm_right) copy_side(ys_a + (HALO + BM - d) * 128, nr_ys + (HALO - d) * 128, nr_bar);
-            }
-            TLOG3(m, 13);
             if (lane == 0) {
                 if (pub_left || pub_right) {
 #pragma unroll
