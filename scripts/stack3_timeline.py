@@ -13,7 +13,8 @@ dev = torch.device('cuda:0')
 P.hparams.clear()
 P.hparams.update(hidden_size=256, b2s_precision=os.environ.get('TL_PREC', 'bf16'))
 torch.manual_seed(0)
-net = P.build_backbone(128, 1, 'wavenet', dict(num_layers=20, num_channels=256, dilation_cycle_length=4)).to(dev).eval()
+CH = int(os.environ.get('TL_C', 256))          # 192: the narrow-model (KS = 3) variant on the padded layout
+net = P.build_backbone(128, 1, 'wavenet', dict(num_layers=20, num_channels=CH, dilation_cycle_length=4)).to(dev).eval()
 torch.nn.init.normal_(net.output_projection.weight, std=0.01)
 eng = net._engine(); eng.pack()
 sess = eng.begin(torch.randn(B, T, 256, device=dev), torch.tensor([399.0], device=dev))
