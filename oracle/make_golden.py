@@ -214,9 +214,56 @@ def aux_main():
              [-12.] * 16, [0.] * 16, 1, 9, 302, infer=False)
 
 
+def voc_case(name, h, B, T, seed, f0_kind='mixed'):
+    """Runs ``Generator(h)(mel, f0)`` of modules/nsf_hifigan/models.py:206-289 (NSF-HiFiGAN, mel + f0 -> waveform) after
+    ``remove_weight_norm()`` (what load_model does, :31-32), with the fan-in scaled random weights of
+    ``oracle.vocoder.random_state_dict`` (the reference's own N(0, 0.01) init would make every block a near-identity), and records
+    the two random draws of SineGen in draw order."""
+    from oracle import vocoder as ov
+    voc = ref_loader.load_vocoder()
+    cfg = ov.NsfHifiGanCfg(**h)
+    hd = voc.AttrDict(dict(h, upsample_rates=list(cfg.upsample_rates), upsample_kernel_sizes=list(cfg.upsample_kernel_sizes),
+                           resblock_kernel_sizes=list(cfg.resblock_kernel_sizes),
+                           resblock_dilation_sizes=[list(d) for d in cfg.resblock_dilation_sizes]))
+    torch.manual_seed(seed)
+    gen = voc.models.Generator(hd).eval()
+    gen.remove_weight_norm()
+    sd = ov.random_state_dict(cfg, seed + 1)
+    missing = gen.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 2)
+    mel = torch.randn((B, cfg.num_mels, T), generator=g) * 1.5 - 4.0
+    f0 = 110.0 * 2 ** (2 * torch.rand((B, T), generator=g))                 # 110 .. 440 Hz
+    if f0_kind == 'mixed':
+        f0[:, T // 3: T // 3 + max(1, T // 4)] = 0.                        # an unvoiced stretch
+        f0[-1, -2:] = 0.
+    arrays = dict(mel=mel, f0=f0)
+    torch.manual_seed(seed + 3)
+    with torch.no_grad():
+        out = gen(mel, f0)
+    if not cfg.mini_nsf:
+        torch.manual_seed(seed + 3)                                         # the same two draws, in the reference's order (:147, :170)
+        arrays['rand_ini'] = torch.rand(1, 1, cfg.harmonic_num + 1)
+        arrays['noise'] = torch.randn(B, T * cfg.hop, cfg.harmonic_num + 1)
+    arrays['out'] = out
+    _save(name, dict(kind='vocoder', h=h), arrays, sd)
+
+
+def voc_main():
+    voc_case('voc_nsf_resblock1', dict(num_mels=16, sampling_rate=16000, upsample_rates=(4, 2, 2), upsample_kernel_sizes=(8, 4, 4),
+                                      upsample_initial_channel=32, resblock='1', resblock_kernel_sizes=(3, 7),
+                                      resblock_dilation_sizes=((1, 3, 5), (1, 3, 5))), 2, 11, 500)
+    voc_case('voc_nsf_resblock2', dict(num_mels=8, sampling_rate=22050, upsample_rates=(4, 4), upsample_kernel_sizes=(8, 8),
+                                      upsample_initial_channel=16, resblock='2', resblock_kernel_sizes=(3, 5),
+                                      resblock_dilation_sizes=((1, 3), (1, 3))), 1, 7, 501)
+    voc_case('voc_mini_nsf', dict(num_mels=8, sampling_rate=16000, upsample_rates=(2, 2, 2), upsample_kernel_sizes=(4, 4, 4),
+                                 upsample_initial_channel=32, resblock='1', resblock_kernel_sizes=(3,),
+                                 resblock_dilation_sizes=((1, 3, 5),), mini_nsf=True), 2, 9, 502)
+
+
 def main():
     aux_main()
     enc_main()
+    voc_main()
     # ---- backbone forward ------------------------------------------------------------------
     backbone_case('bb_wavenet_int_t', 'wavenet', WN_SMALL, 16, 1, 2, 37, torch.tensor([950, 3]), 10)
     backbone_case('bb_wavenet_float_t1', 'wavenet', WN_CYC, 16, 1, 3, 41, torch.tensor([437.25]), 11)
@@ -288,6 +335,8 @@ def main():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'aux':
         aux_main()                                          # only the aux-decoder fixtures
+    elif len(sys.argv) > 1 and sys.argv[1] == 'voc':
+        voc_main()                                          # only the vocoder fixtures
     elif len(sys.argv) > 1 and sys.argv[1] == 'enc':
         enc_main()                                          # only the acoustic-encoder fixtures
     else:

@@ -64,3 +64,28 @@ def set_hparams(**kw):
     ref = load()
     ref.hparams.update(kw)
     return ref.hparams
+
+
+def load_vocoder():
+    """The reference's NSF-HiFiGAN generator module (modules/nsf_hifigan/models.py).  Its imports of ``lightning`` (models.py:8,
+    only ``rank_zero_info``) and ``matplotlib`` (utils.py:1-3, unused by the generator) are stubbed when those packages are absent;
+    no reference file is modified."""
+    load()
+    import importlib
+    for name in ('matplotlib',):
+        try:
+            importlib.import_module(name)
+        except ModuleNotFoundError:
+            stub = types.ModuleType(name)
+            stub.use = lambda *a, **k: None
+            sys.modules[name] = stub
+    try:
+        importlib.import_module('lightning.pytorch.utilities.rank_zero')
+    except ModuleNotFoundError:
+        for name in ('lightning', 'lightning.pytorch', 'lightning.pytorch.utilities', 'lightning.pytorch.utilities.rank_zero'):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        sys.modules['lightning.pytorch.utilities.rank_zero'].rank_zero_info = print
+    import modules.nsf_hifigan.models as models              # noqa: E402
+    from modules.nsf_hifigan.env import AttrDict              # noqa: E402
+    return types.SimpleNamespace(models=models, AttrDict=AttrDict)
+
