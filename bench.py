@@ -437,6 +437,11 @@ def run_secondary(args, dev):
     except Exception as ex:                                 # noqa: BLE001
         out['acoustic_encoder'] = {'error': f'{type(ex).__name__}: {ex}'}
     torch.cuda.empty_cache()
+    try:
+        out['vocoder'] = time_vocoder(args.precision, dev)
+    except Exception as ex:                                 # noqa: BLE001
+        out['vocoder'] = {'error': f'{type(ex).__name__}: {ex}'}
+    torch.cuda.empty_cache()
     P.hparams.clear()
     P.hparams.update(saved)
     return out
@@ -511,6 +516,85 @@ def time_acoustic_encoder(precision, dev, B=16, L=64, T=690, reps=5, extra_hpara
     return {'workload': f'FastSpeech2 acoustic encoder 4x256 (2 heads, rotary, conv-3 FFN), B={B} x {L} tokens -> {T} frames: the '
                         f'condition tensor, once per batch', 'ms_per_call': ms, 'frames_per_s': B * T / (ms * 1e-3),
             'launches_per_call': 2 + 10 * 4 + 2}
+
+
+VOCODER_H = dict(num_mels=128, sampling_rate=44100, upsample_rates=[8, 8, 2, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4, 4],
+                 upsample_initial_channel=512, resblock='1', resblock_kernel_sizes=[3, 7, 11],
+                 resblock_dilation_sizes=[[1, 3, 5]] * 3)
+
+
+def time_vocoder(precision, dev, T=690, reps=3, extra_hparams=None):
+    """The step AFTER the path: NSF-HiFiGAN at the public 44.1 kHz geometry (512 channels, hop 512,
+    residual kernels 3 / 7 / 11), mel + f0 -> waveform for one 8-s utterance (the reference's shape, inference/ds_acoustic.py:227-236)
+    and for a batch of 8.  Fan-in scaled random weights; device-timed with CUDA events; next to it the unmodified reference's Generator
+    in eager PyTorch fp32 on the same GPU when baseline/_ref is installed."""
+    import xiaoicesing_io_b200 as P
+    P.hparams.clear()
+    P.hparams.update(b2s_precision=precision if precision != 'fp32' else 'fp16')
+    P.hparams.update(extra_hparams or {})
+    torch.manual_seed(0)
+    gen = P.vocoder.Generator(dict(VOCODER_H))
+    with torch.no_grad():
+        for n, p in gen.named_parameters():
+            if n.endswith('weight') and p.dim() == 3:
+                fan_in = p.shape[1] * p.shape[2] if not n.startswith('ups.') else p.shape[0] * p.shape[2] / 8
+                p.normal_(0.0, 1.0 / math.sqrt(fan_in))
+    gen = gen.to(dev).eval()
+    sd = {k: v.detach().clone() for k, v in gen.state_dict().items()}
+    ref_gen = None
+    try:
+        from oracle import ref_loader                        # the unmodified reference (baseline/_ref), eager PyTorch on this GPU
+        if ref_loader.available():
+            voc = ref_loader.load_vocoder()
+            ref_gen = voc.models.Generator(voc.AttrDict(dict(VOCODER_H))).eval()
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref_gen.remove_weight_norm()
+            ref_gen.load_state_dict(sd, strict=True)
+            ref_gen = ref_gen.to(dev)
+    except Exception:                                        # noqa: BLE001
+        ref_gen = None
+    hop = 512
+    # dense-conv MACs per mel frame: conv_pre, transposed convs (their non-zero taps), residual blocks
+    macs, ch, rate = 7 * 128 * 512, 512, 1
+    for u, k in zip(VOCODER_H['upsample_rates'], VOCODER_H['upsample_kernel_sizes']):
+        macs += rate * k * ch * (ch // 2)
+        ch //= 2
+        rate *= u
+        macs += rate * ch * ch * sum(6 * kk for kk in VOCODER_H['resblock_kernel_sizes'])
+    res = {'workload': f'NSF-HiFiGAN 44.1 kHz geometry (512 ch, hop 512, resblock kernels 3/7/11), mel [B, {T}, 128] + f0 -> {T * hop} samples '
+                       f'per utterance, once per utterance', 'gflop_per_utterance': 2.0 * macs * T / 1e9}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for B in (1, 8):
+        mel = torch.randn((B, T, 128), device=dev) * 1.5 - 4.0
+        f0 = 110.0 * 2 ** (2 * torch.rand((B, T), device=dev))
+        ri, nz = torch.rand(1, 1, 9, device=dev), torch.randn(B, T * hop, 9, device=dev)
+        ms = timed(lambda: gen.forward_rows(mel, f0, rand_ini=ri, noise=nz))
+        r = {'ms_per_call': ms, 'samples_per_s': B * T * hop / (ms * 1e-3), 'rtf': (ms * 1e-3) / (B * T * hop / 44100.0),
+             'tflops_algorithmic': 2.0 * macs * T * B / (ms * 1e-3) / 1e12}
+        if ref_gen is not None:
+            mel_c = mel.transpose(1, 2).contiguous()
+            with torch.no_grad():
+                ms_ref = timed(lambda: ref_gen(mel_c, f0))
+                torch.manual_seed(1)
+                a = ref_gen(mel_c, f0)
+                torch.manual_seed(1)
+                b = gen(mel_c, f0)                            # same draws from the device generator, in the reference's order
+            r.update(eager_reference_fp32_ms=ms_ref, speedup_vs_eager=ms_ref / ms, max_abs_vs_eager_reference=float((a - b).abs().max()))
+        res[f'B{B}'] = r
+    return res
 
 
 def time_aux_decoder(precision, dev, B=16, T=690, reps=5, extra_hparams=None):

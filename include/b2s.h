@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2S_ABI_VERSION 4
+#define B2S_ABI_VERSION 5
 
 #define B2S_OK 0
 #define B2S_ERR_INVALID_ARGUMENT (-1)
@@ -38,6 +38,7 @@ extern "C" {
 #define B2S_ACT_MISH 2 /* wavenet.py:60 */
 #define B2S_ACT_GELU 3 /* exact erf GELU, lynxnet.py:107,143 */
 #define B2S_ACT_SILU 4
+#define B2S_ACT_LRELU 5 /* leaky_relu(x, 0.1), nsf_hifigan/models.py:15 */
 
 int b2s_abi_version(void);
 const char* b2s_last_error(void);
@@ -385,6 +386,38 @@ int b2s_enc_assemble(const float* enc, const int64_t* mel2ph, const float* spk /
                      int spk_per_frame, const float* const* vals_host,
                      const float* const* w_host, const float* const* bias_host, int n, int n_var_first, int n_var, float* cond, int B,
                      int T, int L, int H, void* stream);
+
+/* ---- NSF-HiFiGAN vocoder (mel + f0 -> waveform, the step AFTER the sampling loop; reference modules/vocoders/nsf_hifigan.py:57-69,
+ * modules/nsf_hifigan/models.py:206-289) ----
+ * Activations are time-major rows r = b * T_i + t of the stage's sample rate, channels zero-padded to a multiple of 64 (Cp).
+ * b2s_tc_conv1d_dil       b2s_tc_conv1d with a dilation: conv_pre (:269), the residual blocks' first convs (:62-64, act =
+ *                         B2S_ACT_LRELU), and the transposed convs (:272) as 3-tap convs over u * Cp output columns
+ * b2s_tc_conv1d_residual  x <- x_src + conv(a) + bias on the fp32 stream, y_h <- leaky_relu(x, y_slope) 16-bit (:64-66, :92-94);
+ *                         x_src NULL = x; y_h NULL = no copy; y_h must not be the conv's input
+ * b2s_voc_phase           phase[b, t] = fmod(sum_{t' < t} wrap(f0[b, t'] / sr * upp), 1), wrap(v) = fmod(v + 0.5, 1) - 0.5 (:138-141;
+ *                         mini_nsf adds the chirp term of :256)
+ * b2s_voc_source          out[b, n] of the harmonic source at the waveform rate: dim = harmonics + 1 > 0: SineGen + SourceModuleHnNSF
+ *                         (:142-147, :160-166, :197-200) with the two random draws given (rand_ini [dim], noise [B, T * upp, dim]);
+ *                         dim == 0: Generator.fastsinegen (:252-262)
+ * b2s_voc_source_add      x[r, :] += bias + sum_j Wt[j, :] * src[b, t * stride - pad + j] (noise_convs / source_conv: Conv1d with one
+ *                         input channel, :273-278); lx_h <- leaky_relu(x, slope) 16-bit; ksize == 0: only the copy.  Wt [ksize, Cp]
+ * b2s_voc_avg_act         out_h <- leaky_relu((x_0 + ... + x_{n-1}) / n, slope) 16-bit, n <= 4 residual blocks (:279-285, :271)
+ * b2s_voc_post            wav[b, t] = tanh(conv_post(leaky_relu(mean of the blocks, slope))) in fp32, W [ksize, C] (:285-288)
+ * b2s_cast_scale_f32_h    16-bit(in * scale): log10 -> ln mel (vocoders/nsf_hifigan.py:60-64) */
+int b2s_tc_conv1d_dil(const void* a_h, const void* W_h, const float* bias, float* out_f32, int ldo, void* out_h, int ldoh, int B, int T,
+                      int Cin, int N, int ksize, int dil, int act, int bf16, void* stream);
+int b2s_tc_conv1d_residual(const void* a_h, const void* W_h, const float* bias, const float* x_src, float* x, void* y_h, float y_slope,
+                           int B, int T, int Cin, int N, int ksize, int dil, int bf16, void* stream);
+int b2s_voc_phase(const float* f0, float* phase, int B, int T, float sr, int upp, int mini_nsf, void* stream);
+int b2s_voc_source(const float* f0, const float* phase, const float* rand_ini, const float* noise, const float* w, const float* bias,
+                   float* out, int B, int T, int upp, int dim, float sr, float sine_amp, float noise_std, float voiced_threshold,
+                   void* stream);
+int b2s_voc_source_add(float* x, void* lx_h, const float* src, const float* Wt, const float* bias, int B, int T, int Cp, int ksize,
+                       int stride, int pad, int n_src, float slope, int bf16, void* stream);
+int b2s_voc_avg_act(const float* const* xs_host, int n_blocks, void* out_h, int64_t n, float slope, int bf16, void* stream);
+int b2s_voc_post(const float* const* xs_host, int n_blocks, const float* W, const float* b0, float* wav, int B, int T, int C, int Cp,
+                 int ksize, float slope, void* stream);
+int b2s_cast_scale_f32_h(const float* in, void* out_h, int64_t n, float scale, int bf16, void* stream);
 
 #ifdef __cplusplus
 }

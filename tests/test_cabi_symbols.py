@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.lib.b2s_abi_version() == 4
+    assert lib.lib.b2s_abi_version() == 5
 
 
 def test_argument_validation_needs_no_gpu(lib):

@@ -73,6 +73,14 @@ _SIGNATURES = {
     'b2s_enc_attention': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'b2s_enc_mask_rows': [_vp, _vp, _i, _i, _vp],
     'b2s_enc_layernorm_mask': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
+    'b2s_tc_conv1d_dil': [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_tc_conv1d_residual': [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'b2s_voc_phase': [_vp, _vp, _i, _i, _f, _i, _i, _vp],
+    'b2s_voc_source': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _vp],
+    'b2s_voc_source_add': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    'b2s_voc_avg_act': [ctypes.POINTER(_vp), _i, _vp, _i64, _f, _i, _vp],
+    'b2s_voc_post': [ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    'b2s_cast_scale_f32_h': [_vp, _vp, _i64, _f, _i, _vp],
     'b2s_enc_assemble': [_vp, _vp, _vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
 }
 
@@ -81,7 +89,7 @@ EXPERIMENTAL = ('b2s_tc_wavenet_stack_t_tiles', 'b2s_tc_cond_retile', 'b2s_tc_wa
 
 EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', 'b2s_has_experiments', 'b2s_tc_wavenet_stack_max_tiles', 'b2s_tc_wavenet_stack3_halo', 'b2s_tc_wavenet_stack3_max_tiles', 'b2s_tc_wavenet_denoiser3_max_utterances', *[n for n in _SIGNATURES if n not in EXPERIMENTAL]]
 
-ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU, ACT_SILU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU, ACT_SILU, ACT_LRELU = 0, 1, 2, 3, 4, 5
 
 
 class B2SError(RuntimeError):
@@ -444,3 +452,42 @@ def enc_assemble(enc, mel2ph, spk, vals, ws, biases, n_var_first, n_var, cond, B
 def lynx_dwconv_h(g_h, Wdw, bias, slope, p_h, B, T, inner, ksize, act, bf16):
     check(lib.b2s_lynx_dwconv_h(ptr(g_h), ptr(Wdw), ptr(bias), ptr(slope), ptr(p_h), B, T, inner, ksize, act, int(bf16),
                                 stream_ptr()), 'b2s_lynx_dwconv_h')
+
+
+# ---- NSF-HiFiGAN vocoder ---------------------------------------------------------------------------
+def tc_conv1d_dil(a_h, W_h, bias, out_f32, ldo, out_h, ldoh, B, T, Cin, N, ksize, dil, act, bf16):
+    check(lib.b2s_tc_conv1d_dil(ptr(a_h), ptr(W_h), ptr(bias), ptr(out_f32), ldo, ptr(out_h), ldoh, B, T, Cin, N, ksize, dil, act,
+                                int(bf16), stream_ptr()), 'b2s_tc_conv1d_dil')
+
+
+def tc_conv1d_residual(a_h, W_h, bias, x_src, x, y_h, y_slope, B, T, Cin, N, ksize, dil, bf16):
+    check(lib.b2s_tc_conv1d_residual(ptr(a_h), ptr(W_h), ptr(bias), ptr(x_src), ptr(x), ptr(y_h), float(y_slope), B, T, Cin, N, ksize,
+                                     dil, int(bf16), stream_ptr()), 'b2s_tc_conv1d_residual')
+
+
+def voc_phase(f0, phase, B, T, sr, upp, mini_nsf):
+    check(lib.b2s_voc_phase(ptr(f0), ptr(phase), B, T, float(sr), upp, int(mini_nsf), stream_ptr()), 'b2s_voc_phase')
+
+
+def voc_source(f0, phase, rand_ini, noise, w, bias, out, B, T, upp, dim, sr, sine_amp, noise_std, thr):
+    check(lib.b2s_voc_source(ptr(f0), ptr(phase), ptr(rand_ini), ptr(noise), ptr(w), ptr(bias), ptr(out), B, T, upp, dim, float(sr),
+                             float(sine_amp), float(noise_std), float(thr), stream_ptr()), 'b2s_voc_source')
+
+
+def voc_source_add(x, lx_h, src, Wt, bias, B, T, Cp, ksize, stride, pad, n_src, slope, bf16):
+    check(lib.b2s_voc_source_add(ptr(x), ptr(lx_h), ptr(src), ptr(Wt), ptr(bias), B, T, Cp, ksize, stride, pad, n_src, float(slope),
+                                 int(bf16), stream_ptr()), 'b2s_voc_source_add')
+
+
+def voc_avg_act(xs, out_h, slope, bf16):
+    arr = (_vp * len(xs))(*[t.data_ptr() for t in xs])
+    check(lib.b2s_voc_avg_act(arr, len(xs), ptr(out_h), xs[0].numel(), float(slope), int(bf16), stream_ptr()), 'b2s_voc_avg_act')
+
+
+def voc_post(xs, W, b0, wav, B, T, C, Cp, ksize, slope):
+    arr = (_vp * len(xs))(*[t.data_ptr() for t in xs])
+    check(lib.b2s_voc_post(arr, len(xs), ptr(W), ptr(b0), ptr(wav), B, T, C, Cp, ksize, float(slope), stream_ptr()), 'b2s_voc_post')
+
+
+def cast_scale_h(inp, out, scale, bf16):
+    check(lib.b2s_cast_scale_f32_h(ptr(inp), ptr(out), inp.numel(), float(scale), int(bf16), stream_ptr()), 'b2s_cast_scale_f32_h')

@@ -37,7 +37,8 @@ void set_error(const char* fmt, ...);
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- activations shared by the fp32 and tensor-core paths -------------------------------------------
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_MISH = 2, ACT_GELU = 3, ACT_SILU = 4 };
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_MISH = 2, ACT_GELU = 3, ACT_SILU = 4, ACT_LRELU = 5 };
+constexpr float LRELU_SLOPE = 0.1f;                        // nsf_hifigan/models.py:15
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -50,6 +51,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
         }
         case ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));   // exact erf GELU
         case ACT_SILU: return x * sigmoid_acc(x);
+        case ACT_LRELU: return x > 0.0f ? x : __fmul_rn(x, LRELU_SLOPE);
         default: return x;
     }
 }

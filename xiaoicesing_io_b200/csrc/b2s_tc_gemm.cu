@@ -38,7 +38,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 2
 constexpr int TMEM_COLS = 512;
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 
-enum Epi : int { EPI_LINEAR = 0, EPI_GATE = 1, EPI_RESSKIP = 2, EPI_SWIGLU = 3, EPI_RESIDUAL = 4 };
+enum Epi : int { EPI_LINEAR = 0, EPI_GATE = 1, EPI_RESSKIP = 2, EPI_SWIGLU = 3, EPI_RESIDUAL = 4, EPI_VRES = 5 };
 
 struct __align__(64) TcP {
     CUtensorMap mapA, mapW;
@@ -63,6 +63,9 @@ struct __align__(64) TcP {
     CUtensorMap mapA3;
     int conv3;
     int tap_c;                 // conv GEMMs: tap k reads rows t + (k - tap_c) * dil (1 for the 3-tap dilated conv, ksize / 2 in general)
+    // EPI_VRES, the vocoder's residual blocks (x <- x_src + acc + bias): the stream that is READ (NULL: x itself) and a leaky ReLU on the 16-bit copy
+    const float* x_src;
+    int y_lrelu; float y_slope;
 };
 
 // ---- 16-bit helpers --------------------------------------------------------------------------------
@@ -132,6 +135,8 @@ __device__ __forceinline__ float4 epilogue_load(const TcP& p, long long r, int c
         return make_float4(c0.x, c0.y, c1.x, c1.y);
     } else if (EPI == EPI_RESIDUAL) {
         return *reinterpret_cast<const float4*>(p.x + r * p.C + col);
+    } else if (EPI == EPI_VRES) {
+        return *reinterpret_cast<const float4*>((p.x_src ? p.x_src : p.x) + r * p.C + col);
     } else if (EPI == EPI_RESSKIP) {
         if (col < p.C) return *reinterpret_cast<const float4*>(p.x + r * p.C + col);
         if (!p.first) return *reinterpret_cast<const float4*>(p.skip + r * p.C + (col - p.C));
@@ -198,6 +203,15 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
         }
         *reinterpret_cast<float4*>(p.x + r * p.C + col) = xn;
         if (p.y_h) store_h4<BF16>(p.y_h, r * p.ldy + col, xn);                                 // 16-bit copy for the next depthwise conv
+    } else if (EPI == EPI_VRES) {
+        float4 xn = add4(in, add4(acc, k.bias));                                               // x = xt + x, nsf_hifigan/models.py:66
+        *reinterpret_cast<float4*>(p.x + r * p.C + col) = xn;
+        if (p.y_h) {                                                                           // leaky_relu(x) for the next conv (:62)
+            if (p.y_lrelu)
+                xn = make_float4(xn.x > 0.f ? xn.x : xn.x * p.y_slope, xn.y > 0.f ? xn.y : xn.y * p.y_slope,
+                                 xn.z > 0.f ? xn.z : xn.z * p.y_slope, xn.w > 0.f ? xn.w : xn.w * p.y_slope);
+            store_h4<BF16>(p.y_h, r * p.ldy + col, xn);
+        }
     } else {   // EPI_RESSKIP: reference column order, [0, C) residual, [C, 2C) skip
         const float inv_sqrt2 = 0.70710678118654752440f;
         const float4 o = add4(acc, k.bias);
@@ -946,6 +960,46 @@ extern "C" int b2s_tc_conv1d(const void* a_h, const void* W_h, const float* bias
     p.bias = bias; p.alpha = 1.0f; p.act = act;
     p.out_f = out_f32; p.ldo = ldo; p.out_h = out_h; p.ldoh = ldoh;
     return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
+}
+
+// Dilated dense Conv1d as one GEMM over ksize taps (the vocoder's residual-block convs, nsf_hifigan/models.py:39-58; its transposed
+// convs are 3-tap convs over u * Cout output columns, see vocoder.py)
+extern "C" int b2s_tc_conv1d_dil(const void* a_h, const void* W_h, const float* bias, float* out_f32, int ldo, void* out_h, int ldoh,
+                                 int B, int T, int Cin, int N, int ksize, int dil, int act, int bf16, void* stream) {
+    B2S_CHECK_ARG(a_h && W_h && (out_f32 || out_h), "b2s_tc_conv1d_dil: null pointer");
+    B2S_CHECK_ARG(Cin % 64 == 0 && N > 0 && ksize >= 1 && (ksize & 1) && ksize <= 63 && dil >= 1,
+                  "b2s_tc_conv1d_dil: needs Cin %% 64 == 0 (Cin=%d), an odd kernel size (%d) and dilation >= 1 (%d)", Cin, ksize, dil);
+    B2S_CHECK_ARG(al16(a_h) && al16(W_h) && (!out_f32 || (ldo % 4 == 0 && al16(out_f32))) && (!out_h || (ldoh % 8 == 0 && al16(out_h))),
+                  "b2s_tc_conv1d_dil: misaligned pointer / leading dimension");
+    if (B * T == 0) return B2S_OK;
+    TcP p{};
+    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16);
+    if (rc) return rc;
+    p.tap_c = ksize / 2;
+    p.bias = bias; p.alpha = 1.0f; p.act = act;
+    p.out_f = out_f32; p.ldo = ldo; p.out_h = out_h; p.ldoh = ldoh;
+    return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
+}
+
+// x <- x_src + conv(a) + bias on the fp32 residual stream, y_h <- leaky_relu(x, y_slope) as 16-bit rows for the next conv
+// (ResBlock1 / ResBlock2, nsf_hifigan/models.py:60-68, :90-95).  x_src NULL: x itself; y_h NULL: no 16-bit copy; y_slope 1: plain copy.
+extern "C" int b2s_tc_conv1d_residual(const void* a_h, const void* W_h, const float* bias, const float* x_src, float* x, void* y_h,
+                                      float y_slope, int B, int T, int Cin, int N, int ksize, int dil, int bf16, void* stream) {
+    B2S_CHECK_ARG(a_h && W_h && x, "b2s_tc_conv1d_residual: null pointer");
+    B2S_CHECK_ARG(Cin % 64 == 0 && N > 0 && N % 8 == 0 && ksize >= 1 && (ksize & 1) && ksize <= 63 && dil >= 1,
+                  "b2s_tc_conv1d_residual: needs Cin %% 64 == 0 (Cin=%d), N %% 8 == 0 (N=%d), an odd kernel size (%d), dilation >= 1 (%d)",
+                  Cin, N, ksize, dil);
+    B2S_CHECK_ARG(al16(a_h) && al16(W_h) && al16(x) && (!x_src || al16(x_src)) && (!y_h || al16(y_h)) && (!bias || al16(bias)),
+                  "b2s_tc_conv1d_residual: misaligned pointer");
+    B2S_CHECK_ARG(y_h != a_h, "b2s_tc_conv1d_residual: y_h must not alias the conv input (neighbouring tiles read its halo rows)");
+    if (B * T == 0) return B2S_OK;
+    TcP p{};
+    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16);
+    if (rc) return rc;
+    p.tap_c = ksize / 2;
+    p.bias = bias; p.x = x; p.x_src = x_src; p.C = N; p.y_h = y_h; p.ldy = N;
+    p.y_lrelu = y_h != nullptr && y_slope != 1.0f; p.y_slope = y_slope;
+    return launch<EPI_VRES>(p, bf16, (cudaStream_t)stream);
 }
 
 // x <- x + gamma * (p * W^T + bias) (fp32 residual stream, per-channel layer scale), optionally also x as 16-bit rows
