@@ -93,6 +93,12 @@ def test_graph_replay_and_seeded_draws():
     ri2 = torch.rand(1, 1, 9, device='cuda')
     nz2 = torch.randn(2, 20 * 512, 9, device='cuda')
     assert torch.equal(a, gen(*args, rand_ini=ri2, noise=nz2))
+    # the residual blocks run on parallel streams (forked / joined inside the graph): same bits as one stream
+    import xiaoicesing_io_b200 as P
+    P.hparams['b2s_voc_streams'] = False
+    gen._engine()._graphs.clear()
+    assert torch.equal(gen(*args, rand_ini=ri.cuda(), noise=nz.cuda()), outs[0])
+    P.hparams.pop('b2s_voc_streams')
     # utterances of a batch are independent: a batch of two copies gives two identical waveforms, equal to the B = 1 run
     m2, f2, n2 = mel[:1].repeat(2, 1, 1).cuda(), f0[:1].repeat(2, 1).cuda(), nz[:1].repeat(2, 1, 1).cuda()
     o2 = gen(m2, f2, rand_ini=ri.cuda(), noise=n2)

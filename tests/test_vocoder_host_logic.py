@@ -40,10 +40,10 @@ def cpu_kernels(monkeypatch):
 
     def tc_conv1d_residual(a, W, b, xs, x, yh, sl, B, T, Cin, N, k, dil, bf):
         assert yh is None or yh.data_ptr() != a.data_ptr(), 'y_h aliases the conv input'
-        v = (x if xs is None else xs) + _conv(a, W, B, T, Cin, N, k, dil) + b
-        x[:] = v
+        v = (x if xs is None else xs).reshape(B * T, N) + _conv(a, W, B, T, Cin, N, k, dil) + b       # the kernel sees [B * T, N] rows
+        x.view(-1)[:] = v.reshape(-1)
         if yh is not None:
-            yh[:] = _lrelu(v, sl).to(yh.dtype)
+            yh.view(-1)[:] = _lrelu(v, sl).to(yh.dtype).reshape(-1)
 
     def cast_scale_h(i, o, sc, bf):
         o.view(-1)[:] = (i.reshape(-1) * sc).to(o.dtype)
@@ -97,6 +97,7 @@ def cpu_kernels(monkeypatch):
     monkeypatch.setattr(C, 'HALF_DTYPES', {'bf16': torch.float32, 'fp16': torch.float32})      # "16-bit" buffers kept exact: logic only
     monkeypatch.setattr(V._VocoderEngine, '_guard', staticmethod(lambda dev: contextlib.nullcontext()))
     monkeypatch.setitem(P.hparams, 'b2s_cuda_graph', False)
+    monkeypatch.setitem(P.hparams, 'b2s_voc_streams', False)
     return V
 
 

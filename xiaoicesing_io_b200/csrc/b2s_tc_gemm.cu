@@ -771,6 +771,8 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
 #endif
     p.cg2 = cg1 ? 0 : 1;
     p.bn = (p.cg2 && N % 192 == 0 && N % 256 != 0) ? 192 : BLOCK_N;      // no half-empty second tile for the C = 192 models
+    if (p.cg2 && N <= 128) p.bn = N <= 64 ? 64 : 128;                    // narrow outputs (the vocoder's late stages, mel heads): an MMA of
+                                                                         // width 64 / 128 is 2.2x / 1.6x shorter than one of width 256
     rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, p.cg2 ? p.bn / 2 : BLOCK_N);
     if (rc) return rc;
     p.B = Bm; p.T = Tm; p.T_utt = T;

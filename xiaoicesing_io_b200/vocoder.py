@@ -6,7 +6,8 @@ Same names as the reference (``Generator``, ``ResBlock1``, ``ResBlock2``, ``Sine
 names, so a reference checkpoint loads with ``strict=True`` - in the weight-norm form it is stored in (``weight_g`` / ``weight_v``,
 folded at load time: what ``load_model`` + ``remove_weight_norm`` leave, models.py:29-32) or in the plain form.  The modules only HOLD
 parameters; ``forward`` is a sequence of libb2s launches on TIME-MAJOR rows (r = b * T_i + t at the stage's sample rate) with the
-channels zero-padded to a multiple of 64 (a padded channel has zero weights and a zero bias, so it is exactly 0 everywhere):
+rows folded so that every GEMM row is at least 64 wide (see "folded rows" below; widths that cannot fold are zero-padded to a
+multiple of 64 - a padded channel has zero weights and a zero bias, so it is exactly 0 everywhere):
 
     cast (x 2.30259 for log10 mels)     b2s_cast_scale_f32_h
     conv_pre + leaky_relu               b2s_tc_conv1d_dil (7 taps, ONE tcgen05 GEMM, lrelu epilogue, 16-bit out)
@@ -29,6 +30,7 @@ inference/ds_acoustic.py:227-236); convolutions never read across utterances.
 """
 from __future__ import annotations
 
+import contextlib
 import json
 import pathlib
 
@@ -120,6 +122,86 @@ def _fold_weight_norm(state_dict, prefix):
                 state_dict[base + 'weight'] = (v.float() * (g.float() / norm)).to(v.dtype)
 
 
+# ---- folded rows ---------------------------------------------------------------------------------------------------------------------
+# The late stages are narrow (64, 32, 16 channels at 1/4 .. 1/1 of the waveform rate): as GEMMs over rows of C channels they would
+# need zero-padded channels (4x the HBM traffic and 4x the MMAs at C = 16).  A time-major stream [T, C] is the SAME memory as
+# [T / f, f * C]: f consecutive samples form one row of f * C "super channels", and a k-tap conv with dilation d over samples is a
+# dense conv over super rows, out[(q, r), co] = sum_{tap, ci} W[co, ci, tap] x[(q + delta, r'), ci] with f * delta + r' = r + (tap - k//2) * d,
+# whose weight matrix [f * C, taps' * f * C] holds the original taps at the matching (r, r', delta) and zeros elsewhere.  The MMA count
+# per sample falls with f (taps' ~ 2 * ceil((k//2) * d / f) + 1 instead of k at f times the rows per MMA), nothing is padded, and
+# at f * C = 256 the MMAs run at full width.  A transposed conv with stride u is the same construction with u output phases per input
+# sample.  Packing is host-side only; the kernels see plain dense convs.
+
+def _fold_choices(lay: int, R: int):
+    """Folds f (samples per GEMM row) a [T * R, lay] stream supports for EVERY T: f | R, f * lay a multiple of 64, at most 256 wide
+    (f = 1: any width that is a multiple of 64)."""
+    return [f_ for f_ in (1, 2, 4, 8, 16, 32, 64) if R % f_ == 0 and (f_ * lay) % 64 == 0 and (f_ == 1 or f_ * lay <= 256)]
+
+
+def _fold_taps(k: int, d: int, f_: int):
+    """Taps of the dense conv over rows of f samples (f = 1: the k dilated taps themselves, the GEMM kernel shifts its A tiles by d)."""
+    if f_ == 1:
+        return k
+    c = k // 2
+    mr = max(-((-c * d) // f_), (f_ - 1 + c * d) // f_)
+    return 2 * mr + 1
+
+
+def _best_fold(k: int, d: int, lay: int, R: int) -> int:
+    """The fold with the fewest tensor-core nanoseconds per sample: taps'(f) K groups of f * lay / 64 blocks x 4 MMAs per 256 rows of
+    f samples; an MMA of width N = f * lay costs ~27 + 0.29 N ns (measured: 64 ns at N = 128, 101 ns at N = 256)."""
+    best = None
+    for f_ in _fold_choices(lay, R):
+        ks = _fold_taps(k, d, f_)
+        if ks > 63:
+            continue
+        n = min(f_ * lay, 256)
+        cost = ks * (f_ * lay / 64) * 4 * (27.0 + 0.29 * n) * max(1, f_ * lay // 256) / f_
+        if best is None or cost < best[0]:
+            best = (cost, f_)
+    if best is None:
+        raise C.B2SError(f'no GEMM row layout for a conv with k={k}, dilation {d} over {lay}-wide rows')
+    return best[1]
+
+
+def _fold_conv(W, b, d: int, f_: int, lay: int):
+    """Conv1d weight [Co, Ci, k] (dilation d, 'same' padding) -> (operand [f * lay, taps' * f * lay], bias [f * lay], taps', the
+    dilation left to the GEMM kernel: d at f = 1, else 1)."""
+    Co, Ci, k = W.shape
+    c, ks = k // 2, _fold_taps(k, d, f_)
+    mr = ks // 2
+    Wg = torch.zeros((f_, lay, ks, f_, lay), device=W.device, dtype=torch.float32)
+    for r in range(f_):
+        for tap in range(k):
+            s_ = r + (tap - c) * d
+            Wg[r, :Co, (s_ // f_ + mr) if f_ > 1 else tap, s_ % f_, :Ci] = W[:, :, tap]
+    bg = torch.zeros((f_, lay), device=W.device, dtype=torch.float32)
+    bg[:, :Co] = b
+    return Wg.reshape(f_ * lay, ks * f_ * lay), bg.reshape(-1).contiguous(), ks, (d if f_ == 1 else 1)
+
+
+def _fold_conv_transpose(W, b, u: int, pad: int, f_in: int, lay_in: int, lay_out: int):
+    """ConvTranspose1d weight [Ci, Co, k] (stride u, padding pad, k - 2 pad = u) over input rows of f_in samples x lay_in channels ->
+    (operand [f_in * u * lay_out, taps' * f_in * lay_in], bias, taps'): output row q holds samples (q f_in + a) u + r, a < f_in, r < u;
+    out[(a, r), co] = sum x[(q + delta, a'), ci] W[ci, co, (a - a' - f_in delta) u + r + pad]."""
+    Ci, Co, k = W.shape
+    span = [dl for dl in range(-64, 65) if any(0 <= (a - a2 - f_in * dl) * u + r + pad < k
+                                               for a in range(f_in) for a2 in range(f_in) for r in range(u))]
+    mr = max(abs(dl) for dl in span)
+    ks = 2 * mr + 1
+    Wg = torch.zeros((f_in, u, lay_out, ks, f_in, lay_in), device=W.device, dtype=torch.float32)
+    for a in range(f_in):
+        for r in range(u):
+            for j in range(ks):
+                for a2 in range(f_in):
+                    kk = (a - a2 - f_in * (j - mr)) * u + r + pad
+                    if 0 <= kk < k:
+                        Wg[a, r, :Co, j, a2, :Ci] = W[:, :, kk].t()
+    bg = torch.zeros((f_in, u, lay_out), device=W.device, dtype=torch.float32)
+    bg[:, :, :Co] = b
+    return Wg.reshape(f_in * u * lay_out, ks * f_in * lay_in), bg.reshape(-1).contiguous(), ks
+
+
 class Generator(nn.Module):
     """Reference modules/nsf_hifigan/models.py:206-299: ``forward(x [B, num_mels, T], f0 [B, T]) -> [B, 1, T * hop]``.
 
@@ -202,6 +284,12 @@ class _VocoderEngine:
         ps = list(self.net.parameters())
         return tuple((p._version, p.data_ptr(), p.dtype) for p in ps) + (str(ps[0].device), hparams.get('b2s_precision'))
 
+    def _side_streams(self, n):
+        ss = self.__dict__.setdefault('_streams', [])
+        while len(ss) < n:
+            ss.append(torch.cuda.Stream(device=self.device))
+        return ss[:n]
+
     @staticmethod
     def _guard(dev):
         """The CUDA device context of every launch; there is no other device to run on."""
@@ -240,29 +328,20 @@ class _VocoderEngine:
         self.stages = []
         ch, nk = c0, net.num_kernels
         n_up = len(h.upsample_rates)
+        lay_in, R_in = self.c0p, 1                  # channel layout (row width) and samples per mel frame of the stream entering a stage
         for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
-            cin, cin_p = ch, _pad64(ch)
+            cin = ch
             ch //= 2
-            cp = _pad64(ch)
+            R = R_in * u
+            # Row width of this stage's streams: the REAL channel count when rows can be folded into >= 64-wide GEMM rows (see
+            # _fold_choices), else zero-padded to a multiple of 64
+            lay = ch if ch % 4 == 0 and _fold_choices(ch, R) else _pad64(ch)
             if (k - u) % 2:
                 raise C.B2SError(f'upsample kernel {k} / rate {u}: the transposed conv does not produce exactly T * {u} samples '
                                  f'(the reference would fail at x + x_source too)')
-            pad = (k - u) // 2
-            # ConvTranspose1d as a dense conv over the input frames: out[q * u + r] = sum_delta x[q + delta] . W[:, :, r + pad - delta * u]
-            deltas = [d for d in range(-16, 17) if any(0 <= r + pad - d * u < k for r in range(u))]
-            mr = max(abs(d) for d in deltas)
-            ks = 2 * mr + 1
-            W = f(net.ups[i].weight)                                              # [cin, ch, k]
-            Wg = torch.zeros((u, cp, ks, cin_p), device=dev, dtype=torch.float32)
-            for r in range(u):
-                for j in range(ks):
-                    kk = r + pad - (j - mr) * u
-                    if 0 <= kk < k:
-                        Wg[r, :ch, j, :cin] = W[:, :, kk].t()
-            bg = torch.zeros((u, cp), device=dev, dtype=torch.float32)
-            bg[:, :ch] = f(net.ups[i].bias)
-            st = dict(u=u, cin_p=cin_p, ch=ch, cp=cp, ks=ks, w_up=Wg.reshape(u * cp, ks * cin_p).to(hd).contiguous(),
-                      b_up=bg.reshape(-1).contiguous(), src=None, blocks=[])
+            f_in = _fold_choices(lay_in, R_in)[0]
+            w_up, b_up, ks_up = _fold_conv_transpose(f(net.ups[i].weight), f(net.ups[i].bias), u, (k - u) // 2, f_in, lay_in, lay)
+            st = dict(u=u, f_in=f_in, lay_in=lay_in, ch=ch, lay=lay, ks=ks_up, w_up=w_up.to(hd).contiguous(), b_up=b_up, src=None, blocks=[])
             src_conv = None
             if not net.mini_nsf:
                 src_conv = net.noise_convs[i]
@@ -271,22 +350,26 @@ class _VocoderEngine:
                 src_conv, s = net.source_conv, 1        # the source runs at sr / prod(rates[2:]) (models.py:216-217) and so does stage 1
             if src_conv is not None:
                 K = src_conv.weight.shape[-1]
-                Wt = torch.zeros((K, cp), device=dev, dtype=torch.float32)
+                Wt = torch.zeros((K, lay), device=dev, dtype=torch.float32)
                 Wt[:, :ch] = f(src_conv.weight)[:, 0, :].t()
                 st['src'] = dict(K=K, stride=s if K > 1 else 1, pad=(s // 2) if K > 1 else 0, Wt=Wt.contiguous(),
-                                 b=padded(src_conv.bias, cp))
+                                 b=padded(src_conv.bias, lay))
+
+            def folded(conv, d):
+                fold = _best_fold(conv.weight.shape[-1], d, lay, R)
+                w, b, ks, dil = _fold_conv(f(conv.weight), f(conv.bias), d, fold, lay)
+                return dict(w=w.to(hd).contiguous(), b=b, ks=ks, f=fold, dil=dil)
+
             for j in range(nk):
                 blk = net.resblocks[i * nk + j]
-                if isinstance(blk, ResBlock1):
-                    pairs = [(conv_operand(c1.weight, cp, cp), padded(c1.bias, cp), conv_operand(c2.weight, cp, cp), padded(c2.bias, cp), d)
-                             for c1, c2, d in zip(blk.convs1, blk.convs2, blk.dilation)]
-                    st['blocks'].append(dict(kind=1, k=blk.kernel_size, convs=pairs))
-                else:
-                    convs = [(conv_operand(c.weight, cp, cp), padded(c.bias, cp), d) for c, d in zip(blk.convs, blk.dilation)]
-                    st['blocks'].append(dict(kind=2, k=blk.kernel_size, convs=convs))
                 if blk.kernel_size % 2 == 0:
                     raise C.B2SError(f'residual-block kernel size {blk.kernel_size}: only odd sizes keep the length (models.py:39-41)')
+                if isinstance(blk, ResBlock1):
+                    st['blocks'].append(dict(kind=1, convs=[(folded(c1, d), folded(c2, 1)) for c1, c2, d in zip(blk.convs1, blk.convs2, blk.dilation)]))
+                else:
+                    st['blocks'].append(dict(kind=2, convs=[folded(c, d) for c, d in zip(blk.convs, blk.dilation)]))
             self.stages.append(st)
+            lay_in, R_in = lay, R
         if nk > 4:
             raise C.B2SError(f'{nk} residual blocks per stage: b2s_voc_avg_act / b2s_voc_post take at most 4')
         self.c_last = ch
@@ -357,44 +440,63 @@ class _VocoderEngine:
         Ti = T
         wav = None
         for i, st in enumerate(self.stages):
-            u, cp = st['u'], st['cp']
-            x = torch.empty((B * Ti * u, cp), device=dev)
-            C.tc_conv1d_dil(a_h, st['w_up'], st['b_up'], x, u * cp, None, 0, B, Ti, st['cin_p'], u * cp, st['ks'], 1, C.ACT_NONE, bf)
+            u, lay, fi = st['u'], st['lay'], st['f_in']
+            x = torch.empty((B * Ti * u, lay), device=dev)
+            n_up = fi * u * lay
+            C.tc_conv1d_dil(a_h, st['w_up'], st['b_up'], x, n_up, None, 0, B, Ti // fi, fi * st['lay_in'], n_up, st['ks'], 1, C.ACT_NONE, bf)
             Ti *= u
             rows = B * Ti
-            lx_h = torch.empty((rows, cp), device=dev, dtype=hd)
+            lx_h = torch.empty((rows, lay), device=dev, dtype=hd)
             sc = st['src']
             if sc is None:
-                C.voc_source_add(x, lx_h, None, None, None, B, Ti, cp, 0, 1, 0, 0, LRELU_SLOPE, bf)
+                C.voc_source_add(x, lx_h, None, None, None, B, Ti, lay, 0, 1, 0, 0, LRELU_SLOPE, bf)
             else:
-                C.voc_source_add(x, lx_h, har, sc['Wt'], sc['b'], B, Ti, cp, sc['K'], sc['stride'], sc['pad'], T * upp, LRELU_SLOPE, bf)
-            t_h = torch.empty((rows, cp), device=dev, dtype=hd)
-            l_a = torch.empty((rows, cp), device=dev, dtype=hd)
-            l_b = None
-            xs = []
-            for blk in st['blocks']:
-                xj = torch.empty((rows, cp), device=dev)
-                k, n = blk['k'], len(blk['convs'])
-                if blk['kind'] == 1:                                                                      # models.py:60-68
-                    for m, (w1, b1, w2, b2, d) in enumerate(blk['convs']):
-                        C.tc_conv1d_dil(lx_h if m == 0 else l_a, w1, b1, None, 0, t_h, cp, B, Ti, cp, cp, k, d, C.ACT_LRELU, bf)
-                        C.tc_conv1d_residual(t_h, w2, b2, x if m == 0 else None, xj, l_a if m + 1 < n else None, LRELU_SLOPE,
-                                             B, Ti, cp, cp, k, 1, bf)
-                else:                                                                                     # models.py:90-95
-                    if l_b is None:
-                        l_b = torch.empty((rows, cp), device=dev, dtype=hd)
-                    pp = (l_a, l_b)
-                    for m, (w, b, d) in enumerate(blk['convs']):
-                        C.tc_conv1d_residual(lx_h if m == 0 else pp[(m + 1) & 1], w, b, x if m == 0 else None, xj,
-                                             pp[m & 1] if m + 1 < n else None, LRELU_SLOPE, B, Ti, cp, cp, k, d, bf)
-                xs.append(xj)
+                C.voc_source_add(x, lx_h, har, sc['Wt'], sc['b'], B, Ti, lay, sc['K'], sc['stride'], sc['pad'], T * upp, LRELU_SLOPE, bf)
+            def conv_act(inp, cv, out_h):                                      # 16-bit leaky_relu(conv + b)
+                w_ = cv['f'] * lay
+                C.tc_conv1d_dil(inp, cv['w'], cv['b'], None, 0, out_h, w_, B, Ti // cv['f'], w_, w_, cv['ks'], cv['dil'], C.ACT_LRELU, bf)
+
+            def conv_res(inp, cv, x_src, xj, y_h):                             # xj <- x_src + conv + b, y_h <- 16-bit leaky_relu(xj)
+                w_ = cv['f'] * lay
+                C.tc_conv1d_residual(inp, cv['w'], cv['b'], x_src, xj, y_h, LRELU_SLOPE, B, Ti // cv['f'], w_, w_, cv['ks'], cv['dil'], bf)
+
+            # The residual blocks of a stage are independent (models.py:279-284): each runs on its own stream, forked from and joined
+            # to the caller's (captured as parallel branches of the CUDA graph).  One utterance fills 22 .. 86 CTA pairs per conv, so
+            # three convs side by side keep the 74 pairs busy; large batches simply queue.  All buffers are allocated and freed on the
+            # caller's stream, around the fork / join.
+            nb = len(st['blocks'])
+            xs = [torch.empty((rows, lay), device=dev) for _ in range(nb)]
+            bufs = [[torch.empty((rows, lay), device=dev, dtype=hd) for _ in range(2 if blk['kind'] == 1 else 3)] for blk in st['blocks']]
+            side = self._side_streams(nb - 1) if (nb > 1 and hparams.get('b2s_voc_streams', True)) else []
+            if side:
+                main = torch.cuda.current_stream()
+                fork = torch.cuda.Event()
+                fork.record(main)
+            for j, blk in enumerate(st['blocks']):
+                branch = contextlib.nullcontext()
+                if side and j > 0:
+                    side[j - 1].wait_event(fork)
+                    branch = torch.cuda.stream(side[j - 1])
+                with branch:
+                    xj, n = xs[j], len(blk['convs'])
+                    if blk['kind'] == 1:                                                                  # models.py:60-68
+                        t_h, l_a = bufs[j]
+                        for m, (c1, c2) in enumerate(blk['convs']):
+                            conv_act(lx_h if m == 0 else l_a, c1, t_h)
+                            conv_res(t_h, c2, x if m == 0 else None, xj, l_a if m + 1 < n else None)
+                    else:                                                                                 # models.py:90-95
+                        pp = bufs[j]
+                        for m, cv in enumerate(blk['convs']):
+                            conv_res(lx_h if m == 0 else pp[(m + 1) & 1], cv, x if m == 0 else None, xj, pp[m & 1] if m + 1 < n else None)
+            for stream in side:
+                main.wait_stream(stream)
             if i + 1 < len(self.stages):
-                a_h = torch.empty((rows, cp), device=dev, dtype=hd)
+                a_h = torch.empty((rows, lay), device=dev, dtype=hd)
                 C.voc_avg_act(xs, a_h, LRELU_SLOPE, bf)                                                   # :285, :271
             else:
                 wav = torch.empty((B, Ti), device=dev)
-                C.voc_post(xs, self.w_post, self.b_post, wav, B, Ti, self.c_last, cp, 7, 0.01)          # :286-288 (default slope)
-            del x, lx_h, t_h, l_a, l_b, xs
+                C.voc_post(xs, self.w_post, self.b_post, wav, B, Ti, self.c_last, lay, 7, 0.01)         # :286-288 (default slope)
+            del x, lx_h, bufs, xs
         return wav
 
 
