@@ -17,5 +17,5 @@ for _ in range(2):
 torch.cuda.synchronize()
 PY
 export PYTHONPATH=$PWD; timeout 300 python /tmp/voc_one.py || exit 1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/voc_launches.csv python /tmp/voc_one.py > gpurun_out/voc_ncu.log 2>&1
+VB=${VB:-1} timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/voc_launches.csv python /tmp/voc_one.py > gpurun_out/voc_ncu.log 2>&1
 echo "ncu rc=$?"; wc -l gpurun_out/voc_launches.csv

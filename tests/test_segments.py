@@ -75,3 +75,42 @@ def test_mel_pt_layout_roundtrip(tmp_path):
         assert set(b) == {'offset', 'mel', 'f0'} and b['offset'] == e['offset']
         assert torch.equal(b['mel'], e['mel']) and torch.equal(b['f0'], e['f0'])
     assert SG.real_time_factor(entries, 1.0, TIMESTEP) == pytest.approx(1.0 / (33 * TIMESTEP))
+
+
+def test_vocode_segments_assembly_follows_the_reference(tmp_path):
+    """Silence up to a segment's offset, cross-fade on overlap (scripts/vocode.py:64-84 with utils/infer_utils.py:89-96), 16-bit WAV
+    (infer_utils.py:99-104) - with a stand-in vocoder (the assembly is host code; the vocoder itself is tested on the GPU)."""
+    import numpy as np
+    from scipy.io import wavfile
+    from xiaoicesing_io_b200 import segments as S
+
+    class Voc:
+        device = torch.device('cpu')
+
+        def spec2wav_torch(self, mel, f0=None):
+            return (mel[0, :, :1] * torch.ones(1, 4)).reshape(-1) * f0[0].repeat_interleave(4)
+
+    sr = 100
+    entries = [dict(offset=0.05, mel=torch.full((1, 10, 3), 0.5), f0=torch.ones(1, 10)),
+               dict(offset=0.30, mel=torch.full((1, 8, 3), -0.25), f0=torch.ones(1, 8)),        # starts at 30 < 5 + 40: overlaps by 15
+               dict(offset=1.00, mel=torch.full((1, 5, 3), 0.1), f0=torch.ones(1, 5))]           # after a gap
+    out = S.vocode_segments(entries, Voc(), sr)
+    # the reference's loop, restated with its own cross_fade formula
+    ref, cur = np.zeros(0), 0
+    for e in entries:
+        w = Voc().spec2wav_torch(e['mel'], f0=e['f0']).numpy()
+        sil = round(e['offset'] * sr) - cur
+        if sil >= 0:
+            ref = np.concatenate([ref, np.zeros(sil), w])
+        else:
+            idx = cur + sil
+            fade = ref.shape[0] - idx
+            k = np.linspace(0, 1.0, num=fade, endpoint=True)
+            ref = np.concatenate([ref[:idx], (1 - k) * ref[idx:] + k * w[:fade], w[fade:]])
+        cur = cur + sil + w.shape[0]
+    assert out.shape == ref.shape == (120,) and np.allclose(out, ref)
+    assert out[:5].tolist() == [0.] * 5 and abs(out[5] - 0.5) < 1e-7 and abs(out[44] + 0.25) < 1e-7 and abs(out[-1] - 0.1) < 1e-7
+    S.save_wav(out, tmp_path / 'a.wav', sr)
+    rate, pcm = wavfile.read(tmp_path / 'a.wav')
+    assert rate == sr and pcm.dtype == np.int16 and pcm[5] == int(0.5 * 32767) and pcm[-1] == int(0.1 * 32767)
+

@@ -760,7 +760,7 @@ static int launch(const TcP& p, int bf16, cudaStream_t st) {
 
 // common geometry: A is [B, T, Kcols]; per-utterance M tiles when conv, flat otherwise
 static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool per_utt, const void* W, int ldw, int N, int K,
-                 int kb_per_tap, int dil, int bf16) {
+                 int kb_per_tap, int dil, int bf16, bool split_n_when_few = false) {
     const int Bm = per_utt ? B : 1, Tm = per_utt ? T : B * T;
     int rc = make_map_act(&p.mapA, A, bf16, a_cols, lda, Tm, Bm, BLOCK_K, BLOCK_M);
     if (rc) return rc;
@@ -773,6 +773,11 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     p.bn = (p.cg2 && N % 192 == 0 && N % 256 != 0) ? 192 : BLOCK_N;      // no half-empty second tile for the C = 192 models
     if (p.cg2 && N <= 128) p.bn = N <= 64 ? 64 : 128;                    // narrow outputs (the vocoder's late stages, mel heads): an MMA of
                                                                          // width 64 / 128 is 2.2x / 1.6x shorter than one of width 256
+    if (split_n_when_few && p.cg2 && p.bn == BLOCK_N && N % 128 == 0) {
+        // one short utterance: fewer tile pairs than half of the CTA pairs -> N tiles of 128 double the tiles at 0.63x the MMA time each
+        const long long pt = (long long)Bm * ((ceil_div(Tm, BLOCK_M) + 1) / 2) * ceil_div(N, BLOCK_N);
+        if (2 * pt <= num_sms() / 2) p.bn = 128;
+    }
     rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, p.cg2 ? p.bn / 2 : BLOCK_N);
     if (rc) return rc;
     p.B = Bm; p.T = Tm; p.T_utt = T;
@@ -975,7 +980,7 @@ extern "C" int b2s_tc_conv1d_dil(const void* a_h, const void* W_h, const float* 
                   "b2s_tc_conv1d_dil: misaligned pointer / leading dimension");
     if (B * T == 0) return B2S_OK;
     TcP p{};
-    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16);
+    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16, true);
     if (rc) return rc;
     p.tap_c = ksize / 2;
     p.bias = bias; p.alpha = 1.0f; p.act = act;
@@ -996,7 +1001,7 @@ extern "C" int b2s_tc_conv1d_residual(const void* a_h, const void* W_h, const fl
     B2S_CHECK_ARG(y_h != a_h, "b2s_tc_conv1d_residual: y_h must not alias the conv input (neighbouring tiles read its halo rows)");
     if (B * T == 0) return B2S_OK;
     TcP p{};
-    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16);
+    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16, true);
     if (rc) return rc;
     p.tap_c = ksize / 2;
     p.bias = bias; p.x = x; p.x_src = x_src; p.C = N; p.y_h = y_h; p.ldy = N;

@@ -14,7 +14,9 @@ at :220-225, :243).  One 8-second segment occupies 6 of the 148 SMs; this module
      rectified flow; the ancestral sampler draws fresh noise per step from the global stream);
   4. on several GPUs partitions the segments by length (``partition_by_length``), every rank sampling its share with no collective,
      and gathers the results once;
-  5. writes the reference's ``.mel.pt`` layout.
+  5. writes the reference's ``.mel.pt`` layout;
+  6. vocodes a ``.mel.pt`` list into one waveform (``vocode_segments``: scripts/vocode.py:64-84, ds_acoustic.py:227-236 - silence up
+     to a segment's offset, linear cross-fade where segments overlap) and writes the 16-bit WAV.
 
 The linguistic encoder that turns a segment into ``condition [T, H]`` (modules/fastspeech) is outside the
 hot path: the caller passes ``cond_fn(segment, frames) -> (condition [T, H], src_spec [T, M] or None, f0 [T] or None)``.
@@ -25,6 +27,7 @@ import json
 import math
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from .partition import partition_by_length
@@ -218,3 +221,44 @@ def real_time_factor(entries: Sequence[dict], seconds: float, timestep: float) -
     """Wall seconds per second of synthesised audio."""
     audio = sum(e['mel'].shape[1] for e in entries) * timestep
     return math.inf if audio == 0 else seconds / audio
+
+
+def cross_fade(a: np.ndarray, b: np.ndarray, idx: int) -> np.ndarray:
+    """utils/infer_utils.py:89-96: ``b`` starts at sample ``idx`` of ``a``; the overlap is a linear fade from ``a`` to ``b``."""
+    result = np.zeros(idx + b.shape[0])
+    fade_len = a.shape[0] - idx
+    result[:idx] = a[:idx]
+    k = np.linspace(0, 1.0, num=fade_len, endpoint=True)
+    result[idx: a.shape[0]] = (1 - k) * a[idx:] + k * b[:fade_len]
+    result[a.shape[0]:] = b[fade_len:]
+    return result
+
+
+def vocode_segments(entries: Sequence[dict], vocoder, sample_rate: int, device=None) -> np.ndarray:
+    """``.mel.pt`` entries ``{'offset', 'mel' [1, T, M], 'f0' [1, T]}`` -> one waveform (float64 numpy, like the reference's):
+    every segment through ``vocoder.spec2wav_torch(mel, f0=f0)`` (one call per segment, ds_acoustic.py:185-187; segments of equal
+    length replay the same CUDA graph), placed at ``round(offset * sample_rate)`` with silence before it or a cross-fade into the
+    previous segment (scripts/vocode.py:64-84, ds_acoustic.py:227-236)."""
+    device = device if device is not None else vocoder.device
+    result = np.zeros(0)
+    current_length = 0
+    for e in entries:
+        wav = vocoder.spec2wav_torch(e['mel'].to(device), f0=e['f0'].to(device)).cpu().numpy()
+        silent_length = round(e.get('offset', 0.) * sample_rate) - current_length
+        if silent_length >= 0:
+            result = np.append(result, np.zeros(silent_length))
+            result = np.append(result, wav)
+        else:
+            result = cross_fade(result, wav, current_length + silent_length)
+        current_length = current_length + silent_length + wav.shape[0]
+    return result
+
+
+def save_wav(wav: np.ndarray, path, sr: int, norm: bool = False) -> None:
+    """utils/infer_utils.py:99-104: 16-bit PCM (``wav * 32767`` truncated to int16)."""
+    from scipy.io import wavfile
+    wav = np.array(wav, dtype=np.float64)
+    if norm:
+        wav = wav / np.abs(wav).max()
+    wavfile.write(str(path), sr, (wav * 32767).astype(np.int16))
+
