@@ -153,7 +153,10 @@ __device__ __forceinline__ void epilogue_quad(const TcP& p, float4 acc, float4 i
         const float lo = p.act == ACT_RELU ? 0.f : -INFINITY;
         float4 v = make_float4(fmaxf(fmaf(p.alpha, acc.x, k.bias.x), lo), fmaxf(fmaf(p.alpha, acc.y, k.bias.y), lo),
                                fmaxf(fmaf(p.alpha, acc.z, k.bias.z), lo), fmaxf(fmaf(p.alpha, acc.w, k.bias.w), lo));
-        if (p.act > ACT_RELU) v = act4_slow(v, p.act);
+        if (p.act == ACT_LRELU)      // inline like ReLU: every conv of the vocoder ends in it (an out-of-line call per quad made its
+            v = make_float4(fmaxf(v.x, LRELU_SLOPE * v.x), fmaxf(v.y, LRELU_SLOPE * v.y),      // first convs epilogue-bound: 164 us
+                            fmaxf(v.z, LRELU_SLOPE * v.z), fmaxf(v.w, LRELU_SLOPE * v.w));     // against 101 us for the residual conv)
+        else if (p.act > ACT_RELU) v = act4_slow(v, p.act);
         if (col + 4 <= p.N) {
             if (p.out_f) *reinterpret_cast<float4*>(p.out_f + r * p.ldo + col) = v;
             if (p.out_h) {
