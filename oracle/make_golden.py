@@ -260,10 +260,73 @@ def voc_main():
                                  resblock_dilation_sizes=((1, 3, 5),), mini_nsf=True), 2, 9, 502)
 
 
+def ds_case(name, hp, param, vocab, spk_map, seed):
+    """Runs the UNMODIFIED ``DiffSingerAcousticInfer.preprocess_input`` (inference/ds_acoustic.py:68-166, with
+    ``BaseSVSInfer.load_speaker_mix``, basics/base_svs_infer.py:37-122) on a synthetic ``.ds`` segment.  The methods are called
+    unbound on a stand-in object that carries exactly the attributes they read (the real constructor loads checkpoints)."""
+    import types
+    da = ref_loader.load_acoustic_infer()
+    ref = ref_loader.load()
+    ref.hparams.clear()
+    ref.hparams.update(hp)
+    cls = da.DiffSingerAcousticInfer
+    me = types.SimpleNamespace(device='cpu', timestep=hp['hop_size'] / hp['audio_sample_rate'],
+                               ph_encoder=da.TokenTextEncoder(vocab_list=vocab), lr=da.LengthRegulator(), spk_map=spk_map,
+                               variances_to_embed={v for v in ('energy', 'breathiness', 'voicing', 'tension') if hp.get(f'use_{v}_embed')})
+    me.load_speaker_mix = types.MethodType(cls.load_speaker_mix, me)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        batch = cls.preprocess_input(me, param, idx=0)
+    arrays = {k: v for k, v in batch.items()}
+    meta = dict(kind='ds_preprocess', hparams=hp, param=param, vocab=vocab, spk_map=spk_map, keys=sorted(batch.keys()))
+    _save(name, meta, arrays, {'unused': torch.zeros(1)})
+
+
+def _ds_param(seed, n_ph, **extra):
+    g = np.random.RandomState(seed)
+    vocab = ['AP', 'SP', 'a', 'ai', 'b', 'ch', 'e', 'i', 'n', 'sh', 'u', 'zh']
+    ph = ['SP'] + [vocab[2 + int(g.randint(len(vocab) - 2))] for _ in range(n_ph - 2)] + ['AP']
+    dur = g.uniform(0.04, 0.37, n_ph)
+    total = float(dur.sum())
+    f0_ts = 0.005
+    n_f0 = int(total / f0_ts) + 7
+    f0 = 220.0 * 2 ** (0.5 * np.sin(np.arange(n_f0) * 0.013) + 0.02 * g.randn(n_f0))
+    p = dict(offset=1.25, ph_seq=' '.join(ph), ph_dur=' '.join('%.6f' % d for d in dur), f0_seq=' '.join('%.1f' % v for v in f0),
+             f0_timestep=str(f0_ts))
+
+    def curve(lo, hi, ts):
+        n = int(total / ts) + 3
+        return ' '.join('%.3f' % v for v in g.uniform(lo, hi, n)), str(ts)
+    for key, (lo, hi, ts) in extra.items():
+        if key in ('energy', 'breathiness', 'voicing', 'tension', 'velocity', 'gender'):
+            p[key], p[f'{key}_timestep'] = curve(lo, hi, ts)
+    return p, vocab
+
+
+def ds_main():
+    base = dict(hop_size=512, audio_sample_rate=44100, use_spk_id=False, use_key_shift_embed=False, use_speed_embed=False)
+    p, vocab = _ds_param(600, 9)
+    ds_case('ds_preprocess_plain', dict(base), p, vocab, None, 600)
+    aug = dict(random_pitch_shifting=dict(range=[-5., 5.]), random_time_stretching=dict(range=[0.5, 2.]))
+    p, vocab = _ds_param(601, 14, energy=(-60., -10., 0.011), breathiness=(-80., -30., 0.02), velocity=(0.3, 2.4, 0.05), gender=(-1.2, 1.2, 0.03))
+    p['spk_mix'] = {'alto': 0.7, 'tenor': 0.5}
+    ds_case('ds_preprocess_all_static_mix', dict(base, use_spk_id=True, use_key_shift_embed=True, use_speed_embed=True, use_energy_embed=True,
+                                                 use_breathiness_embed=True, augmentation_args=aug), p, vocab, {'alto': 0, 'tenor': 3, 'bass': 1}, 601)
+    p, vocab = _ds_param(602, 6, voicing=(-70., -5., 0.0116), tension=(-3., 3., 0.01))
+    p['gender'] = -0.4
+    n = 40
+    p['spk_mix'] = {'alto': ' '.join('%.3f' % v for v in np.linspace(0.1, 0.9, n)), 'bass': 0.25}
+    p['spk_mix_timestep'] = '0.05'
+    ds_case('ds_preprocess_dynamic_mix_static_gender', dict(base, hop_size=256, audio_sample_rate=22050, use_spk_id=True, use_key_shift_embed=True,
+                                                            use_speed_embed=True, use_voicing_embed=True, use_tension_embed=True,
+                                                            augmentation_args=aug), p, vocab, {'alto': 0, 'tenor': 3, 'bass': 1}, 602)
+
+
 def main():
     aux_main()
     enc_main()
     voc_main()
+    ds_main()
     # ---- backbone forward ------------------------------------------------------------------
     backbone_case('bb_wavenet_int_t', 'wavenet', WN_SMALL, 16, 1, 2, 37, torch.tensor([950, 3]), 10)
     backbone_case('bb_wavenet_float_t1', 'wavenet', WN_CYC, 16, 1, 3, 41, torch.tensor([437.25]), 11)
@@ -335,6 +398,8 @@ def main():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'aux':
         aux_main()                                          # only the aux-decoder fixtures
+    elif len(sys.argv) > 1 and sys.argv[1] == 'ds':
+        ds_main()                                           # only the .ds preprocessing fixtures
     elif len(sys.argv) > 1 and sys.argv[1] == 'voc':
         voc_main()                                          # only the vocoder fixtures
     elif len(sys.argv) > 1 and sys.argv[1] == 'enc':

@@ -89,3 +89,26 @@ def load_vocoder():
     from modules.nsf_hifigan.env import AttrDict              # noqa: E402
     return types.SimpleNamespace(models=models, AttrDict=AttrDict)
 
+
+def load_acoustic_infer():
+    """The reference's inference driver module (inference/ds_acoustic.py) with its unrelated imports stubbed when absent (``librosa``
+    in utils/infer_utils.py:3, ``lightning`` / ``matplotlib`` as for the vocoder); no reference file is modified."""
+    load_vocoder()
+    import importlib
+    class _Anything(types.ModuleType):                          # a stand-in package: any attribute is a callable that must not be called
+        __path__ = []
+
+        def __getattr__(self, item):
+            if item.startswith('__'):
+                raise AttributeError(item)
+            return lambda *a, **k: (_ for _ in ()).throw(RuntimeError(f'{self.__name__}.{item} is a stub'))
+    for name in ('librosa', 'librosa.filters', 'tqdm', 'onnxruntime', 'scipy.io.wavfile'):
+        try:
+            importlib.import_module(name)
+        except ModuleNotFoundError:
+            sys.modules[name] = _Anything(name)
+    if isinstance(sys.modules.get('tqdm'), _Anything):
+        sys.modules['tqdm'].tqdm = lambda it, **k: it
+    import inference.ds_acoustic as ds_acoustic                # noqa: E402
+    return ds_acoustic
+

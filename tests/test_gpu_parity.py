@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-3
 BB = GU.fixture_names('bb_')
-DF = [n for n in GU.fixture_names() if not n.startswith(('bb_', 'aux_', 'enc_', 'voc_'))]
+DF = [n for n in GU.fixture_names() if not n.startswith(('bb_', 'aux_', 'enc_', 'voc_', 'ds_'))]
 
 
 def _maxabs(a, b):

@@ -9,7 +9,7 @@ import product_util as PU
 from oracle import denoisers as OD
 from oracle import samplers as OS
 
-DF = [n for n in GU.fixture_names() if not n.startswith(('bb_', 'aux_', 'enc_', 'voc_'))]
+DF = [n for n in GU.fixture_names() if not n.startswith(('bb_', 'aux_', 'enc_', 'voc_', 'ds_'))]
 
 
 def _maxabs(a, b):
