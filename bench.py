@@ -483,9 +483,25 @@ def time_tokens_to_mel(precision, dev, L=64, T=690, reps=10, extra_hparams=None)
         mel = m(tokens, mel2ph, f0, infer=True).diff_out
         torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 1e3 / reps
-    return {'workload': f'one utterance ({L} tokens, {T} frames = 8 s): encoder 4x256 -> aux decoder 6x512 -> shallow DDIM 20 evaluations of '
-                        f'WaveNet 20x256 -> mel', 'ms_per_call': ms, 'rtf': ms * 1e-3 / (T * 512 / 44100.0),
-            'finite': bool(torch.isfinite(mel).all())}
+    res = {'workload': f'one utterance ({L} tokens, {T} frames = 8 s): encoder 4x256 -> aux decoder 6x512 -> shallow DDIM 20 evaluations of '
+                       f'WaveNet 20x256 -> mel', 'ms_per_call': ms, 'rtf': ms * 1e-3 / (T * 512 / 44100.0),
+           'finite': bool(torch.isfinite(mel).all())}
+    try:                                                     # ... and on to the waveform (NSF-HiFiGAN, public 44.1 kHz geometry)
+        P.hparams['mel_base'] = 'e'
+        voc = P.NsfHifiGAN(P.vocoder.Generator(dict(VOCODER_H)).to(dev).eval())
+        for _ in range(4):
+            voc.spec2wav_torch(m(tokens, mel2ph, f0, infer=True).diff_out, f0=f0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            wav = voc.spec2wav_torch(m(tokens, mel2ph, f0, infer=True).diff_out, f0=f0)
+            torch.cuda.synchronize()
+        ms_w = (time.perf_counter() - t0) * 1e3 / reps
+        res['tokens_to_waveform'] = {'ms_per_call': ms_w, 'rtf': ms_w * 1e-3 / (T * 512 / 44100.0), 'samples': int(wav.numel()),
+                                     'finite': bool(torch.isfinite(wav).all())}
+    except Exception as ex:                                  # noqa: BLE001
+        res['tokens_to_waveform'] = {'error': f'{type(ex).__name__}: {ex}'}
+    return res
 
 
 def time_acoustic_encoder(precision, dev, B=16, L=64, T=690, reps=5, extra_hparams=None):
