@@ -151,7 +151,11 @@ def _best_fold(k: int, d: int, lay: int, R: int) -> int:
     """The fold with the fewest tensor-core nanoseconds per sample: taps'(f) K groups of f * lay / 64 blocks x 4 MMAs per 256 rows of
     f samples; an MMA of width N = f * lay costs ~27 + 0.29 N ns (measured: 64 ns at N = 128, 101 ns at N = 256)."""
     best = None
-    for f_ in _fold_choices(lay, R):
+    cap = int(hparams.get('b2s_voc_max_fold', 0) or 0)          # measurement switch: folds above the cap are not considered (0: no cap)
+    choices = _fold_choices(lay, R)
+    if cap:
+        choices = [f_ for f_ in choices if f_ <= cap] or choices[:1]
+    for f_ in choices:
         ks = _fold_taps(k, d, f_)
         if ks > 63:
             continue
@@ -282,7 +286,8 @@ class _VocoderEngine:
 
     def _ver(self):
         ps = list(self.net.parameters())
-        return tuple((p._version, p.data_ptr(), p.dtype) for p in ps) + (str(ps[0].device), hparams.get('b2s_precision'))
+        return tuple((p._version, p.data_ptr(), p.dtype) for p in ps) + (str(ps[0].device), hparams.get('b2s_precision'),
+                                                                           hparams.get('b2s_voc_max_fold'))
 
     def _side_streams(self, n):
         ss = self.__dict__.setdefault('_streams', [])
