@@ -419,6 +419,15 @@ int b2s_voc_post(const float* const* xs_host, int n_blocks, const float* W, cons
                  int ksize, float slope, void* stream);
 int b2s_cast_scale_f32_h(const float* in, void* out_h, int64_t n, float scale, int bf16, void* stream);
 
+/* ---- training-branch losses, forward values (validation during training; reference modules/losses/diff_loss.py:17-37,
+ * modules/losses/reflow_loss.py:18-50) ----
+ * out[0] = mean over [B, F, M, T] of w_b * loss(a * m, b * m): loss = |.| (l1) or (.)^2; m = mask[b, t, 0 or bin] (non_padding, NULL: none);
+ * w_b = the log-normal weight of t_weights[b] (reflow_loss.py:26-33; NULL: 1).  workspace: b2s_masked_loss_workspace_bytes() bytes.
+ * Deterministic (fixed summation order), double accumulation across threads. */
+int b2s_masked_loss_workspace_bytes(void);
+int b2s_masked_loss_f32(const float* a, const float* b, const float* mask, int mask_m, const float* t_weights, int B, int F, int M, int T,
+                        int l1, void* workspace, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

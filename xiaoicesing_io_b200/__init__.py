@@ -11,6 +11,7 @@ Public surface (same names and contracts as the reference's ``modules.backbones`
     FastSpeech2Acoustic, FastSpeech2Encoder   (modules.fastspeech: the producer of the condition tensor, rotary configuration)
     DiffSingerAcoustic, ShallowDiffusionOutput   (modules.toplevel: tokens -> condition -> x_start -> mel, inference)
     vocoder.Generator, vocoder.load_model, NsfHifiGAN   (modules.nsf_hifigan / modules.vocoders: mel + f0 -> waveform)
+    DiffusionLoss, RectifiedFlowLoss   (modules.losses: forward values of the training-branch losses, validation)
     infer.DiffSingerAcousticInfer   (inference.ds_acoustic: .ds segment -> model inputs -> mel -> waveform / .mel.pt)
     hparams  (the global config dict, utils/hparams.py:13)
     segments (batched .ds segment driver: ragged batches, per-segment seeds, .mel.pt writer), partition (multi-GPU), B2SError
@@ -28,7 +29,8 @@ from .hparams import hparams, set_hparams
 from .aux_decoder import AUX_DECODERS, AuxDecoderAdaptor, ConvNeXtDecoder, build_aux_decoder
 from .acoustic_encoder import FastSpeech2Acoustic, FastSpeech2Encoder
 from .toplevel import DiffSingerAcoustic, ShallowDiffusionOutput
-from . import infer, partition, segments, vocoder  # noqa: E402,F401
+from . import infer, losses, partition, segments, vocoder  # noqa: E402,F401
+from .losses import DiffusionLoss, RectifiedFlowLoss
 from .vocoder import NsfHifiGAN
 
 __version__ = '0.2.0'

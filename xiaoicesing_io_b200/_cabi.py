@@ -81,13 +81,14 @@ _SIGNATURES = {
     'b2s_voc_avg_act': [ctypes.POINTER(_vp), _i, _vp, _i64, _f, _i, _vp],
     'b2s_voc_post': [ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     'b2s_cast_scale_f32_h': [_vp, _vp, _i64, _f, _i, _vp],
+    'b2s_masked_loss_f32': [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     'b2s_enc_assemble': [_vp, _vp, _vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
 }
 
 # entry points of B2S_BUILD_EXPERIMENTS=1 builds only (measured-and-rejected variants)
 EXPERIMENTAL = ('b2s_tc_wavenet_stack_t_tiles', 'b2s_tc_cond_retile', 'b2s_tc_wavenet_stack_t', 'b2s_tc_wavenet_denoiser_update')
 
-EXPORTED_SYMBOLS = ['b2s_abi_version', 'b2s_last_error', 'b2s_has_experiments', 'b2s_tc_wavenet_stack_max_tiles', 'b2s_tc_wavenet_stack3_halo', 'b2s_tc_wavenet_stack3_max_tiles', 'b2s_tc_wavenet_denoiser3_max_utterances', *[n for n in _SIGNATURES if n not in EXPERIMENTAL]]
+EXPORTED_SYMBOLS = ['b2s_masked_loss_workspace_bytes', 'b2s_abi_version', 'b2s_last_error', 'b2s_has_experiments', 'b2s_tc_wavenet_stack_max_tiles', 'b2s_tc_wavenet_stack3_halo', 'b2s_tc_wavenet_stack3_max_tiles', 'b2s_tc_wavenet_denoiser3_max_utterances', *[n for n in _SIGNATURES if n not in EXPERIMENTAL]]
 
 ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU, ACT_SILU, ACT_LRELU = 0, 1, 2, 3, 4, 5
 
@@ -116,6 +117,8 @@ def _load():
     lib.b2s_tc_wavenet_stack3_max_tiles.argtypes = [c_int, c_int]
     lib.b2s_tc_wavenet_denoiser3_max_utterances.restype = c_int
     lib.b2s_tc_wavenet_denoiser3_max_utterances.argtypes = [c_int, c_int]
+    lib.b2s_masked_loss_workspace_bytes.restype = c_int
+    lib.b2s_masked_loss_workspace_bytes.argtypes = []
     lib.b2s_has_experiments.restype = c_int
     lib.b2s_has_experiments.argtypes = []
     for name, args in _SIGNATURES.items():
@@ -491,3 +494,12 @@ def voc_post(xs, W, b0, wav, B, T, C, Cp, ksize, slope):
 
 def cast_scale_h(inp, out, scale, bf16):
     check(lib.b2s_cast_scale_f32_h(ptr(inp), ptr(out), inp.numel(), float(scale), int(bf16), stream_ptr()), 'b2s_cast_scale_f32_h')
+
+
+def masked_loss(a, b, mask, t_weights, l1, out):
+    """out[0] = mean(w * loss(a * mask, b * mask)) over a, b [B, F, M, T]; mask [B, T, 1 or M] or None; t_weights [B] or None."""
+    B, F, M, T = a.shape
+    ws = torch.empty(lib.b2s_masked_loss_workspace_bytes() // 8, dtype=torch.float64, device=a.device)
+    check(lib.b2s_masked_loss_f32(ptr(a), ptr(b), ptr(mask), 0 if mask is None else mask.shape[-1], ptr(t_weights), B, F, M, T, int(l1),
+                                  ptr(ws), ptr(out), stream_ptr()), 'b2s_masked_loss_f32')
+

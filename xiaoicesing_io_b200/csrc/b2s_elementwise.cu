@@ -375,3 +375,77 @@ extern "C" int b2s_lynx_dwconv_f32(const float* g, const float* Wdw, const float
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }
+
+// ---- training-branch losses (forward values: validation, SURVEY.md section 8 row f-4 forward half) ---------------------------------
+// mean over [B, F, M, T] of w_b * loss(a * m, b * m), loss = |.| or (.)^2, m = non_padding[b, t, (m)] (modules/losses/diff_loss.py:17-37,
+// reflow_loss.py:18-50; the log-normal time weights of reflow_loss.py:26-33 are computed here from t).  Two kernels: per-block partial
+// sums (fp32 inside a thread, double across threads), then ONE block adds the partials in a fixed order - deterministic.
+namespace b2s {
+constexpr int LOSS_BLOCK = 256, LOSS_MAX_BLOCKS = 1024;
+
+__global__ void __launch_bounds__(LOSS_BLOCK) masked_loss_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                         const float* __restrict__ mask, int mask_m,
+                                                                         const float* __restrict__ tw, int B, int F, int M, int T, int l1,
+                                                                         double* __restrict__ partial) {
+    const long long n = (long long)B * F * M * T;
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)LOSS_BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * LOSS_BLOCK) {
+        const int t = (int)(i % T);
+        const long long r = i / T;
+        const int m = (int)(r % M);
+        const int bb = (int)(r / ((long long)M * F));
+        float x = a[i], y = b[i];
+        if (mask) {
+            const float k = __ldg(mask + ((long long)bb * T + t) * mask_m + (mask_m > 1 ? m : 0));
+            x = __fmul_rn(x, k);
+            y = __fmul_rn(y, k);
+        }
+        const float d = __fsub_rn(x, y);
+        float v = l1 ? fabsf(d) : __fmul_rn(d, d);
+        if (tw) {                                                     // reflow_loss.py:26-33
+            const float eps = 1e-7f;
+            const float tt = fminf(fmaxf(__ldg(tw + bb), eps), 1.0f - eps);
+            const float lg = logf(__fdiv_rn(tt, 1.0f - tt));
+            const float w = __fadd_rn(__fmul_rn(__fdiv_rn(__fdiv_rn(0.398942f, tt), 1.0f - tt), expf(__fmul_rn(-0.5f, __fmul_rn(lg, lg)))), eps);
+            v = __fmul_rn(w, v);
+        }
+        acc += (double)v;
+    }
+    __shared__ double sh[LOSS_BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < LOSS_BLOCK / 32; ++w) s += sh[w];
+        partial[blockIdx.x] = s;
+    }
+}
+
+__global__ void masked_loss_final_kernel(const double* __restrict__ partial, int n_partial, double inv_n, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n_partial; ++i) s += partial[i];
+        out[0] = (float)(s * inv_n);
+    }
+}
+}  // namespace b2s
+
+extern "C" int b2s_masked_loss_workspace_bytes(void) { return b2s::LOSS_MAX_BLOCKS * (int)sizeof(double); }
+
+extern "C" int b2s_masked_loss_f32(const float* a, const float* b, const float* mask, int mask_m, const float* t_weights, int B, int F,
+                                   int M, int T, int l1, void* workspace, float* out, void* stream) {
+    using namespace b2s;
+    B2S_CHECK_ARG(a && b && workspace && out, "b2s_masked_loss_f32: null pointer");
+    B2S_CHECK_ARG(B > 0 && F > 0 && M > 0 && T > 0, "b2s_masked_loss_f32: empty tensor (the reference's mean of nothing is NaN)");
+    B2S_CHECK_ARG(!mask || mask_m == 1 || mask_m == M, "b2s_masked_loss_f32: mask [B, T, %d] does not broadcast over %d bins", mask_m, M);
+    const long long n = (long long)B * F * M * T;
+    long long g = (n + LOSS_BLOCK - 1) / LOSS_BLOCK;
+    const int grid = (int)(g > LOSS_MAX_BLOCKS ? LOSS_MAX_BLOCKS : g);
+    masked_loss_partial_kernel<<<grid, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(a, b, mask, mask_m, t_weights, B, F, M, T, l1,
+                                                                            reinterpret_cast<double*>(workspace));
+    B2S_CHECK_LAUNCH();
+    masked_loss_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(workspace), grid, 1.0 / (double)n, out);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
