@@ -413,7 +413,7 @@ class _VocoderEngine:
                     raise C.B2SError(f'rand_ini needs {dim} values and noise [B, T * {net.upp}, {dim}]')
             else:
                 rand_ini = noise = None
-            key = (self._version, B, T, float(scale))
+            key = (self._version, B, T, float(scale), bool(hparams.get('b2s_voc_streams', True)))      # launch-structure switches are part of the key
             return self._graphs(key, [mel, f0, rand_ini, noise], lambda inp: self._launches(inp, B, T, float(scale)))
 
     def _launches(self, inp, B, T, scale):
