@@ -1,7 +1,7 @@
 // NSF-HiFiGAN vocoder (mel + f0 -> waveform, the step AFTER the sampling loop; reference modules/nsf_hifigan/models.py:206-289): the
 // kernels that are NOT GEMMs.  The dense convolutions (conv_pre, the transposed convs as 3-tap convs over u * C columns, the dilated
 // residual-block convs) run on the tcgen05 kernels of b2s_tc_gemm.cu (b2s_tc_conv1d_dil / b2s_tc_conv1d_residual); activations are
-// time-major rows r = b * T_i + t with the channels zero-padded to a multiple of 64.
+// time-major rows r = b * T_i + t, folded (f samples per GEMM row) or zero-padded to a multiple of 64 channels (vocoder.py).
 //   voc_phase        per-frame phase accumulation of the sine source                   models.py:138-141 (SineGen), :253-259 (mini_nsf)
 //   voc_source       1 + 8 harmonics, uv / noise mix, tanh(linear(.))                  models.py:142-147, :160-166, :197-200; :260-262
 //   voc_source_add   x += noise_conv(source) (strided Conv1d with ONE input channel), 16-bit leaky_relu(x) copy   models.py:273-278, :62
@@ -105,10 +105,13 @@ __global__ void __launch_bounds__(256) voc_source_add_kernel(float* __restrict__
             float4 a = __ldg(reinterpret_cast<const float4*>(bias + c));
             const float* s = src + (long long)b * n_src;
             const long long base = (long long)t * stride - pad;
-            for (int j = 0; j < ksize; ++j) {
-                const long long p = base + j;
-                if (p < 0 || p >= n_src) continue;
-                const float sv = __ldg(s + p);
+            // taps outside [0, n_src) are the conv's zero padding: clip the tap range once, then a branch-free loop the compiler can
+            // unroll (the loads of several taps in flight; with a `continue` per tap the 128-tap stage-0 conv was a latency chain)
+            const int j0 = base < 0 ? (int)(-base) : 0;
+            const int j1 = base + ksize > n_src ? (int)(n_src - base) : ksize;
+#pragma unroll 8
+            for (int j = j0; j < j1; ++j) {
+                const float sv = __ldg(s + base + j);
                 const float4 w = __ldg(reinterpret_cast<const float4*>(Wt + (long long)j * Cp + c));
                 a.x = fmaf(w.x, sv, a.x); a.y = fmaf(w.y, sv, a.y); a.z = fmaf(w.z, sv, a.z); a.w = fmaf(w.w, sv, a.w);
             }
@@ -161,15 +164,38 @@ __global__ void __launch_bounds__(VOC_POST_TILE) voc_post_kernel(VocBlocks xs, c
     const int t0 = blockIdx.x * VOC_POST_TILE;
     const int half = ksize / 2, rows = VOC_POST_TILE + ksize - 1, ld = C + 1;
     float* wsm = tile + rows * ld;
-    for (int i = threadIdx.x; i < rows * C; i += VOC_POST_TILE) {
-        const int rr = i / C, c = i - rr * C;
-        const int t = t0 + rr - half;
-        float v = 0.f;
-        if (t >= 0 && t < T) {
-            v = voc_mean(xs, ((long long)b * T + t) * Cp + c);
-            v = v > 0.f ? v : __fmul_rn(v, slope);
+    if ((C & 3) == 0 && (Cp & 3) == 0) {                                  // 16-byte loads (every shipped geometry: C = 16)
+        const int q = C >> 2;
+        for (int i = threadIdx.x; i < rows * q; i += VOC_POST_TILE) {
+            const int rr = i / q, c = (i - rr * q) * 4;
+            const int t = t0 + rr - half;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < T) {
+                const long long off = ((long long)b * T + t) * Cp + c;
+                v = *reinterpret_cast<const float4*>(xs.x[0] + off);
+                for (int k = 1; k < xs.n; ++k) {
+                    const float4 u = *reinterpret_cast<const float4*>(xs.x[k] + off);
+                    v.x = __fadd_rn(v.x, u.x); v.y = __fadd_rn(v.y, u.y); v.z = __fadd_rn(v.z, u.z); v.w = __fadd_rn(v.w, u.w);
+                }
+                const float d = (float)xs.n;
+                v.x = __fdiv_rn(v.x, d); v.y = __fdiv_rn(v.y, d); v.z = __fdiv_rn(v.z, d); v.w = __fdiv_rn(v.w, d);
+                v.x = v.x > 0.f ? v.x : __fmul_rn(v.x, slope); v.y = v.y > 0.f ? v.y : __fmul_rn(v.y, slope);
+                v.z = v.z > 0.f ? v.z : __fmul_rn(v.z, slope); v.w = v.w > 0.f ? v.w : __fmul_rn(v.w, slope);
+            }
+            float* dst = tile + rr * ld + c;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
         }
-        tile[rr * ld + c] = v;
+    } else {
+        for (int i = threadIdx.x; i < rows * C; i += VOC_POST_TILE) {
+            const int rr = i / C, c = i - rr * C;
+            const int t = t0 + rr - half;
+            float v = 0.f;
+            if (t >= 0 && t < T) {
+                v = voc_mean(xs, ((long long)b * T + t) * Cp + c);
+                v = v > 0.f ? v : __fmul_rn(v, slope);
+            }
+            tile[rr * ld + c] = v;
+        }
     }
     for (int i = threadIdx.x; i < ksize * C; i += VOC_POST_TILE) wsm[i] = __ldg(W + i);
     __syncthreads();

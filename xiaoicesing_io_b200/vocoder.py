@@ -429,16 +429,24 @@ class _VocoderEngine:
             C.cast_scale_h(mel, tmp, scale, bf)
             mel_h = torch.zeros((B * T, Mp), device=dev, dtype=hd)
             mel_h[:, :M] = tmp
-        # ---- harmonic source at the waveform rate (mini_nsf: at sr / prod(rates[2:]))
+        # ---- harmonic source at the waveform rate (mini_nsf: at sr / prod(rates[2:])).  Nothing before the first stage's source conv
+        # needs it: it runs on a side stream next to the mel cast, conv_pre and the first transposed conv, joined where it is read
         upp = net.upp
         phase = torch.empty((B, T), device=dev)
-        C.voc_phase(f0, phase, B, T, net.source_sr, upp, net.mini_nsf)
         har = torch.empty((B, T * upp), device=dev)
-        if net.mini_nsf:
-            C.voc_source(f0, phase, None, None, None, None, har, B, T, upp, 0, net.source_sr, 0., 0., 0.)
-        else:
-            s = self.src
-            C.voc_source(f0, phase, rand_ini, noise, s['w'], s['b'], har, B, T, upp, s['dim'], net.source_sr, s['amp'], s['std'], s['thr'])
+        use_streams = bool(hparams.get('b2s_voc_streams', True))
+        src_branch, src_stream = contextlib.nullcontext(), None
+        if use_streams:
+            src_stream = self._side_streams(1)[0]
+            src_stream.wait_stream(torch.cuda.current_stream())
+            src_branch = torch.cuda.stream(src_stream)
+        with src_branch:
+            C.voc_phase(f0, phase, B, T, net.source_sr, upp, net.mini_nsf)
+            if net.mini_nsf:
+                C.voc_source(f0, phase, None, None, None, None, har, B, T, upp, 0, net.source_sr, 0., 0., 0.)
+            else:
+                s = self.src
+                C.voc_source(f0, phase, rand_ini, noise, s['w'], s['b'], har, B, T, upp, s['dim'], net.source_sr, s['amp'], s['std'], s['thr'])
         # ---- conv_pre (+ the leaky ReLU in front of the first transposed conv)
         a_h = torch.empty((B * T, self.c0p), device=dev, dtype=hd)
         C.tc_conv1d_dil(mel_h, self.w_pre, self.b_pre, None, 0, a_h, self.c0p, B, T, Mp, self.c0p, 7, 1, C.ACT_LRELU, bf)
@@ -453,6 +461,9 @@ class _VocoderEngine:
             rows = B * Ti
             lx_h = torch.empty((rows, lay), device=dev, dtype=hd)
             sc = st['src']
+            if src_stream is not None and sc is not None:
+                torch.cuda.current_stream().wait_stream(src_stream)       # the harmonic source is complete (first use joins the branch)
+                src_stream = None
             if sc is None:
                 C.voc_source_add(x, lx_h, None, None, None, B, Ti, lay, 0, 1, 0, 0, LRELU_SLOPE, bf)
             else:
@@ -502,6 +513,8 @@ class _VocoderEngine:
                 wav = torch.empty((B, Ti), device=dev)
                 C.voc_post(xs, self.w_post, self.b_post, wav, B, Ti, self.c_last, lay, 7, 0.01)         # :286-288 (default slope)
             del x, lx_h, bufs, xs
+        if src_stream is not None:
+            torch.cuda.current_stream().wait_stream(src_stream)
         return wav
 
 
