@@ -66,6 +66,11 @@ struct __align__(64) TcP {
     // EPI_VRES, the vocoder's residual blocks (x <- x_src + acc + bias): the stream that is READ (NULL: x itself) and a leaky ReLU on the 16-bit copy
     const float* x_src;
     int y_lrelu; float y_slope;
+    // Last-wave split (cta_group::2 kernel): the tile pairs [0, vt_full) are whole tiles walked round robin by the CTA pairs; each of the
+    // remaining num_pt - vt_full tile pairs (fewer than half of the CTA pairs) is cut along N into vt_split sub-tiles of bn / vt_split
+    // columns, so that the last, partial wave of a launch (or a launch with fewer tiles than CTA pairs) spreads over the idle pairs.
+    int vt_full, vt_split, vt_total;
+    int no_split;              // 1: never split (the vocoder's convs: three residual blocks run concurrently and fill each other's partial waves)
 };
 
 // ---- 16-bit helpers --------------------------------------------------------------------------------
@@ -429,6 +434,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
 // (6 pipeline stages instead of 4, and half the L2 traffic for the weights: scripts/tc_probe.py showed the single-CTA
 // mainloop sitting on the 6.3 KB/clk L2 slice cap).  Only the leader issues tcgen05.mma / commit; both CTAs' TMA loads
 // complete on the leader's full barrier; both CTAs' epilogue warps arrive on the leader's tempty barrier.
+// virtual tile v -> (tile pair pt, first column n0, width w) under the last-wave split (see TcP::vt_*)
+struct VTile { int pt, n_off, w; };
+__device__ __forceinline__ VTile decode_vtile(const TcP& p, int v) {
+    VTile t;
+    if (v < p.vt_full) { t.pt = v; t.n_off = 0; t.w = p.bn; }
+    else {
+        const int r = v - p.vt_full;
+        t.pt = p.vt_full + r / p.vt_split;
+        t.w = p.bn / p.vt_split;
+        t.n_off = (r % p.vt_split) * t.w;
+    }
+    return t;
+}
+
 constexpr int STAGES2 = 6;
 constexpr int BH_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;       // 16 KB
 constexpr int STAGE2_BYTES = A_BYTES + BH_BYTES;            // 32 KB
@@ -509,12 +528,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
             }
         };
         // (the same prefetch for the fp32 residual-stream rows of the x-updating epilogues was measured: 1-2 % slower)
-        prefetch_cond(pair);
-        for (int pt = pair; pt < num_pt; pt += npairs) {
+        if (pair < p.vt_total) prefetch_cond(decode_vtile(p, pair).pt);
+        for (int v = pair; v < p.vt_total; v += npairs) {
+            const VTile vt = decode_vtile(p, v);
+            const int pt = vt.pt;
             const int n_tile = pt % p.tiles_n, m_tile = 2 * (pt / p.tiles_n) + rank;
             const int b = m_tile / p.tiles_m_per_b, t0 = (m_tile - b * p.tiles_m_per_b) * BLOCK_M;
-            const int n0 = n_tile * p.bn;
-            prefetch_cond(pt + npairs);
+            const int n0 = n_tile * p.bn + vt.n_off;
+            const int wrow = n0 + rank * (vt.w / 2);             // this CTA's half of the (sub-)tile's weight rows; the box stays bn / 2 rows
+            if (v + npairs < p.vt_full) prefetch_cond(v + npairs);
             if (conv3) {
                 for (int cs = 0; cs < p.kb_per_tap; ++cs) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -525,8 +547,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                         tma_load_3d_cg2(sa, &p.mapA3, lbar, cs * BLOCK_K, t0 - CONV3_HALO, b);
 #pragma unroll
                         for (int tap = 0; tap < 3; ++tap)
-                            tma_load_2d_cg2(sa + A3_BYTES + tap * BH_BYTES, &p.mapW, lbar, (tap * p.kb_per_tap + cs) * BLOCK_K,
-                                            n0 + rank * (p.bn / 2));
+                            tma_load_2d_cg2(sa + A3_BYTES + tap * BH_BYTES, &p.mapW, lbar, (tap * p.kb_per_tap + cs) * BLOCK_K, wrow);
                     }
                     __syncwarp();
                     if (++stage == STAGES3) { stage = 0; phase ^= 1; }
@@ -542,7 +563,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
                     tma_load_3d_cg2(sa, &p.mapA, lbar, c0, t0 + (tap - p.tap_c) * p.dil, p.k_layered ? tap : b);
-                    tma_load_2d_cg2(sa + A_BYTES, &p.mapW, lbar, kb * BLOCK_K, n0 + rank * (p.bn / 2));
+                    tma_load_2d_cg2(sa + A_BYTES, &p.mapW, lbar, kb * BLOCK_K, wrow);
                 }
                 __syncwarp();
                 if (++stage == STAGES2) { stage = 0; phase ^= 1; }
@@ -550,10 +571,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
         }
     } else if (warp == 1 && rank == 0) {
         // ===================== MMA issuer (leader CTA): M = 256 across the pair =====================
-        const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, p.bn, BF16);
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
-        for (int pt = pair; pt < num_pt; pt += npairs) {
+        for (int v = pair; v < p.vt_total; v += npairs) {
+            const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, decode_vtile(p, v).w, BF16);      // sub-tiles of the last wave are narrower
             mbar_wait(&tempty[as], aphase ^ 1);          // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -612,10 +633,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
         uint32_t aphase = 0;
         float* stg = stg_all + e * (16 * STG_LD);
         const int cl = (lane & 7) * 4, rsub = lane >> 3;
-        for (int pt = pair; pt < num_pt; pt += npairs) {
+        for (int v = pair; v < p.vt_total; v += npairs) {
+            const VTile vt = decode_vtile(p, v);
+            const int pt = vt.pt, tw = vt.w;                // tw: columns of this (sub-)tile
             const int n_tile = pt % p.tiles_n, m_tile = 2 * (pt / p.tiles_n) + rank;
             const int bt = m_tile / p.tiles_m_per_b, t0 = (m_tile - bt * p.tiles_m_per_b) * BLOCK_M;
-            const int n0 = n_tile * p.bn;
+            const int n0 = n_tile * p.bn + vt.n_off;
             const int tq = t0 + q * 32 + rsub;             // row of iteration i: tq + 4*i
             // per-chunk inputs (cond / x / skip rows of the lane, bias and step-embedding quads) are requested ONE CHUNK AHEAD -
             // the first chunk's before the accumulator wait - so their L2 / HBM latency hides behind the TMEM drain of the
@@ -642,12 +665,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                     }
                 }
             };
-            if (n0 + 32 * sub < p.N) load_chunk(sub);
+            if (sub < tw / 32 && n0 + 32 * sub < p.N) load_chunk(sub);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
-            for (int j = sub; j < p.bn / 32; j += 2) {
+            for (int j = sub; j < tw / 32; j += 2) {
                 const int col0 = n0 + 32 * j;
                 if (col0 >= p.N) break;
                 float acc[32];
@@ -659,7 +682,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                 uint2 cn[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { in[i] = inn[i]; cn[i] = cnn[i]; }
-                if (j + 2 < p.bn / 32 && col0 + 64 < p.N) load_chunk(j + 2);
+                if (j + 2 < tw / 32 && col0 + 64 < p.N) load_chunk(j + 2);
                 tmem_ld_wait();
                 // transpose through the warp's private 16-row staging tile, two passes: thread = row -> lane = 4 columns
 #pragma unroll
@@ -718,7 +741,22 @@ static int launch_one(const TcP& p, cudaStream_t st) {
             B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_cg2_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         }
         const int num_pt = (p.B * p.tiles_m_per_b / 2) * p.tiles_n;
-        const int pairs = num_pt < num_sms() / 2 ? num_pt : num_sms() / 2;
+        // last-wave split: when the tiles left for the last wave (or all tiles of a small launch) occupy at most half of the CTA pairs,
+        // each is cut along N into 2 or 4 sub-tiles (>= 64 columns, whole 32-column epilogue chunks) - an MMA of width 64 / 128 costs
+        // 0.45x / 0.63x of one of width 256, so the partial wave shrinks accordingly (config 5: 384 tile pairs on 74 CTA pairs = 5.2 waves)
+        static const bool no_split = getenv("B2S_GEMM_NOSPLIT") != nullptr;
+        const int maxp = num_sms() / 2;
+        TcP q = p;
+        q.vt_full = num_pt >= maxp ? (num_pt / maxp) * maxp : 0;
+        q.vt_split = 1;
+        const int rem = num_pt - q.vt_full;
+        if (!no_split && !p.no_split && rem > 0 && 2 * rem <= maxp) {
+            q.vt_split = maxp / rem >= 4 ? 4 : 2;
+            while (q.vt_split > 1 && ((p.bn / q.vt_split) % 32 != 0 || p.bn / q.vt_split < 64)) q.vt_split >>= 1;
+        }
+        if (q.vt_split == 1) q.vt_full = num_pt;
+        q.vt_total = q.vt_full + (num_pt - q.vt_full) * q.vt_split;
+        const int pairs = q.vt_total < maxp ? q.vt_total : maxp;
         cudaLaunchConfig_t cfg2{};
         cfg2.gridDim = dim3(2 * pairs);
         cfg2.blockDim = dim3(NTHREADS);
@@ -733,7 +771,7 @@ static int launch_one(const TcP& p, cudaStream_t st) {
         attr2[1].val.programmaticStreamSerializationAllowed = 1;
         cfg2.attrs = attr2;
         cfg2.numAttrs = 2;
-        B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg2, tc_gemm_cg2_kernel<EPI, BF16>, p));
+        B2S_CHECK_CUDA(cudaLaunchKernelEx(&cfg2, tc_gemm_cg2_kernel<EPI, BF16>, q));
         return B2S_OK;
     }
 #ifndef B2S_EXPERIMENTS
@@ -763,7 +801,7 @@ static int launch(const TcP& p, int bf16, cudaStream_t st) {
 
 // common geometry: A is [B, T, Kcols]; per-utterance M tiles when conv, flat otherwise
 static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool per_utt, const void* W, int ldw, int N, int K,
-                 int kb_per_tap, int dil, int bf16, bool split_n_when_few = false) {
+                 int kb_per_tap, int dil, int bf16) {
     const int Bm = per_utt ? B : 1, Tm = per_utt ? T : B * T;
     int rc = make_map_act(&p.mapA, A, bf16, a_cols, lda, Tm, Bm, BLOCK_K, BLOCK_M);
     if (rc) return rc;
@@ -776,11 +814,6 @@ static int setup(TcP& p, const void* A, int lda, int a_cols, int B, int T, bool 
     p.bn = (p.cg2 && N % 192 == 0 && N % 256 != 0) ? 192 : BLOCK_N;      // no half-empty second tile for the C = 192 models
     if (p.cg2 && N <= 128) p.bn = N <= 64 ? 64 : 128;                    // narrow outputs (the vocoder's late stages, mel heads): an MMA of
                                                                          // width 64 / 128 is 2.2x / 1.6x shorter than one of width 256
-    if (split_n_when_few && p.cg2 && p.bn == BLOCK_N && N % 128 == 0) {
-        // one short utterance: fewer tile pairs than half of the CTA pairs -> N tiles of 128 double the tiles at 0.63x the MMA time each
-        const long long pt = (long long)Bm * ((ceil_div(Tm, BLOCK_M) + 1) / 2) * ceil_div(N, BLOCK_N);
-        if (2 * pt <= num_sms() / 2) p.bn = 128;
-    }
     rc = make_map_w(&p.mapW, W, bf16, K, N, ldw, BLOCK_K, p.cg2 ? p.bn / 2 : BLOCK_N);
     if (rc) return rc;
     p.B = Bm; p.T = Tm; p.T_utt = T;
@@ -983,11 +1016,12 @@ extern "C" int b2s_tc_conv1d_dil(const void* a_h, const void* W_h, const float* 
                   "b2s_tc_conv1d_dil: misaligned pointer / leading dimension");
     if (B * T == 0) return B2S_OK;
     TcP p{};
-    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16, true);
+    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16);
     if (rc) return rc;
     p.tap_c = ksize / 2;
     p.bias = bias; p.alpha = 1.0f; p.act = act;
     p.out_f = out_f32; p.ldo = ldo; p.out_h = out_h; p.ldoh = ldoh;
+    p.no_split = 1;            // measured: 1.97 ms (no split) vs 2.03 ms per 8-s utterance with the blocks on three streams
     return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
 }
 
@@ -1004,11 +1038,12 @@ extern "C" int b2s_tc_conv1d_residual(const void* a_h, const void* W_h, const fl
     B2S_CHECK_ARG(y_h != a_h, "b2s_tc_conv1d_residual: y_h must not alias the conv input (neighbouring tiles read its halo rows)");
     if (B * T == 0) return B2S_OK;
     TcP p{};
-    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16, true);
+    int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16);
     if (rc) return rc;
     p.tap_c = ksize / 2;
     p.bias = bias; p.x = x; p.x_src = x_src; p.C = N; p.y_h = y_h; p.ldy = N;
     p.y_lrelu = y_h != nullptr && y_slope != 1.0f; p.y_slope = y_slope;
+    p.no_split = 1;
     return launch<EPI_VRES>(p, bf16, (cudaStream_t)stream);
 }
 
