@@ -474,3 +474,30 @@ def test_lynx_dwconv_h_against_fp64(C, kind, hd, eps, B, T, inner, K):
     err = (out.double() - want).abs()
     mass = F.conv1d(g.double().abs().transpose(1, 2), w.double().abs()[:, None, :], None, padding=K // 2, groups=inner).transpose(1, 2)
     assert float((err - eps * (want.abs() + mass)).max()) < 1e-5, float(err.max())
+
+
+@pytest.mark.parametrize('M,N,K', [(256 * 10, 512, 320), (256 * 42, 512, 128), (256 * 5 + 77, 1024, 192), (256 * 3, 192, 64), (128, 256, 512)])
+def test_tc_linear_last_wave_split_is_bit_identical(C, M, N, K):
+    """The generic GEMM cuts the tiles of its last, partial wave (or of a launch smaller than the chip) along N into 2 - 4 narrower
+    sub-tiles.  A sub-tile accumulates over K in the same order as the whole tile, so the result must equal -
+    bit for bit - the same product computed column block by column block in separate launches (whose own tile counts split differently
+    or not at all), and an fp64 reference within rounding.  Shapes: 20 tile pairs (all split by 2), 84 = one full wave + 10 (split by 4),
+    ragged rows, a 192-wide N tile, a single tile pair."""
+    torch.manual_seed(M + N)
+    A = torch.randn(M, K, device='cuda').half()
+    W = (torch.randn(N, K, device='cuda') / K ** 0.5).half()
+    b = torch.randn(N, device='cuda')
+    out = torch.full((M, N), float('nan'), device='cuda')
+    out_h = torch.zeros((M, N), device='cuda', dtype=torch.float16)
+    C.tc_linear(A, K, M, M, W, K, b, N, K, False, act=C.ACT_GELU, out_f32=out, ldo=N, out_h=out_h, ldoh=N)
+    want = torch.nn.functional.gelu(A.double() @ W.double().t() + b.double())
+    assert float((out.double() - want).abs().max()) < 2e-5 * max(1.0, float(want.abs().max()))
+    for nb in (64, 128):
+        if N % nb:
+            continue
+        parts = torch.full((M, N), float('nan'), device='cuda')
+        for n0 in range(0, N, nb):
+            C.tc_linear(A, K, M, M, W[n0:n0 + nb].contiguous(), K, b[n0:n0 + nb].contiguous(), nb, K, False, act=C.ACT_GELU,
+                        out_f32=parts[:, n0:], ldo=N)
+        assert torch.equal(parts, out), (M, N, K, nb)
+    assert torch.equal(out_h, out.half())
