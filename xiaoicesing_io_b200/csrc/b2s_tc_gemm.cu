@@ -20,6 +20,9 @@
 //   GATE     [g|f] = acc + cond (hoisted conditioner projection, 16-bit, interleaved) ; z = sigmoid(g)*tanh(f)
 //   RESSKIP  x <- (x + acc + b)/sqrt2 (fp32 residual stream), y_next <- x + d_next (16-bit), skip (+)= acc + b
 //   SWIGLU   g = out * silu(gate)  (interleaved)             RESIDUAL   x <- x + acc + b
+//   VRES     x <- x_src + acc + b, y_h <- leaky_relu(x) (the vocoder's residual blocks, nsf_hifigan/models.py:60-68)
+// The shipped kernel is the cta_group::2 variant further down (tc_gemm_cg2_kernel): 256-row MMAs over a CTA pair, N tiles of 256 / 192 /
+// 128 / 64 columns, and a last-wave split that cuts the tiles of a partial last wave along N (decode_vtile).
 #include "b2s_tc.cuh"
 
 #include <stdlib.h>
