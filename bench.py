@@ -584,8 +584,19 @@ def time_vocoder(precision, dev, T=690, reps=3, extra_hparams=None):
         ch //= 2
         rate *= u
         macs += rate * ch * ch * sum(6 * kk for kk in VOCODER_H['resblock_kernel_sizes'])
+    # algorithmic HBM bytes per mel frame: per stage element (rate x channels) the transposed conv writes the fp32 stream (4 B), the source
+    # conv updates it and writes the 16-bit copy (8 + 2), every conv pair reads / writes 16-bit tiles around the fp32 read-modify-write
+    # (2 + 2, then 2 + 4 + 4 + 2; no 16-bit copy after a block's last pair), the block mean reads 3 streams and writes 16 bits (12 + 2)
+    elems, ch, rate = 0, 512, 1
+    for u in VOCODER_H['upsample_rates']:
+        ch //= 2
+        rate *= u
+        elems += rate * ch
+    bytes_per_frame = elems * (14 + 3 * (16 + 16 + 14) + 14)
+    pk = peaks()
     res = {'workload': f'NSF-HiFiGAN 44.1 kHz geometry (512 ch, hop 512, resblock kernels 3/7/11), mel [B, {T}, 128] + f0 -> {T * hop} samples '
-                       f'per utterance, once per utterance', 'gflop_per_utterance': 2.0 * macs * T / 1e9}
+                       f'per utterance, once per utterance', 'gflop_per_utterance': 2.0 * macs * T / 1e9,
+           'hbm_gb_algorithmic_per_utterance': bytes_per_frame * T / 1e9}
 
     def timed(fn):
         for _ in range(3):
@@ -606,6 +617,9 @@ def time_vocoder(precision, dev, T=690, reps=3, extra_hparams=None):
         ms = timed(lambda: gen.forward_rows(mel, f0, rand_ini=ri, noise=nz))
         r = {'ms_per_call': ms, 'samples_per_s': B * T * hop / (ms * 1e-3), 'rtf': (ms * 1e-3) / (B * T * hop / 44100.0),
              'tflops_algorithmic': 2.0 * macs * T * B / (ms * 1e-3) / 1e12}
+        r['frac_of_bf16_peak'] = r['tflops_algorithmic'] / pk['bf16_burst']
+        r['hbm_gbs_algorithmic'] = bytes_per_frame * T * B / (ms * 1e-3) / 1e9          # B = 1 lives in the 126 MB L2: not an HBM figure there
+        r['frac_of_hbm_peak'] = r['hbm_gbs_algorithmic'] / pk['hbm']
         if ref_gen is not None:
             mel_c = mel.transpose(1, 2).contiguous()
             with torch.no_grad():
