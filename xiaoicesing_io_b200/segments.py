@@ -236,21 +236,67 @@ def cross_fade(a: np.ndarray, b: np.ndarray, idx: int) -> np.ndarray:
 
 def vocode_segments(entries: Sequence[dict], vocoder, sample_rate: int, device=None) -> np.ndarray:
     """``.mel.pt`` entries ``{'offset', 'mel' [1, T, M], 'f0' [1, T]}`` -> one waveform (float64 numpy, like the reference's):
-    every segment through ``vocoder.spec2wav_torch(mel, f0=f0)`` (one call per segment, ds_acoustic.py:185-187; segments of equal
-    length replay the same CUDA graph), placed at ``round(offset * sample_rate)`` with silence before it or a cross-fade into the
-    previous segment (scripts/vocode.py:64-84, ds_acoustic.py:227-236)."""
+    every segment through ``vocoder.spec2wav_torch(mel, f0=f0)`` (one call per segment, ds_acoustic.py:185-187), placed at
+    ``round(offset * sample_rate)`` with silence before it or a linear cross-fade into the previous segment (scripts/vocode.py:64-84,
+    ds_acoustic.py:227-236, utils/infer_utils.py:89-96).
+
+    Same samples as the reference's loop, without its quadratic cost: the reference grows the result with ``np.append`` / a fresh
+    ``cross_fade`` array per segment (two copies of everything so far: 2.5 s of host time for 48 segments / 12 minutes of audio); here
+    the segments are vocoded first (device-to-host copies queued behind the kernels), then written once into a preallocated array with
+    the identical fade arithmetic.  Segment lengths rarely repeat, so CUDA-graph capture is switched off for the loop when the project
+    has more distinct lengths than the vocoder's graph cache holds (a capture costs more than the launches it would save)."""
+    from .hparams import hparams
     device = device if device is not None else vocoder.device
-    result = np.zeros(0)
-    current_length = 0
-    for e in entries:
-        wav = vocoder.spec2wav_torch(e['mel'].to(device), f0=e['f0'].to(device)).cpu().numpy()
-        silent_length = round(e.get('offset', 0.) * sample_rate) - current_length
-        if silent_length >= 0:
-            result = np.append(result, np.zeros(silent_length))
-            result = np.append(result, wav)
+    distinct = len({int(e['mel'].shape[1]) for e in entries})
+    saved = hparams.get('b2s_cuda_graph', None)
+    if distinct > 4:
+        hparams['b2s_cuda_graph'] = False
+    try:
+        wavs = []
+        for e in entries:
+            y = vocoder.spec2wav_torch(e['mel'].to(device), f0=e['f0'].to(device))
+            host = torch.empty(y.shape, dtype=y.dtype, pin_memory=True) if y.is_cuda else y
+            if y.is_cuda:
+                host.copy_(y, non_blocking=True)
+            wavs.append(host)
+        if any(w.is_pinned() for w in wavs):
+            torch.cuda.synchronize(device)
+    finally:
+        if distinct > 4:
+            if saved is None:
+                hparams.pop('b2s_cuda_graph', None)
+            else:
+                hparams['b2s_cuda_graph'] = saved
+    # placement: a segment always starts at round(offset * sr) (silence before it, or a fade from there to the end of what exists)
+    starts = [round(e.get('offset', 0.) * sample_rate) for e in entries]
+    ends, cur, ordered = [], 0, True
+    for s0, w in zip(starts, wavs):
+        ordered = ordered and s0 >= 0 and (s0 >= cur or s0 + w.shape[0] >= cur)
+        cur = s0 + w.shape[0]
+        ends.append(cur)
+    if not ordered:                                   # a segment nested inside its predecessor: the reference's literal loop (it raises)
+        result, current_length = np.zeros(0), 0
+        for s0, w in zip(starts, wavs):
+            w = w.numpy()
+            silent_length = s0 - current_length
+            if silent_length >= 0:
+                result = np.append(np.append(result, np.zeros(silent_length)), w)
+            else:
+                result = cross_fade(result, w, current_length + silent_length)
+            current_length = current_length + silent_length + w.shape[0]
+        return result
+    result = np.zeros(ends[-1] if ends else 0)
+    cur = 0
+    for s0, w in zip(starts, wavs):
+        w = w.numpy()
+        if s0 >= cur:
+            result[s0:s0 + w.shape[0]] = w
         else:
-            result = cross_fade(result, wav, current_length + silent_length)
-        current_length = current_length + silent_length + wav.shape[0]
+            fade_len = cur - s0
+            k = np.linspace(0, 1.0, num=fade_len, endpoint=True)
+            result[s0:cur] = (1 - k) * result[s0:cur] + k * w[:fade_len]
+            result[cur:s0 + w.shape[0]] = w[fade_len:]
+        cur = s0 + w.shape[0]
     return result
 
 
