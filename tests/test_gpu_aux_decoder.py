@@ -152,3 +152,34 @@ def test_graphed_launches_policy():
     gl(('c',), [xs[0]], fn)
     assert len(calls) == n + 1 and calls[-1] is False
     P.hparams.clear()
+
+
+def test_graph_cache_does_not_thrash_on_ragged_shapes():
+    """A caller cycling through more shapes than the graph cache holds (one segment per call over a ragged project) must stop paying
+    for captures that are evicted before their first replay; a shape asked for twice in a row is still captured and replayed."""
+    import xiaoicesing_io_b200 as P
+    from xiaoicesing_io_b200._graphs import GraphedLaunches
+    P.hparams.clear()
+    g = GraphedLaunches(max_graphs=2)
+    calls = []
+
+    def fn(inp):
+        calls.append(torch.cuda.is_current_stream_capturing())
+        return inp[0] * 2
+
+    x = {n: torch.full((n,), 1.0, device='cuda') for n in range(1, 8)}
+    for _ in range(2):                                       # two passes over 7 shapes: first sights, then captures (cache of 2 thrashes)
+        for n in range(1, 8):
+            assert torch.equal(g((n,), [x[n]], fn), x[n] * 2)
+    captures_before = sum(calls)
+    assert g._evicted_unused >= 2
+    for _ in range(3):                                       # further passes: no capture at all, everything runs from the host
+        for n in range(1, 8):
+            assert torch.equal(g((n,), [x[n]], fn), x[n] * 2)
+    assert sum(calls) == captures_before
+    n_calls = len(calls)
+    assert (6,) not in g._graphs                            # (the two graphs captured before the guard closed stay cached and replay)
+    for _ in range(4):                                       # a steady shape: second sight in a row captures, then replays (fn not called)
+        assert torch.equal(g((6,), [x[6]], fn), x[6] * 2)
+    assert sum(calls) == captures_before + 1 and len(calls) <= n_calls + 2
+    assert g._evicted_unused == 0

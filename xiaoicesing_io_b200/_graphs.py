@@ -20,10 +20,12 @@ class GraphedLaunches:
         self._graphs: 'OrderedDict[tuple, tuple]' = OrderedDict()
         self._seen: 'OrderedDict[tuple, None]' = OrderedDict()
         self.max_graphs, self.max_seen = max_graphs, max_seen
+        self._evicted_unused, self._last_key = 0, None
 
     def clear(self):
         self._graphs.clear()
         self._seen.clear()
+        self._evicted_unused, self._last_key = 0, None
 
     def __call__(self, key: tuple, inputs: Sequence[Optional[torch.Tensor]], fn: Callable[[List[Optional[torch.Tensor]]], torch.Tensor]
                  ) -> torch.Tensor:
@@ -32,25 +34,35 @@ class GraphedLaunches:
         if not hparams.get('b2s_cuda_graph', True) or torch.cuda.is_current_stream_capturing():
             return fn(list(inputs))
         entry = self._graphs.get(key)
+        # thrash guard (same rule as the sampler's cache, core/_sampling.py): once a cache's worth of graphs in a row has been evicted
+        # without a single replay, nothing new is captured (the cached graphs keep replaying, everything else is launched from the
+        # host) until a key is asked for twice IN A ROW - a steady workload - which is captured and lifts the guard
+        steady = self._last_key == key
+        thrashing = self._evicted_unused >= self.max_graphs and not steady
+        self._last_key = key
         if entry is None:
-            if key not in self._seen:
+            if key not in self._seen or thrashing:
                 self._seen[key] = None
                 while len(self._seen) > self.max_seen:
                     self._seen.popitem(last=False)
                 return fn(list(inputs))
             del self._seen[key]
+            if steady:
+                self._evicted_unused = 0
             static_in = [None if t is None else t.clone() for t in inputs]
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = fn(static_in)
-            entry = (graph, static_in, static_out)
+            entry = [graph, static_in, static_out, 0]
             while len(self._graphs) >= self.max_graphs:
-                self._graphs.popitem(last=False)
+                _, old = self._graphs.popitem(last=False)
+                self._evicted_unused = self._evicted_unused + 1 if old[3] == 0 else 0
             self._graphs[key] = entry
         else:
             self._graphs.move_to_end(key)
-        graph, static_in, static_out = entry
+            entry[3] += 1
+        graph, static_in, static_out, _ = entry
         for s, t in zip(static_in, inputs):
             if s is not None:
                 s.copy_(t)

@@ -176,8 +176,12 @@ def _program_key(prog: Program):
                  tuple(prog.t_values)))
 
 
+_THRASH = {'evicted_unused': 0, 'last_key': None}
+
+
 def clear_graph_cache():
     _GRAPH_CACHE.clear()
+    _THRASH.update(evicted_unused=0, last_key=None)
     _SEEN_KEYS.clear()
 
 
@@ -253,14 +257,28 @@ def _sample_on_device(backbone, prog, cond_bht, B, H, T, F_, M, shape, x_start, 
         graph_key = (id(backbone), eng._packed_version, eng.precision, _program_key(prog), B, T, F_, M, str(device), structure,
                      lens is not None, noise0_in is not None, start_tm)
         entry = _GRAPH_CACHE.get(graph_key)
-        if entry is None and graph_key in _SEEN_KEYS:       # second call with this key: capture
+        cache_max = max(1, int(hparams.get('b2s_graph_cache', _GRAPH_CACHE_MAX)))
+        # Thrash guard: a caller that cycles through more shapes than the cache holds (one segment per call over a ragged project)
+        # would capture every shape on its second sight and lose the graph before its third - captures cost more than the launches
+        # they save.  Once a cache's worth of graphs in a row has been evicted without a single replay, nothing new is captured (the
+        # cached graphs keep replaying, everything else is launched from the host) until a key is asked for twice IN A ROW - a steady
+        # workload - which is captured and lifts the guard.
+        steady = _THRASH['last_key'] == graph_key
+        thrashing = _THRASH['evicted_unused'] >= cache_max and not steady
+        _THRASH['last_key'] = graph_key
+        if entry is None and graph_key in _SEEN_KEYS and not thrashing:       # second call with this key: capture
             del _SEEN_KEYS[graph_key]
-            while len(_GRAPH_CACHE) >= max(1, int(hparams.get('b2s_graph_cache', _GRAPH_CACHE_MAX))):
-                _GRAPH_CACHE.popitem(last=False)            # least recently used graph
+            if steady:
+                _THRASH['evicted_unused'] = 0
+            while len(_GRAPH_CACHE) >= cache_max:
+                _, old = _GRAPH_CACHE.popitem(last=False)   # least recently used graph
+                _THRASH['evicted_unused'] = _THRASH['evicted_unused'] + 1 if getattr(old, 'replays', 0) == 0 else 0
             entry = _GraphedLoop(eng, CompiledProgram(prog, device), B, T, H, F_, M, device, ragged=lens is not None,
                                  ext_noise=noise0_in is not None, start_tm=start_tm)
+            entry.replays = -1                              # the run below is the capture's own
             _GRAPH_CACHE[graph_key] = entry
         if entry is not None:
+            entry.replays = getattr(entry, 'replays', 0) + 1
             _GRAPH_CACHE.move_to_end(graph_key)
             xs = None if x_start is None else x_start.to(device=device, dtype=torch.float32)
             n0 = None if noise0_in is None else noise0_in.to(device=device, dtype=torch.float32)
