@@ -79,3 +79,54 @@ def test_ds_to_wav_batched_equals_the_per_segment_loop(tmp_path):
     # the .mel.pt route of scripts/vocode.py gives a waveform of the same length
     wav2 = P.segments.vocode_segments(loaded, voc, 44100)
     assert wav2.shape == wav.shape
+
+
+def _dist_worker(rank, world, port, n_gpus, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dev = torch.device('cuda', rank if n_gpus >= world else 0)
+    torch.cuda.set_device(dev)
+    nccl = n_gpus >= world
+    dist.init_process_group('nccl' if nccl else 'gloo', rank=rank, world_size=world, **({'device_id': dev} if nccl else {}))
+    try:
+        P, model, voc, vocab = _build(dev)
+        params = []
+        for i, n_ph in enumerate((9, 5, 14, 7, 11, 6)):
+            p, _ = _ds_param(800 + i, n_ph, energy=(-60., -10., 0.011))
+            p['offset'], p['seed'] = 3.0 * i, 40 + i
+            params.append(p)
+        inf = P.infer.DiffSingerAcousticInfer(model, voc, vocab_list=vocab, device=dev)
+        got = inf.infer_segments(params, batched=True)
+        ok = True
+        if rank == 0:
+            dist.destroy_process_group()
+            whole = inf.infer_segments(params, batched=True)            # the same project on one rank
+            ok = len(got) == len(whole) == 6 and all(torch.equal(a['mel'], b['mel']) and torch.equal(a['f0'], b['f0']) for a, b in zip(got, whole))
+        else:
+            ok = got is None
+        q.put((rank, ok))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_ds_driver_across_two_ranks_equals_one_rank():
+    """``infer_segments`` under torch.distributed: segments partitioned by length over two ranks (cuda:0 / cuda:1 with NCCL when the box has
+    two GPUs, else both on cuda:0 with gloo), gathered once on rank 0 - bit-identical to the one-rank run, None on the other rank."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    n_gpus = torch.cuda.device_count()
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, n_gpus, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res

@@ -12,7 +12,8 @@ Two ways through ``run_inference``:
   * ``batched=False``: the reference's loop - one segment per call, reseeded per segment (ds_acoustic.py:209-219);
   * ``batched=True`` (default): the segment driver (segments.py) - conditions and x_start per segment from ``fs2`` / ``aux_decoder``,
     then the sampler over RAGGED batches of segments with per-segment seeded noise; every segment receives the bits of its own
-    B = 1 run for the deterministic samplers, at several times the throughput.
+    B = 1 run for the deterministic samplers, at several times the throughput.  Under ``torch.distributed`` (one process per GPU)
+    the segments are partitioned across the ranks by length; rank 0 receives every mel, vocodes and writes, the others return None.
 Host-side preprocessing is numpy / torch on small per-segment arrays (a few hundred tokens, a few thousand frames), as in the reference.
 """
 from __future__ import annotations
@@ -253,8 +254,17 @@ class DiffSingerAcousticInfer:
         """``params`` -> the ``.mel.pt`` entries ``{'offset', 'mel' [1, T, M] (CPU), 'f0' [1, T] (CPU)}`` in segment order."""
         batches = [self.preprocess_input(p, idx=i) for i, p in enumerate(params)]
         if batched:
-            res = S.sample_segments(self.model.diffusion, params, self._cond_fn(list(zip(params, batches))), self.timestep, self.device,
-                                    seed=seed, **driver_kw)
+            import torch.distributed as dist
+            cond_fn = self._cond_fn(list(zip(params, batches)))
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # one process per GPU: the segments are partitioned by length, every rank runs the producers and the sampler for ITS
+                # segments only (no collective inside the loop), the finished entries are gathered once on rank 0; None elsewhere
+                res = S.sample_segments_distributed(self.model.diffusion, params, cond_fn, self.timestep, self.device, seed=seed, **driver_kw)
+                if res is None:
+                    return None
+            else:
+                got = S.sample_segments(self.model.diffusion, params, cond_fn, self.timestep, self.device, seed=seed, **driver_kw)
+                res = [got[i] for i in range(len(params))]
             return [dict(offset=res[i]['offset'], mel=res[i]['mel'], f0=batches[i]['f0'].cpu()) for i in range(len(params))]
         out = []
         for param, batch in zip(params, batches):
@@ -275,6 +285,8 @@ class DiffSingerAcousticInfer:
         result = None
         for i in range(num_runs):
             entries = self.infer_segments(params, seed=seed, batched=batched)
+            if entries is None:                                  # a rank other than 0 of a multi-GPU run: rank 0 vocodes and writes
+                continue
             path = out_dir / (f'{title}-{str(i).zfill(3)}{suffix}' if num_runs > 1 else title + suffix)
             if save_mel:
                 result = entries
