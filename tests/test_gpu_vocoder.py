@@ -264,3 +264,31 @@ def test_kernels_stay_inside_their_outputs():
                  torch.zeros(1, device='cuda'), har, B, T, 8, 9, 44100, 0.1, 0.003, 0.)
     check('phase / source')
     assert bool(torch.isfinite(har).all()) and bool(torch.isfinite(wav).all())
+
+
+@pytest.mark.parametrize('h', [
+    dict(num_mels=128, sampling_rate=44100, upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=256,
+         resblock='1', resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]]),                  # hop 256, two blocks
+    dict(num_mels=80, sampling_rate=24000, upsample_rates=[8, 8, 4], upsample_kernel_sizes=[16, 16, 8], upsample_initial_channel=128,
+         resblock='2', resblock_kernel_sizes=[3, 5, 7], resblock_dilation_sizes=[[1, 2], [2, 6], [3, 12]]),            # ResBlock2, 80 mels
+    dict(num_mels=128, sampling_rate=44100, upsample_rates=[8, 4, 2, 2, 2, 2], upsample_kernel_sizes=[16, 8, 4, 4, 4, 4],
+         upsample_initial_channel=1024, resblock='1', resblock_kernel_sizes=[3, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]],
+         mini_nsf=True),                                                                                               # 1024 channels, mini_nsf
+], ids=['hop256', 'resblock2_80mel', 'wide_mini_nsf'])
+def test_other_geometries_against_oracle(h):
+    """Geometries other than the public 44.1 kHz one: another hop size, ResBlock2 with even dilations and 80 mel bins (padded to 128
+    GEMM columns), a 1024-channel first stage (two N tiles) with the mini_nsf source - every fold / padding decision of vocoder.py."""
+    cfg = OV.NsfHifiGanCfg(**{k: (tuple(tuple(x) if isinstance(x, list) else x for x in v) if isinstance(v, list) else v)
+                              for k, v in h.items()})
+    sd = OV.random_state_dict(cfg, 21)
+    hop = int(np.prod(h['upsample_rates']))
+    B, T = 2, 29
+    mel, f0, ri, nz = _inputs(B, T, h['num_mels'], hop, 31)
+    with torch.no_grad():
+        ref = OV.generator_forward(sd, cfg, mel, f0, ri, nz)
+    gen = _gen(h, sd, 'fp16')
+    kw = {} if h.get('mini_nsf') else dict(rand_ini=ri.cuda(), noise=nz.cuda())
+    out = gen(mel.cuda(), f0.cuda(), **kw)
+    err = float((out.cpu() - ref).abs().max())
+    print(dict(test='vocoder_geometry', upsample_rates=h['upsample_rates'], max_abs=err, ref_absmax=float(ref.abs().max())))
+    assert out.shape == ref.shape == (B, 1, T * hop) and err <= TOL['fp16'], err

@@ -167,3 +167,37 @@ def test_cpu_module_raises():
     gen.load_state_dict(fx.sd, strict=True)
     with pytest.raises(P.B2SError):
         gen.forward_rows(fx['mel'].transpose(1, 2).contiguous(), fx['f0'])
+
+
+GEOMETRIES = {
+    'hop256': dict(num_mels=128, sampling_rate=44100, upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+                   upsample_initial_channel=256, resblock='1', resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]]),
+    'resblock2_80mel': dict(num_mels=80, sampling_rate=24000, upsample_rates=[8, 8, 4], upsample_kernel_sizes=[16, 16, 8],
+                            upsample_initial_channel=128, resblock='2', resblock_kernel_sizes=[3, 5, 7],
+                            resblock_dilation_sizes=[[1, 2], [2, 6], [3, 12]]),
+    'wide_mini_nsf': dict(num_mels=128, sampling_rate=44100, upsample_rates=[8, 4, 2, 2, 2, 2], upsample_kernel_sizes=[16, 8, 4, 4, 4, 4],
+                          upsample_initial_channel=1024, resblock='1', resblock_kernel_sizes=[3, 11],
+                          resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]], mini_nsf=True),
+}
+
+
+@pytest.mark.parametrize('name', sorted(GEOMETRIES))
+def test_launch_sequence_other_geometries(cpu_kernels, name):
+    """Fold / padding decisions for other hop sizes, ResBlock2 with even dilations, 80 mel bins, a 1024-channel first stage, mini_nsf."""
+    h = GEOMETRIES[name]
+    cfg = OV.NsfHifiGanCfg(**{k: (tuple(tuple(x) if isinstance(x, list) else x for x in v) if isinstance(v, list) else v) for k, v in h.items()})
+    sd = OV.random_state_dict(cfg, 21)
+    hop = int(np.prod(h['upsample_rates']))
+    g = torch.Generator().manual_seed(31)
+    B, T = 2, 7
+    mel = torch.randn(B, h['num_mels'], T, generator=g) * 1.5 - 4
+    f0 = 110 * 2 ** (2 * torch.rand(B, T, generator=g))
+    f0[:, 2:4] = 0
+    ri, nz = torch.rand(1, 1, 9, generator=g), torch.randn(B, T * hop, 9, generator=g)
+    with torch.no_grad():
+        ref = OV.generator_forward(sd, cfg, mel, f0, ri, nz)
+    gen = cpu_kernels.Generator(dict(h))
+    gen.load_state_dict(sd, strict=True)
+    kw = {} if h.get('mini_nsf') else dict(rand_ini=ri, noise=nz)
+    out = gen.forward_rows(mel.transpose(1, 2).contiguous(), f0, **kw)
+    assert out.shape == (B, T * hop) and (out - ref[:, 0]).abs().max().item() < 3e-5
