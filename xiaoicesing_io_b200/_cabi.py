@@ -141,7 +141,8 @@ def require_experiments(what: str):
                        f'B2S_BUILD_EXPERIMENTS=1 to use it')
 
 
-N_CALLS = 0     # successful kernel-launching C-ABI calls so far (every entry point launches exactly one kernel)
+N_CALLS = 0     # successful kernel-launching C-ABI calls so far (every entry point of the sampling path launches exactly one kernel; the
+#                 whole-denoiser entry launches two and b2s_masked_loss_f32, outside the sampling loop, two)
 
 
 def check(rc: int, what: str = ''):
