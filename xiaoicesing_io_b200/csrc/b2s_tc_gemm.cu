@@ -636,6 +636,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
         uint32_t aphase = 0;
         float* stg = stg_all + e * (16 * STG_LD);
         const int cl = (lane & 7) * 4, rsub = lane >> 3;
+        const bool direct16 = EPI == EPI_LINEAR && p.out_h && !p.out_f && !p.y_h && !p.oh_tiled && !p.oh_blk && (p.ldoh & 7) == 0 && (p.N & 31) == 0 &&
+                              ((reinterpret_cast<uintptr_t>(p.out_h) & 15) == 0) && (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         for (int v = pair; v < p.vt_total; v += npairs) {
             const VTile vt = decode_vtile(p, v);
             const int pt = vt.pt, tw = vt.w;                // tw: columns of this (sub-)tile
@@ -678,6 +680,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
                 if (col0 >= p.N) break;
                 float acc[32];
                 tmem_ld32(taddr + j * 32, acc);
+                if (EPI == EPI_LINEAR && direct16) {          // N % 32 == 0: every chunk of the tile takes this path
+                    // 16-bit output only: after tcgen05.ld a thread holds 32 consecutive columns of ITS row - bias / activation / pack
+                    // in registers and four 16-byte stores, no trip through the staging tile (that transpose exists to coalesce the
+                    // fp32 read-modify-write epilogues).  The vocoder's first convs and conv_pre, the aux decoder's GELU GEMM.
+                    tmem_ld_wait();
+                    const int t = t0 + q * 32 + lane;
+                    if (t < p.T) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 bq = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 v = make_float4(fmaf(p.alpha, acc[4 * c], bq.x), fmaf(p.alpha, acc[4 * c + 1], bq.y),
+                                                   fmaf(p.alpha, acc[4 * c + 2], bq.z), fmaf(p.alpha, acc[4 * c + 3], bq.w));
+                            if (p.act == ACT_RELU) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+                            else if (p.act == ACT_LRELU)
+                                v = make_float4(fmaxf(v.x, LRELU_SLOPE * v.x), fmaxf(v.y, LRELU_SLOPE * v.y), fmaxf(v.z, LRELU_SLOPE * v.z),
+                                                fmaxf(v.w, LRELU_SLOPE * v.w));
+                            else if (p.act > ACT_RELU) v = act4_slow(v, p.act);
+                            pk[2 * c] = Half16<BF16>::pack2(v.x, v.y);
+                            pk[2 * c + 1] = Half16<BF16>::pack2(v.z, v.w);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_h) + ((long long)bt * p.T + t) * p.ldoh + col0);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    }
+                    continue;
+                }
                 const int col = col0 + cl;
                 const bool colok = okn;
                 const EpiConst kc = kcn;
