@@ -470,7 +470,7 @@ template <int EPI, int BF16>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_constant__ TcP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const bool conv3 = EPI == EPI_GATE && p.conv3 != 0;
+    const bool conv3 = (EPI == EPI_GATE || EPI == EPI_LINEAR || EPI == EPI_VRES) && p.conv3 != 0;
     const int ring_bytes = conv3 ? STAGES3 * STAGE3_BYTES : STAGES2 * STAGE2_BYTES;
     float* stg_all = reinterpret_cast<float*>(smem + ring_bytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + ring_bytes + STG_BYTES);
@@ -768,7 +768,8 @@ static int launch_one(const TcP& p, cudaStream_t st) {
 #endif
     if (p.cg2) {
         static PerDevice configured2;
-        constexpr int smem_max = EPI == EPI_GATE ? (SMEM3_BYTES > SMEM2_BYTES ? SMEM3_BYTES : SMEM2_BYTES) : SMEM2_BYTES;
+        constexpr bool can3 = EPI == EPI_GATE || EPI == EPI_LINEAR || EPI == EPI_VRES;      // 3-tap convs with the A slab resident across the taps
+        constexpr int smem_max = can3 ? (SMEM3_BYTES > SMEM2_BYTES ? SMEM3_BYTES : SMEM2_BYTES) : SMEM2_BYTES;
         if (configured2.first()) {
             B2S_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_cg2_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         }
@@ -792,7 +793,7 @@ static int launch_one(const TcP& p, cudaStream_t st) {
         cudaLaunchConfig_t cfg2{};
         cfg2.gridDim = dim3(2 * pairs);
         cfg2.blockDim = dim3(NTHREADS);
-        cfg2.dynamicSmemBytes = (EPI == EPI_GATE && p.conv3) ? SMEM3_BYTES : SMEM2_BYTES;
+        cfg2.dynamicSmemBytes = (can3 && p.conv3) ? SMEM3_BYTES : SMEM2_BYTES;
         cfg2.stream = st;
         cudaLaunchAttribute attr2[2];
         attr2[0].id = cudaLaunchAttributeClusterDimension;
@@ -1037,6 +1038,18 @@ extern "C" int b2s_tc_conv1d(const void* a_h, const void* W_h, const float* bias
     return launch<EPI_LINEAR>(p, bf16, (cudaStream_t)stream);
 }
 
+// Three taps with |shift| <= CONV3_HALO rows: ONE load of the activation slab with its halo serves all taps (row-shifted descriptors), as in
+// the WaveNet gate GEMM - most of the vocoder's convs after row folding, and its transposed convs.  68 KB instead of 96 KB of L2 -> SM
+// traffic per three K blocks; the wide (N = 256) folded convs sit on that cap.
+static int conv3_if_three_taps(TcP& p, const void* a_h, int B, int T, int Cin, int ksize, int dil, int bf16) {
+    static const bool on = [] { const char* e = getenv("B2S_VOC_CONV3"); return !e || atoi(e) != 0; }();
+    if (!on || !p.cg2 || ksize != 3 || dil > CONV3_HALO) return B2S_OK;
+    int rc = make_map_act(&p.mapA3, a_h, bf16, Cin, Cin, T, B, BLOCK_K, A3_ROWS);
+    if (rc) return rc;
+    p.conv3 = 1;
+    return B2S_OK;
+}
+
 // Dilated dense Conv1d as one GEMM over ksize taps (the vocoder's residual-block convs, nsf_hifigan/models.py:39-58; its transposed
 // convs are 3-tap convs over u * Cout output columns, see vocoder.py)
 extern "C" int b2s_tc_conv1d_dil(const void* a_h, const void* W_h, const float* bias, float* out_f32, int ldo, void* out_h, int ldoh,
@@ -1051,6 +1064,8 @@ extern "C" int b2s_tc_conv1d_dil(const void* a_h, const void* W_h, const float* 
     int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16);
     if (rc) return rc;
     p.tap_c = ksize / 2;
+    rc = conv3_if_three_taps(p, a_h, B, T, Cin, ksize, dil, bf16);
+    if (rc) return rc;
     p.bias = bias; p.alpha = 1.0f; p.act = act;
     p.out_f = out_f32; p.ldo = ldo; p.out_h = out_h; p.ldoh = ldoh;
     p.no_split = 1;            // measured: 1.97 ms (no split) vs 2.03 ms per 8-s utterance with the blocks on three streams
@@ -1073,6 +1088,8 @@ extern "C" int b2s_tc_conv1d_residual(const void* a_h, const void* W_h, const fl
     int rc = setup(p, a_h, Cin, Cin, B, T, true, W_h, ksize * Cin, N, ksize * Cin, Cin / BLOCK_K, dil, bf16);
     if (rc) return rc;
     p.tap_c = ksize / 2;
+    rc = conv3_if_three_taps(p, a_h, B, T, Cin, ksize, dil, bf16);
+    if (rc) return rc;
     p.bias = bias; p.x = x; p.x_src = x_src; p.C = N; p.y_h = y_h; p.ldy = N;
     p.y_lrelu = y_h != nullptr && y_slope != 1.0f; p.y_slope = y_slope;
     p.no_split = 1;
