@@ -201,3 +201,35 @@ def test_launch_sequence_other_geometries(cpu_kernels, name):
     kw = {} if h.get('mini_nsf') else dict(rand_ini=ri, noise=nz)
     out = gen.forward_rows(mel.transpose(1, 2).contiguous(), f0, **kw)
     assert out.shape == (B, T * hop) and (out - ref[:, 0]).abs().max().item() < 3e-5
+
+
+@pytest.mark.parametrize('k,d,f,C', [(3, 1, 4, 16), (11, 5, 16, 16), (7, 3, 8, 32), (11, 1, 2, 64), (5, 2, 4, 16), (3, 5, 1, 64), (11, 3, 4, 64)])
+def test_folded_conv_equals_the_conv(k, d, f, C):
+    """The row-folding identity on its own: a k-tap conv with dilation d over [T, C] equals the dense conv with the packed operand over
+    [T / f, f * C] (zero padding outside the utterance), for every fold the planner can pick and some it would not."""
+    from xiaoicesing_io_b200.vocoder import _fold_conv
+    g = torch.Generator().manual_seed(k * 100 + d * 10 + f)
+    T = 16 * f + 3 * f
+    W, b = torch.randn(C, C, k, generator=g), torch.randn(C, generator=g)
+    x = torch.randn(2, T, C, generator=g)
+    ref = F.conv1d(x.transpose(1, 2), W, b, padding=(k // 2) * d, dilation=d).transpose(1, 2)                      # [B, T, C]
+    Wg, bg, ks, dil = _fold_conv(W, b, d, f, C)
+    rows = x.reshape(2, T // f, f * C)
+    out = _conv(rows.reshape(-1, f * C), Wg, 2, T // f, f * C, f * C, ks, dil) + bg                                # the GEMM's view
+    assert dil == (d if f == 1 else 1) and out.shape == (2 * T // f, f * C)
+    assert (out.reshape(2, T, C) - ref).abs().max().item() < 1e-5 * ref.abs().max().item()       # fp32 summation order only
+
+
+@pytest.mark.parametrize('u,k,f_in,Ci,Co', [(8, 16, 1, 64, 32), (2, 4, 2, 32, 16), (4, 8, 1, 64, 64), (2, 4, 4, 16, 16), (3, 9, 2, 32, 32)])
+def test_folded_transposed_conv_equals_conv_transpose(u, k, f_in, Ci, Co):
+    """A transposed conv with stride u as a dense conv over input rows of f_in samples whose columns are the f_in * u output phases."""
+    from xiaoicesing_io_b200.vocoder import _fold_conv_transpose
+    g = torch.Generator().manual_seed(u * 100 + k + f_in)
+    T = 12 * f_in
+    W, b = torch.randn(Ci, Co, k, generator=g), torch.randn(Co, generator=g)
+    x = torch.randn(2, T, Ci, generator=g)
+    ref = F.conv_transpose1d(x.transpose(1, 2), W, b, stride=u, padding=(k - u) // 2).transpose(1, 2)               # [B, T * u, Co]
+    Wg, bg, ks = _fold_conv_transpose(W, b, u, (k - u) // 2, f_in, Ci, Co)
+    out = _conv(x.reshape(-1, f_in * Ci), Wg, 2, T // f_in, f_in * Ci, f_in * u * Co, ks, 1) + bg
+    assert ref.shape == (2, T * u, Co)
+    assert (out.reshape(2, T * u, Co) - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
