@@ -261,6 +261,13 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same arrival without release semantics: for barriers that hand back an on-chip resource the waiter does not read through memory
+// (a TMEM accumulator drained with tcgen05.ld + tcgen05.wait::ld: the values are in registers, tcgen05.fence::before_thread_sync orders
+// the tensor-memory reads before the arrival).  The release form makes the arriving thread wait until the warp's preceding GLOBAL stores
+// are performed - for an epilogue that just wrote its tile, that is the whole store latency, per tile (ncu: "membar" stalls).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads of a CTA pair: data lands in the ISSUING CTA's shared memory, bytes complete on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_3d_cg2(void* smem, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2) {
     asm volatile(

@@ -73,6 +73,7 @@ struct __align__(64) TcP {
     // remaining num_pt - vt_full tile pairs (fewer than half of the CTA pairs) is cut along N into vt_split sub-tiles of bn / vt_split
     // columns, so that the last, partial wave of a launch (or a launch with fewer tiles than CTA pairs) spreads over the idle pairs.
     int vt_full, vt_split, vt_total;
+    int relaxed_release;       // 1: the epilogue hands its TMEM accumulator back with a relaxed arrival (no wait for its global stores)
     int no_split;              // 1: never split (the vocoder's convs: three residual blocks run concurrently and fill each other's partial waves)
 };
 
@@ -636,6 +637,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
         uint32_t aphase = 0;
         float* stg = stg_all + e * (16 * STG_LD);
         const int cl = (lane & 7) * 4, rsub = lane >> 3;
+        const bool relaxed_release = p.relaxed_release != 0;
         const bool direct16 = EPI == EPI_LINEAR && p.out_h && !p.out_f && !p.y_h && !p.oh_tiled && !p.oh_blk && (p.ldoh & 7) == 0 && (p.N & 31) == 0 &&
                               ((reinterpret_cast<uintptr_t>(p.out_h) & 15) == 0) && (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         for (int v = pair; v < p.vt_total; v += npairs) {
@@ -742,7 +744,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_cg2_kernel(const __grid_c
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
+            if (lane == 0) {
+                if (relaxed_release) mbar_arrive_cluster_relaxed(mapa_u32(&tempty[as], 0));
+                else mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
+            }
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
@@ -780,6 +785,8 @@ static int launch_one(const TcP& p, cudaStream_t st) {
         static const bool no_split = getenv("B2S_GEMM_NOSPLIT") != nullptr;
         const int maxp = num_sms() / 2;
         TcP q = p;
+        static const bool relaxed = [] { const char* e = getenv("B2S_GEMM_RELAXED_RELEASE"); return !e || atoi(e) != 0; }();
+        q.relaxed_release = relaxed ? 1 : 0;
         q.vt_full = num_pt >= maxp ? (num_pt / maxp) * maxp : 0;
         q.vt_split = 1;
         const int rem = num_pt - q.vt_full;
